@@ -1,0 +1,77 @@
+"""Shared test helpers: golden-fixture loading and comparison utilities."""
+import io
+import os
+import pickle
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import bmnas_oracle as O  # noqa: E402
+
+
+def load(name):
+    z = np.load(os.path.join(GOLDEN, name + '.npz'), allow_pickle=False)
+    return {k: z[k] for k in z.files}
+
+
+def sub(d, prefix):
+    """entries of d under 'prefix/' with the prefix stripped, as torch tensors."""
+    n = len(prefix)
+    return {k[n:]: torch.from_numpy(np.array(v)) for k, v in d.items() if k.startswith(prefix)}
+
+
+def cfg_of(d, step_ops=None):
+    g = lambda k: d['cfg_' + k].item()
+    return O.Cfg(C=int(g('C')), L=int(g('L')), num_input_nodes=int(g('num_input_nodes')), steps=int(g('steps')),
+                 multiplier=int(g('multiplier')), node_steps=int(g('node_steps')),
+                 node_multiplier=int(g('node_multiplier')), drpt=float(g('drpt')),
+                 step_ops=step_ops or O.STEP_STEP_PRIMITIVES)
+
+
+def arch_of(d, prefix):
+    a = sub(d, prefix)
+    return [a[str(i)] for i in range(len(a))]
+
+
+class _RefUnpickler(pickle.Unpickler):
+    """Reference pickles name ``models.search.darts.genotypes``; map onto the oracle's
+    namedtuples so CPU tests do not need the product package."""
+
+    def find_class(self, module, name):
+        if module == 'models.search.darts.genotypes':
+            return getattr(O, name)
+        return super().find_class(module, name)
+
+
+def unpickle_genotype(arr):
+    return _RefUnpickler(io.BytesIO(np.asarray(arr).tobytes())).load()
+
+
+def geno_plain(g):
+    """namedtuple-agnostic structural form of a genotype."""
+    return (list(map(tuple, g.edges)),
+            [(list(map(tuple, s.inner_edges)), list(s.inner_steps), list(s.inner_concat)) for s in g.steps],
+            list(g.concat))
+
+
+def rel_err(a, b):
+    a = torch.as_tensor(a).double().cpu()
+    b = torch.as_tensor(b).double().cpu()
+    denom = b.abs().max().clamp_min(1e-30)
+    return ((a - b).abs().max() / denom).item()
+
+
+def assert_close(a, b, tol, what='', atol=0.0):
+    """max|a-b| <= tol * max|b| + atol"""
+    a = torch.as_tensor(a).double().cpu()
+    b = torch.as_tensor(b).double().cpu()
+    assert a.shape == b.shape, f'{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}'
+    err = (a - b).abs().max().item() if a.numel() else 0.0
+    lim = tol * (b.abs().max().item() if b.numel() else 0.0) + atol
+    assert err <= lim, f'{what}: max abs err {err:.3e} > {lim:.3e} (rel {rel_err(a, b):.3e})'
