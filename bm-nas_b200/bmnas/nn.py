@@ -1,0 +1,228 @@
+"""Head of the search network: classifier GEMM and loss on the same C-ABI kernels.
+
+* Linear            -- nn.Linear drop-in (ntu_darts_searchable.py:100-101, central_classifier);
+                       forward = NT GEMM (bmnas_conv_wgrad as C += A B^T on a bias-initialised
+                       output), backward = bmnas_conv_fwd (dX) + bmnas_conv_dgrad (dW) + bmnas_colsum (db).
+* CrossEntropyLoss / BCEWithLogitsLoss -- mean-reduced criteria of the search scripts
+                       (ntu_darts_searchable.py:25, mmimdb_darts_searchable.py:22), fused
+                       softmax/sigmoid + gradient kernel.
+* SearchHead        -- Searchable_*_Net minus backbones and reshape layers
+                       (ntu_darts_searchable.py:71-179): ``fusion_net`` + ``central_classifier``
+                       with the reference's attribute names, one joint gradient arena.
+"""
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from . import native as N
+from . import runtime as _rt
+
+
+def _conv_struct(B, L, K, M, w_fold=1):
+    st = N.bmnas_conv_params()
+    st.B, st.L, st.K, st.M, st.w_fold, st.n_src, st.n_seg = B, L, K, M, w_fold, 1, 1
+    st.src_C[0] = K
+    st.seg_M[0] = M
+    return st
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, gw_view, gb_view):
+        B, Kc = x.shape
+        Nc = weight.shape[0]
+        s = N.current_stream()
+        L = N.lib()
+        out = torch.empty(B, Nc, device=x.device, dtype=torch.float32)
+        N.check(L.bmnas_bias_rows(ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(_p(bias)), B, Nc, s), 'bias_rows')
+        st = _conv_struct(1, Kc, Nc, B)       # out[m=b][k=class] += sum_l x[b][l] * W[class][l]
+        st.GV = x.data_ptr()
+        st.src[0] = weight.data_ptr()
+        st.gW[0] = out.data_ptr()
+        N.check(L.bmnas_conv_wgrad(ctypes.byref(st), s), 'linear fwd')
+        ctx.save_for_backward(x, weight)
+        ctx.views = (gw_view, gb_view)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        gw_view, gb_view = ctx.views
+        g = g.contiguous()
+        B, Kc = x.shape
+        Nc = weight.shape[0]
+        s = N.current_stream()
+        L = N.lib()
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x)
+            st = _conv_struct(1, Kc, Nc, B)   # gx[b][l] = sum_class g[b][class] * W[class][l]
+            st.W[0] = g.data_ptr()
+            st.src[0] = weight.data_ptr()
+            st.Z = gx.data_ptr()
+            N.check(L.bmnas_conv_fwd(ctypes.byref(st), s), 'linear dgrad')
+        if gw_view is not None:
+            st = _conv_struct(1, Kc, Nc, B)   # gW[class][l] = sum_b g[b][class] * x[b][l]
+            st.W[0] = g.data_ptr()
+            st.GV = x.data_ptr()
+            st.gsrc[0] = gw_view.data_ptr()
+            N.check(L.bmnas_conv_dgrad(ctypes.byref(st), s), 'linear wgrad')
+        if gb_view is not None:
+            N.check(L.bmnas_colsum(ctypes.c_void_p(gb_view.data_ptr()), ctypes.c_void_p(g.data_ptr()), B, Nc, s),
+                    'linear bgrad')
+        return gx, None, None, None, None
+
+
+def _assign_grad(t, view):
+    if view is None:
+        return
+    if t.grad is None:
+        t.grad = view
+    elif t.grad.data_ptr() != view.data_ptr():
+        t.grad.add_(view)
+
+
+class Linear(nn.Linear):
+    """nn.Linear whose forward/backward run on the bmnas GEMM kernels; weight/bias gradients are written
+    straight into the module's gradient arena (see runtime.GradArena)."""
+
+    def forward(self, x):
+        if not x.is_cuda and not N.VALIDATE_ONLY:
+            raise N.NativeError('bmnas.nn.Linear has no CPU implementation')
+        x = x if x.is_contiguous() else x.contiguous()
+        leaves = [p for p in (self.weight, self.bias) if p is not None and p.requires_grad]
+        gw = gb = None
+        if leaves and torch.is_grad_enabled():
+            ar = _rt.arena_for(self, leaves, x.device)
+            gw = ar.view(self.weight) if self.weight.requires_grad else None
+            gb = ar.view(self.bias) if (self.bias is not None and self.bias.requires_grad) else None
+        out = _LinearFn.apply(x, self.weight, self.bias, gw, gb)
+        if gw is not None or gb is not None:
+            w, b = self.weight, self.bias
+
+            def hook(_g, w=w, b=b, gw=gw, gb=gb):
+                _assign_grad(w, gw)
+                if b is not None:
+                    _assign_grad(b, gb)
+            if out.requires_grad:
+                out.register_hook(hook)
+        return out
+
+
+class _LossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, kind, ws):
+        logits = logits if logits.is_contiguous() else logits.contiguous()
+        B, n = logits.shape
+        st = N.bmnas_loss_params()
+        st.B, st.n_classes, st.kind = B, n, kind
+        loss = torch.empty((), device=logits.device, dtype=torch.float32)
+        gl = torch.empty_like(logits)
+        st.logits, st.loss, st.glogits = logits.data_ptr(), loss.data_ptr(), gl.data_ptr()
+        if kind == 0:
+            st.labels = target.data_ptr()
+        else:
+            st.targets = target.data_ptr()
+        st.partials, st.counter = ws[0].data_ptr(), ws[1].data_ptr()
+        N.check(N.lib().bmnas_loss_fwd(ctypes.byref(st), N.current_stream()), 'loss fwd')
+        ctx.save_for_backward(gl)
+        ctx.shape = (B, n)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        gl, = ctx.saved_tensors
+        B, n = ctx.shape
+        st = N.bmnas_loss_params()
+        st.B, st.n_classes = B, n
+        out = torch.empty_like(gl)
+        g = g.contiguous()
+        st.glogits, st.gscale, st.gout_logits = gl.data_ptr(), g.data_ptr(), out.data_ptr()
+        N.check(N.lib().bmnas_loss_bwd(ctypes.byref(st), N.current_stream()), 'loss bwd')
+        return out, None, None, None
+
+
+class _Loss(nn.Module):
+    _kind = 0
+
+    def _ws(self, device):
+        ws = self.__dict__.get('_bm_ws')
+        if ws is None or ws[0].device != device:
+            st = N.bmnas_loss_params()
+            n = int(N.lib().bmnas_loss_partials_size(ctypes.byref(st)))
+            ws = (torch.zeros(n, device=device), torch.zeros(1, dtype=torch.int32, device=device))
+            self.__dict__['_bm_ws'] = ws
+        return ws
+
+    def forward(self, logits, target):
+        if not logits.is_cuda and not N.VALIDATE_ONLY:
+            raise N.NativeError('bmnas losses have no CPU implementation')
+        if self._kind == 0:
+            target = target.to(torch.int64).contiguous()
+        else:
+            target = target.to(torch.float32).contiguous()
+        return _LossFn.apply(logits, target, self._kind, self._ws(logits.device))
+
+
+class CrossEntropyLoss(_Loss):
+    _kind = 0
+
+
+class BCEWithLogitsLoss(_Loss):
+    _kind = 1
+
+
+class SearchHead(nn.Module):
+    """fusion network + classifier: what the search step optimises once backbone features are given.
+    ``genotype=None`` builds the searchable hypernet, otherwise the found network."""
+
+    def __init__(self, args, num_outputs, criterion=None, genotype=None):
+        super().__init__()
+        from models.search.darts.model_search import FusionNetwork
+        from models.search.darts.model import Found_FusionNetwork
+        self.args = args
+        self._criterion = criterion
+        if genotype is None:
+            self.fusion_net = FusionNetwork(steps=args.steps, multiplier=args.multiplier,
+                                            num_input_nodes=args.num_input_nodes, num_keep_edges=2, args=args,
+                                            criterion=criterion)
+            mult = args.multiplier
+        else:
+            self.fusion_net = Found_FusionNetwork(len(genotype.edges) // 2, len(genotype.concat),
+                                                  args.num_input_nodes, 2, args, criterion, genotype)
+            mult = len(genotype.concat)
+        self.central_classifier = Linear(args.C * args.L * mult, num_outputs)
+
+    def _joint_arena(self, device):
+        ar = self.__dict__.get('_bm_joint')
+        leaves = ([p for p in self.fusion_net.parameters() if p.requires_grad] + self.arch_parameters() +
+                  [p for p in self.central_classifier.parameters() if p.requires_grad])
+        if ar is None or ar.flat.device != device or not ar.covers(leaves):
+            ar = _rt.GradArena(leaves, device)
+            self.__dict__['_bm_joint'] = ar
+            self.fusion_net._bm_arena = ar
+            self.central_classifier._bm_arena = ar
+            self.fusion_net.__dict__.pop('_bm_cache', None)
+        return ar
+
+    def forward(self, feats):
+        self._joint_arena(feats[0].device)
+        return self.central_classifier(self.fusion_net(feats))
+
+    def genotype(self):
+        return self.fusion_net.genotype()
+
+    def arch_parameters(self):
+        return self.fusion_net.arch_parameters() if hasattr(self.fusion_net, 'arch_parameters') else []
+
+    def central_params(self):
+        return [{'params': self.fusion_net.parameters()}, {'params': self.central_classifier.parameters()}]
+
+    def _loss(self, feats, labels):
+        return self._criterion(self(feats), labels)

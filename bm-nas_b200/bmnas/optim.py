@@ -1,0 +1,109 @@
+"""FusedAdam: torch.optim.Adam semantics (coupled L2 decay, bias correction) in ONE
+multi-tensor CUDA launch, with lr and step count resident on the device so that a
+captured CUDA graph picks up the schedule value written before each replay.
+Replaces the two Adam instances of the search (ntu_darts_searchable.py:42 and :46-47) and
+the per-iteration ``optimizer.load_state_dict`` LR push (scheduler.py:42-46).
+"""
+import ctypes
+
+import torch
+
+from . import native as N
+
+BLOCK_ELEMS = 1024
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        super().__init__(params, defaults)
+        self.grad_scale = 1.0
+        self._g = {}          # group index -> device state
+
+    # -------------------------------------------------------------- device state
+    def _group_state(self, gi, group):
+        ps = [p for p in group['params'] if p.grad is not None]
+        if not ps:
+            return None
+        sig = tuple((p.data_ptr(), p.grad.data_ptr()) for p in ps)
+        st = self._g.get(gi)
+        if st is not None and st['sig'] == sig:
+            return st
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError('FusedAdam: parameter/gradient pointers changed during CUDA-graph capture; '
+                               'run a warm-up step first')
+        dev = ps[0].device
+        old = st
+        sizes = [p.numel() for p in ps]
+        padded = [(n + 3) // 4 * 4 for n in sizes]
+        tot = sum(padded)
+        if old is not None and old['tot'] == tot:
+            m, v, step, lr = old['m'], old['v'], old['step'], old['lr']
+        else:
+            m = torch.zeros(tot, device=dev)
+            v = torch.zeros(tot, device=dev)
+            step = torch.zeros(1, dtype=torch.int64, device=dev)
+            lr = torch.full((1,), float(group['lr']), device=dev)
+        table = (N.bmnas_adam_tensor * len(ps))()
+        off, blk = 0, 0
+        for i, p in enumerate(ps):
+            if not p.is_contiguous() or not p.grad.is_contiguous() or p.dtype != torch.float32:
+                raise ValueError('FusedAdam needs contiguous fp32 parameters and gradients')
+            table[i].p = p.data_ptr()
+            table[i].g = p.grad.data_ptr()
+            table[i].m = m.data_ptr() + off * 4
+            table[i].v = v.data_ptr() + off * 4
+            table[i].n = sizes[i]
+            table[i].block_start = blk
+            off += padded[i]
+            blk += (sizes[i] + BLOCK_ELEMS - 1) // BLOCK_ELEMS
+        raw = bytes(table)
+        host = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+        dtab = host.to(dev)
+        st = dict(sig=sig, tot=tot, m=m, v=v, step=step, lr=lr, table=dtab, n=len(ps), blocks=blk,
+                  counter=torch.zeros(1, dtype=torch.int32, device=dev), lr_host=float(group['lr']),
+                  params=ps)
+        self._g[gi] = st
+        return st
+
+    def set_lr(self, lr, pinned=None):
+        """write the learning rate for the next step (host value + device scalar, async, graph-safe)"""
+        for gi, group in enumerate(self.param_groups):
+            group['lr'] = float(lr)
+            st = self._g.get(gi)
+            if st is not None:
+                if pinned is not None:
+                    pinned.fill_(float(lr))
+                    st['lr'].copy_(pinned, non_blocking=True)
+                else:
+                    st['lr'].fill_(float(lr))
+                st['lr_host'] = float(lr)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        s = None
+        for gi, group in enumerate(self.param_groups):
+            st = self._group_state(gi, group)
+            if st is None:
+                continue
+            if st['lr_host'] != float(group['lr']):
+                if torch.cuda.is_current_stream_capturing():
+                    raise RuntimeError('FusedAdam: change the lr with set_lr() before replaying a captured step')
+                st['lr'].fill_(float(group['lr']))
+                st['lr_host'] = float(group['lr'])
+            p = N.bmnas_adam_params()
+            p.n_tensors, p.block_elems, p.total_blocks = st['n'], BLOCK_ELEMS, st['blocks']
+            p.tensors = st['table'].data_ptr()
+            p.lr = st['lr'].data_ptr()
+            p.beta1, p.beta2 = group['betas']
+            p.eps, p.weight_decay, p.grad_scale = group['eps'], group['weight_decay'], self.grad_scale
+            p.step = st['step'].data_ptr()
+            p.counter = st['counter'].data_ptr()
+            s = s or N.current_stream()
+            N.check(N.lib().bmnas_adam_step(ctypes.byref(p), s), 'adam')
+        return loss
+
+    def zero_grad(self, set_to_none=True):
+        """Gradients live in a static arena that every backward overwrites: nothing to clear."""
+        return None

@@ -1,0 +1,603 @@
+"""Static launch plans ("programs") for the fusion-cell hot path.
+
+A Program is built once per (shape, mode) and holds
+  * every intermediate buffer, pre-allocated in HBM,
+  * an ordered list of prepared C-ABI kernel calls for the forward pass and one for
+    the backward pass (parameter blocks already filled in),
+  * "slots": the few pointers that change per call (user inputs, injected masks).
+Running a program is a tight loop of ctypes calls on the current CUDA stream -- no
+allocation, no host sync -- so the whole thing is legal inside CUDA-graph capture.
+
+The emitters below restate the reference control flow
+  FusionCell.forward   models/search/darts/model_search.py:50-68
+  NodeCell.forward     models/search/darts/node_search.py:48-70
+  Found_*.forward      models/search/darts/model.py:133-160, node.py:45-76
+as kernel sequences; the backward sequence is derived at build time by unwinding
+a stack of closures, tracking which gradient buffer has been written so far
+(first writer overwrites, later writers accumulate).
+"""
+import ctypes
+import zlib
+
+import torch
+
+from . import native as N
+
+OP_IDS = {'Sum': N.BMNAS_OP_SUM, 'ScaleDotAttn': N.BMNAS_OP_ATTN, 'LinearGLU': N.BMNAS_OP_GLU,
+          'ConcatFC': N.BMNAS_OP_FC_RELU, 'CatConvMish': N.BMNAS_OP_FC_MISH}
+ATTN_DROP = 0.1          # node_operations.py:89
+BN_MOMENTUM, BN_EPS = 0.1, 1e-5
+
+
+class Slot:
+    """A tensor supplied at call time (user input, injected dropout mask, upstream gradient)."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __repr__(self):
+        return f'Slot({self.name})'
+
+
+def uid_of(name):
+    return zlib.crc32(name.encode()) & 0xffffffff
+
+
+class Program:
+    def __init__(self, device, B, C, L, training, drpt):
+        self.device = device
+        self.B, self.C, self.L = B, C, L
+        self.training = bool(training)
+        self.drpt = float(drpt)
+        self.fwd, self.bwd = [], []
+        self._cur = self.fwd
+        self._stack = []
+        self._bindings = {}
+        self._keep = []
+        self._grads = {}         # id(state tensor) or slot name -> grad buffer
+        self._written = set()    # data_ptrs of grad buffers already written in the backward order
+        self._zero_ranges = []   # (tensor) zeroed at the start of every backward
+        self.mask_slots = {}     # dropout site name -> Slot (parity mode)
+        self.use_masks = False
+        self.rng_state = None
+        self.sample_offset = 0
+        self.outputs = {}
+        self.generation = 0
+        self.n_fwd_launches = 0
+        self.n_bwd_launches = 0
+
+    # ------------------------------------------------------------------ storage
+    def buf(self, *shape, dtype=torch.float32, zero=False):
+        t = (torch.zeros if zero else torch.empty)(*shape, dtype=dtype, device=self.device)
+        self._keep.append(t)
+        return t
+
+    def counter(self, n=1):
+        return self.buf(max(int(n), 1), dtype=torch.int32, zero=True)
+
+    def ensure_rng(self):
+        if self.rng_state is None:
+            from . import rng
+            self.rng_state = self.buf(2, dtype=torch.int64, zero=True)
+            self.rng_state[0] = rng.next_seed()
+        return self.rng_state
+
+    def grad_of(self, t):
+        key = t.name if isinstance(t, Slot) else id(t)
+        g = self._grads.get(key)
+        if g is None:
+            g = self.buf(self.B, self.C, self.L)
+            self._grads[key] = g
+        return g
+
+    def out_grad(self, slot, buf):
+        """`buf` receives the gradient of the call-time input `slot` (written by a kernel directly)"""
+        self._grads[slot.name] = buf
+        self._written.add(buf.data_ptr())
+
+    def seed_grad(self, t, slot):
+        """the gradient of program output t arrives from outside through `slot`"""
+        self._grads[id(t)] = slot
+
+    def has_grad(self, t):
+        key = t.name if isinstance(t, Slot) else id(t)
+        g = self._grads.get(key)
+        if isinstance(g, Slot):
+            return True
+        return g is not None and g.data_ptr() in self._written
+
+    def acc(self, g):
+        """accumulate flag for grad buffer g in the backward order being emitted"""
+        if g is None:
+            return 0
+        assert not isinstance(g, Slot), 'cannot accumulate into an upstream-gradient slot'
+        k = g.data_ptr()
+        if k in self._written:
+            return 1
+        self._written.add(k)
+        return 0
+
+    # ------------------------------------------------------------------ struct plumbing
+    def setp(self, st, field, val, idx=None, offset=0):
+        if isinstance(val, Slot):
+            self._bindings.setdefault(val.name, []).append((st, field, idx, offset))
+            p = None
+        elif val is None:
+            p = None
+        else:
+            self._keep.append(val)
+            p = val.data_ptr() + offset
+        if idx is None:
+            setattr(st, field, p)
+        else:
+            getattr(st, field)[idx] = p
+
+    def bind(self, name, tensor):
+        base = tensor.data_ptr()
+        for st, field, idx, off in self._bindings.get(name, ()):
+            if idx is None:
+                setattr(st, field, base + off)
+            else:
+                getattr(st, field)[idx] = base + off
+
+    def emit(self, name, st):
+        self._cur.append(N.Call(name, st))
+
+    def on_backward(self, fn):
+        self._stack.append(fn)
+
+    def finalize(self):
+        """derive the backward launch list by unwinding the closure stack"""
+        self._cur = self.bwd
+        while self._stack:
+            self._stack.pop()()
+        self._cur = None
+        self.n_fwd_launches = len(self.fwd) + (1 if self.rng_state is not None else 0)
+        self.n_bwd_launches = len(self.bwd) + len(self._zero_ranges)
+
+    # ------------------------------------------------------------------ execution
+    def run_forward(self):
+        s = N.current_stream()
+        if self.rng_state is not None:
+            N.check(N.lib().bmnas_rng_advance(ctypes.c_void_p(self.rng_state.data_ptr()), s), 'rng_advance')
+        for c in self.fwd:
+            c(s)
+        self.generation += 1
+
+    def run_backward(self):
+        s = N.current_stream()
+        L = N.lib()
+        for t in self._zero_ranges:
+            N.check(L.bmnas_zero(ctypes.c_void_p(t.data_ptr()), ctypes.c_longlong(t.numel() * t.element_size()), s),
+                    'zero')
+        for c in self.bwd:
+            c(s)
+
+    # ------------------------------------------------------------------ dropout helper
+    def _drop(self, site, p):
+        """(mask Slot or None, needs rng) for a dropout site"""
+        if not self.training or p <= 0.0:
+            return None
+        if self.use_masks:
+            sl = self.mask_slots.get(site)
+            if sl is None:
+                sl = Slot('mask:' + site)
+                self.mask_slots[site] = sl
+            return sl
+        self.ensure_rng()
+        return None
+
+    # ------------------------------------------------------------------ kernels: edge mix
+    def mix(self, xs, w, w_off, logits, out, gw=None, need=None):
+        """out = sum_j w[w_off+j, skip] * xs[j]; registers the backward."""
+        xs = list(xs)
+        n = len(xs)
+        assert 1 <= n <= N.BMNAS_MAX_MIX
+        numel = self.B * self.C * self.L
+        st = N.bmnas_mix_params()
+        st.n, st.w_is_logits, st.numel = n, int(logits), numel
+        for j, x in enumerate(xs):
+            self.setp(st, 'x', x, j)
+        self.setp(st, 'w', w, offset=w_off * 8)
+        self.setp(st, 'out', out)
+        self.emit('bmnas_mix_fwd', st)
+        need = need if need is not None else [True] * n
+
+        def bwd():
+            if not self.has_grad(out):
+                return
+            sb = N.bmnas_mix_params()
+            sb.n, sb.w_is_logits, sb.numel = n, int(logits), numel
+            any_out = gw is not None
+            for j, x in enumerate(xs):
+                self.setp(sb, 'x', x, j)
+                if need[j]:
+                    g = self.grad_of(x)
+                    sb.gx_accum[j] = self.acc(g)
+                    self.setp(sb, 'gx', g, j)
+                    any_out = True
+            if not any_out:
+                return
+            self.setp(sb, 'w', w, offset=w_off * 8)
+            self.setp(sb, 'gout', self.grad_of(out))
+            if gw is not None:
+                self.setp(sb, 'gw', gw, offset=w_off * 8)
+                self.setp(sb, 'partials', self.buf(int(N.lib().bmnas_mix_partials_size(ctypes.byref(sb)))))
+                self.setp(sb, 'counter', self.counter())
+            self.emit('bmnas_mix_bwd', sb)
+        self.on_backward(bwd)
+
+    # ------------------------------------------------------------------ kernels: conv (+BN stats) and its backward
+    def conv(self, srcs, src_C, segs, w_fold, bn):
+        """segs: list of dict(W=, bias=, M=, rm=, rv=, nbt=, gW=, gbias=).  Returns dict(Z, mean, rstd, M, st)."""
+        st = N.bmnas_conv_params()
+        K = sum(src_C)
+        M = sum(s['M'] for s in segs)
+        st.B, st.L, st.K, st.w_fold, st.n_src, st.n_seg, st.M = self.B, self.L, K, w_fold, len(srcs), len(segs), M
+        st.bn_mode = (1 if self.training else 2) if bn else 0
+        st.momentum, st.eps = BN_MOMENTUM, BN_EPS
+        for i, (s, c) in enumerate(zip(srcs, src_C)):
+            self.setp(st, 'src', s, i)
+            st.src_C[i] = c
+        for i, sg in enumerate(segs):
+            st.seg_M[i] = sg['M']
+            self.setp(st, 'W', sg['W'], i)
+            self.setp(st, 'bias', sg.get('bias'), i)
+            if bn:
+                self.setp(st, 'running_mean', sg['rm'], i)
+                self.setp(st, 'running_var', sg['rv'], i)
+                self.setp(st, 'num_batches_tracked', sg['nbt'], i)
+        Z = self.buf(self.B, M, self.L)
+        self.setp(st, 'Z', Z)
+        mean = rstd = None
+        if bn:
+            mean, rstd = self.buf(M), self.buf(M)
+            self.setp(st, 'mean', mean)
+            self.setp(st, 'rstd', rstd)
+            if self.training:
+                self.setp(st, 'stat_part', self.buf(int(N.lib().bmnas_conv_stat_part_size(ctypes.byref(st)))))
+                self.setp(st, 'counter', self.counter(N.lib().bmnas_conv_num_counters(ctypes.byref(st))))
+        self.emit('bmnas_conv_fwd', st)
+        return dict(Z=Z, mean=mean, rstd=rstd, M=M, K=K, srcs=srcs, src_C=src_C, segs=segs, w_fold=w_fold)
+
+    def conv_backward(self, cv, GV, coef, need_src):
+        """dgrad into the source grads + wgrad into the parameter grad views."""
+        srcs, src_C, segs = cv['srcs'], cv['src_C'], cv['segs']
+
+        def base():
+            st = N.bmnas_conv_params()
+            st.B, st.L, st.K, st.w_fold, st.n_src, st.n_seg, st.M = (self.B, self.L, cv['K'], cv['w_fold'], len(srcs),
+                                                                    len(segs), cv['M'])
+            for i, (s, c) in enumerate(zip(srcs, src_C)):
+                self.setp(st, 'src', s, i)
+                st.src_C[i] = c
+            for i, sg in enumerate(segs):
+                st.seg_M[i] = sg['M']
+                self.setp(st, 'W', sg['W'], i)
+            self.setp(st, 'GV', GV)
+            self.setp(st, 'Z', cv['Z'])
+            if coef is not None:
+                self.setp(st, 'coef_a', coef[0])
+                self.setp(st, 'coef_b', coef[1])
+                self.setp(st, 'coef_c', coef[2])
+            return st
+
+        if any(need_src):
+            st = base()
+            for i, s in enumerate(srcs):
+                if need_src[i]:
+                    g = self.grad_of(s)
+                    st.gsrc_accum[i] = self.acc(g)
+                    self.setp(st, 'gsrc', g, i)
+            self.emit('bmnas_conv_dgrad', st)
+        if any(sg.get('gW') is not None or sg.get('gbias') is not None for sg in segs):
+            st = base()
+            for i, sg in enumerate(segs):
+                self.setp(st, 'gW', sg.get('gW'), i)
+                self.setp(st, 'gbias', sg.get('gbias'), i)
+            self.emit('bmnas_conv_wgrad', st)
+
+    # ------------------------------------------------------------------ kernels: step-node mixed op
+    def node_op(self, x, y, ops, P, G, prefix_of, gamma, gamma_off, logits, out, g_gamma=None,
+                need_x=True, need_y=True):
+        """ops: list of primitive names; prefix_of(k) -> parameter prefix of op k.
+        x, y: tensors/Slots (x is y => aliased).  Emits conv (if any conv-backed op) + node kernels."""
+        C, L = self.C, self.L
+        alias = x is y
+        segs, z_off, off = [], {}, 0
+        for k, name in enumerate(ops):
+            if name in ('LinearGLU', 'ConcatFC', 'CatConvMish'):
+                rows = 2 * C if name == 'LinearGLU' else C
+                pre = prefix_of(k)
+                segs.append(dict(W=P[pre + '.conv.weight'], bias=P[pre + '.conv.bias'], M=rows,
+                                 rm=P[pre + '.bn.running_mean'], rv=P[pre + '.bn.running_var'],
+                                 nbt=P[pre + '.bn.num_batches_tracked'],
+                                 gW=G.get(pre + '.conv.weight'), gbias=G.get(pre + '.conv.bias')))
+                z_off[k] = off
+                off += rows
+        assert len(segs) <= N.BMNAS_MAX_SEG
+        cv = None
+        if segs:
+            cv = self.conv([x] if alias else [x, y], [C] if alias else [C, C], segs, 2 if alias else 1, bn=True)
+        M = cv['M'] if cv else 0
+
+        def fill(st):
+            st.B, st.C, st.L, st.n_ops, st.M = self.B, C, L, len(ops), M
+            st.training, st.gamma_is_logits, st.alias_xy = int(self.training), int(logits), int(alias)
+            st.sample_offset = self.sample_offset
+            self.setp(st, 'x', x)
+            self.setp(st, 'y', y)
+            if cv:
+                self.setp(st, 'Z', cv['Z'])
+                self.setp(st, 'mean', cv['mean'])
+                self.setp(st, 'rstd', cv['rstd'])
+            if gamma is not None:
+                self.setp(st, 'gamma', gamma, offset=gamma_off * 4)
+            for k, name in enumerate(ops):
+                pre = prefix_of(k)
+                st.op_type[k] = OP_IDS[name]
+                st.z_off[k] = z_off.get(k, 0)
+                p = 0.0 if name == 'Sum' else (ATTN_DROP if name == 'ScaleDotAttn' else self.drpt)
+                st.p_drop[k] = p
+                st.op_uid[k] = uid_of(pre)
+                if name != 'Sum':
+                    self.setp(st, 'mask', self._drop(pre + '.dropout', p), k)
+                if name == 'ScaleDotAttn':
+                    self.setp(st, 'ln_w', P[pre + '.ln.weight'], k)
+                    self.setp(st, 'ln_b', P[pre + '.ln.bias'], k)
+                elif name != 'Sum':
+                    self.setp(st, 'bn_w', P[pre + '.bn.weight'], k)
+                    self.setp(st, 'bn_b', P[pre + '.bn.bias'], k)
+            if self.rng_state is not None:
+                self.setp(st, 'rng_state', self.rng_state)
+
+        st = N.bmnas_node_params()
+        fill(st)
+        self.setp(st, 'out', out)
+        self.emit('bmnas_node_fwd', st)
+
+        def bwd():
+            if not self.has_grad(out):
+                return
+            sb = N.bmnas_node_params()
+            fill(sb)
+            self.setp(sb, 'gout', self.grad_of(out))
+            if need_x:
+                gx = self.grad_of(x)
+                sb.gx_accum = self.acc(gx)
+                self.setp(sb, 'gx', gx)
+            if need_y and not alias:
+                gy = self.grad_of(y)
+                sb.gy_accum = self.acc(gy)
+                self.setp(sb, 'gy', gy)
+            coef = GV = None
+            if cv:
+                GV = self.buf(self.B, M, L)
+                coef = (self.buf(M), self.buf(M), self.buf(M))
+                self.setp(sb, 'GV', GV)
+                self.setp(sb, 'coef_a', coef[0])
+                self.setp(sb, 'coef_b', coef[1])
+                self.setp(sb, 'coef_c', coef[2])
+            if g_gamma is not None:
+                self.setp(sb, 'g_gamma', g_gamma, offset=gamma_off * 4)
+            for k, name in enumerate(ops):
+                pre = prefix_of(k)
+                if name == 'ScaleDotAttn':
+                    self.setp(sb, 'g_ln_w', G.get(pre + '.ln.weight'), k)
+                    self.setp(sb, 'g_ln_b', G.get(pre + '.ln.bias'), k)
+                elif name != 'Sum':
+                    self.setp(sb, 'g_bn_w', G.get(pre + '.bn.weight'), k)
+                    self.setp(sb, 'g_bn_b', G.get(pre + '.bn.bias'), k)
+            self.setp(sb, 'partials', self.buf(int(N.lib().bmnas_node_partials_size(ctypes.byref(sb)))))
+            self.setp(sb, 'counter', self.counter())
+            self.emit('bmnas_node_bwd', sb)
+            if cv:
+                self.conv_backward(cv, GV, coef, [need_x] if alias else [need_x, need_y])
+        self.on_backward(bwd)
+
+    # ------------------------------------------------------------------ kernels: LayerNorm blocks
+    def ln_cat(self, srcs, src_C, residual, ln_w, ln_b, g_ln_w, g_ln_b, relu, out, need_src=None, need_res=True):
+        Ctot = sum(src_C)
+
+        def fill(st):
+            st.B, st.L, st.Ctot, st.n_src, st.mode, st.relu_out = self.B, self.L, Ctot, len(srcs), 0, int(relu)
+            st.training = int(self.training)
+            for i, (s, c) in enumerate(zip(srcs, src_C)):
+                self.setp(st, 'src', s, i)
+                st.src_C[i] = c
+            self.setp(st, 'residual', residual)
+            self.setp(st, 'ln_w', ln_w)
+            self.setp(st, 'ln_b', ln_b)
+        st = N.bmnas_ln_params()
+        fill(st)
+        self.setp(st, 'out', out)
+        self.emit('bmnas_ln_fwd', st)
+        need_src = need_src if need_src is not None else [True] * len(srcs)
+
+        def bwd():
+            if not self.has_grad(out):
+                return
+            sb = N.bmnas_ln_params()
+            fill(sb)
+            self.setp(sb, 'gout', self.grad_of(out))
+            for i, s in enumerate(srcs):
+                if need_src[i]:
+                    g = self.grad_of(s)
+                    sb.gsrc_accum[i] = self.acc(g)
+                    self.setp(sb, 'gsrc', g, i)
+            if residual is not None and need_res:
+                g = self.grad_of(residual)
+                sb.gres_accum = self.acc(g)
+                self.setp(sb, 'gresidual', g)
+            self.setp(sb, 'g_ln_w', g_ln_w)
+            self.setp(sb, 'g_ln_b', g_ln_b)
+            self.emit('bmnas_ln_bwd', sb)
+        self.on_backward(bwd)
+
+    def ln_tail(self, cv, residual, bn_w, bn_b, g_bn_w, g_bn_b, ln_w, ln_b, g_ln_w, g_ln_b, site, out,
+                need_src, need_res=True):
+        C = self.C
+        mask = self._drop(site, self.drpt)
+
+        def fill(st):
+            st.B, st.L, st.Ctot, st.n_src, st.mode, st.relu_out = self.B, self.L, C, 1, 1, 0
+            st.training, st.p_drop, st.op_uid = int(self.training), self.drpt, uid_of(site)
+            st.sample_offset = self.sample_offset
+            st.src_C[0] = C
+            self.setp(st, 'src', cv['Z'], 0)
+            self.setp(st, 'residual', residual)
+            self.setp(st, 'mean', cv['mean'])
+            self.setp(st, 'rstd', cv['rstd'])
+            self.setp(st, 'bn_w', bn_w)
+            self.setp(st, 'bn_b', bn_b)
+            self.setp(st, 'mask', mask)
+            if self.rng_state is not None:
+                self.setp(st, 'rng_state', self.rng_state)
+            self.setp(st, 'ln_w', ln_w)
+            self.setp(st, 'ln_b', ln_b)
+        st = N.bmnas_ln_params()
+        fill(st)
+        self.setp(st, 'out', out)
+        self.emit('bmnas_ln_fwd', st)
+
+        def bwd():
+            if not self.has_grad(out):
+                return
+            sb = N.bmnas_ln_params()
+            fill(sb)
+            self.setp(sb, 'gout', self.grad_of(out))
+            GV = self.buf(self.B, C, self.L)
+            coef = (self.buf(C), self.buf(C), self.buf(C))
+            self.setp(sb, 'gsrc', GV, 0)
+            if need_res:
+                g = self.grad_of(residual)
+                sb.gres_accum = self.acc(g)
+                self.setp(sb, 'gresidual', g)
+            self.setp(sb, 'g_ln_w', g_ln_w)
+            self.setp(sb, 'g_ln_b', g_ln_b)
+            self.setp(sb, 'g_bn_w', g_bn_w)
+            self.setp(sb, 'g_bn_b', g_bn_b)
+            self.setp(sb, 'coef_a', coef[0])
+            self.setp(sb, 'coef_b', coef[1])
+            self.setp(sb, 'coef_c', coef[2])
+            self.setp(sb, 'partials', self.buf(int(N.lib().bmnas_ln_partials_size(ctypes.byref(sb)))))
+            self.setp(sb, 'counter', self.counter())
+            self.emit('bmnas_ln_bwd', sb)
+            self.conv_backward(cv, GV, coef, need_src)
+        self.on_backward(bwd)
+
+    # ------------------------------------------------------------------ composite: node cell tail
+    def node_tail(self, states, need, x, need_x, P, G, prefix, nm, out):
+        """cat(states[-nm:]) -> [conv -> BN -> ReLU -> dropout] -> += x -> LayerNorm  (node_search.py:59-68)"""
+        C = self.C
+        last = states[-nm:]
+        nlast = need[-nm:]
+        if nm != 1:
+            seg = dict(W=P[prefix + '.out_conv.weight'], bias=P[prefix + '.out_conv.bias'], M=C,
+                       rm=P[prefix + '.bn.running_mean'], rv=P[prefix + '.bn.running_var'],
+                       nbt=P[prefix + '.bn.num_batches_tracked'],
+                       gW=G.get(prefix + '.out_conv.weight'), gbias=G.get(prefix + '.out_conv.bias'))
+            assert nm <= N.BMNAS_MAX_SRC
+            cv = self.conv(last, [C] * nm, [seg], 1, bn=True)
+            self.ln_tail(cv, x, P[prefix + '.bn.weight'], P[prefix + '.bn.bias'], G.get(prefix + '.bn.weight'),
+                         G.get(prefix + '.bn.bias'), P[prefix + '.ln.weight'], P[prefix + '.ln.bias'],
+                         G.get(prefix + '.ln.weight'), G.get(prefix + '.ln.bias'), prefix + '.out_dropout', out,
+                         need_src=nlast, need_res=need_x)
+        else:
+            self.ln_cat(last, [C], x, P[prefix + '.ln.weight'], P[prefix + '.ln.bias'], G.get(prefix + '.ln.weight'),
+                        G.get(prefix + '.ln.bias'), False, out, need_src=nlast, need_res=need_x)
+
+    # ------------------------------------------------------------------ composite: searchable node cell
+    def node_cell_search(self, x, y, need_x, need_y, edge_w, node_w, logits, g_edge_w, g_node_w, P, G, prefix,
+                         ops, ns, nm, out):
+        """NodeCell.forward node_search.py:48-70 (prefix ends with '.node_cell')."""
+        states, need = [x, y], [need_x, need_y]
+        off = 0
+        for i in range(ns):
+            t = self.buf(self.B, self.C, self.L)
+            self.mix(states, edge_w, off, logits, t, gw=g_edge_w, need=list(need))
+            s = self.buf(self.B, self.C, self.L)
+            pre = f'{prefix}.node_ops.{i}'
+            self.node_op(t, t, ops, P, G, (lambda k, pre=pre: f'{pre}._ops.{k}'), node_w, i * len(ops), logits, s,
+                         g_gamma=g_node_w)
+            off += len(states)
+            states.append(s)
+            need.append(True)
+        self.node_tail(states, need, x, need_x, P, G, prefix, nm, out)
+
+    # ------------------------------------------------------------------ composite: found node cell
+    def node_cell_found(self, x, y, need_x, need_y, gene, P, G, prefix, ns, nm, out):
+        """Found_NodeCell.forward node.py:45-76."""
+        states, need = [x, y], [need_x, need_y]
+        zero = None
+        for i in range(ns):
+            (n0, i0), (n1, i1) = gene.inner_edges[2 * i], gene.inner_edges[2 * i + 1]
+            ins, nd = [], []
+            for nme, idx in ((n0, i0), (n1, i1)):
+                if nme == 'skip':
+                    ins.append(states[idx])
+                    nd.append(need[idx])
+                else:   # 'none' == Zero: x.mul(0.)  (finite inputs)
+                    if zero is None:
+                        zero = self.buf(self.B, self.C, self.L, zero=True)
+                    ins.append(zero)
+                    nd.append(False)
+            s = self.buf(self.B, self.C, self.L)
+            pre = f'{prefix}.node_ops.{i}'
+            self.node_op(ins[0], ins[1], [gene.inner_steps[i]], P, G, (lambda k, pre=pre: pre), None, 0, False, s,
+                         need_x=nd[0], need_y=nd[1])
+            states.append(s)
+            need.append(True)
+        self.node_tail(states, need, x, need_x, P, G, prefix, nm, out)
+
+    # ------------------------------------------------------------------ composite: cells
+    def cell_tail(self, states, need, P, G, prefix, mult, out):
+        """cat(states[-m:]) -> LayerNorm([C*m, L]) -> ReLU -> view(B,-1)   (model_search.py:63-67)"""
+        assert mult <= N.BMNAS_MAX_SRC
+        self.ln_cat(states[-mult:], [self.C] * mult, None, P[prefix + '.ln.weight'], P[prefix + '.ln.bias'],
+                    G.get(prefix + '.ln.weight'), G.get(prefix + '.ln.bias'), True, out, need_src=need[-mult:])
+
+    def cell_search(self, feats, need_feats, alphas, g_alphas, node_arch, g_node_arch, logits, P, G, prefix,
+                    steps, mult, ops, ns, nm):
+        """FusionCell.forward model_search.py:50-68.  node_arch[i] = (betas_i, gammas_i)."""
+        states, need = list(feats), list(need_feats)
+        off = 0
+        for i in range(steps):
+            s_in = self.buf(self.B, self.C, self.L)
+            self.mix(states, alphas, off, logits, s_in, gw=g_alphas, need=list(need))
+            s = self.buf(self.B, self.C, self.L)
+            gb, gg = g_node_arch[i] if g_node_arch is not None else (None, None)
+            self.node_cell_search(s_in, s_in, True, True, node_arch[i][0], node_arch[i][1], logits, gb, gg, P, G,
+                                  f'{prefix}._step_nodes.{i}.node_cell', ops, ns, nm, s)
+            off += len(states)
+            states.append(s)
+            need.append(True)
+        out = self.buf(self.B, mult * self.C, self.L)
+        self.cell_tail(states, need, P, G, prefix, mult, out)
+        return out
+
+    def cell_found(self, feats, need_feats, genotype, P, G, prefix, ns, nm):
+        """Found_Random_FusionCell.forward model.py:133-160."""
+        states, need = list(feats), list(need_feats)
+        steps = len(genotype.edges) // 2
+        mult = len(genotype.concat)
+        zero = None
+        for i in range(steps):
+            hs, nd = [], []
+            for nme, idx in (genotype.edges[2 * i], genotype.edges[2 * i + 1]):
+                if nme == 'skip':
+                    hs.append(states[idx])
+                    nd.append(need[idx])
+                else:
+                    if zero is None:
+                        zero = self.buf(self.B, self.C, self.L, zero=True)
+                    hs.append(zero)
+                    nd.append(False)
+            s = self.buf(self.B, self.C, self.L)
+            self.node_cell_found(hs[0], hs[1], nd[0], nd[1], genotype.steps[i], P, G,
+                                 f'{prefix}._step_nodes.{i}.node_cell', ns, nm, s)
+            states.append(s)
+            need.append(True)
+        out = self.buf(self.B, mult * self.C, self.L)
+        self.cell_tail(states, need, P, G, prefix, mult, out)
+        return out

@@ -1,0 +1,185 @@
+// Edge mix (softmax-weighted sum of candidate input tensors) forward/backward.
+// Pure streaming kernels: float4 loads, one pass, grid sized in multiples of the
+// SM count; d(alpha) dot products reduced warp-shuffle -> block -> fixed-order
+// last-block sum (deterministic).
+#include "common.cuh"
+
+namespace bmnas {
+
+constexpr int kMixThreads = 256;
+constexpr int kMixMaxBlocks = kNumSMs * 4;
+
+__device__ __forceinline__ void mix_weights(const bmnas_mix_params& p, float* ws, float* wn) {
+    if (threadIdx.x < p.n) {
+        float a = p.w[2 * threadIdx.x], b = p.w[2 * threadIdx.x + 1];
+        if (p.w_is_logits) {
+            float s = 1.f / (1.f + expf(a - b));  // softmax over (none, skip) -> skip weight
+            ws[threadIdx.x] = s;
+            wn[threadIdx.x] = 1.f - s;
+        } else {
+            ws[threadIdx.x] = b;
+            wn[threadIdx.x] = a;
+        }
+    }
+    __syncthreads();
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kMixThreads) k_mix_fwd(const bmnas_mix_params p) {
+    __shared__ float ws[BMNAS_MAX_MIX], wn[BMNAS_MAX_MIX];
+    mix_weights(p, ws, wn);
+    const long long nvec = p.numel / VEC;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        if (VEC == 4) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < p.n; ++j) {
+                float4 v = __ldg(reinterpret_cast<const float4*>(p.x[j]) + i);
+                float w = ws[j];
+                acc.x = fmaf(w, v.x, acc.x);
+                acc.y = fmaf(w, v.y, acc.y);
+                acc.z = fmaf(w, v.z, acc.z);
+                acc.w = fmaf(w, v.w, acc.w);
+            }
+            reinterpret_cast<float4*>(p.out)[i] = acc;
+        } else {
+            float acc = 0.f;
+            for (int j = 0; j < p.n; ++j) acc = fmaf(ws[j], __ldg(p.x[j] + i), acc);
+            p.out[i] = acc;
+        }
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kMixThreads) k_mix_bwd(const bmnas_mix_params p) {
+    __shared__ float ws[BMNAS_MAX_MIX], wn[BMNAS_MAX_MIX];
+    __shared__ float red[BMNAS_MAX_MIX * 32];
+    mix_weights(p, ws, wn);
+    float dot[BMNAS_MAX_MIX];
+#pragma unroll
+    for (int j = 0; j < BMNAS_MAX_MIX; ++j) dot[j] = 0.f;
+    const long long nvec = p.numel / VEC;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        if (VEC == 4) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(p.gout) + i);
+#pragma unroll
+            for (int j = 0; j < BMNAS_MAX_MIX; ++j) {
+                if (j < p.n) {
+                    if (p.gw) {
+                        float4 v = __ldg(reinterpret_cast<const float4*>(p.x[j]) + i);
+                        dot[j] += g.x * v.x + g.y * v.y + g.z * v.z + g.w * v.w;
+                    }
+                    if (p.gx[j]) {
+                        float w = ws[j];
+                        float4* d = reinterpret_cast<float4*>(p.gx[j]) + i;
+                        float4 o = make_float4(w * g.x, w * g.y, w * g.z, w * g.w);
+                        if (p.gx_accum[j]) {
+                            float4 c = *d;
+                            o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
+                        }
+                        *d = o;
+                    }
+                }
+            }
+        } else {
+            const float g = __ldg(p.gout + i);
+#pragma unroll
+            for (int j = 0; j < BMNAS_MAX_MIX; ++j) {
+                if (j < p.n) {
+                    if (p.gw) dot[j] += g * __ldg(p.x[j] + i);
+                    if (p.gx[j]) {
+                        float o = ws[j] * g;
+                        if (p.gx_accum[j]) o += p.gx[j][i];
+                        p.gx[j][i] = o;
+                    }
+                }
+            }
+        }
+    }
+    if (!p.gw) return;
+    block_sum<BMNAS_MAX_MIX>(dot, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int j = 0; j < BMNAS_MAX_MIX; ++j)
+            if (j < p.n) p.partials[(long long)blockIdx.x * p.n + j] = dot[j];
+    }
+    if (last_block(p.counter, gridDim.x)) {
+        if (threadIdx.x < p.n) {
+            const int j = threadIdx.x;
+            float d = 0.f;
+            for (unsigned b = 0; b < gridDim.x; ++b) d += ld_cg(p.partials + (long long)b * p.n + j);
+            if (p.w_is_logits) {
+                // 2-way softmax backward; dL/dw_none == 0 for finite inputs (Zero op: x*0)
+                float gs = ws[j] * wn[j] * d;
+                p.gw[2 * j] = -gs;
+                p.gw[2 * j + 1] = gs;
+            } else {
+                p.gw[2 * j] = 0.f;
+                p.gw[2 * j + 1] = d;
+            }
+        }
+    }
+}
+
+static bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
+
+static int mix_blocks(long long nvec) {
+    long long b = (nvec + kMixThreads - 1) / kMixThreads;
+    if (b < 1) b = 1;
+    if (b > kMixMaxBlocks) b = kMixMaxBlocks;
+    return (int)b;
+}
+
+static int mix_vec(const bmnas_mix_params* p, bool bwd) {
+    if (p->numel % 4) return 1;
+    for (int j = 0; j < p->n; ++j) {
+        if (!aligned16(p->x[j])) return 1;
+        if (bwd && p->gx[j] && !aligned16(p->gx[j])) return 1;
+    }
+    if (!bwd && !aligned16(p->out)) return 1;
+    if (bwd && !aligned16(p->gout)) return 1;
+    return 4;
+}
+
+}  // namespace bmnas
+
+using namespace bmnas;
+
+extern "C" long long bmnas_mix_partials_size(const bmnas_mix_params* p) {
+    (void)p;
+    return (long long)kMixMaxBlocks * BMNAS_MAX_MIX;
+}
+
+extern "C" int bmnas_mix_fwd(const bmnas_mix_params* p, void* stream) {
+    if (!p || p->n < 1 || p->n > BMNAS_MAX_MIX || p->numel <= 0 || !p->w || !p->out) return BMNAS_EINVAL;
+    for (int j = 0; j < p->n; ++j)
+        if (!p->x[j]) return BMNAS_EINVAL;
+    BMNAS_DRY_RETURN();
+    cudaStream_t s = (cudaStream_t)stream;
+    const int vec = mix_vec(p, false);
+    const int blocks = mix_blocks(p->numel / vec);
+    if (vec == 4)
+        k_mix_fwd<4><<<blocks, kMixThreads, 0, s>>>(*p);
+    else
+        k_mix_fwd<1><<<blocks, kMixThreads, 0, s>>>(*p);
+    BMNAS_LAUNCH_CHECK();
+    return BMNAS_OK;
+}
+
+extern "C" int bmnas_mix_bwd(const bmnas_mix_params* p, void* stream) {
+    if (!p || p->n < 1 || p->n > BMNAS_MAX_MIX || p->numel <= 0 || !p->w || !p->gout) return BMNAS_EINVAL;
+    if (p->gw && (!p->partials || !p->counter)) return BMNAS_EINVAL;
+    for (int j = 0; j < p->n; ++j)
+        if (!p->x[j]) return BMNAS_EINVAL;
+    BMNAS_DRY_RETURN();
+    cudaStream_t s = (cudaStream_t)stream;
+    const int vec = mix_vec(p, true);
+    const int blocks = mix_blocks(p->numel / vec);
+    if (vec == 4)
+        k_mix_bwd<4><<<blocks, kMixThreads, 0, s>>>(*p);
+    else
+        k_mix_bwd<1><<<blocks, kMixThreads, 0, s>>>(*p);
+    BMNAS_LAUNCH_CHECK();
+    return BMNAS_OK;
+}

@@ -1,0 +1,334 @@
+/*
+ * bmnas_b200.h -- C ABI of the B200-native BM-NAS search-step kernels.
+ *
+ * The reference (Somedaywilldo/BM-NAS) has no FFI layer: its "operator API" is the
+ * Python class surface of models/search/darts/.  Each entry point below replaces
+ * the chain of eager ATen calls behind one of those classes; the reference
+ * file:line each one stands in for is cited on the declaration.  INTEGRATION.md
+ * shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Rules of the ABI
+ *   - plain C: POD parameter blocks, raw DEVICE pointers, explicit sizes; no torch types;
+ *   - all tensors are fp32, contiguous, laid out (B, C, L) with L fastest
+ *     (exactly the reference's activation layout);
+ *   - no allocation and no host synchronisation inside; the caller passes outputs
+ *     and workspaces; every call is stream-ordered on `stream` (a cudaStream_t) and
+ *     legal under CUDA-graph capture;
+ *   - returns 0 on success, a negative BMNAS_E* code otherwise (bmnas_strerror()).
+ *   - "counter" workspaces are unsigned ints that must be zero before the first
+ *     use; every kernel leaves them zero again.
+ *
+ * NOTE: bm-nas_b200/bmnas/native.py parses this file to build its ctypes
+ * structures.  Keep declarations in the simple `type name;` / `type name[MACRO];`
+ * form, one per line.
+ */
+#ifndef BMNAS_B200_H
+#define BMNAS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BMNAS_MAX_MIX 16 /* candidate inputs of one edge mix                  */
+#define BMNAS_MAX_SRC 4  /* tensors in a virtual channel concat               */
+#define BMNAS_MAX_SEG 4  /* stacked output-channel segments of one conv GEMM  */
+#define BMNAS_MAX_OPS 8  /* candidate primitives of one NodeMixedOp           */
+
+#define BMNAS_OK 0
+#define BMNAS_EINVAL -1   /* bad shape / unsupported size / null pointer */
+#define BMNAS_ELAUNCH -2  /* CUDA launch failure                         */
+
+/* step-node primitive ids (models/search/darts/node_operations.py:9-14, 66-82) */
+#define BMNAS_OP_SUM 0
+#define BMNAS_OP_ATTN 1
+#define BMNAS_OP_GLU 2
+#define BMNAS_OP_FC_RELU 3
+#define BMNAS_OP_FC_MISH 4
+
+const char* bmnas_strerror(int code);
+int bmnas_abi_version(void);
+
+/* ------------------------------------------------------------------------
+ * Edge mix: out = sum_j w_j[skip] * x_j   (PRIMITIVES = [none, skip])
+ * replaces FusionMixedOp.forward + the python sum over edges:
+ *   models/search/darts/operations.py:95-106 (Zero :14-20, Identity :88-93),
+ *   model_search.py:58, node_search.py:54.
+ * w is (n,2).  w_is_logits=1: w holds raw alpha/beta rows and the per-edge
+ * 2-way softmax (model_search.py:95, node_search.py:102) is taken in-kernel;
+ * the backward then returns d/d(logits).
+ * ---------------------------------------------------------------------- */
+typedef struct bmnas_mix_params {
+    int n;
+    int w_is_logits;
+    long long numel;
+    const float* x[BMNAS_MAX_MIX];
+    const float* w;
+    float* out;
+    const float* gout;
+    float* gx[BMNAS_MAX_MIX];
+    int gx_accum[BMNAS_MAX_MIX];
+    float* gw;
+    float* partials;
+    unsigned int* counter;
+} bmnas_mix_params;
+int bmnas_mix_fwd(const bmnas_mix_params* p, void* stream);
+int bmnas_mix_bwd(const bmnas_mix_params* p, void* stream);
+long long bmnas_mix_partials_size(const bmnas_mix_params* p); /* floats */
+
+/* ------------------------------------------------------------------------
+ * 1x1 convolution over a virtual channel concat, with fused bias and
+ * train-mode BatchNorm statistics:
+ *     Z[b, m, l] = sum_k Weff[m, k] * U[b, k, l] + bias[m]
+ * U = channel-concat of src[0..n_src) (never materialised); the output rows are
+ * the stacked segments W[0..n_seg) (LinearGLU's 2C rows and ConcatFC's C rows
+ * share one GEMM).  Each W[i] is (seg_M[i], w_fold*K) row major and
+ * Weff[m,k] = sum_f W[m, f*K + k]: w_fold=2 folds cat([t, t]) (search mode calls
+ * every step node with x is y: model_search.py:59, node_search.py:55).
+ * replaces torch.cat + nn.Conv1d(k=1) + the statistics half of nn.BatchNorm1d:
+ *   node_operations.py:30-34 (LinearGLU), :49-53 (ConcatFC), :75-79 (CatConvMish),
+ *   node_search.py:59-62 (out_conv + bn).
+ * bn_mode 1: batch mean / rstd over (B, L) -> mean, rstd; running statistics are
+ * updated (momentum, unbiased variance) and num_batches_tracked incremented.
+ * bn_mode 2: mean/rstd are filled from the running statistics (eval).
+ * dgrad / wgrad are the two backward GEMMs.  The upstream gradient operand is
+ *     dz[b,m,l] = coef_a[m]*GV[b,m,l] + coef_b[m]*Z[b,m,l] + coef_c[m]
+ * (BatchNorm backward folded into the operand load; coef_* NULL => dz = GV).
+ * gW / gbias are accumulated atomically (red.add) onto whatever the caller put
+ * there: zero for a gradient, the broadcast bias when conv_wgrad is used as the
+ * NT GEMM of the classifier forward.
+ * ---------------------------------------------------------------------- */
+typedef struct bmnas_conv_params {
+    int B;
+    int L;
+    int K;
+    int w_fold;
+    int n_src;
+    int n_seg;
+    int M;
+    int bn_mode;
+    int splits;
+    float momentum;
+    float eps;
+    int src_C[BMNAS_MAX_SRC];
+    int seg_M[BMNAS_MAX_SEG];
+    const float* src[BMNAS_MAX_SRC];
+    const float* W[BMNAS_MAX_SEG];
+    const float* bias[BMNAS_MAX_SEG];
+    float* Z;
+    float* stat_part;
+    unsigned int* counter;
+    float* mean;
+    float* rstd;
+    float* running_mean[BMNAS_MAX_SEG];
+    float* running_var[BMNAS_MAX_SEG];
+    long long* num_batches_tracked[BMNAS_MAX_SEG];
+    const float* GV;
+    const float* coef_a;
+    const float* coef_b;
+    const float* coef_c;
+    float* gsrc[BMNAS_MAX_SRC];
+    int gsrc_accum[BMNAS_MAX_SRC];
+    float* gW[BMNAS_MAX_SEG];
+    float* gbias[BMNAS_MAX_SEG];
+} bmnas_conv_params;
+int bmnas_conv_fwd(const bmnas_conv_params* p, void* stream);
+int bmnas_conv_dgrad(const bmnas_conv_params* p, void* stream);
+int bmnas_conv_wgrad(const bmnas_conv_params* p, void* stream);
+long long bmnas_conv_stat_part_size(const bmnas_conv_params* p); /* floats  */
+int bmnas_conv_num_counters(const bmnas_conv_params* p);         /* uints   */
+
+/* ------------------------------------------------------------------------
+ * Step-node mixed op: out = sum_k gamma~_k * op_k(x, y), evaluated per sample
+ * from the x / y tiles staged once in shared memory; per-op outputs are never
+ * written to HBM.
+ * replaces NodeMixedOp.forward and every primitive's forward:
+ *   node_operations.py:110-120 (mixed), :16-20 Sum, :84-108 ScaledDotAttn,
+ *   :22-39 LinearGLU (BN apply + GLU + dropout), :41-56 ConcatFC, :66-82 CatConvMish.
+ * gamma NULL => every listed op has weight 1 (found network / stand-alone op,
+ * node.py:45-62).  gamma_is_logits=1 => softmax over n_ops taken in-kernel
+ * (node_search.py:103) and g_gamma is d/d(logits).
+ * Dropout: mask[k] (uint8 keep mask, (B,C,L)) if given, else Philox keyed by
+ * (rng_state[0], rng_state[1], op_uid[k], global element index) when
+ * training && p_drop[k] > 0.
+ * Backward recomputes the primitives from (x, y, Z), writes GV = dL/d(BN output)
+ * for the conv-backed ops, reduces dL/dgamma, BN affine grads and the
+ * coefficients for the conv backward operand (see bmnas_conv_params).
+ * ---------------------------------------------------------------------- */
+typedef struct bmnas_node_params {
+    int B;
+    int C;
+    int L;
+    int n_ops;
+    int M;
+    int training;
+    int gamma_is_logits;
+    int alias_xy;
+    int gx_accum;
+    int gy_accum;
+    long long sample_offset;
+    int op_type[BMNAS_MAX_OPS];
+    int z_off[BMNAS_MAX_OPS];
+    float p_drop[BMNAS_MAX_OPS];
+    unsigned int op_uid[BMNAS_MAX_OPS];
+    const float* x;
+    const float* y;
+    const float* Z;
+    const float* mean;
+    const float* rstd;
+    const float* bn_w[BMNAS_MAX_OPS];
+    const float* bn_b[BMNAS_MAX_OPS];
+    const float* ln_w[BMNAS_MAX_OPS];
+    const float* ln_b[BMNAS_MAX_OPS];
+    const unsigned char* mask[BMNAS_MAX_OPS];
+    const unsigned long long* rng_state;
+    const float* gamma;
+    float* out;
+    const float* gout;
+    float* gx;
+    float* gy;
+    float* GV;
+    float* g_gamma;
+    float* g_bn_w[BMNAS_MAX_OPS];
+    float* g_bn_b[BMNAS_MAX_OPS];
+    float* g_ln_w[BMNAS_MAX_OPS];
+    float* g_ln_b[BMNAS_MAX_OPS];
+    float* coef_a;
+    float* coef_b;
+    float* coef_c;
+    float* partials;
+    unsigned int* counter;
+} bmnas_node_params;
+int bmnas_node_fwd(const bmnas_node_params* p, void* stream);
+int bmnas_node_bwd(const bmnas_node_params* p, void* stream);
+long long bmnas_node_partials_size(const bmnas_node_params* p); /* floats */
+
+/* ------------------------------------------------------------------------
+ * LayerNorm block over a virtual channel concat.
+ * mode 0 (CAT):  v = cat(src[0..n_src)) [+ residual];  out = LN_{[Ctot,L]}(v) [ReLU]
+ *   replaces FusionCell tail  model_search.py:63-67  (cat -> LayerNorm -> ReLU -> view)
+ *   and NodeCell tail with node_multiplier == 1  node_search.py:59,67-68.
+ * mode 1 (TAIL): v = dropout(ReLU(BN(src[0]))) + residual;  out = LN_{[C,L]}(v)
+ *   src[0] is the out_conv GEMM output; replaces node_search.py:62-68 / node.py:69-74.
+ * Backward writes the source grads (CAT) or GV = dL/d(BN output) (TAIL, gsrc[0]),
+ * the residual grad, accumulates LN affine grads atomically and finalises BN
+ * affine grads + conv-backward coefficients.
+ * ---------------------------------------------------------------------- */
+typedef struct bmnas_ln_params {
+    int B;
+    int L;
+    int Ctot;
+    int n_src;
+    int mode;
+    int relu_out;
+    int training;
+    int gres_accum;
+    float p_drop;
+    unsigned int op_uid;
+    long long sample_offset;
+    int src_C[BMNAS_MAX_SRC];
+    int gsrc_accum[BMNAS_MAX_SRC];
+    const float* src[BMNAS_MAX_SRC];
+    const float* residual;
+    const float* mean;
+    const float* rstd;
+    const float* bn_w;
+    const float* bn_b;
+    const unsigned char* mask;
+    const unsigned long long* rng_state;
+    const float* ln_w;
+    const float* ln_b;
+    float* out;
+    const float* gout;
+    float* gsrc[BMNAS_MAX_SRC];
+    float* gresidual;
+    float* g_ln_w;
+    float* g_ln_b;
+    float* g_bn_w;
+    float* g_bn_b;
+    float* coef_a;
+    float* coef_b;
+    float* coef_c;
+    float* partials;
+    unsigned int* counter;
+} bmnas_ln_params;
+int bmnas_ln_fwd(const bmnas_ln_params* p, void* stream);
+int bmnas_ln_bwd(const bmnas_ln_params* p, void* stream);
+long long bmnas_ln_partials_size(const bmnas_ln_params* p); /* floats */
+
+/* ------------------------------------------------------------------------
+ * Loss head: mean cross-entropy (kind 0, int64 labels) or mean
+ * BCE-with-logits (kind 1, float targets), criterion of
+ * ntu_darts_searchable.py:25 / mmimdb_darts_searchable.py:22.
+ * fwd writes the scalar loss and glogits = d loss / d logits; bwd scales
+ * glogits by the upstream scalar *gscale into gout_logits.
+ * bias helpers for the classifier (nn.Linear, ntu_darts_searchable.py:100-101):
+ * bmnas_bias_rows broadcasts bias into (rows, n); bmnas_colsum reduces (rows,n)->(n).
+ * ---------------------------------------------------------------------- */
+typedef struct bmnas_loss_params {
+    int B;
+    int n_classes;
+    int kind;
+    const float* logits;
+    const long long* labels;
+    const float* targets;
+    float* loss;
+    float* glogits;
+    const float* gscale;
+    float* gout_logits;
+    float* partials;
+    unsigned int* counter;
+} bmnas_loss_params;
+int bmnas_loss_fwd(const bmnas_loss_params* p, void* stream);
+int bmnas_loss_bwd(const bmnas_loss_params* p, void* stream);
+long long bmnas_loss_partials_size(const bmnas_loss_params* p); /* floats */
+int bmnas_bias_rows(float* out, const float* bias, int rows, int n, void* stream);
+int bmnas_colsum(float* out, const float* in, int rows, int n, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Multi-tensor Adam, identical arithmetic to torch.optim.Adam (coupled L2 weight
+ * decay, bias correction, eps outside the sqrt):
+ *   weights  ntu_darts_searchable.py:42    arch  :46-47   (architect.py:24 step)
+ * tensors is a DEVICE array of n_tensors descriptors.  lr and step live in
+ * device memory so a captured CUDA graph sees the per-iteration schedule value
+ * (replaces scheduler.update_optimizer's state_dict round trip, scheduler.py:42-46).
+ * grad_scale multiplies every gradient first (1/world_size after an all-reduce).
+ * ---------------------------------------------------------------------- */
+typedef struct bmnas_adam_tensor {
+    float* p;
+    const float* g;
+    float* m;
+    float* v;
+    long long n;
+    long long block_start;
+} bmnas_adam_tensor;
+typedef struct bmnas_adam_params {
+    int n_tensors;
+    int block_elems;
+    long long total_blocks;
+    const bmnas_adam_tensor* tensors;
+    const float* lr;
+    float beta1;
+    float beta2;
+    float eps;
+    float weight_decay;
+    float grad_scale;
+    long long* step;
+    unsigned int* counter;
+} bmnas_adam_params;
+int bmnas_adam_step(const bmnas_adam_params* p, void* stream);
+
+/* stream-ordered zero fill (cudaMemsetAsync) and ABI self-description for binding tests */
+int bmnas_zero(void* ptr, long long nbytes, void* stream);
+int bmnas_sizeof_params(int which); /* 0 mix, 1 conv, 2 node, 3 ln, 4 loss, 5 adam_tensor, 6 adam */
+
+/* validate-only mode: every entry point checks its parameter block and returns before launching
+ * (lets host-side logic and bindings be tested on a machine without a GPU). */
+int bmnas_set_validate_only(int on);
+
+/* rng_state = {seed, step}: advance the step counter on-device (one launch per search step) */
+int bmnas_rng_advance(unsigned long long* rng_state, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BMNAS_B200_H */
