@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- search-step throughput of the BM-NAS fusion-cell hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config ntu|mmimdb|ego]
+
+One "step" = one search step (arch step on a dev batch + weight step on a train batch,
+train_searchable/ntu.py:70-93 + architect.py:21-29) over synthetic frozen-backbone
+features.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the exact
+definitions of value / e2e / roofline / cpu_baseline.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, 'bm-nas_b200'))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CONFIGS = {
+    # SURVEY 8 / App. B defaults
+    'ntu': dict(C=128, L=8, num_input_nodes=8, steps=2, multiplier=2, node_steps=2, node_multiplier=2, drpt=0.2,
+                B=96, classes=60, loss='ce', eta_max=1e-3, weight_decay=3e-4),
+    'mmimdb': dict(C=192, L=16, num_input_nodes=6, steps=2, multiplier=2, node_steps=1, node_multiplier=1, drpt=0.1,
+                   B=32, classes=23, loss='bce', eta_max=1e-3, weight_decay=1e-4),
+    'ego': dict(C=128, L=8, num_input_nodes=8, steps=2, multiplier=2, node_steps=3, node_multiplier=3, drpt=0.05,
+                B=96, classes=83, loss='ce', eta_max=3e-3, weight_decay=1e-4),
+}
+L2_BYTES = 126 * 1024 * 1024
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d['hbm_gbs'], bf16=d['bf16_tflops'], bf16_sustained=d['bf16_tflops_sustained'], src='measured')
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src='fallback')
+
+
+# ----------------------------------------------------------------------------- CPU reference arm (oracle port)
+def cpu_reference(cfgname, steps, warmup, max_seconds=25.0):
+    """times oracle/bmnas_oracle.py (the CPU restatement of the reference's path, pinned against the
+    reference by tests/golden) on all host cores.  Returns (samples_per_s, ms_per_step, cores, steps_done)."""
+    from oracle import bmnas_oracle as O
+    c = CONFIGS[cfgname]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.Cfg(c['C'], c['L'], c['num_input_nodes'], c['steps'], c['multiplier'], c['node_steps'],
+                c['node_multiplier'], c['drpt'])
+    P = O.init_params(cfg, c['classes'], seed=2, prefix='cell')
+    arch = O.init_arch(cfg, seed=2)
+    st = O.SearchState(cfg, P, arch, eta_max=c['eta_max'], weight_decay=c['weight_decay'], loss=c['loss'])
+    dev = O.synthetic_batch(cfg, c['B'], c['classes'], seed=2, loss=c['loss'])
+    trn = O.synthetic_batch(cfg, c['B'], c['classes'], seed=3, loss=c['loss'])
+    g = torch.Generator().manual_seed(7)
+
+    def masks():
+        # the reference draws fresh dropout masks every forward; do the same work here
+        m = {}
+        for name in _dropout_sites(cfg):
+            p = 0.1 if name.endswith('_ops.1.dropout') else cfg.drpt
+            m['fusion_net.' + name] = (torch.rand(c['B'], cfg.C, cfg.L, generator=g) >= p).to(torch.uint8)
+        return m
+    for _ in range(warmup):
+        st.search_step(dev, trn, masks(), masks())
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        st.search_step(dev, trn, masks(), masks())
+        done += 1
+        if time.perf_counter() - t0 > max_seconds:
+            break
+    dt = time.perf_counter() - t0
+    return c['B'] * done / dt, 1e3 * dt / done, cores, done
+
+
+def _dropout_sites(cfg):
+    sites = []
+    for i in range(cfg.steps):
+        nc = f'cell._step_nodes.{i}.node_cell'
+        for j in range(cfg.node_steps):
+            for k in (1, 2, 3):
+                sites.append(f'{nc}.node_ops.{j}._ops.{k}.dropout')
+        if cfg.node_multiplier != 1:
+            sites.append(f'{nc}.out_dropout')
+    return sites
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class Clocks:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ----------------------------------------------------------------------------- our arm
+def make_pool(c, n_batches, seed, device, pinned=False):
+    """synthetic (B,C,L) unit-normal features + labels; one flat tensor per batch"""
+    g = torch.Generator().manual_seed(seed)
+    pool = []
+    for _ in range(n_batches):
+        f = torch.randn(c['num_input_nodes'], c['B'], c['C'], c['L'], generator=g)
+        if c['loss'] == 'ce':
+            y = torch.randint(0, c['classes'], (c['B'],), generator=g)
+        else:
+            y = (torch.rand(c['B'], c['classes'], generator=g) < 0.2).float()
+        if pinned:
+            pool.append((f.pin_memory(), y.pin_memory()))
+        else:
+            pool.append((f.to(device), y.to(device)))
+    return pool
+
+
+def kernel_roofline(head, ss, c, pk):
+    """average duration of the dominant fused MixedOp kernels (bmnas_node_fwd / bmnas_node_bwd), timed live with
+    CUDA events around R back-to-back launches of the prepared parameter blocks on the launching stream."""
+    from bmnas import native as N
+    runner = [r for r in head.fusion_net._bm_cache.values() if r.prog.training][0]
+    prog = runner.prog
+    s = N.current_stream()
+    res = {}
+    R = 200
+    for name, calls in (('bmnas_node_fwd', prog.fwd), ('bmnas_node_bwd', prog.bwd)):
+        call = [x for x in calls if x.name == name][0]
+        for _ in range(20):
+            call(s)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(R):
+            call(s)
+        e1.record()
+        torch.cuda.synchronize()
+        res[name] = e0.elapsed_time(e1) * 1e3 / R      # us per launch
+    T1 = c['C'] * c['L'] * 4
+    M = 3 * c['C']
+    # algorithmic bytes per sample of the fused node kernel: x (aliased with y) + Z (3C rows) in, out
+    fwd_bytes = c['B'] * (T1 + M * c['L'] * 4 + T1)
+    t = res['bmnas_node_fwd'] * 1e-6
+    ach = fwd_bytes / t / 1e9
+    return {'bound': 'hbm', 'kernel': 'bmnas_node_fwd (fused NodeMixedOp forward)', 'achieved': round(ach, 2),
+            'peak': pk['hbm'], 'peak_source': pk['src'], 'unit': 'GB/s', 'frac': round(ach / pk['hbm'], 5),
+            'traffic': None, 'avg_launch_us': {k: round(v, 3) for k, v in res.items()},
+            'algorithmic_bytes_per_launch': fwd_bytes,
+            'note': 'B=%d working set is L2-resident and the kernel is latency-bound at this size; see DESIGN.md' % c['B']}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from bmnas import native as N
+    from bmnas.nn import SearchHead, CrossEntropyLoss, BCEWithLogitsLoss
+    from bmnas.search import SearchStep
+    import types
+    rank = int(os.environ.get('RANK', 0))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f'--gpus {args.gpus} but WORLD_SIZE={world}')
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    group = None
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+        group = dist.group.WORLD
+    c = dict(CONFIGS[args.config])
+    if args.batch:
+        c['B'] = args.batch
+    torch.manual_seed(2)                              # main_darts_searchable_ntu.py:17 (all ranks: identical replicas)
+    a = types.SimpleNamespace(**{k: c[k] for k in ('C', 'L', 'num_input_nodes', 'steps', 'multiplier', 'node_steps',
+                                                    'node_multiplier', 'drpt')}, weight_decay=c['weight_decay'])
+    crit = CrossEntropyLoss() if c['loss'] == 'ce' else BCEWithLogitsLoss()
+    head = SearchHead(a, c['classes'], criterion=crit).to(device)
+    from bmnas import runtime as rt
+    rt.SAMPLE_OFFSET[0] = rank * c['B']               # world-size-invariant dropout streams
+    ss = SearchStep(head, crit, c['B'], c['classes'], loss_kind=c['loss'], eta_max=c['eta_max'],
+                    weight_decay=c['weight_decay'], nbpe=400.0, use_graphs=not args.no_graphs, group=group)
+    # input pool larger than L2 so every step's inputs come from HBM
+    per_batch = c['num_input_nodes'] * c['B'] * c['C'] * c['L'] * 4
+    n_pool = max(4, int(1.3 * L2_BYTES / per_batch) + 1)
+    n_pool += n_pool % 2
+    pool = make_pool(c, n_pool, 100 + rank, device)
+    ss.load('dev', *pool[0]); ss.load('train', *pool[1])
+    ss.prepare(warmup=3, restore=False)
+    n_weights = sum(p.numel() for p in head.parameters())
+    n_arch = sum(p.numel() for p in head.arch_parameters())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(K, loader, read_loss):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(K):
+            loader(i)
+            la, lw = ss.step()
+            if read_loss:
+                lw_host = lw.item()               # device->host read of the step's result
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        return e0.elapsed_time(e1), wall          # device time span of the K steps (idle gaps included)
+
+    def load_dev(i):
+        ss.load('dev', *pool[(2 * i) % n_pool]); ss.load('train', *pool[(2 * i + 1) % n_pool])
+    for i in range(args.warmup):
+        load_dev(i); ss.step()
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    dev_ms, wall = timed(args.steps, load_dev, read_loss=False)
+    # ---- end to end: pinned host inputs, H2D every step, D2H loss read every step
+    hpool = make_pool(c, 8, 500 + rank, device, pinned=True)
+
+    def load_host(i):
+        ss.load('dev', *hpool[(2 * i) % 8]); ss.load('train', *hpool[(2 * i + 1) % 8])
+    for i in range(max(3, args.warmup)):
+        load_host(i); ss.step()
+    e2e_ms, e2e_wall = timed(args.steps, load_host, read_loss=True)
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([dev_ms, e2e_wall * 1e3], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms_wall = t.tolist()
+    gB = c['B'] * world
+    ms_per_step = dev_ms / args.steps
+    value = gB / (ms_per_step * 1e-3)
+    e2e_value = gB * args.steps / (e2e_ms_wall * 1e-3)
+    lab_bytes = c['B'] * (8 if c['loss'] == 'ce' else 4 * c['classes'])
+    out = None
+    if rank == 0:
+        pk = peaks()
+        roof = kernel_roofline(head, ss, c, pk)
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            v, ms, cores, done = cpu_reference(args.config, 40, 3, max_seconds=20.0)
+            cpu = {'value': round(v, 1), 'unit': 'samples/s', 'cores': cores, 'kind': 'port', 'ms_per_step': round(ms, 2),
+                   'sample': f'{done} search steps of the same workload (B={c["B"]}) on the oracle port, '
+                             f'torch CPU fp32, {cores} threads'}
+        out = {
+            'metric': 'search-step samples/sec (fwd+bwd+arch step, fwd+bwd+weight step)', 'value': round(value, 1),
+            'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': round(ms_per_step, 4), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': f'{args.config.upper()} fusion search step on synthetic frozen-backbone features, '
+                                   f'B={c["B"]} per GPU, C={c["C"]}, L={c["L"]}, n_in={c["num_input_nodes"]}, '
+                                   f'steps={c["steps"]}, node_steps={c["node_steps"]}, classes={c["classes"]}',
+                       'global_batch': gB, 'weights': n_weights, 'arch_scalars': n_arch,
+                       'parallelism': f'dp{world} (batch-sharded, one NCCL all-reduce of the flat grad arena per half step)',
+                       'cuda_graphs': not args.no_graphs,
+                       'l2_policy': f'inputs larger than L2: pool of {n_pool} distinct resident batches '
+                                    f'({n_pool * per_batch / 2**20:.0f} MiB) rotated every step'},
+            'e2e': {'value': round(e2e_value, 1), 'unit': 'samples/s',
+                    'h2d_bytes_per_step': 2 * (per_batch + lab_bytes), 'd2h_bytes_per_step': 4,
+                    'ms_per_step': round(e2e_ms_wall / args.steps, 4),
+                    'how': 'SearchStep.load() from pinned host memory + SearchStep.step() + loss.item() every step, '
+                           'wall clock between barriers'},
+            'gpu_launches': (ss.launches_per_step or 0) * args.steps,
+            'launches_per_step': ss.launches_per_step,
+            'roofline': roof, 'cpu_baseline': cpu, 'clocks': clk,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    c = CONFIGS[args.config]
+    v, ms, cores, done = cpu_reference(args.config, max(args.steps, 1), max(args.warmup, 1), max_seconds=120.0)
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'search-step samples/sec (fwd+bwd+arch step, fwd+bwd+weight step)',
+        'value': round(v, 1), 'unit': 'samples/s', 'n_gpus': args.gpus, 'steps': done, 'warmup': args.warmup,
+        'ms_per_step': round(ms, 3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'{args.config.upper()} fusion search step on synthetic frozen-backbone features, '
+                               f'B={c["B"]}, C={c["C"]}, L={c["L"]}', 'global_batch': c['B']},
+        'cpu_baseline': {'value': round(v, 1), 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+                         'sample': f'{done} search steps on the oracle port (torch CPU fp32, {cores} threads)'},
+        'e2e': {'value': round(v, 1), 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--config', default='ntu', choices=list(CONFIGS))
+    ap.add_argument('--batch', type=int, default=0, help='per-GPU batch override')
+    ap.add_argument('--no-graphs', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        args.warmup = max(args.warmup, 3)
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

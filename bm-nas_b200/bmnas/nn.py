@@ -39,12 +39,12 @@ class _LinearFn(torch.autograd.Function):
         s = N.current_stream()
         L = N.lib()
         out = torch.empty(B, Nc, device=x.device, dtype=torch.float32)
-        N.check(L.bmnas_bias_rows(ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(_p(bias)), B, Nc, s), 'bias_rows')
+        N.launch('bmnas_bias_rows', ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(_p(bias)), B, Nc, s)
         st = _conv_struct(1, Kc, Nc, B)       # out[m=b][k=class] += sum_l x[b][l] * W[class][l]
         st.GV = x.data_ptr()
         st.src[0] = weight.data_ptr()
         st.gW[0] = out.data_ptr()
-        N.check(L.bmnas_conv_wgrad(ctypes.byref(st), s), 'linear fwd')
+        N.launch('bmnas_conv_wgrad', ctypes.byref(st), s)
         ctx.save_for_backward(x, weight)
         ctx.views = (gw_view, gb_view)
         ctx.has_bias = bias is not None
@@ -66,16 +66,15 @@ class _LinearFn(torch.autograd.Function):
             st.W[0] = g.data_ptr()
             st.src[0] = weight.data_ptr()
             st.Z = gx.data_ptr()
-            N.check(L.bmnas_conv_fwd(ctypes.byref(st), s), 'linear dgrad')
+            N.launch('bmnas_conv_fwd', ctypes.byref(st), s)
         if gw_view is not None:
             st = _conv_struct(1, Kc, Nc, B)   # gW[class][l] = sum_b g[b][class] * x[b][l]
             st.W[0] = g.data_ptr()
             st.GV = x.data_ptr()
             st.gsrc[0] = gw_view.data_ptr()
-            N.check(L.bmnas_conv_dgrad(ctypes.byref(st), s), 'linear wgrad')
+            N.launch('bmnas_conv_dgrad', ctypes.byref(st), s)
         if gb_view is not None:
-            N.check(L.bmnas_colsum(ctypes.c_void_p(gb_view.data_ptr()), ctypes.c_void_p(g.data_ptr()), B, Nc, s),
-                    'linear bgrad')
+            N.launch('bmnas_colsum', ctypes.c_void_p(gb_view.data_ptr()), ctypes.c_void_p(g.data_ptr()), B, Nc, s)
         return gx, None, None, None, None
 
 
@@ -130,7 +129,7 @@ class _LossFn(torch.autograd.Function):
         else:
             st.targets = target.data_ptr()
         st.partials, st.counter = ws[0].data_ptr(), ws[1].data_ptr()
-        N.check(N.lib().bmnas_loss_fwd(ctypes.byref(st), N.current_stream()), 'loss fwd')
+        N.launch('bmnas_loss_fwd', ctypes.byref(st), N.current_stream())
         ctx.save_for_backward(gl)
         ctx.shape = (B, n)
         return loss
@@ -144,7 +143,7 @@ class _LossFn(torch.autograd.Function):
         out = torch.empty_like(gl)
         g = g.contiguous()
         st.glogits, st.gscale, st.gout_logits = gl.data_ptr(), g.data_ptr(), out.data_ptr()
-        N.check(N.lib().bmnas_loss_bwd(ctypes.byref(st), N.current_stream()), 'loss bwd')
+        N.launch('bmnas_loss_bwd', ctypes.byref(st), N.current_stream())
         return out, None, None, None
 
 

@@ -10,6 +10,10 @@ import torch
 
 from . import native as N
 
+
+def _capturing():
+    return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+
 BLOCK_ELEMS = 1024
 
 
@@ -29,7 +33,7 @@ class FusedAdam(torch.optim.Optimizer):
         st = self._g.get(gi)
         if st is not None and st['sig'] == sig:
             return st
-        if torch.cuda.is_current_stream_capturing():
+        if _capturing():
             raise RuntimeError('FusedAdam: parameter/gradient pointers changed during CUDA-graph capture; '
                                'run a warm-up step first')
         dev = ps[0].device
@@ -66,17 +70,14 @@ class FusedAdam(torch.optim.Optimizer):
         self._g[gi] = st
         return st
 
-    def set_lr(self, lr, pinned=None):
-        """write the learning rate for the next step (host value + device scalar, async, graph-safe)"""
+    def set_lr(self, lr):
+        """write the learning rate for the next step: host value + device scalar (stream-ordered fill, so a
+        captured step replayed afterwards sees it)"""
         for gi, group in enumerate(self.param_groups):
             group['lr'] = float(lr)
             st = self._g.get(gi)
             if st is not None:
-                if pinned is not None:
-                    pinned.fill_(float(lr))
-                    st['lr'].copy_(pinned, non_blocking=True)
-                else:
-                    st['lr'].fill_(float(lr))
+                st['lr'].fill_(float(lr))
                 st['lr_host'] = float(lr)
 
     @torch.no_grad()
@@ -88,7 +89,7 @@ class FusedAdam(torch.optim.Optimizer):
             if st is None:
                 continue
             if st['lr_host'] != float(group['lr']):
-                if torch.cuda.is_current_stream_capturing():
+                if _capturing():
                     raise RuntimeError('FusedAdam: change the lr with set_lr() before replaying a captured step')
                 st['lr'].fill_(float(group['lr']))
                 st['lr_host'] = float(group['lr'])
@@ -101,7 +102,7 @@ class FusedAdam(torch.optim.Optimizer):
             p.step = st['step'].data_ptr()
             p.counter = st['counter'].data_ptr()
             s = s or N.current_stream()
-            N.check(N.lib().bmnas_adam_step(ctypes.byref(p), s), 'adam')
+            N.launch('bmnas_adam_step', ctypes.byref(p), s)
         return loss
 
     def zero_grad(self, set_to_none=True):

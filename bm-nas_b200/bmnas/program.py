@@ -57,6 +57,7 @@ class Program:
         self._grads = {}         # id(state tensor) or slot name -> grad buffer
         self._written = set()    # data_ptrs of grad buffers already written in the backward order
         self._zero_ranges = []   # (tensor) zeroed at the start of every backward
+        self.drop_p = {}         # dropout site name -> p (read from the nn.Dropout modules)
         self.mask_slots = {}     # dropout site name -> Slot (parity mode)
         self.use_masks = False
         self.rng_state = None
@@ -159,7 +160,7 @@ class Program:
     def run_forward(self):
         s = N.current_stream()
         if self.rng_state is not None:
-            N.check(N.lib().bmnas_rng_advance(ctypes.c_void_p(self.rng_state.data_ptr()), s), 'rng_advance')
+            N.launch('bmnas_rng_advance', ctypes.c_void_p(self.rng_state.data_ptr()), s)
         for c in self.fwd:
             c(s)
         self.generation += 1
@@ -168,12 +169,14 @@ class Program:
         s = N.current_stream()
         L = N.lib()
         for t in self._zero_ranges:
-            N.check(L.bmnas_zero(ctypes.c_void_p(t.data_ptr()), ctypes.c_longlong(t.numel() * t.element_size()), s),
-                    'zero')
+            N.launch('bmnas_zero', ctypes.c_void_p(t.data_ptr()), ctypes.c_longlong(t.numel() * t.element_size()), s)
         for c in self.bwd:
             c(s)
 
     # ------------------------------------------------------------------ dropout helper
+    def p_of(self, site, default):
+        return float(self.drop_p.get(site, default))
+
     def _drop(self, site, p):
         """(mask Slot or None, needs rng) for a dropout site"""
         if not self.training or p <= 0.0:
@@ -337,7 +340,7 @@ class Program:
                 pre = prefix_of(k)
                 st.op_type[k] = OP_IDS[name]
                 st.z_off[k] = z_off.get(k, 0)
-                p = 0.0 if name == 'Sum' else (ATTN_DROP if name == 'ScaleDotAttn' else self.drpt)
+                p = 0.0 if name == 'Sum' else self.p_of(pre + '.dropout', ATTN_DROP if name == 'ScaleDotAttn' else self.drpt)
                 st.p_drop[k] = p
                 st.op_uid[k] = uid_of(pre)
                 if name != 'Sum':
@@ -437,11 +440,12 @@ class Program:
     def ln_tail(self, cv, residual, bn_w, bn_b, g_bn_w, g_bn_b, ln_w, ln_b, g_ln_w, g_ln_b, site, out,
                 need_src, need_res=True):
         C = self.C
-        mask = self._drop(site, self.drpt)
+        p_tail = self.p_of(site, self.drpt)
+        mask = self._drop(site, p_tail)
 
         def fill(st):
             st.B, st.L, st.Ctot, st.n_src, st.mode, st.relu_out = self.B, self.L, C, 1, 1, 0
-            st.training, st.p_drop, st.op_uid = int(self.training), self.drpt, uid_of(site)
+            st.training, st.p_drop, st.op_uid = int(self.training), p_tail, uid_of(site)
             st.sample_offset = self.sample_offset
             st.src_C[0] = C
             self.setp(st, 'src', cv['Z'], 0)

@@ -17,6 +17,9 @@ from . import native as N
 from .program import Program, Slot
 
 
+SAMPLE_OFFSET = [0]      # global index of this rank's first sample (world-size-invariant dropout streams)
+
+
 class GradArena:
     def __init__(self, tensors, device):
         self.tensors = [t for t in tensors]
@@ -124,7 +127,7 @@ def _prep(t, device):
     return t if t.is_contiguous() else t.contiguous()
 
 
-def run(root, kind, inputs, build, leaves, C, L, drpt, key_extra=(), masks=None):
+def run(root, kind, inputs, build, leaves, C, L, drpt, key_extra=(), masks=None, drop_p=None):
     """Execute (building and caching on first use) the launch plan of `root` for these inputs.
 
     build(prog, in_slots, need) -> out buffer; must emit the whole forward and register backwards.
@@ -139,7 +142,8 @@ def run(root, kind, inputs, build, leaves, C, L, drpt, key_extra=(), masks=None)
     need = tuple(bool(t.requires_grad and grad_on) for t in inputs)
     B = inputs[0].shape[0]
     use_masks = masks is not None
-    key = (kind, B, C, L, device.index, bool(root.training), use_masks, need) + tuple(key_extra)
+    drop_key = tuple(sorted(drop_p.items())) if drop_p else ()
+    key = (kind, B, C, L, device.index, bool(root.training), use_masks, need, SAMPLE_OFFSET[0], drop_key) + tuple(key_extra)
     cache = root.__dict__.setdefault('_bm_cache', {})
     leaves = [t for t in leaves if t.requires_grad]
     ptr_sig = tuple(t.data_ptr() for t in leaves)
@@ -153,6 +157,8 @@ def run(root, kind, inputs, build, leaves, C, L, drpt, key_extra=(), masks=None)
         arena = arena_for(root, leaves, device)
         prog = Program(device, B, C, L, root.training, drpt)
         prog.use_masks = use_masks
+        prog.drop_p = dict(drop_p or {})
+        prog.sample_offset = SAMPLE_OFFSET[0]
         in_slots = [f'in{i}' for i in range(len(inputs))]
         G = _GradViews(arena)
         out = build(prog, [Slot(n) for n in in_slots], need, G)

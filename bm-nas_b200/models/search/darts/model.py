@@ -8,7 +8,7 @@ import torch.nn as nn
 from bmnas import runtime as _rt
 
 from .node import Found_FusionNode
-from .node_operations import collect_masks
+from .node_operations import _dropkw
 from .operations import OPS
 
 
@@ -46,7 +46,7 @@ class Found_FusionCell(nn.Module):
             G.attach(P)
             return prog.cell_found(slots, list(need), gt, P, G, prefix, args.node_steps, args.node_multiplier)
         out = _rt.run(owner, 'cell_found', list(feats), build, list(self.parameters()), C, L, args.drpt,
-                      key_extra=(len(feats),), masks=collect_masks(self, prefix))
+                      key_extra=(len(feats),), **_dropkw(self, prefix))
         return out.view(B, -1)
 
     def forward(self, input_features):

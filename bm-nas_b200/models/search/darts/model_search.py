@@ -13,7 +13,7 @@ import torch.nn.functional as F
 from bmnas import runtime as _rt
 
 from .genotypes import PRIMITIVES, Genotype
-from .node_operations import collect_masks
+from .node_operations import _dropkw
 from .node_search import FusionNode
 from .operations import FusionMixedOp
 
@@ -68,7 +68,7 @@ class FusionCell(nn.Module):
         ins = list(feats) + ([] if alpha_logits else [alphas])
         leaves = list(self.parameters()) + self.arch_parameters() + list(extra_leaves)
         out = _rt.run(owner, 'cell_search', ins, build, leaves, C, L, args.drpt,
-                      key_extra=(n_in, alpha_logits, tuple(ops)), masks=collect_masks(self, prefix))
+                      key_extra=(n_in, alpha_logits, tuple(ops)), **_dropkw(self, prefix))
         return out.view(B, -1)
 
     def forward(self, input_features, weights):

@@ -8,7 +8,7 @@ import torch.nn as nn
 
 from bmnas import runtime as _rt
 
-from .node_operations import STEP_STEP_OPS, collect_masks
+from .node_operations import STEP_STEP_OPS, _dropkw
 from .operations import OPS
 
 
@@ -53,7 +53,7 @@ class Found_NodeCell(nn.Module):
             prog.node_cell_found(xs, ys, need[0], need[0] if alias else need[1], gene, P, G, 'node_cell', ns, nm, out)
             return out
         return _rt.run(owner, 'node_found', [x] if alias else [x, y], build, list(self.parameters()), C, L,
-                       self.args.drpt, key_extra=(alias,), masks=collect_masks(self, 'node_cell'))
+                       self.args.drpt, key_extra=(alias,), **_dropkw(self, 'node_cell'))
 
     def forward(self, x, y):
         return self._run(self, x, y)

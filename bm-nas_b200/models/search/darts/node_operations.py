@@ -24,15 +24,22 @@ STEP_STEP_OPS = {
 }
 
 
-def collect_masks(root, prefix=''):
-    """{dropout-site-name: injected uint8 mask} for every nn.Dropout below root that has one, or None."""
-    masks = {}
+def collect_dropout(root, prefix=''):
+    """({site: injected uint8 keep mask} or None, {site: p}) over every nn.Dropout below root.
+    The probabilities are read from the modules, so ``module.dropout.p = ...`` behaves as in torch."""
+    masks, ps = {}, {}
     for name, m in root.named_modules(prefix=prefix):
         if isinstance(m, nn.Dropout):
+            ps[name] = float(m.p)
             im = getattr(m, 'injected_mask', None)
             if im is not None:
                 masks[name] = im
-    return masks or None
+    return (masks or None), ps
+
+
+def _dropkw(root, prefix):
+    masks, ps = collect_dropout(root, prefix)
+    return dict(masks=masks, drop_p=ps)
 
 
 class _Primitive(nn.Module):
@@ -56,7 +63,7 @@ class _Primitive(nn.Module):
             return out
         leaves = list(self.parameters())
         return _rt.run(self, 'prim', [x] if alias else [x, y], build, leaves, C, L, drpt,
-                       key_extra=(alias,), masks=collect_masks(self, 'op'))
+                       key_extra=(alias,), **_dropkw(self, 'op'))
 
 
 class Sum(_Primitive):
@@ -143,4 +150,4 @@ class NodeMixedOp(nn.Module):
             return out
         ins = [x, weights] if alias else [x, y, weights]
         return _rt.run(self, 'mixed', ins, build, list(self.parameters()), C, L, self._drpt,
-                       key_extra=(alias, tuple(names)), masks=collect_masks(self, 'mix'))
+                       key_extra=(alias, tuple(names)), **_dropkw(self, 'mix'))

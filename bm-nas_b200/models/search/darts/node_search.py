@@ -16,7 +16,7 @@ from bmnas import runtime as _rt
 
 from . import genotypes as _gt
 from .genotypes import STEP_EDGE_PRIMITIVES, StepGenotype
-from .node_operations import NodeMixedOp, collect_masks
+from .node_operations import NodeMixedOp, _dropkw
 from .operations import FusionMixedOp
 
 
@@ -77,7 +77,7 @@ class NodeCell(nn.Module):
             ins += [edge_w, node_w]
         leaves = list(self.parameters()) + list(arch_leaves)
         return _rt.run(owner, 'node_search', ins, build, leaves, C, L, self.args.drpt,
-                       key_extra=(alias, logits, tuple(ops)), masks=collect_masks(self, 'node_cell'))
+                       key_extra=(alias, logits, tuple(ops)), **_dropkw(self, 'node_cell'))
 
     def forward(self, x, y, edge_weights, node_weights):
         return self._run(self, x, y, edge_weights, node_weights, False, [])
