@@ -225,7 +225,7 @@ class Program:
             self.setp(sb, 'gout', self.grad_of(out))
             if gw is not None:
                 self.setp(sb, 'gw', gw, offset=w_off * 8)
-                self.setp(sb, 'partials', self.buf(int(N.lib().bmnas_mix_partials_size(ctypes.byref(sb)))))
+                self.setp(sb, 'partials', self.buf(int(N.lib().bmnas_mix_partials_size(ctypes.byref(sb))), zero=True))
                 self.setp(sb, 'counter', self.counter())
             self.emit('bmnas_mix_bwd', sb)
         self.on_backward(bwd)
@@ -391,7 +391,7 @@ class Program:
                 elif name != 'Sum':
                     self.setp(sb, 'g_bn_w', G.get(pre + '.bn.weight'), k)
                     self.setp(sb, 'g_bn_b', G.get(pre + '.bn.bias'), k)
-            self.setp(sb, 'partials', self.buf(int(N.lib().bmnas_node_partials_size(ctypes.byref(sb)))))
+            self.setp(sb, 'partials', self.buf(int(N.lib().bmnas_node_partials_size(ctypes.byref(sb))), zero=True))
             self.setp(sb, 'counter', self.counter())
             self.emit('bmnas_node_bwd', sb)
             if cv:
@@ -484,7 +484,7 @@ class Program:
             self.setp(sb, 'coef_a', coef[0])
             self.setp(sb, 'coef_b', coef[1])
             self.setp(sb, 'coef_c', coef[2])
-            self.setp(sb, 'partials', self.buf(int(N.lib().bmnas_ln_partials_size(ctypes.byref(sb)))))
+            self.setp(sb, 'partials', self.buf(int(N.lib().bmnas_ln_partials_size(ctypes.byref(sb))), zero=True))
             self.setp(sb, 'counter', self.counter())
             self.emit('bmnas_ln_bwd', sb)
             self.conv_backward(cv, GV, coef, need_src)

@@ -1,39 +1,28 @@
 // fp32 (FFMA) GEMM family for the 1x1 convolutions of the fusion cell:
 //   conv_fwd   Z[b,m,l]  = sum_k Weff[m,k] U[b,k,l] + bias[m]      (+ BN batch statistics)
 //   conv_dgrad dU[b,k,l] = sum_m Weff[m,k] dz[b,m,l]
-//   conv_wgrad dW[m,k]   = sum_{b,l} dz[b,m,l] U[b,k,l],  dbias[m] = sum dz
+//   conv_wgrad dW[m,k]  += sum_{b,l} dz[b,m,l] U[b,k,l],  dbias[m] += sum dz
 // U is a virtual channel concat (never materialised), the output rows are stacked
 // weight segments, w_fold folds cat([t,t]); dz is produced on the fly from
 // (GV, Z, coef) = BatchNorm backward fused into the operand load.
-// This is the fp32-exact path (parity 1e-5 vs the reference on CPU); the bf16
-// tcgen05 path lives in gemm_tc.cu.
-// 64x64x16 tiles, 256 threads, 4x4 register micro-tiles, register prefetch of
-// the next K chunk.  All shapes are bounds-checked (M, K, N arbitrary).
+// This is the fp32-exact path (parity 1e-5 vs the reference on CPU).
+//
+// Shape of the problem on this path: reductions are short (C..3C = 128..768) and at the
+// reference batch (B*L = 768 columns) the whole GEMM is ~0.1 GFLOP, i.e. latency bound.
+// So: 32x32 output tiles (hundreds of CTAs -> every SM busy), the ENTIRE reduction
+// extent of both operands staged in shared memory with one burst of independent
+// 128-bit loads (one DRAM/L2 round trip, up to 384 reduction rows per pass), then a
+// dependency-free FFMA loop (4x2 register micro-tile, 128 threads).
 #include "common.cuh"
 
 namespace bmnas {
 
-constexpr int TM = 64, TN = 64, TK = 16, GT = 256;
-constexpr int PAD = 4;
+constexpr int TM = 32, TN = 32, GT = 128;
+constexpr int LDA = TM + 4, LDB = TN + 4;      // padded rows keep 16-byte alignment and spread banks
+constexpr int KC_MAX = 384;                    // reduction rows staged per pass (2 CTAs/SM at 110 KB)
 
-struct Tiles {
-    float A[TK][TM + PAD];
-    float B[TK][TN + PAD];
-};
-
-__device__ __forceinline__ void mma_chunk(const Tiles& t, float (&acc)[4][4], int ty, int tx) {
-#pragma unroll
-    for (int kk = 0; kk < TK; ++kk) {
-        const float4 a = *reinterpret_cast<const float4*>(&t.A[kk][ty * 4]);
-        const float4 b = *reinterpret_cast<const float4*>(&t.B[kk][tx * 4]);
-        const float av[4] = {a.x, a.y, a.z, a.w};
-        const float bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-    }
-}
+__host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+__host__ __device__ inline size_t gemm_smem_bytes(int kc) { return (size_t)kc * (LDA + LDB) * sizeof(float); }
 
 // row m of the stacked weight: pointer to W_seg[m_local][0]; also returns segment/local index
 __device__ __forceinline__ const float* w_row(const bmnas_conv_params& p, int m, int ldw, int* seg, int* ml) {
@@ -75,75 +64,156 @@ __device__ __forceinline__ Wf wf_merge(Wf a, Wf b) {
     return r;
 }
 
+// acc[4][2] += A[kk][ty*4 .. +3] (x) B[kk][tx*2 .. +1] over kk < kc
+__device__ __forceinline__ void mma_tile(const float* As, const float* Bs, int kc, float (&acc)[4][2], int ty, int tx) {
+#pragma unroll 8
+    for (int kk = 0; kk < kc; ++kk) {
+        const float4 a = *reinterpret_cast<const float4*>(As + kk * LDA + ty * 4);
+        const float2 b = *reinterpret_cast<const float2*>(Bs + kk * LDB + tx * 2);
+        acc[0][0] = fmaf(a.x, b.x, acc[0][0]); acc[0][1] = fmaf(a.x, b.y, acc[0][1]);
+        acc[1][0] = fmaf(a.y, b.x, acc[1][0]); acc[1][1] = fmaf(a.y, b.y, acc[1][1]);
+        acc[2][0] = fmaf(a.z, b.x, acc[2][0]); acc[2][1] = fmaf(a.z, b.y, acc[2][1]);
+        acc[3][0] = fmaf(a.w, b.x, acc[3][0]); acc[3][1] = fmaf(a.w, b.y, acc[3][1]);
+    }
+}
+
+// upstream-gradient operand with BatchNorm backward folded in (scalar / float4)
+__device__ __forceinline__ float dz1(const bmnas_conv_params& p, long long idx, int m) {
+    float g = __ldg(p.GV + idx);
+    if (p.coef_a) g = fmaf(__ldg(p.coef_a + m), g, fmaf(__ldg(p.coef_b + m), __ldg(p.Z + idx), __ldg(p.coef_c + m)));
+    return g;
+}
+__device__ __forceinline__ float4 dz4(const bmnas_conv_params& p, long long idx, int m) {
+    float4 g = __ldg(reinterpret_cast<const float4*>(p.GV + idx));
+    if (p.coef_a) {
+        const float a = __ldg(p.coef_a + m), b = __ldg(p.coef_b + m), c = __ldg(p.coef_c + m);
+        const float4 z = __ldg(reinterpret_cast<const float4*>(p.Z + idx));
+        g.x = fmaf(a, g.x, fmaf(b, z.x, c));
+        g.y = fmaf(a, g.y, fmaf(b, z.y, c));
+        g.z = fmaf(a, g.z, fmaf(b, z.z, c));
+        g.w = fmaf(a, g.w, fmaf(b, z.w, c));
+    }
+    return g;
+}
+
+// issue U independent loads per thread before the first dependent store (memory-level parallelism:
+// the staging phase is ONE latency round trip per U*GT elements instead of one per element)
+template <int U, class T, class Load, class Store>
+__device__ __forceinline__ void batched(int total, T zero, Load ld, Store st) {
+    for (int base = 0; base < total; base += GT * U) {
+        T v[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int u = base + j * GT + threadIdx.x;
+            v[j] = u < total ? ld(u) : zero;
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int u = base + j * GT + threadIdx.x;
+            if (u < total) st(u, v[j]);
+        }
+    }
+}
+
+// stage a [kc x 32 columns] activation-like operand: Bs[r][col] = X(row r0+r, column n0+col), rows < rmax,
+// columns < N, zero elsewhere.  get4/get1 fetch 4 / 1 consecutive l of one (sample, row).
+template <class Get4, class Get1>
+__device__ __forceinline__ void stage_cols(float* Bs, int kc, int r0, int rmax, int n0, int N, int L, bool vec,
+                                           Get4 get4, Get1 get1) {
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (vec) {  // L % 4 == 0: 8 float4 per staged row
+        batched<8>(kc * 8, z4,
+                   [&](int u) {
+                       const int c4 = u & 7, r = u >> 3;
+                       const int n = n0 + c4 * 4, row = r0 + r;
+                       return (n < N && row < rmax) ? get4(n / L, row, n % L) : z4;
+                   },
+                   [&](int u, float4 v) { *reinterpret_cast<float4*>(Bs + (u >> 3) * LDB + (u & 7) * 4) = v; });
+    } else {
+        batched<8>(kc * TN, 0.f,
+                   [&](int u) {
+                       const int c = u & 31, r = u >> 5;
+                       const int n = n0 + c, row = r0 + r;
+                       return (n < N && row < rmax) ? get1(n / L, row, n % L) : 0.f;
+                   },
+                   [&](int u, float v) { Bs[(u >> 5) * LDB + (u & 31)] = v; });
+    }
+}
+
 // ------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(GT, 2) k_conv_fwd(const bmnas_conv_params p, const int N, const int n_col_tiles) {
-    __shared__ __align__(16) Tiles t;
+__global__ void __launch_bounds__(GT) k_conv_fwd(const bmnas_conv_params p, const int N, const int n_col_tiles,
+                                                  const int KC) {
+    extern __shared__ __align__(16) float smem[];
+    float* As = smem;
+    float* Bs = smem + (size_t)KC * LDA;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
     const int K = p.K, M = p.M, L = p.L, ldw = p.w_fold * p.K;
+    const bool vecB = (L & 3) == 0;
+    const bool vecA = (K & 3) == 0;
 
-    // A loader: kk = tid&15, rows mi + 16 i
-    const int a_kk = tid & 15, a_mi = tid >> 4;
-    const float* a_row[4];
+    float acc[4][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = m0 + a_mi + 16 * i;
-        a_row[i] = m < M ? w_row(p, m, ldw, nullptr, nullptr) : nullptr;
-    }
-    // B loader: col = tid&63, kk = (tid>>6) + 4 i
-    const int b_col = tid & 63, b_kq = tid >> 6;
-    const int nB = n0 + b_col;
-    const bool vB = nB < N;
-    const int bB = vB ? nB / L : 0, lB = vB ? nB % L : 0;
+    for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.f;
 
-    float ra[4], rb[4];
-    auto load = [&](int k0) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int k = k0 + a_kk;
-            float v = 0.f;
-            if (a_row[i] && k < K) {
-                v = __ldg(a_row[i] + k);
-                if (p.w_fold == 2) v += __ldg(a_row[i] + K + k);
-            }
-            ra[i] = v;
+    for (int k0 = 0; k0 < K; k0 += KC) {
+        const int kc = min(KC, round_up(K - k0, 4));
+        if (k0) __syncthreads();
+        // A: As[k][m] = Weff[m0+m][k0+k]; lanes walk m (conflict-free transposed stores), float4 along k
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (vecA) {
+            batched<8>((kc >> 2) * TM, z4,
+                       [&](int u) {
+                           const int m = u & 31, k4 = (u >> 5) << 2;
+                           float4 v = z4;
+                           if (m0 + m < M && k0 + k4 < K) {
+                               const float* r = w_row(p, m0 + m, ldw, nullptr, nullptr) + k0 + k4;
+                               v = __ldg(reinterpret_cast<const float4*>(r));
+                               if (p.w_fold == 2) {
+                                   const float4 w = __ldg(reinterpret_cast<const float4*>(r + K));
+                                   v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+                               }
+                           }
+                           return v;
+                       },
+                       [&](int u, float4 v) {
+                           const int m = u & 31, k4 = (u >> 5) << 2;
+                           As[(k4 + 0) * LDA + m] = v.x; As[(k4 + 1) * LDA + m] = v.y;
+                           As[(k4 + 2) * LDA + m] = v.z; As[(k4 + 3) * LDA + m] = v.w;
+                       });
+        } else {
+            batched<8>(kc * TM, 0.f,
+                       [&](int u) {
+                           const int m = u & 31, k = u >> 5;
+                           float v = 0.f;
+                           if (m0 + m < M && k0 + k < K) {
+                               const float* r = w_row(p, m0 + m, ldw, nullptr, nullptr) + k0 + k;
+                               v = __ldg(r);
+                               if (p.w_fold == 2) v += __ldg(r + K);
+                           }
+                           return v;
+                       },
+                       [&](int u, float v) { As[(u >> 5) * LDA + (u & 31)] = v; });
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int k = k0 + b_kq + 4 * i;
-            float v = 0.f;
-            if (vB && k < K) {
-                int s, kl;
-                src_of(p, k, &s, &kl);
-                v = __ldg(p.src[s] + ((long long)bB * p.src_C[s] + kl) * L + lB);
-            }
-            rb[i] = v;
-        }
-    };
-
-    float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-
-    load(0);
-    for (int k0 = 0; k0 < K; k0 += TK) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            t.A[a_kk][a_mi + 16 * i] = ra[i];
-            t.B[b_kq + 4 * i][b_col] = rb[i];
-        }
+        stage_cols(Bs, kc, k0, K, n0, N, L, vecB,
+                   [&](int b, int k, int l) {
+                       int s, kl;
+                       src_of(p, k, &s, &kl);
+                       return __ldg(reinterpret_cast<const float4*>(p.src[s] + ((long long)b * p.src_C[s] + kl) * L + l));
+                   },
+                   [&](int b, int k, int l) {
+                       int s, kl;
+                       src_of(p, k, &s, &kl);
+                       return __ldg(p.src[s] + ((long long)b * p.src_C[s] + kl) * L + l);
+                   });
         __syncthreads();
-        if (k0 + TK < K) load(k0 + TK);
-        mma_chunk(t, acc, ty, tx);
-        __syncthreads();
+        mma_tile(As, Bs, kc, acc, ty, tx);
     }
 
     // ---- epilogue: bias, store, per-tile BN statistics
     const int cnt = min(TN, N - n0);
-    const int nb = n0 + tx * 4;
-    const bool vec = (L % 4 == 0) && (nb + 3 < N);
+    const int nb = n0 + tx * 2;
+    const bool vec = ((L & 1) == 0) && (nb + 1 < N);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int m = m0 + ty * 4 + i;
@@ -153,34 +223,22 @@ __global__ void __launch_bounds__(GT, 2) k_conv_fwd(const bmnas_conv_params p, c
             w_row(p, m, ldw, &s, &ml);
             if (p.bias[s]) bias = __ldg(p.bias[s] + ml);
         }
-        float z[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) z[j] = acc[i][j] + bias;
+        const float z0 = acc[i][0] + bias, z1 = acc[i][1] + bias;
         if (m < M) {
             if (vec) {
-                const int b = nb / L, l = nb % L;
-                *reinterpret_cast<float4*>(p.Z + ((long long)b * M + m) * L + l) = make_float4(z[0], z[1], z[2], z[3]);
+                *reinterpret_cast<float2*>(p.Z + ((long long)(nb / L) * M + m) * L + (nb % L)) = make_float2(z0, z1);
             } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int n = nb + j;
-                    if (n < N) p.Z[((long long)(n / L) * M + m) * L + (n % L)] = z[j];
-                }
+                if (nb < N) p.Z[((long long)(nb / L) * M + m) * L + (nb % L)] = z0;
+                if (nb + 1 < N) p.Z[((long long)((nb + 1) / L) * M + m) * L + ((nb + 1) % L)] = z1;
             }
         }
         if (p.bn_mode == 1) {
-            float s = 0.f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) s += (nb + j < N) ? z[j] : 0.f;
+            float s = (nb < N ? z0 : 0.f) + (nb + 1 < N ? z1 : 0.f);
 #pragma unroll
             for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             const float mean = s / (float)cnt;
-            float d2 = 0.f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float d = z[j] - mean;
-                d2 += (nb + j < N) ? d * d : 0.f;
-            }
+            const float d0 = z0 - mean, d1 = z1 - mean;
+            float d2 = (nb < N ? d0 * d0 : 0.f) + (nb + 1 < N ? d1 * d1 : 0.f);
 #pragma unroll
             for (int o = 8; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
             if (tx == 0 && m < M) {
@@ -205,7 +263,8 @@ __global__ void __launch_bounds__(GT, 2) k_conv_fwd(const bmnas_conv_params p, c
     }
     if (p.bn_mode != 1) return;
 
-    // ---- last CTA of this row-tile merges the per-column-tile statistics (Chan), fixed order
+    // ---- last CTA of this row-tile merges the per-column-tile statistics (Chan), fixed order:
+    //      4 lanes per row walk interleaved tiles, then a lane-symmetric butterfly
     if (!last_block(p.counter + blockIdx.y, gridDim.x)) return;
     const int r = tid >> 2, q = tid & 3;
     const int m = m0 + r;
@@ -223,8 +282,7 @@ __global__ void __launch_bounds__(GT, 2) k_conv_fwd(const bmnas_conv_params p, c
         b.n = __shfl_xor_sync(0xffffffffu, w.n, o);
         b.mean = __shfl_xor_sync(0xffffffffu, w.mean, o);
         b.m2 = __shfl_xor_sync(0xffffffffu, w.m2, o);
-        // merge in a lane-independent order so all 4 lanes agree bit-for-bit
-        w = ((q & o) == 0) ? wf_merge(w, b) : wf_merge(b, w);
+        w = ((q & o) == 0) ? wf_merge(w, b) : wf_merge(b, w);  // same operand order in both lanes
     }
     if (q == 0 && m < M) {
         const float var = w.m2 / (float)N;
@@ -241,69 +299,65 @@ __global__ void __launch_bounds__(GT, 2) k_conv_fwd(const bmnas_conv_params p, c
     }
 }
 
-// upstream-gradient operand with BatchNorm backward folded in
-__device__ __forceinline__ float load_dz(const bmnas_conv_params& p, long long idx, int m) {
-    float g = __ldg(p.GV + idx);
-    if (p.coef_a) g = fmaf(__ldg(p.coef_a + m), g, fmaf(__ldg(p.coef_b + m), __ldg(p.Z + idx), __ldg(p.coef_c + m)));
-    return g;
-}
-
 // ------------------------------------------------------------------ dgrad
-__global__ void __launch_bounds__(GT, 2) k_conv_dgrad(const bmnas_conv_params p, const int N) {
-    __shared__ __align__(16) Tiles t;
+__global__ void __launch_bounds__(GT) k_conv_dgrad(const bmnas_conv_params p, const int N, const int KC) {
+    extern __shared__ __align__(16) float smem[];
+    float* As = smem;
+    float* Bs = smem + (size_t)KC * LDA;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int kt0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
     const int K = p.K, M = p.M, L = p.L, ldw = p.w_fold * p.K;
+    const bool vecB = (L & 3) == 0;
+    const bool vecA = (K & 3) == 0;
 
-    const int a_kl = tid & 63, a_mq = tid >> 6;  // A[mm][k]: k fastest (coalesced along W rows)
-    const int b_col = tid & 63, b_mq = tid >> 6;
-    const int nB = n0 + b_col;
-    const bool vB = nB < N;
-    const int bB = vB ? nB / L : 0, lB = vB ? nB % L : 0;
-
-    float ra[4], rb[4];
-    auto load = [&](int mk0) {
+    float acc[4][2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int m = mk0 + a_mq + 4 * i, k = kt0 + a_kl;
-            float v = 0.f;
-            if (m < M && k < K) {
-                const float* r = w_row(p, m, ldw, nullptr, nullptr);
-                v = __ldg(r + k);
-                if (p.w_fold == 2) v += __ldg(r + K + k);
-            }
-            ra[i] = v;
+    for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.f;
+
+    for (int mk0 = 0; mk0 < M; mk0 += KC) {
+        const int kc = min(KC, round_up(M - mk0, 4));
+        if (mk0) __syncthreads();
+        // A: As[mm][k] = Weff[mk0+mm][kt0+k]: straight (coalesced) copies of weight-row slices
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (vecA) {
+            batched<8>(kc * 8, z4,
+                       [&](int u) {
+                           const int k4 = (u & 7) << 2, mm = u >> 3;
+                           float4 v = z4;
+                           if (mk0 + mm < M && kt0 + k4 < K) {
+                               const float* r = w_row(p, mk0 + mm, ldw, nullptr, nullptr) + kt0 + k4;
+                               v = __ldg(reinterpret_cast<const float4*>(r));
+                               if (p.w_fold == 2) {
+                                   const float4 w = __ldg(reinterpret_cast<const float4*>(r + K));
+                                   v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+                               }
+                           }
+                           return v;
+                       },
+                       [&](int u, float4 v) { *reinterpret_cast<float4*>(As + (u >> 3) * LDA + ((u & 7) << 2)) = v; });
+        } else {
+            batched<8>(kc * TM, 0.f,
+                       [&](int u) {
+                           const int k = u & 31, mm = u >> 5;
+                           float v = 0.f;
+                           if (mk0 + mm < M && kt0 + k < K) {
+                               const float* r = w_row(p, mk0 + mm, ldw, nullptr, nullptr) + kt0 + k;
+                               v = __ldg(r);
+                               if (p.w_fold == 2) v += __ldg(r + K);
+                           }
+                           return v;
+                       },
+                       [&](int u, float v) { As[(u >> 5) * LDA + (u & 31)] = v; });
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int m = mk0 + b_mq + 4 * i;
-            float v = 0.f;
-            if (vB && m < M) v = load_dz(p, ((long long)bB * M + m) * L + lB, m);
-            rb[i] = v;
-        }
-    };
-
-    float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-
-    load(0);
-    for (int mk0 = 0; mk0 < M; mk0 += TK) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            t.A[a_mq + 4 * i][a_kl] = ra[i];
-            t.B[b_mq + 4 * i][b_col] = rb[i];
-        }
+        stage_cols(Bs, kc, mk0, M, n0, N, L, vecB,
+                   [&](int b, int m, int l) { return dz4(p, ((long long)b * M + m) * L + l, m); },
+                   [&](int b, int m, int l) { return dz1(p, ((long long)b * M + m) * L + l, m); });
         __syncthreads();
-        if (mk0 + TK < M) load(mk0 + TK);
-        mma_chunk(t, acc, ty, tx);
-        __syncthreads();
+        mma_tile(As, Bs, kc, acc, ty, tx);
     }
 
-    const int nb = n0 + tx * 4;
-    const bool vec = (L % 4 == 0) && (nb + 3 < N);
+    const int nb = n0 + tx * 2;
+    const bool vec = ((L & 1) == 0) && (nb + 1 < N);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int k = kt0 + ty * 4 + i;
@@ -314,17 +368,16 @@ __global__ void __launch_bounds__(GT, 2) k_conv_dgrad(const bmnas_conv_params p,
         if (!dst) continue;
         const bool accum = p.gsrc_accum[s] != 0;
         if (vec) {
-            const int b = nb / L, l = nb % L;
-            float4* d = reinterpret_cast<float4*>(dst + ((long long)b * p.src_C[s] + kl) * L + l);
-            float4 o = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            float2* d = reinterpret_cast<float2*>(dst + ((long long)(nb / L) * p.src_C[s] + kl) * L + (nb % L));
+            float2 o = make_float2(acc[i][0], acc[i][1]);
             if (accum) {
-                const float4 c = *d;
-                o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
+                const float2 c = *d;
+                o.x += c.x; o.y += c.y;
             }
             *d = o;
         } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 2; ++j) {
                 const int n = nb + j;
                 if (n < N) {
                     float* d = dst + ((long long)(n / L) * p.src_C[s] + kl) * L + (n % L);
@@ -336,77 +389,77 @@ __global__ void __launch_bounds__(GT, 2) k_conv_dgrad(const bmnas_conv_params p,
 }
 
 // ------------------------------------------------------------------ wgrad
-__global__ void __launch_bounds__(GT, 2) k_conv_wgrad(const bmnas_conv_params p, const int N, const int chunkN) {
-    __shared__ __align__(16) Tiles t;
+// stage a [kc reduction columns x 32 rows] operand TRANSPOSED: S[nn][r] = X(row r0+r, column nk0+nn)
+template <class Get4, class Get1>
+__device__ __forceinline__ void stage_rows_t(float* S, int ld, int kc, int r0, int rmax, int nk0, int nend, int L,
+                                             bool vec, Get4 get4, Get1 get1) {
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (vec) {  // lanes: l4 fastest, then row  (bank = 16*l4 + row for L = 8: conflict-free)
+        const int q = L >> 2;  // float4 per (sample,row)
+        batched<8>((kc >> 2) * TM, z4,
+                   [&](int u) {
+                       const int l4 = u % q, r = (u / q) & 31, sm = u / (q * TM);
+                       const int n = nk0 + sm * L + l4 * 4, row = r0 + r;
+                       return (n < nend && row < rmax) ? get4(n / L, row, n % L) : z4;
+                   },
+                   [&](int u, float4 v) {
+                       const int l4 = u % q, r = (u / q) & 31, sm = u / (q * TM);
+                       const int nn = sm * L + l4 * 4;
+                       S[(nn + 0) * ld + r] = v.x; S[(nn + 1) * ld + r] = v.y;
+                       S[(nn + 2) * ld + r] = v.z; S[(nn + 3) * ld + r] = v.w;
+                   });
+    } else {
+        batched<8>(kc * TM, 0.f,
+                   [&](int u) {
+                       const int nn = u % kc, r = u / kc;
+                       const int n = nk0 + nn, row = r0 + r;
+                       return (n < nend && row < rmax) ? get1(n / L, row, n % L) : 0.f;
+                   },
+                   [&](int u, float v) { S[(u % kc) * ld + (u / kc)] = v; });
+    }
+}
+
+__global__ void __launch_bounds__(GT) k_conv_wgrad(const bmnas_conv_params p, const int N, const int chunkN,
+                                                    const int KC) {
+    extern __shared__ __align__(16) float smem[];
+    float* As = smem;
+    float* Bs = smem + (size_t)KC * LDA;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int kt0 = blockIdx.x * TN, m0 = blockIdx.y * TM;
     const int K = p.K, M = p.M, L = p.L, ldw = p.w_fold * p.K;
     const int nbeg = blockIdx.z * chunkN, nend = min(N, nbeg + chunkN);
+    // vector staging needs whole samples per chunk: chunkN and KC are multiples of L when vec
+    const bool vec = ((L & 3) == 0) && (KC % L == 0) && (chunkN % L == 0);
 
-    const int l_nn = tid & 15, l_ri = tid >> 4;  // both loaders: reduction index fastest
-    float ca[4], cb[4], cc[4];
-    const float* ub[4];
-    int ucs[4], ukl[4];
+    float acc[4][2], rs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = m0 + l_ri + 16 * i;
-        ca[i] = 1.f; cb[i] = 0.f; cc[i] = 0.f;
-        if (p.coef_a && m < M) {
-            ca[i] = __ldg(p.coef_a + m); cb[i] = __ldg(p.coef_b + m); cc[i] = __ldg(p.coef_c + m);
-        }
-        const int k = kt0 + l_ri + 16 * i;
-        ub[i] = nullptr; ucs[i] = 0; ukl[i] = 0;
-        if (k < K) {
-            int s, kl;
-            src_of(p, k, &s, &kl);
-            ub[i] = p.src[s]; ucs[i] = p.src_C[s]; ukl[i] = kl;
-        }
-    }
+    for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.f;
 
-    float ra[4], rb[4];
-    auto load = [&](int nk0) {
-        const int n = nk0 + l_nn;
-        const bool v = n < nend;
-        const int b = v ? n / L : 0, l = v ? n % L : 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int m = m0 + l_ri + 16 * i;
-            float x = 0.f;
-            if (v && m < M) {
-                const long long idx = ((long long)b * M + m) * L + l;
-                x = __ldg(p.GV + idx);
-                if (p.coef_a) x = fmaf(ca[i], x, fmaf(cb[i], __ldg(p.Z + idx), cc[i]));
+    for (int nk0 = nbeg; nk0 < nend; nk0 += KC) {
+        const int kc = min(KC, round_up(nend - nk0, vec ? L : 4));
+        if (nk0 != nbeg) __syncthreads();
+        stage_rows_t(As, LDA, kc, m0, M, nk0, nend, L, vec,
+                     [&](int b, int m, int l) { return dz4(p, ((long long)b * M + m) * L + l, m); },
+                     [&](int b, int m, int l) { return dz1(p, ((long long)b * M + m) * L + l, m); });
+        stage_rows_t(Bs, LDB, kc, kt0, K, nk0, nend, L, vec,
+                     [&](int b, int k, int l) {
+                         int s, kl;
+                         src_of(p, k, &s, &kl);
+                         return __ldg(reinterpret_cast<const float4*>(p.src[s] + ((long long)b * p.src_C[s] + kl) * L + l));
+                     },
+                     [&](int b, int k, int l) {
+                         int s, kl;
+                         src_of(p, k, &s, &kl);
+                         return __ldg(p.src[s] + ((long long)b * p.src_C[s] + kl) * L + l);
+                     });
+        __syncthreads();
+        mma_tile(As, Bs, kc, acc, ty, tx);
+        if (blockIdx.x == 0 && tx == 0) {  // bias gradient: row sums of dz
+            for (int kk = 0; kk < kc; ++kk) {
+                const float4 a = *reinterpret_cast<const float4*>(As + kk * LDA + ty * 4);
+                rs[0] += a.x; rs[1] += a.y; rs[2] += a.z; rs[3] += a.w;
             }
-            ra[i] = x;
-            float u = 0.f;
-            if (v && ub[i]) u = __ldg(ub[i] + ((long long)b * ucs[i] + ukl[i]) * L + l);
-            rb[i] = u;
         }
-    };
-
-    float acc[4][4], rs[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-
-    if (nbeg < nend) load(nbeg);
-    for (int nk0 = nbeg; nk0 < nend; nk0 += TK) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            t.A[l_nn][l_ri + 16 * i] = ra[i];
-            t.B[l_nn][l_ri + 16 * i] = rb[i];
-        }
-        __syncthreads();
-        if (nk0 + TK < nend) load(nk0 + TK);
-        mma_chunk(t, acc, ty, tx);
-        if (blockIdx.x == 0 && tx == 0) {
-#pragma unroll
-            for (int kk = 0; kk < TK; ++kk)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) rs[i] += t.A[kk][ty * 4 + i];
-        }
-        __syncthreads();
     }
 
 #pragma unroll
@@ -418,8 +471,8 @@ __global__ void __launch_bounds__(GT, 2) k_conv_wgrad(const bmnas_conv_params p,
         if (p.gW[s]) {
             float* row = p.gW[s] + (long long)ml * ldw;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int k = kt0 + tx * 4 + j;
+            for (int j = 0; j < 2; ++j) {
+                const int k = kt0 + tx * 2 + j;
                 if (k < K) {
                     for (int f = 0; f < p.w_fold; ++f) atomicAdd(row + f * K + k, acc[i][j]);
                 }
@@ -438,6 +491,16 @@ static int conv_check(const bmnas_conv_params* p) {
     for (int i = 0; i < p->n_seg; ++i) m += p->seg_M[i];
     if (k != p->K || m != p->M) return BMNAS_EINVAL;
     if ((long long)p->B * p->L > 0x7fffffffLL) return BMNAS_EINVAL;
+    return BMNAS_OK;
+}
+
+template <class Kern>
+static int set_smem(Kern kern, size_t bytes, size_t* configured) {
+    if (bytes > 48 * 1024 && bytes > *configured) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+            return BMNAS_ELAUNCH;
+        *configured = bytes;
+    }
     return BMNAS_OK;
 }
 
@@ -467,8 +530,11 @@ extern "C" int bmnas_conv_fwd(const bmnas_conv_params* p, void* stream) {
     }
     BMNAS_DRY_RETURN();
     const int N = p->B * p->L;
+    const int KC = min(KC_MAX, round_up(p->K, 4));
+    static size_t configured = 0;
+    if ((e = set_smem(k_conv_fwd, gemm_smem_bytes(KC), &configured))) return e;
     dim3 grid((N + TN - 1) / TN, (p->M + TM - 1) / TM);
-    k_conv_fwd<<<grid, GT, 0, (cudaStream_t)stream>>>(*p, N, (int)grid.x);
+    k_conv_fwd<<<grid, GT, gemm_smem_bytes(KC), (cudaStream_t)stream>>>(*p, N, (int)grid.x, KC);
     BMNAS_LAUNCH_CHECK();
     return BMNAS_OK;
 }
@@ -482,8 +548,11 @@ extern "C" int bmnas_conv_dgrad(const bmnas_conv_params* p, void* stream) {
         if (!p->W[i]) return BMNAS_EINVAL;
     BMNAS_DRY_RETURN();
     const int N = p->B * p->L;
+    const int KC = min(KC_MAX, round_up(p->M, 4));
+    static size_t configured = 0;
+    if ((e = set_smem(k_conv_dgrad, gemm_smem_bytes(KC), &configured))) return e;
     dim3 grid((N + TN - 1) / TN, (p->K + TM - 1) / TM);
-    k_conv_dgrad<<<grid, GT, 0, (cudaStream_t)stream>>>(*p, N);
+    k_conv_dgrad<<<grid, GT, gemm_smem_bytes(KC), (cudaStream_t)stream>>>(*p, N, KC);
     BMNAS_LAUNCH_CHECK();
     return BMNAS_OK;
 }
@@ -496,20 +565,23 @@ extern "C" int bmnas_conv_wgrad(const bmnas_conv_params* p, void* stream) {
     for (int i = 0; i < p->n_src; ++i)
         if (!p->src[i]) return BMNAS_EINVAL;
     BMNAS_DRY_RETURN();
-    const int N = p->B * p->L;
+    const int N = p->B * p->L, L = p->L;
     const int tiles = ((p->K + TN - 1) / TN) * ((p->M + TM - 1) / TM);
+    const int unit = ((L & 3) == 0 && L <= KC_MAX) ? L : 4;   // chunk granularity (whole samples when vectorised)
     int splits = p->splits;
     if (splits <= 0) {
-        splits = (2 * kNumSMs + tiles - 1) / tiles;
-        const int maxs = (N + 4 * TK - 1) / (4 * TK);  // at least 4 K-chunks per split
+        splits = (2 * kNumSMs + tiles - 1) / tiles;          // ~2 CTAs per SM
+        const int maxs = (N + 63) / 64;                      // at least 64 reduction columns per split
         if (splits > maxs) splits = maxs;
         if (splits < 1) splits = 1;
     }
-    int chunkN = (N + splits - 1) / splits;
-    chunkN = ((chunkN + TK - 1) / TK) * TK;
+    int chunkN = round_up((N + splits - 1) / splits, unit);
     splits = (N + chunkN - 1) / chunkN;
+    int KC = min(round_up(chunkN, unit), (KC_MAX / unit) * unit);
+    static size_t configured = 0;
+    if ((e = set_smem(k_conv_wgrad, gemm_smem_bytes(KC), &configured))) return e;
     dim3 grid((p->K + TN - 1) / TN, (p->M + TM - 1) / TM, splits);
-    k_conv_wgrad<<<grid, GT, 0, (cudaStream_t)stream>>>(*p, N, chunkN);
+    k_conv_wgrad<<<grid, GT, gemm_smem_bytes(KC), (cudaStream_t)stream>>>(*p, N, chunkN, KC);
     BMNAS_LAUNCH_CHECK();
     return BMNAS_OK;
 }

@@ -105,10 +105,18 @@ __global__ void __launch_bounds__(kMixThreads) k_mix_bwd(const bmnas_mix_params 
             if (j < p.n) p.partials[(long long)blockIdx.x * p.n + j] = dot[j];
     }
     if (last_block(p.counter, gridDim.x)) {
+        // fixed-order parallel reduction over the blocks: one warp per edge, lanes stride over blocks
+        const int lane = threadIdx.x & 31;
+        for (int j = threadIdx.x >> 5; j < p.n; j += kMixThreads / 32) {
+            float d = 0.f;
+            for (unsigned b = lane; b < gridDim.x; b += 32) d += ld_cg(p.partials + (long long)b * p.n + j);
+            d = warp_sum(d);
+            if (lane == 0) red[j] = d;
+        }
+        __syncthreads();
         if (threadIdx.x < p.n) {
             const int j = threadIdx.x;
-            float d = 0.f;
-            for (unsigned b = 0; b < gridDim.x; ++b) d += ld_cg(p.partials + (long long)b * p.n + j);
+            const float d = red[j];
             if (p.w_is_logits) {
                 // 2-way softmax backward; dL/dw_none == 0 for finite inputs (Zero op: x*0)
                 float gs = ws[j] * wn[j] * d;

@@ -3,10 +3,13 @@
 // LinearGLU and ConcatFC / CatConvMish epilogues on the pre-BN conv output Z),
 // softmax(gamma) weighted sum in the epilogue; per-op outputs never reach HBM.
 // The backward recomputes the primitives, emits GV = dL/d(BN output) for the conv
-// GEMMs, reduces dL/dgamma (warp shuffle -> block -> fixed-order last-block sum),
+// GEMMs, reduces dL/dgamma (warp shuffle -> block -> fixed-order last-block tree),
 // the BatchNorm affine grads and the coefficients that fold BatchNorm-backward
 // into the conv backward operand loads.
-// One CTA per sample (grid-stride over samples), 256 threads.
+// One CTA per sample (grid-stride over samples), 256 threads, every thread owns
+// groups of G=4 consecutive elements (128-bit global traffic, one Philox call per
+// group and dropout site); per-channel BatchNorm constants are folded once per CTA
+// into shared memory.
 #include "common.cuh"
 
 namespace bmnas {
@@ -17,22 +20,24 @@ constexpr int kNodeMaxBlocksBwd = kNumSMs * 2;
 
 struct NodeSmem {
     float *xs, *ys, *gs, *as, *dxs, *dys, *S, *S2, *Sp, *S1s, *S2s, *lnG, *lnH, *red, *gw;
+    float *rs, *mr, *bw, *bb, *tot;
 };
 
 __host__ __device__ inline size_t rnd4(size_t n) { return (n + 3) & ~(size_t)3; }
 
 __host__ __device__ inline size_t node_smem_floats(int C, int L, int M, bool bwd) {
-    const size_t CL = rnd4((size_t)C * L), LL = rnd4((size_t)L * L);
+    const size_t CL = rnd4((size_t)C * L), LL = rnd4((size_t)L * L), Mr = rnd4((size_t)M);
     size_t n = 0;
     n += 3 * CL;                            // xs, ys, as
     n += 2 * LL + (LL > NTH ? LL : NTH);    // S, S2, Sp
     n += 8 * 32 + 8;                        // red, gw
-    if (bwd) n += 5 * CL + 2 * rnd4((size_t)M);  // gs, dxs, dys, lnG, lnH, S1s, S2s
+    n += 4 * Mr;                            // rs, mr, bw, bb
+    if (bwd) n += 5 * CL + 2 * Mr + (2 * Mr + 8);  // gs, dxs, dys, lnG, lnH, S1s, S2s, tot
     return n + 16;
 }
 
 __device__ __forceinline__ NodeSmem node_carve(float* base, int C, int L, int M, bool bwd) {
-    const size_t CL = rnd4((size_t)C * L), LL = rnd4((size_t)L * L);
+    const size_t CL = rnd4((size_t)C * L), LL = rnd4((size_t)L * L), Mr = rnd4((size_t)M);
     NodeSmem s;
     float* q = base;
     s.xs = q; q += CL;
@@ -43,17 +48,79 @@ __device__ __forceinline__ NodeSmem node_carve(float* base, int C, int L, int M,
     s.Sp = q; q += (LL > NTH ? LL : NTH);
     s.red = q; q += 8 * 32;
     s.gw = q; q += 8;
-    s.gs = s.dxs = s.dys = s.S1s = s.S2s = s.lnG = s.lnH = nullptr;
+    s.rs = q; q += Mr;
+    s.mr = q; q += Mr;
+    s.bw = q; q += Mr;
+    s.bb = q; q += Mr;
+    s.gs = s.dxs = s.dys = s.S1s = s.S2s = s.lnG = s.lnH = s.tot = nullptr;
     if (bwd) {
         s.gs = q; q += CL;
         s.dxs = q; q += CL;
         s.dys = q; q += CL;
         s.lnG = q; q += CL;
         s.lnH = q; q += CL;
-        s.S1s = q; q += rnd4((size_t)M);
-        s.S2s = q; q += rnd4((size_t)M);
+        s.S1s = q; q += Mr;
+        s.S2s = q; q += Mr;
+        s.tot = q; q += 2 * Mr + 8;
     }
     return s;
+}
+
+// ---- G-wide element groups -------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ void ldg_v(const float* p, float (&v)[G]) {
+    if (G == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = t.x; v[1 % G] = t.y; v[2 % G] = t.z; v[3 % G] = t.w;
+    } else {
+        v[0] = __ldg(p);
+    }
+}
+template <int G>
+__device__ __forceinline__ void lds_v(const float* p, float (&v)[G]) {
+    if (G == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x; v[1 % G] = t.y; v[2 % G] = t.z; v[3 % G] = t.w;
+    } else {
+        v[0] = *p;
+    }
+}
+template <int G>
+__device__ __forceinline__ void st_v(float* p, const float (&v)[G]) {
+    if (G == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1 % G], v[2 % G], v[3 % G]);
+    else *p = v[0];
+}
+
+// dropout scales of one group (0 or 1/(1-p); 1 when inactive).  li/gi = local/global index of its first element.
+template <int G>
+__device__ __forceinline__ void drop_v(bool active, const unsigned char* mask, const unsigned long long* rng,
+                                       uint32_t uid, long long li, unsigned long long gi, float p, float (&ds)[G]) {
+    if (!active) {
+#pragma unroll
+        for (int j = 0; j < G; ++j) ds[j] = 1.f;
+        return;
+    }
+    const float keep = 1.f / (1.f - p);
+    if (mask) {
+        if (G == 4) {
+            const uchar4 m = *reinterpret_cast<const uchar4*>(mask + li);
+            ds[0] = m.x ? keep : 0.f; ds[1 % G] = m.y ? keep : 0.f; ds[2 % G] = m.z ? keep : 0.f; ds[3 % G] = m.w ? keep : 0.f;
+        } else {
+            ds[0] = mask[li] ? keep : 0.f;
+        }
+    } else if (G == 4) {   // one Philox call covers the group (same stream as the per-element philox_keep)
+        const unsigned long long seed = rng[0], step = rng[1];
+        const uint2 key = make_uint2((uint32_t)seed ^ (uid * 0x9E3779B1u), (uint32_t)(seed >> 32) + uid);
+        const uint4 r = philox4x32(make_uint4((uint32_t)(gi >> 2), (uint32_t)(gi >> 34), (uint32_t)step,
+                                              (uint32_t)(step >> 32)), key);
+        const float sc = 1.0f / 16777216.0f;
+        ds[0] = ((float)(r.x >> 8) * sc >= p) ? keep : 0.f;
+        ds[1 % G] = ((float)(r.y >> 8) * sc >= p) ? keep : 0.f;
+        ds[2 % G] = ((float)(r.z >> 8) * sc >= p) ? keep : 0.f;
+        ds[3 % G] = ((float)(r.w >> 8) * sc >= p) ? keep : 0.f;
+    } else {
+        ds[0] = philox_keep(rng, uid, gi, p) ? keep : 0.f;
+    }
 }
 
 // out[i*L+j] = scale * sum_c A[c*L+i] * Bm[c*L+j]   (L x L contraction over channels)
@@ -63,9 +130,14 @@ __device__ __forceinline__ void lxl_contract(const float* A, const float* Bm, fl
     const int nslice = pairs <= NTH ? NTH / pairs : 1;
     for (int w = threadIdx.x; w < nslice * pairs; w += NTH) {
         const int s = w / pairs, pr = w - s * pairs, i = pr / L, j = pr - i * L;
-        float acc = 0.f;
-        for (int c = s; c < C; c += nslice) acc = fmaf(A[c * L + i], Bm[c * L + j], acc);
-        Sp[w] = acc;
+        float a0 = 0.f, a1 = 0.f;
+        int c = s;
+        for (; c + nslice < C; c += 2 * nslice) {
+            a0 = fmaf(A[c * L + i], Bm[c * L + j], a0);
+            a1 = fmaf(A[(c + nslice) * L + i], Bm[(c + nslice) * L + j], a1);
+        }
+        if (c < C) a0 = fmaf(A[c * L + i], Bm[c * L + j], a0);
+        Sp[w] = a0 + a1;
     }
     __syncthreads();
     for (int pr = threadIdx.x; pr < pairs; pr += NTH) {
@@ -85,8 +157,10 @@ __device__ __forceinline__ void load_tile(float* dst, const float* src, int CL) 
     }
 }
 
-__device__ __forceinline__ void node_weights(const bmnas_node_params& p, float* gw) {
+// softmax(gamma) (or given weights / ones) and the folded per-channel BatchNorm constants
+__device__ __forceinline__ void node_setup(const bmnas_node_params& p, const NodeSmem& sm) {
     if (threadIdx.x == 0) {
+        float* gw = sm.gw;
         if (!p.gamma) {
             for (int k = 0; k < p.n_ops; ++k) gw[k] = 1.f;
         } else if (p.gamma_is_logits) {
@@ -102,57 +176,88 @@ __device__ __forceinline__ void node_weights(const bmnas_node_params& p, float* 
             for (int k = 0; k < p.n_ops; ++k) gw[k] = p.gamma[k];
         }
     }
+    for (int k = 0; k < p.n_ops; ++k) {
+        const int ty = p.op_type[k];
+        if (ty == BMNAS_OP_SUM || ty == BMNAS_OP_ATTN) continue;
+        const int rows = ty == BMNAS_OP_GLU ? 2 * p.C : p.C, zo = p.z_off[k];
+        for (int ml = threadIdx.x; ml < rows; ml += NTH) {
+            const int m = zo + ml;
+            const float r = __ldg(p.rstd + m);
+            sm.rs[m] = r;
+            sm.mr[m] = __ldg(p.mean + m) * r;
+            sm.bw[m] = __ldg(p.bn_w[k] + ml);
+            sm.bb[m] = __ldg(p.bn_b[k] + ml);
+        }
+    }
     __syncthreads();
 }
 
 // attention forward for one sample: P (L x L) in sm.S, dropped output a[c,i] in sm.as,
 // returns LayerNorm statistics of a.  (ScaledDotAttn.forward node_operations.py:92-108)
+template <int G>
 __device__ __forceinline__ void attn_forward(const bmnas_node_params& p, const NodeSmem& sm, int k, int b,
                                              float* mean_out, float* rstd_out) {
-    const int C = p.C, L = p.L, CL = C * L;
+    const int C = p.C, L = p.L, CL = C * L, LL = L * L;
     lxl_contract(sm.xs, sm.ys, sm.Sp, sm.S, C, L, 1.f / sqrtf((float)C));  // S[i][j] = q_i . k_j / sqrt(C)
-    for (int i = threadIdx.x; i < L; i += NTH) {  // softmax over key positions j
+    // softmax over key positions j, one thread per (i, j)
+    for (int pr = threadIdx.x; pr < LL; pr += NTH) {
+        const int i = pr / L;
         float mx = -INFINITY;
         for (int j = 0; j < L; ++j) mx = fmaxf(mx, sm.S[i * L + j]);
+        sm.S2[pr] = expf(sm.S[pr] - mx);
+    }
+    __syncthreads();
+    for (int pr = threadIdx.x; pr < LL; pr += NTH) {
+        const int i = pr / L;
         float s = 0.f;
-        for (int j = 0; j < L; ++j) {
-            const float e = expf(sm.S[i * L + j] - mx);
-            sm.S[i * L + j] = e;
-            s += e;
-        }
-        const float inv = 1.f / s;
-        for (int j = 0; j < L; ++j) sm.S[i * L + j] *= inv;
+        for (int j = 0; j < L; ++j) s += sm.S2[i * L + j];
+        sm.S[pr] = sm.S2[pr] / s;
     }
     __syncthreads();
     const bool drop = p.training && p.p_drop[k] > 0.f;
     float s0[1] = {0.f}, s1[1] = {0.f};
-    for (int e = threadIdx.x; e < CL; e += NTH) {
-        const int c = e / L, i = e - c * L;
-        float o = 0.f;
-        for (int j = 0; j < L; ++j) o = fmaf(sm.S[i * L + j], sm.ys[c * L + j], o);
-        const long long li = (long long)b * CL + e;
-        o *= drop_scale(drop, p.mask[k], p.rng_state, p.op_uid[k], li,
-                        (unsigned long long)(p.sample_offset + b) * CL + e, p.p_drop[k]);
-        sm.as[e] = o;
-        s0[0] += o;
+    for (int g = threadIdx.x; g < CL / G; g += NTH) {
+        const int e0 = g * G, c = e0 / L, i0 = e0 - c * L;
+        float o[G], ds[G];
+#pragma unroll
+        for (int q = 0; q < G; ++q) o[q] = 0.f;
+        for (int j = 0; j < L; ++j) {
+            const float yv = sm.ys[c * L + j];
+#pragma unroll
+            for (int q = 0; q < G; ++q) o[q] = fmaf(sm.S[(i0 + q) * L + j], yv, o[q]);
+        }
+        drop_v<G>(drop, p.mask[k], p.rng_state, p.op_uid[k], (long long)b * CL + e0,
+                  (unsigned long long)(p.sample_offset + b) * CL + e0, p.p_drop[k], ds);
+#pragma unroll
+        for (int q = 0; q < G; ++q) {
+            o[q] *= ds[q];
+            s0[0] += o[q];
+        }
+        st_v<G>(sm.as + e0, o);
     }
     block_sum<1>(s0, sm.red);
     const float mean = s0[0] / (float)CL;
-    for (int e = threadIdx.x; e < CL; e += NTH) {
-        const float d = sm.as[e] - mean;
-        s1[0] += d * d;
+    for (int g = threadIdx.x; g < CL / G; g += NTH) {
+        float o[G];
+        lds_v<G>(sm.as + g * G, o);
+#pragma unroll
+        for (int q = 0; q < G; ++q) {
+            const float d = o[q] - mean;
+            s1[0] += d * d;
+        }
     }
     block_sum<1>(s1, sm.red);
     *mean_out = mean;
     *rstd_out = 1.f / sqrtf(s1[0] / (float)CL + kLnEps);
 }
 
+template <int G>
 __global__ void __launch_bounds__(NTH) k_node_fwd(const bmnas_node_params p) {
     extern __shared__ __align__(16) float smem[];
     const int C = p.C, L = p.L, CL = C * L, M = p.M;
     NodeSmem sm = node_carve(smem, C, L, M, false);
     if (p.alias_xy) sm.ys = sm.xs;
-    node_weights(p, sm.gw);
+    node_setup(p, sm);
     int k_attn = -1;
     for (int k = 0; k < p.n_ops; ++k)
         if (p.op_type[k] == BMNAS_OP_ATTN) k_attn = k;
@@ -163,63 +268,83 @@ __global__ void __launch_bounds__(NTH) k_node_fwd(const bmnas_node_params p) {
         if (!p.alias_xy) load_tile(sm.ys, p.y + (long long)b * CL, CL);
         __syncthreads();
         float a_mean = 0.f, a_rstd = 0.f;
-        if (k_attn >= 0) attn_forward(p, sm, k_attn, b, &a_mean, &a_rstd);
+        if (k_attn >= 0) attn_forward<G>(p, sm, k_attn, b, &a_mean, &a_rstd);
         const float* Zb = p.Z ? p.Z + (long long)b * M * L : nullptr;
-        for (int e = threadIdx.x; e < CL; e += NTH) {
-            const int c = e / L;
-            const float xv = sm.xs[e], yv = sm.ys[e];
-            const long long li = (long long)b * CL + e;
-            const unsigned long long gi = (unsigned long long)(p.sample_offset + b) * CL + e;
-            float acc = 0.f;
+        for (int g = threadIdx.x; g < CL / G; g += NTH) {
+            const int e0 = g * G, c = e0 / L;
+            const long long li = (long long)b * CL + e0;
+            const unsigned long long gi = (unsigned long long)(p.sample_offset + b) * CL + e0;
+            float xv[G], yv[G], acc[G];
+            lds_v<G>(sm.xs + e0, xv);
+            lds_v<G>(sm.ys + e0, yv);
+#pragma unroll
+            for (int q = 0; q < G; ++q) acc[q] = 0.f;
             for (int k = 0; k < p.n_ops; ++k) {
-                float o;
                 const int ty = p.op_type[k];
+                const float wk = sm.gw[k];
+                float o[G];
                 if (ty == BMNAS_OP_SUM) {
-                    o = xv + yv;
+#pragma unroll
+                    for (int q = 0; q < G; ++q) o[q] = xv[q] + yv[q];
                 } else if (ty == BMNAS_OP_ATTN) {
-                    o = (sm.as[e] - a_mean) * a_rstd * __ldg(p.ln_w[k] + e) + __ldg(p.ln_b[k] + e);
+                    float a[G], gw_[G], gb_[G];
+                    lds_v<G>(sm.as + e0, a);
+                    ldg_v<G>(p.ln_w[k] + e0, gw_);
+                    ldg_v<G>(p.ln_b[k] + e0, gb_);
+#pragma unroll
+                    for (int q = 0; q < G; ++q) o[q] = (a[q] - a_mean) * a_rstd * gw_[q] + gb_[q];
                 } else {
-                    const int zo = p.z_off[k];
+                    const int m = p.z_off[k] + c;
                     const bool drop = p.training && p.p_drop[k] > 0.f;
-                    const float ds = drop_scale(drop, p.mask[k], p.rng_state, p.op_uid[k], li, gi, p.p_drop[k]);
-                    const float va = (__ldg(Zb + (long long)zo * L + e) - __ldg(p.mean + zo + c)) *
-                                         __ldg(p.rstd + zo + c) * __ldg(p.bn_w[k] + c) + __ldg(p.bn_b[k] + c);
+                    float ds[G], z[G];
+                    drop_v<G>(drop, p.mask[k], p.rng_state, p.op_uid[k], li, gi, p.p_drop[k], ds);
+                    ldg_v<G>(Zb + (long long)p.z_off[k] * L + e0, z);
+                    const float r = sm.rs[m], mr = sm.mr[m], w = sm.bw[m], bb = sm.bb[m];
                     if (ty == BMNAS_OP_GLU) {
-                        const float vg = (__ldg(Zb + (long long)(zo + C) * L + e) - __ldg(p.mean + zo + C + c)) *
-                                             __ldg(p.rstd + zo + C + c) * __ldg(p.bn_w[k] + C + c) +
-                                         __ldg(p.bn_b[k] + C + c);
-                        o = va * sigmoidf_(vg) * ds;
-                    } else if (ty == BMNAS_OP_FC_RELU) {
-                        o = fmaxf(va, 0.f) * ds;
+                        float zg[G];
+                        ldg_v<G>(Zb + (long long)(p.z_off[k] + C) * L + e0, zg);
+                        const float r2 = sm.rs[m + C], mr2 = sm.mr[m + C], w2 = sm.bw[m + C], bb2 = sm.bb[m + C];
+#pragma unroll
+                        for (int q = 0; q < G; ++q) {
+                            const float va = fmaf(fmaf(z[q], r, -mr), w, bb);
+                            const float vg = fmaf(fmaf(zg[q], r2, -mr2), w2, bb2);
+                            o[q] = va * sigmoidf_(vg) * ds[q];
+                        }
                     } else {
-                        o = mishf_(va) * ds;
+#pragma unroll
+                        for (int q = 0; q < G; ++q) {
+                            const float va = fmaf(fmaf(z[q], r, -mr), w, bb);
+                            o[q] = (ty == BMNAS_OP_FC_RELU ? fmaxf(va, 0.f) : mishf_(va)) * ds[q];
+                        }
                     }
                 }
-                acc = fmaf(sm.gw[k], o, acc);
+#pragma unroll
+                for (int q = 0; q < G; ++q) acc[q] = fmaf(wk, o[q], acc[q]);
             }
-            p.out[li] = acc;
+            st_v<G>(p.out + li, acc);
         }
     }
 }
 
-// add v into acc[m] for the channel m shared by the L consecutive lanes of a segment
+// add v (already summed over the thread's group) into acc[m]; the L/G lanes that share channel m are
+// adjacent and aligned, so a segmented shuffle + one plain store per channel is race-free and deterministic
 template <bool SEG>
-__device__ __forceinline__ void chan_add(float* acc, int m, float v, int L, bool active) {
+__device__ __forceinline__ void chan_add(float* acc, int m, float v, int lanes, bool active) {
     if (SEG) {
-        for (int o = L >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (active && ((threadIdx.x & (L - 1)) == 0)) acc[m] += v;
+        for (int o = lanes >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (active && ((threadIdx.x & (lanes - 1)) == 0)) acc[m] += v;
     } else {
         if (active) atomicAdd(acc + m, v);
     }
 }
 
-template <bool SEG>
+template <int G, bool SEG>
 __global__ void __launch_bounds__(NTH) k_node_bwd(const bmnas_node_params p) {
     extern __shared__ __align__(16) float smem[];
     const int C = p.C, L = p.L, CL = C * L, M = p.M;
     NodeSmem sm = node_carve(smem, C, L, M, true);
     if (p.alias_xy) sm.ys = sm.xs;
-    node_weights(p, sm.gw);
+    node_setup(p, sm);
     int k_attn = -1;
     for (int k = 0; k < p.n_ops; ++k)
         if (p.op_type[k] == BMNAS_OP_ATTN) k_attn = k;
@@ -235,6 +360,8 @@ __global__ void __launch_bounds__(NTH) k_node_bwd(const bmnas_node_params p) {
 #pragma unroll
     for (int k = 0; k < BMNAS_MAX_OPS; ++k) dg[k] = 0.f;
     const float inv_sqrt_c = 1.f / sqrtf((float)C);
+    const int lanes = SEG ? L / G : 1;   // lanes sharing one channel
+    const int NG = CL / G;
 
     for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
         __syncthreads();
@@ -243,83 +370,122 @@ __global__ void __launch_bounds__(NTH) k_node_bwd(const bmnas_node_params p) {
         load_tile(sm.gs, p.gout + (long long)b * CL, CL);
         __syncthreads();
         float a_mean = 0.f, a_rstd = 0.f;
-        if (k_attn >= 0) attn_forward(p, sm, k_attn, b, &a_mean, &a_rstd);
+        if (k_attn >= 0) attn_forward<G>(p, sm, k_attn, b, &a_mean, &a_rstd);
         const float* Zb = p.Z ? p.Z + (long long)b * M * L : nullptr;
         float* GVb = p.GV ? p.GV + (long long)b * M * L : nullptr;
         float lnsum[2] = {0.f, 0.f};  // sum q, sum q*ohat for the attention LayerNorm backward
 
-        for (int e0 = 0; e0 < CL; e0 += NTH) {
-            const int e = e0 + threadIdx.x;
-            const bool act = e < CL;
-            const int ee = act ? e : 0;
-            const int c = ee / L;
-            const float xv = sm.xs[ee], yv = sm.ys[ee], g = act ? sm.gs[ee] : 0.f;
-            const long long li = (long long)b * CL + ee;
-            const unsigned long long gi = (unsigned long long)(p.sample_offset + b) * CL + ee;
-            float gxe = 0.f, gye = 0.f;
+        for (int g0 = 0; g0 < NG; g0 += NTH) {
+            const int g = g0 + threadIdx.x;
+            const bool act = g < NG;
+            const int e0 = act ? g * G : 0, c = e0 / L;
+            const long long li = (long long)b * CL + e0;
+            const unsigned long long gi = (unsigned long long)(p.sample_offset + b) * CL + e0;
+            float xv[G], yv[G], gv_[G], gxe[G], gye[G];
+            lds_v<G>(sm.xs + e0, xv);
+            lds_v<G>(sm.ys + e0, yv);
+            lds_v<G>(sm.gs + e0, gv_);
+#pragma unroll
+            for (int q = 0; q < G; ++q) {
+                if (!act) gv_[q] = 0.f;
+                gxe[q] = 0.f;
+                gye[q] = 0.f;
+            }
 #pragma unroll
             for (int k = 0; k < BMNAS_MAX_OPS; ++k) {
                 if (k >= p.n_ops) break;
                 const int ty = p.op_type[k];
                 const float wk = sm.gw[k];
                 if (ty == BMNAS_OP_SUM) {
-                    dg[k] += g * (xv + yv);
-                    gxe += wk * g;
-                    gye += wk * g;
-                } else if (ty == BMNAS_OP_ATTN) {
-                    const float oh = (sm.as[ee] - a_mean) * a_rstd;
-                    const float G = __ldg(p.ln_w[k] + ee);
-                    dg[k] += g * (oh * G + __ldg(p.ln_b[k] + ee));
-                    const float go = wk * g;
-                    if (act) {
-                        sm.lnG[ee] += go * oh;
-                        sm.lnH[ee] += go;
+#pragma unroll
+                    for (int q = 0; q < G; ++q) {
+                        dg[k] += gv_[q] * (xv[q] + yv[q]);
+                        gxe[q] += wk * gv_[q];
+                        gye[q] += wk * gv_[q];
                     }
-                    const float q = go * G;
-                    lnsum[0] += q;
-                    lnsum[1] += q * oh;
+                } else if (ty == BMNAS_OP_ATTN) {
+                    float a[G], Gw[G], Gb[G], lg[G], lh[G];
+                    lds_v<G>(sm.as + e0, a);
+                    ldg_v<G>(p.ln_w[k] + e0, Gw);
+                    ldg_v<G>(p.ln_b[k] + e0, Gb);
+                    lds_v<G>(sm.lnG + e0, lg);
+                    lds_v<G>(sm.lnH + e0, lh);
+#pragma unroll
+                    for (int q = 0; q < G; ++q) {
+                        const float oh = (a[q] - a_mean) * a_rstd;
+                        dg[k] += gv_[q] * (oh * Gw[q] + Gb[q]);
+                        const float go = wk * gv_[q];
+                        lg[q] += go * oh;
+                        lh[q] += go;
+                        const float qq = go * Gw[q];
+                        lnsum[0] += qq;
+                        lnsum[1] += qq * oh;
+                    }
+                    if (act) {
+                        st_v<G>(sm.lnG + e0, lg);
+                        st_v<G>(sm.lnH + e0, lh);
+                    }
                 } else {
-                    const int zo = p.z_off[k];
+                    const int zo = p.z_off[k], m = zo + c;
                     const bool drop = p.training && p.p_drop[k] > 0.f;
-                    const float ds = drop_scale(drop, p.mask[k], p.rng_state, p.op_uid[k], li, gi, p.p_drop[k]);
-                    const float zha = (__ldg(Zb + (long long)zo * L + ee) - __ldg(p.mean + zo + c)) * __ldg(p.rstd + zo + c);
-                    const float va = zha * __ldg(p.bn_w[k] + c) + __ldg(p.bn_b[k] + c);
-                    const float go = wk * g * ds;
+                    float ds[G], z[G];
+                    drop_v<G>(drop, p.mask[k], p.rng_state, p.op_uid[k], li, gi, p.p_drop[k], ds);
+                    ldg_v<G>(Zb + (long long)zo * L + e0, z);
+                    const float r = sm.rs[m], mr = sm.mr[m], w = sm.bw[m], bb = sm.bb[m];
                     if (ty == BMNAS_OP_GLU) {
-                        const float zhg = (__ldg(Zb + (long long)(zo + C) * L + ee) - __ldg(p.mean + zo + C + c)) *
-                                          __ldg(p.rstd + zo + C + c);
-                        const float vg = zhg * __ldg(p.bn_w[k] + C + c) + __ldg(p.bn_b[k] + C + c);
-                        const float s = sigmoidf_(vg);
-                        dg[k] += g * (va * s * ds);
-                        const float gva = go * s, gvg = go * va * s * (1.f - s);
+                        float zg[G], gva[G], gvg[G];
+                        ldg_v<G>(Zb + (long long)(zo + C) * L + e0, zg);
+                        const float r2 = sm.rs[m + C], mr2 = sm.mr[m + C], w2 = sm.bw[m + C], bb2 = sm.bb[m + C];
+                        float s1a = 0.f, s2a = 0.f, s1g = 0.f, s2g = 0.f;
+#pragma unroll
+                        for (int q = 0; q < G; ++q) {
+                            const float zha = fmaf(z[q], r, -mr), zhg = fmaf(zg[q], r2, -mr2);
+                            const float va = fmaf(zha, w, bb), vg = fmaf(zhg, w2, bb2);
+                            const float s = sigmoidf_(vg);
+                            dg[k] += gv_[q] * (va * s * ds[q]);
+                            const float go = wk * gv_[q] * ds[q];
+                            gva[q] = go * s;
+                            gvg[q] = go * va * s * (1.f - s);
+                            s1a += gva[q]; s2a += gva[q] * zha;
+                            s1g += gvg[q]; s2g += gvg[q] * zhg;
+                        }
                         if (act) {
-                            GVb[(long long)zo * L + ee] = gva;
-                            GVb[(long long)(zo + C) * L + ee] = gvg;
+                            st_v<G>(GVb + (long long)zo * L + e0, gva);
+                            st_v<G>(GVb + (long long)(zo + C) * L + e0, gvg);
                         }
-                        chan_add<SEG>(sm.S1s, zo + c, gva, L, act);
-                        chan_add<SEG>(sm.S2s, zo + c, gva * zha, L, act);
-                        chan_add<SEG>(sm.S1s, zo + C + c, gvg, L, act);
-                        chan_add<SEG>(sm.S2s, zo + C + c, gvg * zhg, L, act);
+                        chan_add<SEG>(sm.S1s, m, s1a, lanes, act);
+                        chan_add<SEG>(sm.S2s, m, s2a, lanes, act);
+                        chan_add<SEG>(sm.S1s, m + C, s1g, lanes, act);
+                        chan_add<SEG>(sm.S2s, m + C, s2g, lanes, act);
                     } else {
-                        float o, d;
-                        if (ty == BMNAS_OP_FC_RELU) {
-                            o = fmaxf(va, 0.f);
-                            d = va > 0.f ? 1.f : 0.f;
-                        } else {
-                            o = mishf_(va);
-                            d = mish_grad(va);
+                        float gvv[G];
+                        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                        for (int q = 0; q < G; ++q) {
+                            const float zha = fmaf(z[q], r, -mr);
+                            const float va = fmaf(zha, w, bb);
+                            float o, d;
+                            if (ty == BMNAS_OP_FC_RELU) {
+                                o = fmaxf(va, 0.f);
+                                d = va > 0.f ? 1.f : 0.f;
+                            } else {
+                                o = mishf_(va);
+                                d = mish_grad(va);
+                            }
+                            dg[k] += gv_[q] * (o * ds[q]);
+                            gvv[q] = wk * gv_[q] * ds[q] * d;
+                            s1 += gvv[q];
+                            s2 += gvv[q] * zha;
                         }
-                        dg[k] += g * (o * ds);
-                        const float gv = go * d;
-                        if (act) GVb[(long long)zo * L + ee] = gv;
-                        chan_add<SEG>(sm.S1s, zo + c, gv, L, act);
-                        chan_add<SEG>(sm.S2s, zo + c, gv * zha, L, act);
+                        if (act) st_v<G>(GVb + (long long)zo * L + e0, gvv);
+                        chan_add<SEG>(sm.S1s, m, s1, lanes, act);
+                        chan_add<SEG>(sm.S2s, m, s2, lanes, act);
                     }
                 }
             }
             if (act) {
-                sm.dxs[ee] = gxe;
-                sm.dys[ee] = gye;
+                st_v<G>(sm.dxs + e0, gxe);
+                st_v<G>(sm.dys + e0, gye);
             }
         }
 
@@ -329,64 +495,106 @@ __global__ void __launch_bounds__(NTH) k_node_bwd(const bmnas_node_params p) {
             const float mq = lnsum[0] / (float)CL, mqo = lnsum[1] / (float)CL;
             const float wk = sm.gw[k];
             const bool drop = p.training && p.p_drop[k] > 0.f;
-            for (int e = threadIdx.x; e < CL; e += NTH) {
-                const float oh = (sm.as[e] - a_mean) * a_rstd;
-                const float q = wk * sm.gs[e] * __ldg(p.ln_w[k] + e);
-                float dd = a_rstd * (q - mq - oh * mqo);
-                const long long li = (long long)b * CL + e;
-                dd *= drop_scale(drop, p.mask[k], p.rng_state, p.op_uid[k], li,
-                                 (unsigned long long)(p.sample_offset + b) * CL + e, p.p_drop[k]);
-                sm.as[e] = dd;  // dO[c,i]
+            for (int g = threadIdx.x; g < NG; g += NTH) {
+                const int e0 = g * G;
+                float a[G], Gw[G], gg[G], ds[G], dd[G];
+                lds_v<G>(sm.as + e0, a);
+                ldg_v<G>(p.ln_w[k] + e0, Gw);
+                lds_v<G>(sm.gs + e0, gg);
+                drop_v<G>(drop, p.mask[k], p.rng_state, p.op_uid[k], (long long)b * CL + e0,
+                          (unsigned long long)(p.sample_offset + b) * CL + e0, p.p_drop[k], ds);
+#pragma unroll
+                for (int q = 0; q < G; ++q) {
+                    const float oh = (a[q] - a_mean) * a_rstd;
+                    dd[q] = a_rstd * (wk * gg[q] * Gw[q] - mq - oh * mqo) * ds[q];
+                }
+                st_v<G>(sm.as + e0, dd);  // dO[c,i]
             }
             __syncthreads();
             lxl_contract(sm.as, sm.ys, sm.Sp, sm.S2, C, L, 1.f);  // dP[i][j] = sum_c dO[c,i] y[c,j]
-            for (int i = threadIdx.x; i < L; i += NTH) {
+            for (int pr = threadIdx.x; pr < L * L; pr += NTH) {    // dS = P o (dP - rowdot) / sqrt(C)
+                const int i = pr / L;
                 float rd = 0.f;
                 for (int j = 0; j < L; ++j) rd = fmaf(sm.S2[i * L + j], sm.S[i * L + j], rd);
-                for (int j = 0; j < L; ++j)
-                    sm.S2[i * L + j] = sm.S[i * L + j] * (sm.S2[i * L + j] - rd) * inv_sqrt_c;  // dS / sqrt(C)
+                sm.Sp[pr] = sm.S[pr] * (sm.S2[pr] - rd) * inv_sqrt_c;
             }
             __syncthreads();
-            for (int e = threadIdx.x; e < CL; e += NTH) {
-                const int c = e / L, i = e - c * L;
-                float dx = 0.f, dy = 0.f;
-                for (int j = 0; j < L; ++j) dx = fmaf(sm.S2[i * L + j], sm.ys[c * L + j], dx);
-                // dy[c, j=i] = sum_i' dO[c,i'] P[i'][j] + x[c,i'] dS[i'][j]
-                for (int ii = 0; ii < L; ++ii) {
-                    dy = fmaf(sm.as[c * L + ii], sm.S[ii * L + i], dy);
-                    dy = fmaf(sm.xs[c * L + ii], sm.S2[ii * L + i], dy);
+            for (int g = threadIdx.x; g < NG; g += NTH) {
+                const int e0 = g * G, c = e0 / L, i0 = e0 - c * L;
+                float dx[G], dy[G];
+                lds_v<G>(sm.dxs + e0, dx);
+                lds_v<G>(sm.dys + e0, dy);
+                for (int j = 0; j < L; ++j) {
+                    const float yj = sm.ys[c * L + j], dOj = sm.as[c * L + j], xj = sm.xs[c * L + j];
+#pragma unroll
+                    for (int q = 0; q < G; ++q) {
+                        dx[q] = fmaf(sm.Sp[(i0 + q) * L + j], yj, dx[q]);        // dx[c,i] += dS[i][j] y[c,j]
+                        dy[q] = fmaf(dOj, sm.S[j * L + i0 + q], dy[q]);          // dy[c,i] += dO[c,j] P[j][i]
+                        dy[q] = fmaf(xj, sm.Sp[j * L + i0 + q], dy[q]);          //          + x[c,j] dS[j][i]
+                    }
                 }
-                sm.dxs[e] += dx;
-                sm.dys[e] += dy;
+                st_v<G>(sm.dxs + e0, dx);
+                st_v<G>(sm.dys + e0, dy);
             }
         }
         __syncthreads();
-        for (int e = threadIdx.x; e < CL; e += NTH) {
-            const long long li = (long long)b * CL + e;
+        for (int g = threadIdx.x; g < NG; g += NTH) {
+            const int e0 = g * G;
+            const long long li = (long long)b * CL + e0;
+            float dx[G], dy[G];
+            lds_v<G>(sm.dxs + e0, dx);
+            lds_v<G>(sm.dys + e0, dy);
             if (p.alias_xy) {
                 if (p.gx) {
-                    const float v = sm.dxs[e] + sm.dys[e];
-                    p.gx[li] = p.gx_accum ? p.gx[li] + v : v;
+                    float o[G];
+#pragma unroll
+                    for (int q = 0; q < G; ++q) o[q] = dx[q] + dy[q];
+                    if (p.gx_accum) {
+                        float c_[G];
+                        lds_v<G>(p.gx + li, c_);
+#pragma unroll
+                        for (int q = 0; q < G; ++q) o[q] += c_[q];
+                    }
+                    st_v<G>(p.gx + li, o);
                 }
             } else {
-                if (p.gx) p.gx[li] = p.gx_accum ? p.gx[li] + sm.dxs[e] : sm.dxs[e];
-                if (p.gy) p.gy[li] = p.gy_accum ? p.gy[li] + sm.dys[e] : sm.dys[e];
+                if (p.gx) {
+                    if (p.gx_accum) {
+                        float c_[G];
+                        lds_v<G>(p.gx + li, c_);
+#pragma unroll
+                        for (int q = 0; q < G; ++q) dx[q] += c_[q];
+                    }
+                    st_v<G>(p.gx + li, dx);
+                }
+                if (p.gy) {
+                    if (p.gy_accum) {
+                        float c_[G];
+                        lds_v<G>(p.gy + li, c_);
+#pragma unroll
+                        for (int q = 0; q < G; ++q) dy[q] += c_[q];
+                    }
+                    st_v<G>(p.gy + li, dy);
+                }
             }
         }
     }
 
-    // ---- per-CTA partials -> global, then last CTA finalises
+    // ---- per-CTA sums -> one global accumulator (red.add), then the last CTA finalises.
+    //      (a fixed-order reduction of per-CTA partials by a single CTA costs ~100 dependent L2 round
+    //      trips; the accumulator is self-cleaning like the counter)
     block_sum<BMNAS_MAX_OPS>(dg, sm.red);
     __syncthreads();
     const int PW = 2 * M + BMNAS_MAX_OPS;
-    float* part = p.partials + (long long)blockIdx.x * PW;
+    float* gacc = p.partials;
     for (int i = threadIdx.x; i < M; i += NTH) {
-        part[i] = sm.S1s[i];
-        part[M + i] = sm.S2s[i];
+        atomicAdd(gacc + i, sm.S1s[i]);
+        atomicAdd(gacc + M + i, sm.S2s[i]);
     }
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int k = 0; k < BMNAS_MAX_OPS; ++k) part[2 * M + k] = dg[k];
+        for (int k = 0; k < BMNAS_MAX_OPS; ++k)
+            if (k < p.n_ops) atomicAdd(gacc + 2 * M + k, dg[k]);
     }
     if (k_attn >= 0 && p.g_ln_w[k_attn]) {
         for (int e = threadIdx.x; e < CL; e += NTH) {
@@ -395,7 +603,11 @@ __global__ void __launch_bounds__(NTH) k_node_bwd(const bmnas_node_params p) {
         }
     }
     if (!last_block(p.counter, gridDim.x)) return;
-
+    for (int v = threadIdx.x; v < PW; v += NTH) {
+        sm.tot[v] = ld_cg(gacc + v);
+        gacc[v] = 0.f;
+    }
+    __syncthreads();
     const float n = (float)p.B * (float)L;
     for (int k = 0; k < p.n_ops; ++k) {
         const int ty = p.op_type[k];
@@ -403,38 +615,29 @@ __global__ void __launch_bounds__(NTH) k_node_bwd(const bmnas_node_params p) {
         const int rows = ty == BMNAS_OP_GLU ? 2 * C : C, zo = p.z_off[k];
         for (int ml = threadIdx.x; ml < rows; ml += NTH) {
             const int m = zo + ml;
-            float s1 = 0.f, s2 = 0.f;
-            for (unsigned cta = 0; cta < gridDim.x; ++cta) {
-                s1 += ld_cg(p.partials + (long long)cta * PW + m);
-                s2 += ld_cg(p.partials + (long long)cta * PW + M + m);
-            }
+            const float s1 = sm.tot[m], s2 = sm.tot[M + m];
             if (p.g_bn_w[k]) {
                 p.g_bn_w[k][ml] = s2;
                 p.g_bn_b[k][ml] = s1;
             }
-            const float rs = p.rstd[m], mu = p.mean[m];
+            const float rs = sm.rs[m], mur = sm.mr[m];   // mean * rstd
             if (p.training) {
-                const float a = p.bn_w[k][ml] * rs, m1 = s1 / n, m2 = s2 / n;
+                const float a = sm.bw[m] * rs, m1 = s1 / n, m2 = s2 / n;
                 p.coef_a[m] = a;
                 p.coef_b[m] = -a * rs * m2;
-                p.coef_c[m] = a * (mu * rs * m2 - m1);
+                p.coef_c[m] = a * (mur * m2 - m1);
             } else {  // eval-mode BN is a fixed affine map
-                p.coef_a[m] = p.bn_w[k][ml] * rs;
+                p.coef_a[m] = sm.bw[m] * rs;
                 p.coef_b[m] = 0.f;
                 p.coef_c[m] = 0.f;
             }
         }
     }
     if (p.g_gamma && threadIdx.x == 0) {
-        float d[BMNAS_MAX_OPS];
         float dot = 0.f;
-        for (int k = 0; k < p.n_ops; ++k) {
-            float s = 0.f;
-            for (unsigned cta = 0; cta < gridDim.x; ++cta) s += ld_cg(p.partials + (long long)cta * PW + 2 * M + k);
-            d[k] = s;
-            dot += sm.gw[k] * s;
-        }
-        for (int k = 0; k < p.n_ops; ++k) p.g_gamma[k] = p.gamma_is_logits ? sm.gw[k] * (d[k] - dot) : d[k];
+        for (int k = 0; k < p.n_ops; ++k) dot += sm.gw[k] * sm.tot[2 * M + k];
+        for (int k = 0; k < p.n_ops; ++k)
+            p.g_gamma[k] = p.gamma_is_logits ? sm.gw[k] * (sm.tot[2 * M + k] - dot) : sm.tot[2 * M + k];
     }
 }
 
@@ -465,6 +668,32 @@ static int node_check(const bmnas_node_params* p, bool bwd) {
     return BMNAS_OK;
 }
 
+static bool al16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
+
+// 128-bit groups need L % 4 == 0 (a group never straddles a channel) and 16-byte aligned tensors
+static bool node_vec_ok(const bmnas_node_params* p, bool bwd) {
+    if (p->L % 4) return false;
+    if (!al16(p->x) || !al16(p->y) || !al16(p->Z) || !al16(p->out) || !al16(p->gout) || !al16(p->gx) || !al16(p->gy) ||
+        !al16(p->GV))
+        return false;
+    for (int k = 0; k < p->n_ops; ++k) {
+        if (!al16(p->ln_w[k]) || !al16(p->ln_b[k]) || !al16(p->g_ln_w[k]) || !al16(p->g_ln_b[k])) return false;
+        if (p->mask[k] && (reinterpret_cast<uintptr_t>(p->mask[k]) & 3u)) return false;
+    }
+    (void)bwd;
+    return true;
+}
+
+template <class Kern>
+static int node_smem_attr(Kern kern, size_t smem, size_t* configured) {
+    if (smem > 48 * 1024 && smem > *configured) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return BMNAS_ELAUNCH;
+        *configured = smem;
+    }
+    return BMNAS_OK;
+}
+
 }  // namespace bmnas
 
 using namespace bmnas;
@@ -479,14 +708,15 @@ extern "C" int bmnas_node_fwd(const bmnas_node_params* p, void* stream) {
     const size_t smem = node_smem_floats(p->C, p->L, p->M, false) * sizeof(float);
     if (smem > 227 * 1024) return BMNAS_EINVAL;
     BMNAS_DRY_RETURN();
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        if (cudaFuncSetAttribute(k_node_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return BMNAS_ELAUNCH;
-        configured = smem;
-    }
+    const bool vec = node_vec_ok(p, false);
+    static size_t configured[2] = {0, 0};
+    e = vec ? node_smem_attr(k_node_fwd<4>, smem, &configured[1]) : node_smem_attr(k_node_fwd<1>, smem, &configured[0]);
+    if (e) return e;
     const int blocks = p->B < kNodeMaxBlocksFwd ? p->B : kNodeMaxBlocksFwd;
-    k_node_fwd<<<blocks, NTH, smem, (cudaStream_t)stream>>>(*p);
+    if (vec)
+        k_node_fwd<4><<<blocks, NTH, smem, (cudaStream_t)stream>>>(*p);
+    else
+        k_node_fwd<1><<<blocks, NTH, smem, (cudaStream_t)stream>>>(*p);
     BMNAS_LAUNCH_CHECK();
     return BMNAS_OK;
 }
@@ -496,20 +726,22 @@ extern "C" int bmnas_node_bwd(const bmnas_node_params* p, void* stream) {
     if (e) return e;
     const size_t smem = node_smem_floats(p->C, p->L, p->M, true) * sizeof(float);
     if (smem > 227 * 1024) return BMNAS_EINVAL;
-    const bool seg = (p->L & (p->L - 1)) == 0 && p->L <= 32;
     BMNAS_DRY_RETURN();
-    static size_t configured[2] = {0, 0};
-    if (smem > 48 * 1024 && smem > configured[seg]) {
-        cudaError_t ce = seg ? cudaFuncSetAttribute(k_node_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                             : cudaFuncSetAttribute(k_node_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (ce != cudaSuccess) return BMNAS_ELAUNCH;
-        configured[seg] = smem;
-    }
+    const bool vec = node_vec_ok(p, true);
+    const int lanes = p->L / 4;
+    const bool seg = vec && lanes >= 1 && lanes <= 32 && (lanes & (lanes - 1)) == 0;
+    static size_t configured[3] = {0, 0, 0};
     const int blocks = p->B < kNodeMaxBlocksBwd ? p->B : kNodeMaxBlocksBwd;
-    if (seg)
-        k_node_bwd<true><<<blocks, NTH, smem, (cudaStream_t)stream>>>(*p);
-    else
-        k_node_bwd<false><<<blocks, NTH, smem, (cudaStream_t)stream>>>(*p);
+    if (vec && seg) {
+        if ((e = node_smem_attr(k_node_bwd<4, true>, smem, &configured[0]))) return e;
+        k_node_bwd<4, true><<<blocks, NTH, smem, (cudaStream_t)stream>>>(*p);
+    } else if (vec) {
+        if ((e = node_smem_attr(k_node_bwd<4, false>, smem, &configured[1]))) return e;
+        k_node_bwd<4, false><<<blocks, NTH, smem, (cudaStream_t)stream>>>(*p);
+    } else {
+        if ((e = node_smem_attr(k_node_bwd<1, false>, smem, &configured[2]))) return e;
+        k_node_bwd<1, false><<<blocks, NTH, smem, (cudaStream_t)stream>>>(*p);
+    }
     BMNAS_LAUNCH_CHECK();
     return BMNAS_OK;
 }
