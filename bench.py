@@ -184,6 +184,31 @@ def kernel_roofline(head, ss, c, pk):
             'note': 'B=%d working set is L2-resident and the kernel is latency-bound at this size; see DESIGN.md' % c['B']}
 
 
+def profile_kernels(head, R=100):
+    """warm per-launch time of every prepared call of the training plan (back-to-back replays, CUDA events)"""
+    from bmnas import native as N
+    import ctypes
+    runner = [r for r in head.fusion_net._bm_cache.values() if r.prog.training][0]
+    prog = runner.prog
+    s = N.current_stream()
+    rows = []
+    for phase, calls in (('fwd', prog.fwd), ('bwd', prog.bwd)):
+        for i, call in enumerate(calls):
+            for _ in range(5):
+                call(s)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(R):
+                call(s)
+            e1.record()
+            torch.cuda.synchronize()
+            st = call.st
+            dims = {k: getattr(st, k) for k in ('B', 'L', 'K', 'M', 'C', 'n', 'Ctot', 'n_src', 'w_fold', 'mode', 'n_ops')
+                    if hasattr(st, k)}
+            rows.append((phase, i, call.name, round(e0.elapsed_time(e1) * 1e3 / R, 2), dims))
+    return rows
+
+
 def run_ours(args):
     import torch.distributed as dist
     from bmnas import native as N
@@ -270,6 +295,12 @@ def run_ours(args):
     e2e_value = gB * args.steps / (e2e_ms_wall * 1e-3)
     lab_bytes = c['B'] * (8 if c['loss'] == 'ce' else 4 * c['classes'])
     out = None
+    if rank == 0 and args.profile_kernels:
+        rows = profile_kernels(head)
+        tot = sum(r[3] for r in rows)
+        print('# warm per-launch time of the training plan (one fwd+bwd of the fusion network), total %.1f us' % tot)
+        for r in rows:
+            print('%s %3d %-18s %8.2f us  %s' % r)
     if rank == 0:
         pk = peaks()
         roof = kernel_roofline(head, ss, c, pk)
@@ -337,6 +368,7 @@ def main():
     ap.add_argument('--batch', type=int, default=0, help='per-GPU batch override')
     ap.add_argument('--no-graphs', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--profile-kernels', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

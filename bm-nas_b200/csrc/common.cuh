@@ -46,12 +46,9 @@ __device__ __forceinline__ void block_sum(float (&v)[NV], float* red) {
         for (int i = 0; i < NV; ++i) red[i * 32 + warp] = v[i];
     }
     __syncthreads();
+    // every warp re-reduces the per-warp partials with the same butterfly: identical bits in all threads
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        float s = 0.f;
-        for (int w = 0; w < nw; ++w) s += red[i * 32 + w];  // fixed order
-        v[i] = s;
-    }
+    for (int i = 0; i < NV; ++i) v[i] = warp_sum(lane < nw ? red[i * 32 + lane] : 0.f);
 }
 
 // "last block done" election. Returns true in every thread of the block that
@@ -75,7 +72,7 @@ __device__ __forceinline__ bool last_block(unsigned int* counter, unsigned int e
 __device__ __forceinline__ float ld_cg(const float* p) { return __ldcg(p); }
 
 // ---------------------------------------------------------------- Philox4x32-10
-__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+static __device__ __noinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
@@ -114,8 +111,8 @@ __device__ __forceinline__ float drop_scale(bool active, const unsigned char* ma
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 __device__ __forceinline__ float softplusf_(float x) { return x > 20.f ? x : log1pf(expf(x)); }
-__device__ __forceinline__ float mishf_(float x) { return x * tanhf(softplusf_(x)); }
-__device__ __forceinline__ float mish_grad(float x) {
+static __device__ __noinline__ float mishf_(float x) { return x * tanhf(softplusf_(x)); }
+static __device__ __noinline__ float mish_grad(float x) {
     float sp = softplusf_(x), t = tanhf(sp);
     return t + x * sigmoidf_(x) * (1.f - t * t);
 }

@@ -17,7 +17,7 @@
 
 namespace bmnas {
 
-constexpr int TM = 32, TN = 32, GT = 128;
+constexpr int TM = 32, TN = 32, GT = 256;
 constexpr int LDA = TM + 4, LDB = TN + 4;      // padded rows keep 16-byte alignment and spread banks
 constexpr int KC_MAX = 384;                    // reduction rows staged per pass (2 CTAs/SM at 110 KB)
 
@@ -64,16 +64,15 @@ __device__ __forceinline__ Wf wf_merge(Wf a, Wf b) {
     return r;
 }
 
-// acc[4][2] += A[kk][ty*4 .. +3] (x) B[kk][tx*2 .. +1] over kk < kc
-__device__ __forceinline__ void mma_tile(const float* As, const float* Bs, int kc, float (&acc)[4][2], int ty, int tx) {
+// acc[2][2] += A[kk][ty*2 .. +1] (x) B[kk][tx*2 .. +1] over kk < kc   (16 x 16 threads cover 32 x 32)
+constexpr int MR = 2;
+__device__ __forceinline__ void mma_tile(const float* As, const float* Bs, int kc, float (&acc)[MR][2], int ty, int tx) {
 #pragma unroll 8
     for (int kk = 0; kk < kc; ++kk) {
-        const float4 a = *reinterpret_cast<const float4*>(As + kk * LDA + ty * 4);
+        const float2 a = *reinterpret_cast<const float2*>(As + kk * LDA + ty * 2);
         const float2 b = *reinterpret_cast<const float2*>(Bs + kk * LDB + tx * 2);
         acc[0][0] = fmaf(a.x, b.x, acc[0][0]); acc[0][1] = fmaf(a.x, b.y, acc[0][1]);
         acc[1][0] = fmaf(a.y, b.x, acc[1][0]); acc[1][1] = fmaf(a.y, b.y, acc[1][1]);
-        acc[2][0] = fmaf(a.z, b.x, acc[2][0]); acc[2][1] = fmaf(a.z, b.y, acc[2][1]);
-        acc[3][0] = fmaf(a.w, b.x, acc[3][0]); acc[3][1] = fmaf(a.w, b.y, acc[3][1]);
     }
 }
 
@@ -115,72 +114,85 @@ __device__ __forceinline__ void batched(int total, T zero, Load ld, Store st) {
     }
 }
 
-// stage a [kc x 32 columns] activation-like operand: Bs[r][col] = X(row r0+r, column n0+col), rows < rmax,
-// columns < N, zero elsewhere.  get4/get1 fetch 4 / 1 consecutive l of one (sample, row).
-template <class Get4, class Get1>
-__device__ __forceinline__ void stage_cols(float* Bs, int kc, int r0, int rmax, int n0, int N, int L, bool vec,
-                                           Get4 get4, Get1 get1) {
+// both operands of a tile staged in ONE pass: U loads of A and U loads of B are in flight per thread
+// before the first dependent shared-memory store
+template <int U, class LA, class SA, class LB, class SB>
+__device__ __forceinline__ void stage2(int totalA, LA ldA, SA stA, int totalB, LB ldB, SB stB) {
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (vec) {  // L % 4 == 0: 8 float4 per staged row
-        batched<8>(kc * 8, z4,
-                   [&](int u) {
-                       const int c4 = u & 7, r = u >> 3;
-                       const int n = n0 + c4 * 4, row = r0 + r;
-                       return (n < N && row < rmax) ? get4(n / L, row, n % L) : z4;
-                   },
-                   [&](int u, float4 v) { *reinterpret_cast<float4*>(Bs + (u >> 3) * LDB + (u & 7) * 4) = v; });
-    } else {
-        batched<8>(kc * TN, 0.f,
-                   [&](int u) {
-                       const int c = u & 31, r = u >> 5;
-                       const int n = n0 + c, row = r0 + r;
-                       return (n < N && row < rmax) ? get1(n / L, row, n % L) : 0.f;
-                   },
-                   [&](int u, float v) { Bs[(u >> 5) * LDB + (u & 31)] = v; });
+    for (int base = 0; base < totalA || base < totalB; base += GT * U) {
+        float4 va[U], vb[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int u = base + j * GT + threadIdx.x;
+            va[j] = u < totalA ? ldA(u) : z4;
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int u = base + j * GT + threadIdx.x;
+            vb[j] = u < totalB ? ldB(u) : z4;
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int u = base + j * GT + threadIdx.x;
+            if (u < totalA) stA(u, va[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int u = base + j * GT + threadIdx.x;
+            if (u < totalB) stB(u, vb[j]);
+        }
     }
 }
 
 // ------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(GT) k_conv_fwd(const bmnas_conv_params p, const int N, const int n_col_tiles,
-                                                  const int KC) {
+template <bool VEC>
+__global__ void __launch_bounds__(GT, 1) k_conv_fwd(const bmnas_conv_params p, const int N, const int n_col_tiles,
+                                                     const int KC) {
     extern __shared__ __align__(16) float smem[];
     float* As = smem;
     float* Bs = smem + (size_t)KC * LDA;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
     const int K = p.K, M = p.M, L = p.L, ldw = p.w_fold * p.K;
-    const bool vecB = (L & 3) == 0;
-    const bool vecA = (K & 3) == 0;
-
-    float acc[4][2];
+    float acc[MR][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.f;
+    for (int i = 0; i < MR; ++i) acc[i][0] = acc[i][1] = 0.f;
 
     for (int k0 = 0; k0 < K; k0 += KC) {
         const int kc = min(KC, round_up(K - k0, 4));
         if (k0) __syncthreads();
         // A: As[k][m] = Weff[m0+m][k0+k]; lanes walk m (conflict-free transposed stores), float4 along k
+        // B: Bs[k][col] = U[k0+k][n0+col]: 8 float4 per staged row
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (vecA) {
-            batched<8>((kc >> 2) * TM, z4,
-                       [&](int u) {
-                           const int m = u & 31, k4 = (u >> 5) << 2;
-                           float4 v = z4;
-                           if (m0 + m < M && k0 + k4 < K) {
-                               const float* r = w_row(p, m0 + m, ldw, nullptr, nullptr) + k0 + k4;
-                               v = __ldg(reinterpret_cast<const float4*>(r));
-                               if (p.w_fold == 2) {
-                                   const float4 w = __ldg(reinterpret_cast<const float4*>(r + K));
-                                   v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
-                               }
-                           }
-                           return v;
-                       },
-                       [&](int u, float4 v) {
-                           const int m = u & 31, k4 = (u >> 5) << 2;
-                           As[(k4 + 0) * LDA + m] = v.x; As[(k4 + 1) * LDA + m] = v.y;
-                           As[(k4 + 2) * LDA + m] = v.z; As[(k4 + 3) * LDA + m] = v.w;
-                       });
+        if (VEC) {
+            stage2<6>((kc >> 2) * TM,
+                      [&](int u) {
+                          const int m = u & 31, k4 = (u >> 5) << 2;
+                          float4 v = z4;
+                          if (m0 + m < M && k0 + k4 < K) {
+                              const float* r = w_row(p, m0 + m, ldw, nullptr, nullptr) + k0 + k4;
+                              v = __ldg(reinterpret_cast<const float4*>(r));
+                              if (p.w_fold == 2) {
+                                  const float4 w = __ldg(reinterpret_cast<const float4*>(r + K));
+                                  v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+                              }
+                          }
+                          return v;
+                      },
+                      [&](int u, float4 v) {
+                          const int m = u & 31, k4 = (u >> 5) << 2;
+                          As[(k4 + 0) * LDA + m] = v.x; As[(k4 + 1) * LDA + m] = v.y;
+                          As[(k4 + 2) * LDA + m] = v.z; As[(k4 + 3) * LDA + m] = v.w;
+                      },
+                      kc * 8,
+                      [&](int u) {
+                          const int n = n0 + (u & 7) * 4, k = k0 + (u >> 3);
+                          if (n >= N || k >= K) return z4;
+                          int s, kl;
+                          src_of(p, k, &s, &kl);
+                          return __ldg(reinterpret_cast<const float4*>(p.src[s] + ((long long)(n / L) * p.src_C[s] + kl) * L + (n % L)));
+                      },
+                      [&](int u, float4 v) { *reinterpret_cast<float4*>(Bs + (u >> 3) * LDB + (u & 7) * 4) = v; });
         } else {
             batched<8>(kc * TM, 0.f,
                        [&](int u) {
@@ -194,18 +206,16 @@ __global__ void __launch_bounds__(GT) k_conv_fwd(const bmnas_conv_params p, cons
                            return v;
                        },
                        [&](int u, float v) { As[(u >> 5) * LDA + (u & 31)] = v; });
+            batched<8>(kc * TN, 0.f,
+                       [&](int u) {
+                           const int n = n0 + (u & 31), k = k0 + (u >> 5);
+                           if (n >= N || k >= K) return 0.f;
+                           int s, kl;
+                           src_of(p, k, &s, &kl);
+                           return __ldg(p.src[s] + ((long long)(n / L) * p.src_C[s] + kl) * L + (n % L));
+                       },
+                       [&](int u, float v) { Bs[(u >> 5) * LDB + (u & 31)] = v; });
         }
-        stage_cols(Bs, kc, k0, K, n0, N, L, vecB,
-                   [&](int b, int k, int l) {
-                       int s, kl;
-                       src_of(p, k, &s, &kl);
-                       return __ldg(reinterpret_cast<const float4*>(p.src[s] + ((long long)b * p.src_C[s] + kl) * L + l));
-                   },
-                   [&](int b, int k, int l) {
-                       int s, kl;
-                       src_of(p, k, &s, &kl);
-                       return __ldg(p.src[s] + ((long long)b * p.src_C[s] + kl) * L + l);
-                   });
         __syncthreads();
         mma_tile(As, Bs, kc, acc, ty, tx);
     }
@@ -215,8 +225,8 @@ __global__ void __launch_bounds__(GT) k_conv_fwd(const bmnas_conv_params p, cons
     const int nb = n0 + tx * 2;
     const bool vec = ((L & 1) == 0) && (nb + 1 < N);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = m0 + ty * 4 + i;
+    for (int i = 0; i < MR; ++i) {
+        const int m = m0 + ty * MR + i;
         float bias = 0.f;
         if (m < M) {
             int s, ml;
@@ -266,18 +276,30 @@ __global__ void __launch_bounds__(GT) k_conv_fwd(const bmnas_conv_params p, cons
     // ---- last CTA of this row-tile merges the per-column-tile statistics (Chan), fixed order:
     //      4 lanes per row walk interleaved tiles, then a lane-symmetric butterfly
     if (!last_block(p.counter + blockIdx.y, gridDim.x)) return;
-    const int r = tid >> 2, q = tid & 3;
+    const int r = tid >> 3, q = tid & 7;          // 8 lanes per row walk interleaved column tiles
     const int m = m0 + r;
     Wf w = {0.f, 0.f, 0.f};
     if (m < M) {
-        for (int tix = q; tix < n_col_tiles; tix += 4) {
-            const float* pp = p.stat_part + ((long long)tix * M + m) * 2;
-            Wf b = {(float)min(TN, N - tix * TN), ld_cg(pp), ld_cg(pp + 1)};
-            w = wf_merge(w, b);
+        for (int t0 = q; t0 < n_col_tiles; t0 += 8 * 4) {   // 4 independent loads in flight per lane
+            float2 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int tix = t0 + 8 * j;
+                v[j] = tix < n_col_tiles ? __ldcg(reinterpret_cast<const float2*>(p.stat_part + ((long long)tix * M + m) * 2))
+                                         : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int tix = t0 + 8 * j;
+                if (tix < n_col_tiles) {
+                    Wf b = {(float)min(TN, N - tix * TN), v[j].x, v[j].y};
+                    w = wf_merge(w, b);
+                }
+            }
         }
     }
 #pragma unroll
-    for (int o = 1; o <= 2; o <<= 1) {
+    for (int o = 1; o <= 4; o <<= 1) {
         Wf b;
         b.n = __shfl_xor_sync(0xffffffffu, w.n, o);
         b.mean = __shfl_xor_sync(0xffffffffu, w.mean, o);
@@ -300,41 +322,48 @@ __global__ void __launch_bounds__(GT) k_conv_fwd(const bmnas_conv_params p, cons
 }
 
 // ------------------------------------------------------------------ dgrad
-__global__ void __launch_bounds__(GT) k_conv_dgrad(const bmnas_conv_params p, const int N, const int KC) {
+template <bool VEC>
+__global__ void __launch_bounds__(GT, 1) k_conv_dgrad(const bmnas_conv_params p, const int N, const int KC) {
     extern __shared__ __align__(16) float smem[];
     float* As = smem;
     float* Bs = smem + (size_t)KC * LDA;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int kt0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
     const int K = p.K, M = p.M, L = p.L, ldw = p.w_fold * p.K;
-    const bool vecB = (L & 3) == 0;
-    const bool vecA = (K & 3) == 0;
 
-    float acc[4][2];
+    float acc[MR][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.f;
+    for (int i = 0; i < MR; ++i) acc[i][0] = acc[i][1] = 0.f;
 
     for (int mk0 = 0; mk0 < M; mk0 += KC) {
         const int kc = min(KC, round_up(M - mk0, 4));
         if (mk0) __syncthreads();
         // A: As[mm][k] = Weff[mk0+mm][kt0+k]: straight (coalesced) copies of weight-row slices
+        // B: Bs[mm][col] = dz[mk0+mm][n0+col] (BatchNorm backward folded into the load)
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (vecA) {
-            batched<8>(kc * 8, z4,
-                       [&](int u) {
-                           const int k4 = (u & 7) << 2, mm = u >> 3;
-                           float4 v = z4;
-                           if (mk0 + mm < M && kt0 + k4 < K) {
-                               const float* r = w_row(p, mk0 + mm, ldw, nullptr, nullptr) + kt0 + k4;
-                               v = __ldg(reinterpret_cast<const float4*>(r));
-                               if (p.w_fold == 2) {
-                                   const float4 w = __ldg(reinterpret_cast<const float4*>(r + K));
-                                   v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
-                               }
-                           }
-                           return v;
-                       },
-                       [&](int u, float4 v) { *reinterpret_cast<float4*>(As + (u >> 3) * LDA + ((u & 7) << 2)) = v; });
+        if (VEC) {
+            stage2<6>(kc * 8,
+                      [&](int u) {
+                          const int k4 = (u & 7) << 2, mm = u >> 3;
+                          float4 v = z4;
+                          if (mk0 + mm < M && kt0 + k4 < K) {
+                              const float* r = w_row(p, mk0 + mm, ldw, nullptr, nullptr) + kt0 + k4;
+                              v = __ldg(reinterpret_cast<const float4*>(r));
+                              if (p.w_fold == 2) {
+                                  const float4 w = __ldg(reinterpret_cast<const float4*>(r + K));
+                                  v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+                              }
+                          }
+                          return v;
+                      },
+                      [&](int u, float4 v) { *reinterpret_cast<float4*>(As + (u >> 3) * LDA + ((u & 7) << 2)) = v; },
+                      kc * 8,
+                      [&](int u) {
+                          const int n = n0 + (u & 7) * 4, m = mk0 + (u >> 3);
+                          if (n >= N || m >= M) return z4;
+                          return dz4(p, ((long long)(n / L) * M + m) * L + (n % L), m);
+                      },
+                      [&](int u, float4 v) { *reinterpret_cast<float4*>(Bs + (u >> 3) * LDB + (u & 7) * 4) = v; });
         } else {
             batched<8>(kc * TM, 0.f,
                        [&](int u) {
@@ -348,10 +377,14 @@ __global__ void __launch_bounds__(GT) k_conv_dgrad(const bmnas_conv_params p, co
                            return v;
                        },
                        [&](int u, float v) { As[(u >> 5) * LDA + (u & 31)] = v; });
+            batched<8>(kc * TN, 0.f,
+                       [&](int u) {
+                           const int n = n0 + (u & 31), m = mk0 + (u >> 5);
+                           if (n >= N || m >= M) return 0.f;
+                           return dz1(p, ((long long)(n / L) * M + m) * L + (n % L), m);
+                       },
+                       [&](int u, float v) { Bs[(u >> 5) * LDB + (u & 31)] = v; });
         }
-        stage_cols(Bs, kc, mk0, M, n0, N, L, vecB,
-                   [&](int b, int m, int l) { return dz4(p, ((long long)b * M + m) * L + l, m); },
-                   [&](int b, int m, int l) { return dz1(p, ((long long)b * M + m) * L + l, m); });
         __syncthreads();
         mma_tile(As, Bs, kc, acc, ty, tx);
     }
@@ -359,8 +392,8 @@ __global__ void __launch_bounds__(GT) k_conv_dgrad(const bmnas_conv_params p, co
     const int nb = n0 + tx * 2;
     const bool vec = ((L & 1) == 0) && (nb + 1 < N);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int k = kt0 + ty * 4 + i;
+    for (int i = 0; i < MR; ++i) {
+        const int k = kt0 + ty * MR + i;
         if (k >= K) continue;
         int s, kl;
         src_of(p, k, &s, &kl);
@@ -389,38 +422,9 @@ __global__ void __launch_bounds__(GT) k_conv_dgrad(const bmnas_conv_params p, co
 }
 
 // ------------------------------------------------------------------ wgrad
-// stage a [kc reduction columns x 32 rows] operand TRANSPOSED: S[nn][r] = X(row r0+r, column nk0+nn)
-template <class Get4, class Get1>
-__device__ __forceinline__ void stage_rows_t(float* S, int ld, int kc, int r0, int rmax, int nk0, int nend, int L,
-                                             bool vec, Get4 get4, Get1 get1) {
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (vec) {  // lanes: l4 fastest, then row  (bank = 16*l4 + row for L = 8: conflict-free)
-        const int q = L >> 2;  // float4 per (sample,row)
-        batched<8>((kc >> 2) * TM, z4,
-                   [&](int u) {
-                       const int l4 = u % q, r = (u / q) & 31, sm = u / (q * TM);
-                       const int n = nk0 + sm * L + l4 * 4, row = r0 + r;
-                       return (n < nend && row < rmax) ? get4(n / L, row, n % L) : z4;
-                   },
-                   [&](int u, float4 v) {
-                       const int l4 = u % q, r = (u / q) & 31, sm = u / (q * TM);
-                       const int nn = sm * L + l4 * 4;
-                       S[(nn + 0) * ld + r] = v.x; S[(nn + 1) * ld + r] = v.y;
-                       S[(nn + 2) * ld + r] = v.z; S[(nn + 3) * ld + r] = v.w;
-                   });
-    } else {
-        batched<8>(kc * TM, 0.f,
-                   [&](int u) {
-                       const int nn = u % kc, r = u / kc;
-                       const int n = nk0 + nn, row = r0 + r;
-                       return (n < nend && row < rmax) ? get1(n / L, row, n % L) : 0.f;
-                   },
-                   [&](int u, float v) { S[(u % kc) * ld + (u / kc)] = v; });
-    }
-}
-
-__global__ void __launch_bounds__(GT) k_conv_wgrad(const bmnas_conv_params p, const int N, const int chunkN,
-                                                    const int KC) {
+template <bool VEC>
+__global__ void __launch_bounds__(GT, 1) k_conv_wgrad(const bmnas_conv_params p, const int N, const int chunkN,
+                                                       const int KC) {
     extern __shared__ __align__(16) float smem[];
     float* As = smem;
     float* Bs = smem + (size_t)KC * LDA;
@@ -428,43 +432,76 @@ __global__ void __launch_bounds__(GT) k_conv_wgrad(const bmnas_conv_params p, co
     const int kt0 = blockIdx.x * TN, m0 = blockIdx.y * TM;
     const int K = p.K, M = p.M, L = p.L, ldw = p.w_fold * p.K;
     const int nbeg = blockIdx.z * chunkN, nend = min(N, nbeg + chunkN);
-    // vector staging needs whole samples per chunk: chunkN and KC are multiples of L when vec
-    const bool vec = ((L & 3) == 0) && (KC % L == 0) && (chunkN % L == 0);
+    // vector staging needs whole samples per chunk: the host makes chunkN and KC multiples of L when VEC
+    const bool vec = VEC;
 
-    float acc[4][2], rs[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc[MR][2], rs[MR] = {0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.f;
+    for (int i = 0; i < MR; ++i) acc[i][0] = acc[i][1] = 0.f;
 
     for (int nk0 = nbeg; nk0 < nend; nk0 += KC) {
         const int kc = min(KC, round_up(nend - nk0, vec ? L : 4));
         if (nk0 != nbeg) __syncthreads();
-        stage_rows_t(As, LDA, kc, m0, M, nk0, nend, L, vec,
-                     [&](int b, int m, int l) { return dz4(p, ((long long)b * M + m) * L + l, m); },
-                     [&](int b, int m, int l) { return dz1(p, ((long long)b * M + m) * L + l, m); });
-        stage_rows_t(Bs, LDB, kc, kt0, K, nk0, nend, L, vec,
-                     [&](int b, int k, int l) {
-                         int s, kl;
-                         src_of(p, k, &s, &kl);
-                         return __ldg(reinterpret_cast<const float4*>(p.src[s] + ((long long)b * p.src_C[s] + kl) * L + l));
-                     },
-                     [&](int b, int k, int l) {
-                         int s, kl;
-                         src_of(p, k, &s, &kl);
-                         return __ldg(p.src[s] + ((long long)b * p.src_C[s] + kl) * L + l);
-                     });
+        if (VEC) {
+            const int q = L >> 2;   // float4 per (sample,row); lanes: l4 fastest, then row
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            auto st_t = [&](float* S, int ld, int u, float4 v) {
+                const int l4 = u % q, r = (u / q) & 31, sm = u / (q * TM);
+                const int nn = sm * L + l4 * 4;
+                S[(nn + 0) * ld + r] = v.x; S[(nn + 1) * ld + r] = v.y;
+                S[(nn + 2) * ld + r] = v.z; S[(nn + 3) * ld + r] = v.w;
+            };
+            stage2<6>((kc >> 2) * TM,
+                      [&](int u) {
+                          const int l4 = u % q, r = (u / q) & 31, sm = u / (q * TM);
+                          const int n = nk0 + sm * L + l4 * 4, m = m0 + r;
+                          if (n >= nend || m >= M) return z4;
+                          return dz4(p, ((long long)(n / L) * M + m) * L + (n % L), m);
+                      },
+                      [&](int u, float4 v) { st_t(As, LDA, u, v); },
+                      (kc >> 2) * TM,
+                      [&](int u) {
+                          const int l4 = u % q, r = (u / q) & 31, sm = u / (q * TM);
+                          const int n = nk0 + sm * L + l4 * 4, k = kt0 + r;
+                          if (n >= nend || k >= K) return z4;
+                          int s, kl;
+                          src_of(p, k, &s, &kl);
+                          return __ldg(reinterpret_cast<const float4*>(p.src[s] + ((long long)(n / L) * p.src_C[s] + kl) * L + (n % L)));
+                      },
+                      [&](int u, float4 v) { st_t(Bs, LDB, u, v); });
+        } else {
+            batched<8>(kc * TM, 0.f,
+                       [&](int u) {
+                           const int nn = u % kc, r = u / kc;
+                           const int n = nk0 + nn, m = m0 + r;
+                           if (n >= nend || m >= M) return 0.f;
+                           return dz1(p, ((long long)(n / L) * M + m) * L + (n % L), m);
+                       },
+                       [&](int u, float v) { As[(u % kc) * LDA + (u / kc)] = v; });
+            batched<8>(kc * TM, 0.f,
+                       [&](int u) {
+                           const int nn = u % kc, r = u / kc;
+                           const int n = nk0 + nn, k = kt0 + r;
+                           if (n >= nend || k >= K) return 0.f;
+                           int s, kl;
+                           src_of(p, k, &s, &kl);
+                           return __ldg(p.src[s] + ((long long)(n / L) * p.src_C[s] + kl) * L + (n % L));
+                       },
+                       [&](int u, float v) { Bs[(u % kc) * LDB + (u / kc)] = v; });
+        }
         __syncthreads();
         mma_tile(As, Bs, kc, acc, ty, tx);
         if (blockIdx.x == 0 && tx == 0) {  // bias gradient: row sums of dz
             for (int kk = 0; kk < kc; ++kk) {
-                const float4 a = *reinterpret_cast<const float4*>(As + kk * LDA + ty * 4);
-                rs[0] += a.x; rs[1] += a.y; rs[2] += a.z; rs[3] += a.w;
+                const float2 a = *reinterpret_cast<const float2*>(As + kk * LDA + ty * MR);
+                rs[0] += a.x; rs[1] += a.y;
             }
         }
     }
 
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = m0 + ty * 4 + i;
+    for (int i = 0; i < MR; ++i) {
+        const int m = m0 + ty * MR + i;
         if (m >= M) continue;
         int s, ml;
         w_row(p, m, ldw, &s, &ml);
@@ -514,6 +551,19 @@ extern "C" long long bmnas_conv_stat_part_size(const bmnas_conv_params* p) {
 }
 extern "C" int bmnas_conv_num_counters(const bmnas_conv_params* p) { return (p->M + TM - 1) / TM; }
 
+static bool gal16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
+
+// 128-bit staging: L % 4 == 0 and K % 4 == 0 (rows of every operand are whole float4s) and 16-byte alignment
+static bool conv_vec_ok(const bmnas_conv_params* p, bool need_gv) {
+    if ((p->L & 3) || (p->K & 3)) return false;
+    for (int i = 0; i < p->n_src; ++i)
+        if (!gal16(p->src[i]) || (p->src_C[i] & 3 && p->n_src > 1 && (p->L & 3))) return false;
+    for (int i = 0; i < p->n_seg; ++i)
+        if (!gal16(p->W[i])) return false;
+    if (need_gv && (!gal16(p->GV) || !gal16(p->Z))) return false;
+    return true;
+}
+
 extern "C" int bmnas_conv_fwd(const bmnas_conv_params* p, void* stream) {
     int e = conv_check(p);
     if (e) return e;
@@ -531,10 +581,16 @@ extern "C" int bmnas_conv_fwd(const bmnas_conv_params* p, void* stream) {
     BMNAS_DRY_RETURN();
     const int N = p->B * p->L;
     const int KC = min(KC_MAX, round_up(p->K, 4));
-    static size_t configured = 0;
-    if ((e = set_smem(k_conv_fwd, gemm_smem_bytes(KC), &configured))) return e;
+    const bool vec = conv_vec_ok(p, false);
+    static size_t configured[2] = {0, 0};
+    e = vec ? set_smem(k_conv_fwd<true>, gemm_smem_bytes(KC), &configured[1])
+            : set_smem(k_conv_fwd<false>, gemm_smem_bytes(KC), &configured[0]);
+    if (e) return e;
     dim3 grid((N + TN - 1) / TN, (p->M + TM - 1) / TM);
-    k_conv_fwd<<<grid, GT, gemm_smem_bytes(KC), (cudaStream_t)stream>>>(*p, N, (int)grid.x, KC);
+    if (vec)
+        k_conv_fwd<true><<<grid, GT, gemm_smem_bytes(KC), (cudaStream_t)stream>>>(*p, N, (int)grid.x, KC);
+    else
+        k_conv_fwd<false><<<grid, GT, gemm_smem_bytes(KC), (cudaStream_t)stream>>>(*p, N, (int)grid.x, KC);
     BMNAS_LAUNCH_CHECK();
     return BMNAS_OK;
 }
@@ -549,10 +605,17 @@ extern "C" int bmnas_conv_dgrad(const bmnas_conv_params* p, void* stream) {
     BMNAS_DRY_RETURN();
     const int N = p->B * p->L;
     const int KC = min(KC_MAX, round_up(p->M, 4));
-    static size_t configured = 0;
-    if ((e = set_smem(k_conv_dgrad, gemm_smem_bytes(KC), &configured))) return e;
+    bool vec = (p->L & 3) == 0 && (p->K & 3) == 0 && gal16(p->GV) && (!p->coef_a || gal16(p->Z));
+    for (int i = 0; i < p->n_seg; ++i) vec = vec && gal16(p->W[i]);
+    static size_t configured[2] = {0, 0};
+    e = vec ? set_smem(k_conv_dgrad<true>, gemm_smem_bytes(KC), &configured[1])
+            : set_smem(k_conv_dgrad<false>, gemm_smem_bytes(KC), &configured[0]);
+    if (e) return e;
     dim3 grid((N + TN - 1) / TN, (p->K + TM - 1) / TM);
-    k_conv_dgrad<<<grid, GT, gemm_smem_bytes(KC), (cudaStream_t)stream>>>(*p, N, KC);
+    if (vec)
+        k_conv_dgrad<true><<<grid, GT, gemm_smem_bytes(KC), (cudaStream_t)stream>>>(*p, N, KC);
+    else
+        k_conv_dgrad<false><<<grid, GT, gemm_smem_bytes(KC), (cudaStream_t)stream>>>(*p, N, KC);
     BMNAS_LAUNCH_CHECK();
     return BMNAS_OK;
 }
@@ -567,7 +630,9 @@ extern "C" int bmnas_conv_wgrad(const bmnas_conv_params* p, void* stream) {
     BMNAS_DRY_RETURN();
     const int N = p->B * p->L, L = p->L;
     const int tiles = ((p->K + TN - 1) / TN) * ((p->M + TM - 1) / TM);
-    const int unit = ((L & 3) == 0 && L <= KC_MAX) ? L : 4;   // chunk granularity (whole samples when vectorised)
+    bool vec = (L & 3) == 0 && L <= KC_MAX && gal16(p->GV) && (!p->coef_a || gal16(p->Z));
+    for (int i = 0; i < p->n_src; ++i) vec = vec && gal16(p->src[i]);
+    const int unit = vec ? L : 4;   // chunk granularity (whole samples when vectorised)
     int splits = p->splits;
     if (splits <= 0) {
         splits = (2 * kNumSMs + tiles - 1) / tiles;          // ~2 CTAs per SM
@@ -577,11 +642,16 @@ extern "C" int bmnas_conv_wgrad(const bmnas_conv_params* p, void* stream) {
     }
     int chunkN = round_up((N + splits - 1) / splits, unit);
     splits = (N + chunkN - 1) / chunkN;
-    int KC = min(round_up(chunkN, unit), (KC_MAX / unit) * unit);
-    static size_t configured = 0;
-    if ((e = set_smem(k_conv_wgrad, gemm_smem_bytes(KC), &configured))) return e;
+    const int KC = min(round_up(chunkN, unit), (KC_MAX / unit) * unit);
+    static size_t configured[2] = {0, 0};
+    e = vec ? set_smem(k_conv_wgrad<true>, gemm_smem_bytes(KC), &configured[1])
+            : set_smem(k_conv_wgrad<false>, gemm_smem_bytes(KC), &configured[0]);
+    if (e) return e;
     dim3 grid((p->K + TN - 1) / TN, (p->M + TM - 1) / TM, splits);
-    k_conv_wgrad<<<grid, GT, gemm_smem_bytes(KC), (cudaStream_t)stream>>>(*p, N, chunkN, KC);
+    if (vec)
+        k_conv_wgrad<true><<<grid, GT, gemm_smem_bytes(KC), (cudaStream_t)stream>>>(*p, N, chunkN, KC);
+    else
+        k_conv_wgrad<false><<<grid, GT, gemm_smem_bytes(KC), (cudaStream_t)stream>>>(*p, N, chunkN, KC);
     BMNAS_LAUNCH_CHECK();
     return BMNAS_OK;
 }

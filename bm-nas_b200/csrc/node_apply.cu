@@ -20,7 +20,7 @@ constexpr int kNodeMaxBlocksBwd = kNumSMs * 2;
 
 struct NodeSmem {
     float *xs, *ys, *gs, *as, *dxs, *dys, *S, *S2, *Sp, *S1s, *S2s, *lnG, *lnH, *red, *gw;
-    float *rs, *mr, *bw, *bb, *tot;
+    float *rs, *mr, *bw, *bb, *tot, *dgs;
 };
 
 __host__ __device__ inline size_t rnd4(size_t n) { return (n + 3) & ~(size_t)3; }
@@ -32,7 +32,7 @@ __host__ __device__ inline size_t node_smem_floats(int C, int L, int M, bool bwd
     n += 2 * LL + (LL > NTH ? LL : NTH);    // S, S2, Sp
     n += 8 * 32 + 8;                        // red, gw
     n += 4 * Mr;                            // rs, mr, bw, bb
-    if (bwd) n += 5 * CL + 2 * Mr + (2 * Mr + 8);  // gs, dxs, dys, lnG, lnH, S1s, S2s, tot
+    if (bwd) n += 5 * CL + 2 * Mr + (2 * Mr + 8) + BMNAS_MAX_OPS * NTH;  // gs, dxs, dys, lnG, lnH, S1s, S2s, tot, dgs
     return n + 16;
 }
 
@@ -52,7 +52,7 @@ __device__ __forceinline__ NodeSmem node_carve(float* base, int C, int L, int M,
     s.mr = q; q += Mr;
     s.bw = q; q += Mr;
     s.bb = q; q += Mr;
-    s.gs = s.dxs = s.dys = s.S1s = s.S2s = s.lnG = s.lnH = s.tot = nullptr;
+    s.gs = s.dxs = s.dys = s.S1s = s.S2s = s.lnG = s.lnH = s.tot = s.dgs = nullptr;
     if (bwd) {
         s.gs = q; q += CL;
         s.dxs = q; q += CL;
@@ -62,6 +62,7 @@ __device__ __forceinline__ NodeSmem node_carve(float* base, int C, int L, int M,
         s.S1s = q; q += Mr;
         s.S2s = q; q += Mr;
         s.tot = q; q += 2 * Mr + 8;
+        s.dgs = q; q += BMNAS_MAX_OPS * NTH;
     }
     return s;
 }
@@ -356,9 +357,10 @@ __global__ void __launch_bounds__(NTH) k_node_bwd(const bmnas_node_params p) {
         sm.lnG[i] = 0.f;
         sm.lnH[i] = 0.f;
     }
-    float dg[BMNAS_MAX_OPS];
+    // per-thread dL/dgamma partials live in shared memory slots so the loop over primitives stays a real
+    // loop (an unrolled 8-way switch made this kernel 240 KB of SASS and instruction-fetch bound)
 #pragma unroll
-    for (int k = 0; k < BMNAS_MAX_OPS; ++k) dg[k] = 0.f;
+    for (int k = 0; k < BMNAS_MAX_OPS; ++k) sm.dgs[k * NTH + threadIdx.x] = 0.f;
     const float inv_sqrt_c = 1.f / sqrtf((float)C);
     const int lanes = SEG ? L / G : 1;   // lanes sharing one channel
     const int NG = CL / G;
@@ -391,15 +393,15 @@ __global__ void __launch_bounds__(NTH) k_node_bwd(const bmnas_node_params p) {
                 gxe[q] = 0.f;
                 gye[q] = 0.f;
             }
-#pragma unroll
-            for (int k = 0; k < BMNAS_MAX_OPS; ++k) {
-                if (k >= p.n_ops) break;
+#pragma unroll 1
+            for (int k = 0; k < p.n_ops; ++k) {
                 const int ty = p.op_type[k];
                 const float wk = sm.gw[k];
+                float dgk = 0.f;
                 if (ty == BMNAS_OP_SUM) {
 #pragma unroll
                     for (int q = 0; q < G; ++q) {
-                        dg[k] += gv_[q] * (xv[q] + yv[q]);
+                        dgk += gv_[q] * (xv[q] + yv[q]);
                         gxe[q] += wk * gv_[q];
                         gye[q] += wk * gv_[q];
                     }
@@ -413,7 +415,7 @@ __global__ void __launch_bounds__(NTH) k_node_bwd(const bmnas_node_params p) {
 #pragma unroll
                     for (int q = 0; q < G; ++q) {
                         const float oh = (a[q] - a_mean) * a_rstd;
-                        dg[k] += gv_[q] * (oh * Gw[q] + Gb[q]);
+                        dgk += gv_[q] * (oh * Gw[q] + Gb[q]);
                         const float go = wk * gv_[q];
                         lg[q] += go * oh;
                         lh[q] += go;
@@ -442,7 +444,7 @@ __global__ void __launch_bounds__(NTH) k_node_bwd(const bmnas_node_params p) {
                             const float zha = fmaf(z[q], r, -mr), zhg = fmaf(zg[q], r2, -mr2);
                             const float va = fmaf(zha, w, bb), vg = fmaf(zhg, w2, bb2);
                             const float s = sigmoidf_(vg);
-                            dg[k] += gv_[q] * (va * s * ds[q]);
+                            dgk += gv_[q] * (va * s * ds[q]);
                             const float go = wk * gv_[q] * ds[q];
                             gva[q] = go * s;
                             gvg[q] = go * va * s * (1.f - s);
@@ -472,7 +474,7 @@ __global__ void __launch_bounds__(NTH) k_node_bwd(const bmnas_node_params p) {
                                 o = mishf_(va);
                                 d = mish_grad(va);
                             }
-                            dg[k] += gv_[q] * (o * ds[q]);
+                            dgk += gv_[q] * (o * ds[q]);
                             gvv[q] = wk * gv_[q] * ds[q] * d;
                             s1 += gvv[q];
                             s2 += gvv[q] * zha;
@@ -482,6 +484,7 @@ __global__ void __launch_bounds__(NTH) k_node_bwd(const bmnas_node_params p) {
                         chan_add<SEG>(sm.S2s, m, s2, lanes, act);
                     }
                 }
+                sm.dgs[k * NTH + threadIdx.x] += dgk;
             }
             if (act) {
                 st_v<G>(sm.dxs + e0, gxe);
@@ -583,6 +586,9 @@ __global__ void __launch_bounds__(NTH) k_node_bwd(const bmnas_node_params p) {
     // ---- per-CTA sums -> one global accumulator (red.add), then the last CTA finalises.
     //      (a fixed-order reduction of per-CTA partials by a single CTA costs ~100 dependent L2 round
     //      trips; the accumulator is self-cleaning like the counter)
+    float dg[BMNAS_MAX_OPS];
+#pragma unroll
+    for (int k = 0; k < BMNAS_MAX_OPS; ++k) dg[k] = sm.dgs[k * NTH + threadIdx.x];
     block_sum<BMNAS_MAX_OPS>(dg, sm.red);
     __syncthreads();
     const int PW = 2 * M + BMNAS_MAX_OPS;
