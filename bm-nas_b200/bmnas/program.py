@@ -17,6 +17,7 @@ a stack of closures, tracking which gradient buffer has been written so far
 (first writer overwrites, later writers accumulate).
 """
 import ctypes
+import os
 import zlib
 
 import torch
@@ -37,6 +38,17 @@ class Slot:
 
     def __repr__(self):
         return f'Slot({self.name})'
+
+
+SIDE_WGRAD = os.environ.get('BMNAS_SIDE_WGRAD', '1') != '0'   # weight-gradient GEMMs on a side stream (parallel graph branch); see conv_backward
+_side_streams = {}
+
+
+def side_stream(device):
+    st = _side_streams.get(device)
+    if st is None:
+        st = _side_streams[device] = torch.cuda.Stream(device=device)
+    return st
 
 
 def uid_of(name):
@@ -64,6 +76,8 @@ class Program:
         self.sample_offset = 0
         self.outputs = {}
         self.generation = 0
+        self._prep = []          # convs whose weight images bmnas_wprep refreshes at the start of every forward
+        self._prep_calls = []
         self.n_fwd_launches = 0
         self.n_bwd_launches = 0
 
@@ -153,7 +167,23 @@ class Program:
         while self._stack:
             self._stack.pop()()
         self._cur = None
-        self.n_fwd_launches = len(self.fwd) + (1 if self.rng_state is not None else 0)
+        for i0 in range(0, len(self._prep), N.BMNAS_MAX_PREP):
+            group = self._prep[i0:i0 + N.BMNAS_MAX_PREP]
+            st = N.bmnas_wprep_params()
+            st.n = len(group)
+            q = 0
+            for i, c in enumerate(group):
+                st.M[i], st.K[i], st.w_fold[i], st.n_seg[i] = c['M'], c['K'], c['fold'], len(c['segs'])
+                for j, (W, m) in enumerate(c['segs']):
+                    st.seg_M[i * N.BMNAS_MAX_SEG + j] = m
+                    self.setp(st, 'W', W, i * N.BMNAS_MAX_SEG + j)
+                self.setp(st, 'img_fwd', c['img_f'], i)
+                self.setp(st, 'img_dgrad', c['img_d'], i)
+                st.q_start[i] = q
+                q += (c['img_f'].numel() + c['img_d'].numel()) // 8
+            st.q_start[len(group)] = q
+            self._prep_calls.append(N.Call('bmnas_wprep', st))
+        self.n_fwd_launches = len(self.fwd) + len(self._prep_calls) + (1 if self.rng_state is not None else 0)
         self.n_bwd_launches = len(self.bwd) + len(self._zero_ranges)
 
     # ------------------------------------------------------------------ execution
@@ -161,17 +191,37 @@ class Program:
         s = N.current_stream()
         if self.rng_state is not None:
             N.launch('bmnas_rng_advance', ctypes.c_void_p(self.rng_state.data_ptr()), s)
+        for c in self._prep_calls:
+            c(s)
         for c in self.fwd:
             c(s)
         self.generation += 1
 
     def run_backward(self):
         s = N.current_stream()
-        L = N.lib()
         for t in self._zero_ranges:
             N.launch('bmnas_zero', ctypes.c_void_p(t.data_ptr()), ctypes.c_longlong(t.numel() * t.element_size()), s)
+        if not SIDE_WGRAD or N.VALIDATE_ONLY:
+            for c in self.bwd:
+                c(s)
+            return
+        main = torch.cuda.current_stream()
+        side = side_stream(self.device)
+        sp = ctypes.c_void_p(side.cuda_stream)
+        forked = False
         for c in self.bwd:
-            c(s)
+            if c.name == 'bmnas_conv_wgrad':
+                ev = c.keep
+                if not ev:
+                    ev = c.keep = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                c(sp)
+                forked = True
+            else:
+                c(s)
+        if forked:
+            main.wait_stream(side)
 
     # ------------------------------------------------------------------ dropout helper
     def p_of(self, site, default):
@@ -252,6 +302,14 @@ class Program:
                 self.setp(st, 'num_batches_tracked', sg['nbt'], i)
         Z = self.buf(self.B, M, self.L)
         self.setp(st, 'Z', Z)
+        # tensor-core-ready weight images (refreshed by ONE bmnas_wprep launch at the start of every forward)
+        img_f = img_d = None
+        if (N.lib().bmnas_get_gemm_mode() != 0 and K % 4 == 0 and self.L % 4 == 0 and all(c % 4 == 0 for c in src_C)
+                and all(sg['W'].data_ptr() % 16 == 0 for sg in segs)):
+            img_f = self.buf(int(N.lib().bmnas_wimg_floats(M, K, 0)))
+            img_d = self.buf(int(N.lib().bmnas_wimg_floats(M, K, 1)))
+            self.setp(st, 'wimg_fwd', img_f)
+            self._prep.append(dict(M=M, K=K, fold=w_fold, segs=[(sg['W'], sg['M']) for sg in segs], img_f=img_f, img_d=img_d))
         mean = rstd = None
         if bn:
             mean, rstd = self.buf(M), self.buf(M)
@@ -261,7 +319,7 @@ class Program:
                 self.setp(st, 'stat_part', self.buf(int(N.lib().bmnas_conv_stat_part_size(ctypes.byref(st)))))
                 self.setp(st, 'counter', self.counter(N.lib().bmnas_conv_num_counters(ctypes.byref(st))))
         self.emit('bmnas_conv_fwd', st)
-        return dict(Z=Z, mean=mean, rstd=rstd, M=M, K=K, srcs=srcs, src_C=src_C, segs=segs, w_fold=w_fold)
+        return dict(Z=Z, mean=mean, rstd=rstd, M=M, K=K, srcs=srcs, src_C=src_C, segs=segs, w_fold=w_fold, img_d=img_d)
 
     def conv_backward(self, cv, GV, coef, need_src):
         """dgrad into the source grads + wgrad into the parameter grad views."""
@@ -279,12 +337,22 @@ class Program:
                 self.setp(st, 'W', sg['W'], i)
             self.setp(st, 'GV', GV)
             self.setp(st, 'Z', cv['Z'])
+            self.setp(st, 'wimg_dgrad', cv.get('img_d'))
             if coef is not None:
                 self.setp(st, 'coef_a', coef[0])
                 self.setp(st, 'coef_b', coef[1])
                 self.setp(st, 'coef_c', coef[2])
             return st
 
+        # wgrad first: nothing downstream reads the parameter gradients before the optimiser, so
+        # run_backward() forks it onto a side stream right behind the kernel that produced GV/coef and the
+        # main chain continues with dgrad (a parallel branch of the captured CUDA graph)
+        if any(sg.get('gW') is not None or sg.get('gbias') is not None for sg in segs):
+            st = base()
+            for i, sg in enumerate(segs):
+                self.setp(st, 'gW', sg.get('gW'), i)
+                self.setp(st, 'gbias', sg.get('gbias'), i)
+            self.emit('bmnas_conv_wgrad', st)
         if any(need_src):
             st = base()
             for i, s in enumerate(srcs):
@@ -293,12 +361,6 @@ class Program:
                     st.gsrc_accum[i] = self.acc(g)
                     self.setp(st, 'gsrc', g, i)
             self.emit('bmnas_conv_dgrad', st)
-        if any(sg.get('gW') is not None or sg.get('gbias') is not None for sg in segs):
-            st = base()
-            for i, sg in enumerate(segs):
-                self.setp(st, 'gW', sg.get('gW'), i)
-                self.setp(st, 'gbias', sg.get('gbias'), i)
-            self.emit('bmnas_conv_wgrad', st)
 
     # ------------------------------------------------------------------ kernels: step-node mixed op
     def node_op(self, x, y, ops, P, G, prefix_of, gamma, gamma_off, logits, out, g_gamma=None,

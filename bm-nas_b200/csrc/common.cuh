@@ -16,7 +16,35 @@ extern int bmnas_validate_only_flag;
         if (bmnas_validate_only_flag) return BMNAS_OK; \
     } while (0)
 
+extern int bmnas_pdl_flag;
+
 namespace bmnas {
+
+// Programmatic dependent launch: every kernel is launched with the stream-serialization attribute and
+// opens with launch_dependents + wait, so the NEXT kernel's CTAs are scheduled (and run their
+// parameter/shared-memory prologue) while this one is still executing; griddepcontrol.wait blocks until the
+// preceding grid has completed and its writes are visible, so data dependencies are unchanged.  Under stream
+// capture the attribute becomes a programmatic edge of the CUDA graph.
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <class... KArgs, class... Args>
+static inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                            Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = bmnas_pdl_flag ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 constexpr float kBnEps = 1e-5f;

@@ -14,6 +14,7 @@
 // 128-bit loads (one DRAM/L2 round trip, up to 384 reduction rows per pass), then a
 // dependency-free FFMA loop (4x2 register micro-tile, 128 threads).
 #include "common.cuh"
+#include "gemm_shared.cuh"
 
 namespace bmnas {
 
@@ -23,46 +24,6 @@ constexpr int KC_MAX = 384;                    // reduction rows staged per pass
 
 __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 __host__ __device__ inline size_t gemm_smem_bytes(int kc) { return (size_t)kc * (LDA + LDB) * sizeof(float); }
-
-// row m of the stacked weight: pointer to W_seg[m_local][0]; also returns segment/local index
-__device__ __forceinline__ const float* w_row(const bmnas_conv_params& p, int m, int ldw, int* seg, int* ml) {
-    int s = 0;
-    while (s + 1 < p.n_seg && m >= p.seg_M[s]) {
-        m -= p.seg_M[s];
-        ++s;
-    }
-    if (seg) *seg = s;
-    if (ml) *ml = m;
-    return p.W[s] + (long long)m * ldw;
-}
-
-// channel k of the virtual concat -> (source, local channel)
-__device__ __forceinline__ void src_of(const bmnas_conv_params& p, int k, int* s, int* kl) {
-    int i = 0;
-    while (i + 1 < p.n_src && k >= p.src_C[i]) {
-        k -= p.src_C[i];
-        ++i;
-    }
-    *s = i;
-    *kl = k;
-}
-
-struct Wf {  // Welford triple
-    float n, mean, m2;
-};
-__device__ __forceinline__ Wf wf_merge(Wf a, Wf b) {
-    Wf r;
-    r.n = a.n + b.n;
-    if (r.n <= 0.f) {
-        r.mean = 0.f;
-        r.m2 = 0.f;
-        return r;
-    }
-    const float d = b.mean - a.mean;
-    r.mean = a.mean + d * (b.n / r.n);
-    r.m2 = a.m2 + b.m2 + d * d * (a.n * b.n / r.n);
-    return r;
-}
 
 // acc[2][2] += A[kk][ty*2 .. +1] (x) B[kk][tx*2 .. +1] over kk < kc   (16 x 16 threads cover 32 x 32)
 constexpr int MR = 2;
@@ -74,25 +35,6 @@ __device__ __forceinline__ void mma_tile(const float* As, const float* Bs, int k
         acc[0][0] = fmaf(a.x, b.x, acc[0][0]); acc[0][1] = fmaf(a.x, b.y, acc[0][1]);
         acc[1][0] = fmaf(a.y, b.x, acc[1][0]); acc[1][1] = fmaf(a.y, b.y, acc[1][1]);
     }
-}
-
-// upstream-gradient operand with BatchNorm backward folded in (scalar / float4)
-__device__ __forceinline__ float dz1(const bmnas_conv_params& p, long long idx, int m) {
-    float g = __ldg(p.GV + idx);
-    if (p.coef_a) g = fmaf(__ldg(p.coef_a + m), g, fmaf(__ldg(p.coef_b + m), __ldg(p.Z + idx), __ldg(p.coef_c + m)));
-    return g;
-}
-__device__ __forceinline__ float4 dz4(const bmnas_conv_params& p, long long idx, int m) {
-    float4 g = __ldg(reinterpret_cast<const float4*>(p.GV + idx));
-    if (p.coef_a) {
-        const float a = __ldg(p.coef_a + m), b = __ldg(p.coef_b + m), c = __ldg(p.coef_c + m);
-        const float4 z = __ldg(reinterpret_cast<const float4*>(p.Z + idx));
-        g.x = fmaf(a, g.x, fmaf(b, z.x, c));
-        g.y = fmaf(a, g.y, fmaf(b, z.y, c));
-        g.z = fmaf(a, g.z, fmaf(b, z.z, c));
-        g.w = fmaf(a, g.w, fmaf(b, z.w, c));
-    }
-    return g;
 }
 
 // issue U independent loads per thread before the first dependent store (memory-level parallelism:
@@ -148,6 +90,7 @@ __device__ __forceinline__ void stage2(int totalA, LA ldA, SA stA, int totalB, L
 template <bool VEC>
 __global__ void __launch_bounds__(GT, 1) k_conv_fwd(const bmnas_conv_params p, const int N, const int n_col_tiles,
                                                      const int KC) {
+    pdl_prologue();
     extern __shared__ __align__(16) float smem[];
     float* As = smem;
     float* Bs = smem + (size_t)KC * LDA;
@@ -260,70 +203,19 @@ __global__ void __launch_bounds__(GT, 1) k_conv_fwd(const bmnas_conv_params p, c
     }
 
     if (p.bn_mode == 2) {  // eval: statistics come from the running buffers
-        if (blockIdx.x == 0 && tid < TM) {
-            const int m = m0 + tid;
-            if (m < M) {
-                int s, ml;
-                w_row(p, m, ldw, &s, &ml);
-                p.mean[m] = p.running_mean[s][ml];
-                p.rstd[m] = 1.f / sqrtf(p.running_var[s][ml] + p.eps);
-            }
-        }
+        if (blockIdx.x == 0 && tid < TM) bn_eval_stats(p, m0 + tid, ldw);
         return;
     }
     if (p.bn_mode != 1) return;
-
-    // ---- last CTA of this row-tile merges the per-column-tile statistics (Chan), fixed order:
-    //      4 lanes per row walk interleaved tiles, then a lane-symmetric butterfly
+    // ---- last CTA of this row-tile merges the per-column-tile statistics (Chan), fixed order
     if (!last_block(p.counter + blockIdx.y, gridDim.x)) return;
-    const int r = tid >> 3, q = tid & 7;          // 8 lanes per row walk interleaved column tiles
-    const int m = m0 + r;
-    Wf w = {0.f, 0.f, 0.f};
-    if (m < M) {
-        for (int t0 = q; t0 < n_col_tiles; t0 += 8 * 4) {   // 4 independent loads in flight per lane
-            float2 v[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int tix = t0 + 8 * j;
-                v[j] = tix < n_col_tiles ? __ldcg(reinterpret_cast<const float2*>(p.stat_part + ((long long)tix * M + m) * 2))
-                                         : make_float2(0.f, 0.f);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int tix = t0 + 8 * j;
-                if (tix < n_col_tiles) {
-                    Wf b = {(float)min(TN, N - tix * TN), v[j].x, v[j].y};
-                    w = wf_merge(w, b);
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int o = 1; o <= 4; o <<= 1) {
-        Wf b;
-        b.n = __shfl_xor_sync(0xffffffffu, w.n, o);
-        b.mean = __shfl_xor_sync(0xffffffffu, w.mean, o);
-        b.m2 = __shfl_xor_sync(0xffffffffu, w.m2, o);
-        w = ((q & o) == 0) ? wf_merge(w, b) : wf_merge(b, w);  // same operand order in both lanes
-    }
-    if (q == 0 && m < M) {
-        const float var = w.m2 / (float)N;
-        p.mean[m] = w.mean;
-        p.rstd[m] = 1.f / sqrtf(var + p.eps);
-        int s, ml;
-        w_row(p, m, ldw, &s, &ml);
-        if (p.running_mean[s]) {
-            const float unb = w.m2 / (float)max(N - 1, 1);
-            p.running_mean[s][ml] = (1.f - p.momentum) * p.running_mean[s][ml] + p.momentum * w.mean;
-            p.running_var[s][ml] = (1.f - p.momentum) * p.running_var[s][ml] + p.momentum * unb;
-            if (ml == 0 && p.num_batches_tracked[s]) *p.num_batches_tracked[s] += 1;
-        }
-    }
+    bn_finalize_rows(p, N, n_col_tiles, TN, m0, TM, ldw);
 }
 
 // ------------------------------------------------------------------ dgrad
 template <bool VEC>
 __global__ void __launch_bounds__(GT, 1) k_conv_dgrad(const bmnas_conv_params p, const int N, const int KC) {
+    pdl_prologue();
     extern __shared__ __align__(16) float smem[];
     float* As = smem;
     float* Bs = smem + (size_t)KC * LDA;
@@ -425,6 +317,7 @@ __global__ void __launch_bounds__(GT, 1) k_conv_dgrad(const bmnas_conv_params p,
 template <bool VEC>
 __global__ void __launch_bounds__(GT, 1) k_conv_wgrad(const bmnas_conv_params p, const int N, const int chunkN,
                                                        const int KC) {
+    pdl_prologue();
     extern __shared__ __align__(16) float smem[];
     float* As = smem;
     float* Bs = smem + (size_t)KC * LDA;
@@ -545,6 +438,22 @@ static int set_smem(Kern kern, size_t bytes, size_t* configured) {
 
 using namespace bmnas;
 
+namespace bmnas {
+bool tc_eligible(const bmnas_conv_params* p, int mode);
+int tc_conv_fwd(const bmnas_conv_params* p, int x3, cudaStream_t stream);
+int tc_conv_dgrad(const bmnas_conv_params* p, int x3, cudaStream_t stream);
+int tc_conv_wgrad(const bmnas_conv_params* p, int x3, cudaStream_t stream);
+}  // namespace bmnas
+
+// GEMM engine: 0 = fp32 FFMA tiles, 1 = tcgen05 3xTF32 (fp32-class accuracy), 2 = tcgen05 1xTF32 (reduced precision)
+int bmnas_gemm_mode_flag = 1;
+extern "C" int bmnas_set_gemm_mode(int mode) {
+    if (mode < 0 || mode > 2) return BMNAS_EINVAL;
+    bmnas_gemm_mode_flag = mode;
+    return BMNAS_OK;
+}
+extern "C" int bmnas_get_gemm_mode(void) { return bmnas_gemm_mode_flag; }
+
 extern "C" long long bmnas_conv_stat_part_size(const bmnas_conv_params* p) {
     const long long N = (long long)p->B * p->L;
     return ((N + TN - 1) / TN) * p->M * 2;
@@ -579,6 +488,7 @@ extern "C" int bmnas_conv_fwd(const bmnas_conv_params* p, void* stream) {
             if (!p->running_mean[i] || !p->running_var[i]) return BMNAS_EINVAL;
     }
     BMNAS_DRY_RETURN();
+    if (bmnas_gemm_mode_flag && tc_eligible(p, 0)) return tc_conv_fwd(p, bmnas_gemm_mode_flag == 1, (cudaStream_t)stream);
     const int N = p->B * p->L;
     const int KC = min(KC_MAX, round_up(p->K, 4));
     const bool vec = conv_vec_ok(p, false);
@@ -588,9 +498,9 @@ extern "C" int bmnas_conv_fwd(const bmnas_conv_params* p, void* stream) {
     if (e) return e;
     dim3 grid((N + TN - 1) / TN, (p->M + TM - 1) / TM);
     if (vec)
-        k_conv_fwd<true><<<grid, GT, gemm_smem_bytes(KC), (cudaStream_t)stream>>>(*p, N, (int)grid.x, KC);
+        launch_k(k_conv_fwd<true>, grid, GT, gemm_smem_bytes(KC), (cudaStream_t)stream, *p, N, (int)grid.x, KC);
     else
-        k_conv_fwd<false><<<grid, GT, gemm_smem_bytes(KC), (cudaStream_t)stream>>>(*p, N, (int)grid.x, KC);
+        launch_k(k_conv_fwd<false>, grid, GT, gemm_smem_bytes(KC), (cudaStream_t)stream, *p, N, (int)grid.x, KC);
     BMNAS_LAUNCH_CHECK();
     return BMNAS_OK;
 }
@@ -603,6 +513,7 @@ extern "C" int bmnas_conv_dgrad(const bmnas_conv_params* p, void* stream) {
     for (int i = 0; i < p->n_seg; ++i)
         if (!p->W[i]) return BMNAS_EINVAL;
     BMNAS_DRY_RETURN();
+    if (bmnas_gemm_mode_flag && tc_eligible(p, 1)) return tc_conv_dgrad(p, bmnas_gemm_mode_flag == 1, (cudaStream_t)stream);
     const int N = p->B * p->L;
     const int KC = min(KC_MAX, round_up(p->M, 4));
     bool vec = (p->L & 3) == 0 && (p->K & 3) == 0 && gal16(p->GV) && (!p->coef_a || gal16(p->Z));
@@ -613,9 +524,9 @@ extern "C" int bmnas_conv_dgrad(const bmnas_conv_params* p, void* stream) {
     if (e) return e;
     dim3 grid((N + TN - 1) / TN, (p->K + TM - 1) / TM);
     if (vec)
-        k_conv_dgrad<true><<<grid, GT, gemm_smem_bytes(KC), (cudaStream_t)stream>>>(*p, N, KC);
+        launch_k(k_conv_dgrad<true>, grid, GT, gemm_smem_bytes(KC), (cudaStream_t)stream, *p, N, KC);
     else
-        k_conv_dgrad<false><<<grid, GT, gemm_smem_bytes(KC), (cudaStream_t)stream>>>(*p, N, KC);
+        launch_k(k_conv_dgrad<false>, grid, GT, gemm_smem_bytes(KC), (cudaStream_t)stream, *p, N, KC);
     BMNAS_LAUNCH_CHECK();
     return BMNAS_OK;
 }
@@ -628,6 +539,7 @@ extern "C" int bmnas_conv_wgrad(const bmnas_conv_params* p, void* stream) {
     for (int i = 0; i < p->n_src; ++i)
         if (!p->src[i]) return BMNAS_EINVAL;
     BMNAS_DRY_RETURN();
+    if (bmnas_gemm_mode_flag && tc_eligible(p, 2)) return tc_conv_wgrad(p, bmnas_gemm_mode_flag == 1, (cudaStream_t)stream);
     const int N = p->B * p->L, L = p->L;
     const int tiles = ((p->K + TN - 1) / TN) * ((p->M + TM - 1) / TM);
     bool vec = (L & 3) == 0 && L <= KC_MAX && gal16(p->GV) && (!p->coef_a || gal16(p->Z));
@@ -649,9 +561,9 @@ extern "C" int bmnas_conv_wgrad(const bmnas_conv_params* p, void* stream) {
     if (e) return e;
     dim3 grid((p->K + TN - 1) / TN, (p->M + TM - 1) / TM, splits);
     if (vec)
-        k_conv_wgrad<true><<<grid, GT, gemm_smem_bytes(KC), (cudaStream_t)stream>>>(*p, N, chunkN, KC);
+        launch_k(k_conv_wgrad<true>, grid, GT, gemm_smem_bytes(KC), (cudaStream_t)stream, *p, N, chunkN, KC);
     else
-        k_conv_wgrad<false><<<grid, GT, gemm_smem_bytes(KC), (cudaStream_t)stream>>>(*p, N, chunkN, KC);
+        launch_k(k_conv_wgrad<false>, grid, GT, gemm_smem_bytes(KC), (cudaStream_t)stream, *p, N, chunkN, KC);
     BMNAS_LAUNCH_CHECK();
     return BMNAS_OK;
 }

@@ -1,0 +1,134 @@
+// Helpers shared by the FFMA (gemm.cu) and tcgen05 (gemm_tc.cu) GEMM kernels: stacked-weight /
+// virtual-concat addressing, the BatchNorm-backward operand fold, Welford/Chan statistics merge and the
+// "last CTA of the row tile" BatchNorm finalize.
+#pragma once
+#include "common.cuh"
+
+namespace bmnas {
+
+// row m of the stacked weight: pointer to W_seg[m_local][0]; also returns segment/local index
+__device__ __forceinline__ const float* w_row(const bmnas_conv_params& p, int m, int ldw, int* seg, int* ml) {
+    int s = 0;
+    while (s + 1 < p.n_seg && m >= p.seg_M[s]) {
+        m -= p.seg_M[s];
+        ++s;
+    }
+    if (seg) *seg = s;
+    if (ml) *ml = m;
+    return p.W[s] + (long long)m * ldw;
+}
+
+// channel k of the virtual concat -> (source, local channel)
+__device__ __forceinline__ void src_of(const bmnas_conv_params& p, int k, int* s, int* kl) {
+    int i = 0;
+    while (i + 1 < p.n_src && k >= p.src_C[i]) {
+        k -= p.src_C[i];
+        ++i;
+    }
+    *s = i;
+    *kl = k;
+}
+
+struct Wf {  // Welford triple
+    float n, mean, m2;
+};
+__device__ __forceinline__ Wf wf_merge(Wf a, Wf b) {
+    Wf r;
+    r.n = a.n + b.n;
+    if (r.n <= 0.f) {
+        r.mean = 0.f;
+        r.m2 = 0.f;
+        return r;
+    }
+    const float d = b.mean - a.mean;
+    r.mean = a.mean + d * (b.n / r.n);
+    r.m2 = a.m2 + b.m2 + d * d * (a.n * b.n / r.n);
+    return r;
+}
+
+// upstream-gradient operand with BatchNorm backward folded in (scalar / float4)
+__device__ __forceinline__ float dz1(const bmnas_conv_params& p, long long idx, int m) {
+    float g = __ldg(p.GV + idx);
+    if (p.coef_a) g = fmaf(__ldg(p.coef_a + m), g, fmaf(__ldg(p.coef_b + m), __ldg(p.Z + idx), __ldg(p.coef_c + m)));
+    return g;
+}
+__device__ __forceinline__ float4 dz4(const bmnas_conv_params& p, long long idx, int m) {
+    float4 g = __ldg(reinterpret_cast<const float4*>(p.GV + idx));
+    if (p.coef_a) {
+        const float a = __ldg(p.coef_a + m), b = __ldg(p.coef_b + m), c = __ldg(p.coef_c + m);
+        const float4 z = __ldg(reinterpret_cast<const float4*>(p.Z + idx));
+        g.x = fmaf(a, g.x, fmaf(b, z.x, c));
+        g.y = fmaf(a, g.y, fmaf(b, z.y, c));
+        g.z = fmaf(a, g.z, fmaf(b, z.z, c));
+        g.w = fmaf(a, g.w, fmaf(b, z.w, c));
+    }
+    return g;
+}
+
+// eval-mode BatchNorm: statistics come from the running buffers (row m of the stacked output)
+__device__ __forceinline__ void bn_eval_stats(const bmnas_conv_params& p, int m, int ldw) {
+    if (m >= p.M) return;
+    int s, ml;
+    w_row(p, m, ldw, &s, &ml);
+    p.mean[m] = p.running_mean[s][ml];
+    p.rstd[m] = 1.f / sqrtf(p.running_var[s][ml] + p.eps);
+}
+
+// Train-mode BatchNorm finalize for rows [m0, m0+rows): merge the per-column-tile (mean, M2) partials in
+// stat_part (tile width tile_w columns, Chan's parallel update in a fixed order: 8 lanes per row walk
+// interleaved tiles, then a lane-symmetric butterfly), write mean / rstd, update the running statistics
+// (momentum, unbiased variance) and num_batches_tracked.  Called by every thread of ONE CTA (>= 256 threads
+// used as 32 rows x 8 lanes per pass).
+__device__ __forceinline__ void bn_finalize_rows(const bmnas_conv_params& p, int N, int n_col_tiles, int tile_w, int m0,
+                                                 int rows, int ldw) {
+    const int tid = threadIdx.x;
+    const int M = p.M;
+    for (int rb = 0; rb < rows; rb += 32) {
+        const int r = tid >> 3, q = tid & 7;
+        const int m = m0 + rb + r;
+        if (r >= 32) continue;
+        Wf w = {0.f, 0.f, 0.f};
+        if (m < M) {
+            for (int t0 = q; t0 < n_col_tiles; t0 += 8 * 4) {   // 4 independent loads in flight per lane
+                float2 v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int tix = t0 + 8 * j;
+                    v[j] = tix < n_col_tiles ? __ldcg(reinterpret_cast<const float2*>(p.stat_part + ((long long)tix * M + m) * 2))
+                                             : make_float2(0.f, 0.f);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int tix = t0 + 8 * j;
+                    if (tix < n_col_tiles) {
+                        Wf b = {(float)min(tile_w, N - tix * tile_w), v[j].x, v[j].y};
+                        w = wf_merge(w, b);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 1; o <= 4; o <<= 1) {
+            Wf b;
+            b.n = __shfl_xor_sync(0xffffffffu, w.n, o);
+            b.mean = __shfl_xor_sync(0xffffffffu, w.mean, o);
+            b.m2 = __shfl_xor_sync(0xffffffffu, w.m2, o);
+            w = ((q & o) == 0) ? wf_merge(w, b) : wf_merge(b, w);  // same operand order in both lanes
+        }
+        if (q == 0 && m < M) {
+            const float var = w.m2 / (float)N;
+            p.mean[m] = w.mean;
+            p.rstd[m] = 1.f / sqrtf(var + p.eps);
+            int s, ml;
+            w_row(p, m, ldw, &s, &ml);
+            if (p.running_mean[s]) {
+                const float unb = w.m2 / (float)max(N - 1, 1);
+                p.running_mean[s][ml] = (1.f - p.momentum) * p.running_mean[s][ml] + p.momentum * w.mean;
+                p.running_var[s][ml] = (1.f - p.momentum) * p.running_var[s][ml] + p.momentum * unb;
+                if (ml == 0 && p.num_batches_tracked[s]) *p.num_batches_tracked[s] += 1;
+            }
+        }
+    }
+}
+
+}  // namespace bmnas

@@ -1,0 +1,724 @@
+// tcgen05 (5th-gen tensor core) GEMM family for the 1x1 convolutions of the fusion cell -- the sm_100a
+// contraction path behind bmnas_conv_fwd / bmnas_conv_dgrad / bmnas_conv_wgrad:
+//   FWD    Z[b,m,l]  = sum_k Weff[m,k] U[b,k,l] + bias[m]      (+ BN batch statistics per output row)
+//   DGRAD  dU[b,k,l] = sum_m Weff[m,k] dz[b,m,l]
+//   WGRAD  dW[m,k]  += sum_{b,l} dz[b,m,l] U[b,k,l],  dbias[m] += sum dz
+// One CTA owns a 128-row x BN-column accumulator tile that lives in TENSOR MEMORY (TMEM); a single
+// elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (UMMA M=128, N=BN, K=8) on shared-memory
+// operand descriptors; tcgen05.commit arrives on mbarriers that recycle the operand ring and release the
+// epilogue, which reads the accumulators back with tcgen05.ld (one TMEM lane = one output row per thread,
+// so bias, BatchNorm row statistics and the row-wise stores need no cross-thread traffic).
+//
+// Precision.  The reference computes in fp32 and the parity gate is 1e-5, which a plain TF32 product
+// (10-bit mantissa) cannot meet.  Mode 3xTF32 splits every operand element into hi = tf32(v) and
+// lo = v - hi while it is staged and issues three MMAs per k-step (lo*hi + hi*lo + hi*hi) into the same
+// fp32 TMEM accumulator: the dropped lo*lo term is O(2^-22).  Mode 1xTF32 stages hi only (one MMA per
+// k-step, half the shared memory); it is the reduced-precision mode (north_star's 2e-2 class).
+//
+// Operand staging.  Both operands are written in the canonical K-major SWIZZLE_NONE ("interleave")
+// UMMA layout: core matrix = 8 rows x 16 bytes stored as 128 contiguous bytes, LBO (next 16-byte chunk
+// along K) = 128 B, SBO (next 8-row group) = 1 KB for a 32-element K slab.  The virtual channel concat,
+// the cat([t,t]) weight fold, the (B,C,L) -> (column, k) transposition and BatchNorm-backward
+// (dz = a*GV + b*Z + c) are applied to the ACTIVATION operand in a global->register->shared staging pass,
+// which is also where its hi/lo split happens.  The WEIGHT operand does not change inside a half step, so
+// bmnas_wprep (k_wprep below) folds, transposes, splits and lays it out ONCE per forward as ready-made
+// shared-memory images (one contiguous [hi 16 KB | lo 16 KB] block per 128-row x 32-k slab); the GEMM CTAs
+// then fetch a slab with a single TMA bulk copy (cp.async.bulk ... mbarrier::complete_tx) two slabs ahead
+// of the MMAs.  A 4-stage ring lets the next slab's loads fly while the current slab's MMAs run.
+#include "common.cuh"
+#include "gemm_shared.cuh"
+
+namespace bmnas {
+namespace tc {
+
+constexpr int TCT = 256;  // threads per CTA (8 warps: all stage; all read TMEM in the epilogue)
+constexpr int TCM = 128;  // accumulator rows per CTA = UMMA M
+constexpr int KC = 32;    // reduction elements per ring stage (4 UMMA k-steps of 8 tf32)
+constexpr int NST_MAX = 4;  // ring stages (3 when four would not fit in 227 KB)
+constexpr int FWD = 0, DGRAD = 1, WGRAD = 2;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, 0x989680;\n\t"
+            "selp.b32 %0, 1, 0, P1;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(s32(bar)), "r"(phase)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(s32(bar)) : "memory");
+}
+// TMA bulk copy global -> shared; completion is signalled on `bar` as transaction bytes
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst_smem)),
+                 "l"(src), "r"(bytes), "r"(s32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(dst_smem)), "r"(ncols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols));
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, tf32 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns: thread t of the warp receives lane (base lane + t)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4, [16,30) leading byte offset>>4, [32,46) stride byte offset>>4, [46,48) version=1
+__device__ __forceinline__ uint64_t kdesc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6)=1, a=tf32 [7,10)=2, b=tf32 [10,13)=2,
+// a/b K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float tf32_hi(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+// write one 16-byte K-chunk (4 reduction elements of one operand row) as hi (and lo) tf32 values
+template <bool X3>
+__device__ __forceinline__ void put_chunk(uint8_t* hi_base, uint8_t* lo_base, uint32_t off, float4 v) {
+    float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    *reinterpret_cast<float4*>(hi_base + off) = h;
+    if (X3) *reinterpret_cast<float4*>(lo_base + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+}
+
+template <int BN, bool X3>
+struct Smem {
+    static constexpr uint32_t A_BYTES = TCM * KC * 4;   // 16 KB
+    static constexpr uint32_t B_BYTES = BN * KC * 4;
+    static constexpr uint32_t STAGE = (X3 ? 2u : 1u) * (A_BYTES + B_BYTES);
+    static constexpr int NST = (NST_MAX * STAGE + 1024 <= 227u * 1024u) ? NST_MAX : 3;
+    static constexpr uint32_t TOTAL = NST * STAGE + 1024;  // + alignment slack
+    static constexpr uint32_t SBO = (KC / 4) * 128;     // bytes between 8-row groups
+    static constexpr uint32_t LBO = 128;                // bytes between 16-byte K chunks
+};
+
+// --------------------------------------------------------------------------------------------------
+// MODE FWD  : rows = output channels m (tile blockIdx.y), cols = n=(b,l) (tile blockIdx.x), red = k
+// MODE DGRAD: rows = input channels k  (tile blockIdx.y), cols = n=(b,l) (tile blockIdx.x), red = m
+// MODE WGRAD: rows = output channels m (tile blockIdx.y), cols = input channels k (tile blockIdx.x),
+//             red = n in [blockIdx.z*chunkN, ...)
+// --------------------------------------------------------------------------------------------------
+template <int MODE, int BN, bool X3>
+__global__ void __launch_bounds__(TCT, 1) k_gemm_tc(const bmnas_conv_params p, const int N, const int aux) {
+    pdl_prologue();
+    using S = Smem<BN, X3>;
+    constexpr int NST = S::NST;
+    constexpr int LA = NST - 2;                    // TMA runs this many slabs ahead of the MMAs
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t bars[2 * NST_MAX + 1];     // [0,NST) slot free, [NST_MAX, NST_MAX+NST) weight slab landed, last: done
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float rowsum[TCM];
+    __shared__ float2 halfstat[TCM];
+    uint64_t* bar_free = bars;
+    uint64_t* bar_full = bars + NST_MAX;
+    uint64_t* bar_done = bars + 2 * NST_MAX;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int K = p.K, M = p.M, L = p.L, ldw = p.w_fold * p.K;
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+
+    if (warp == 0) tmem_alloc(&tmem_base_s, TMEM_COLS);
+    if (tid == 32) {
+        for (int i = 0; i <= 2 * NST_MAX; ++i) mbar_init(&bars[i], 1);
+        fence_barrier_init();
+    }
+    if (MODE == WGRAD && tid < TCM) rowsum[tid] = 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base_s;
+
+    const int row0 = blockIdx.y * TCM;
+    const int col0 = blockIdx.x * BN;
+    const int n_rows = MODE == DGRAD ? K : M;                   // valid accumulator rows overall
+    int r_beg = 0, r_end = MODE == FWD ? K : (MODE == DGRAD ? M : N);
+    if (MODE == WGRAD) {
+        r_beg = blockIdx.z * aux;
+        r_end = min(N, r_beg + aux);
+    }
+    const int n_chunks = (r_end - r_beg + KC - 1) / KC;
+
+    // prepared weight images (bmnas_wprep): slab (row tile rt, reduction slab c) = [hi 16 KB | lo 16 KB]
+    const float* img = MODE == FWD ? p.wimg_fwd : (MODE == DGRAD ? p.wimg_dgrad : nullptr);
+    const bool use_img = img != nullptr;
+    constexpr uint32_t IMG_SLAB = 2u * S::A_BYTES;
+    constexpr uint32_t IMG_COPY = (X3 ? 2u : 1u) * S::A_BYTES;
+    const uint8_t* img_rt = reinterpret_cast<const uint8_t*>(img) + (size_t)blockIdx.y * (size_t)n_chunks * IMG_SLAB;
+    auto tma_slab = [&](int c) {   // thread 0 only
+        const int st = c % NST;
+        mbar_expect_tx(&bar_full[st], IMG_COPY);
+        tma_bulk_g2s(smem + (size_t)st * S::STAGE, img_rt + (size_t)c * IMG_SLAB, IMG_COPY, &bar_full[st]);
+    };
+    if (use_img && tid == 0) {
+        for (int c = 0; c < LA && c < n_chunks; ++c) tma_slab(c);
+    }
+
+    constexpr int QA = TCM * (KC / 4) / TCT;            // 16-byte chunks of A per thread per stage (4)
+    constexpr int QB = (BN * (KC / 4) + TCT - 1) / TCT; // ... of B (BN=32: 1, 64: 2, 128: 4)
+    // raw staging registers: loads only in load_stage (no dependent math, so the loads stay in flight across
+    // the barrier and the MMA issue); fold / BatchNorm-backward / hi-lo split happen in store_stage
+    float4 ra[QA], ra2[QA], rb[QB], rb2[QB];
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool has_coef = MODE != FWD && p.coef_a != nullptr;
+
+    auto load_stage = [&](int r0) {
+        if (!use_img) {
+#pragma unroll
+            for (int it = 0; it < QA; ++it) {
+                const int q = it * TCT + tid;
+                float4 v = z4, v2 = z4;
+                if (MODE == FWD) {
+                    const int r8 = q & 7, kc = (q >> 3) & 7, rg = q >> 6;
+                    const int m = row0 + rg * 8 + r8, k = r0 + kc * 4;
+                    if (m < M && k < K) {
+                        const float* w = w_row(p, m, ldw, nullptr, nullptr) + k;
+                        v = __ldg(reinterpret_cast<const float4*>(w));
+                        if (p.w_fold == 2) v2 = __ldg(reinterpret_cast<const float4*>(w + K));
+                    }
+                } else if (MODE == DGRAD) {
+                    const int row = q & (TCM - 1), mc = q >> 7;
+                    const int k = row0 + row, m = r0 + mc * 4;
+                    if (k < K) {
+                        float e[4], f[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            e[j] = f[j] = 0.f;
+                            if (m + j < M) {
+                                const float* w = w_row(p, m + j, ldw, nullptr, nullptr) + k;
+                                e[j] = __ldg(w);
+                                if (p.w_fold == 2) f[j] = __ldg(w + K);
+                            }
+                        }
+                        v = make_float4(e[0], e[1], e[2], e[3]);
+                        v2 = make_float4(f[0], f[1], f[2], f[3]);
+                    }
+                } else {
+                    const int r8 = q & 7, kc = (q >> 3) & 7, rg = q >> 6;
+                    const int m = row0 + rg * 8 + r8, n = r0 + kc * 4;
+                    if (m < M && n < r_end) {
+                        const long long idx = ((long long)(n / L) * M + m) * L + (n % L);
+                        v = __ldg(reinterpret_cast<const float4*>(p.GV + idx));
+                        if (has_coef) v2 = __ldg(reinterpret_cast<const float4*>(p.Z + idx));
+                    }
+                }
+                ra[it] = v;
+                ra2[it] = v2;
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < QB; ++it) {
+            const int q = it * TCT + tid;
+            float4 v = z4, v2 = z4;
+            if (q < BN * (KC / 4)) {
+                if (MODE == WGRAD) {
+                    const int r8 = q & 7, kc = (q >> 3) & 7, rg = q >> 6;
+                    const int k = col0 + rg * 8 + r8, n = r0 + kc * 4;
+                    if (k < K && n < r_end) {
+                        int s, kl;
+                        src_of(p, k, &s, &kl);
+                        v = __ldg(reinterpret_cast<const float4*>(p.src[s] + ((long long)(n / L) * p.src_C[s] + kl) * L + (n % L)));
+                    }
+                } else {
+                    const int nl = q % BN, kc = q / BN;
+                    const int n = col0 + nl, r = r0 + kc * 4;
+                    if (n < N) {
+                        const int b = n / L, l = n - b * L;
+                        float e[4], f[4];
+                        if (MODE == FWD) {
+                            int s = 0, kl = 0;
+                            if (r < K) src_of(p, r, &s, &kl);   // a 4-chunk never straddles sources (C % 4 == 0)
+                            const float* u = p.src[s] + ((long long)b * p.src_C[s] + kl) * L + l;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                e[j] = (r + j < K) ? __ldg(u + (long long)j * L) : 0.f;
+                                f[j] = 0.f;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const long long idx = ((long long)b * M + r + j) * L + l;
+                                e[j] = (r + j < M) ? __ldg(p.GV + idx) : 0.f;
+                                f[j] = (has_coef && r + j < M) ? __ldg(p.Z + idx) : 0.f;
+                            }
+                        }
+                        v = make_float4(e[0], e[1], e[2], e[3]);
+                        v2 = make_float4(f[0], f[1], f[2], f[3]);
+                    }
+                }
+            }
+            rb[it] = v;
+            rb2[it] = v2;
+        }
+    };
+
+    // dz = a[m]*GV + b[m]*Z + c[m] for 4 reduction rows m..m+3 (DGRAD B) or one row m (WGRAD A)
+    auto bn_fold4 = [&](float4 g, float4 z, int m, bool per_elem) {
+        if (!has_coef) return g;
+        if (per_elem) {
+            float gg[4] = {g.x, g.y, g.z, g.w}, zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                gg[j] = (m + j < M) ? fmaf(__ldg(p.coef_a + m + j), gg[j], fmaf(__ldg(p.coef_b + m + j), zz[j], __ldg(p.coef_c + m + j))) : 0.f;
+            return make_float4(gg[0], gg[1], gg[2], gg[3]);
+        }
+        const float a = __ldg(p.coef_a + m), b = __ldg(p.coef_b + m), c = __ldg(p.coef_c + m);
+        return make_float4(fmaf(a, g.x, fmaf(b, z.x, c)), fmaf(a, g.y, fmaf(b, z.y, c)), fmaf(a, g.z, fmaf(b, z.z, c)),
+                           fmaf(a, g.w, fmaf(b, z.w, c)));
+    };
+
+    // ---- register -> shared (fold / BN-backward, hi/lo split, canonical K-major core-matrix layout)
+    auto store_stage = [&](int stage, int r0) {
+        uint8_t* base = smem + (size_t)stage * S::STAGE;
+        uint8_t* a_hi = base;
+        uint8_t* a_lo = base + S::A_BYTES;                       // only used when X3
+        uint8_t* b_hi = base + (X3 ? 2u : 1u) * S::A_BYTES;
+        uint8_t* b_lo = b_hi + S::B_BYTES;
+        if (!use_img) {
+#pragma unroll
+            for (int it = 0; it < QA; ++it) {
+                const int q = it * TCT + tid;
+                uint32_t off;
+                float4 v = ra[it];
+                if (MODE == DGRAD) {
+                    const int row = q & (TCM - 1), mc = q >> 7;
+                    off = (uint32_t)(row >> 3) * S::SBO + (uint32_t)mc * S::LBO + (uint32_t)(row & 7) * 16u;
+                    v.x += ra2[it].x; v.y += ra2[it].y; v.z += ra2[it].z; v.w += ra2[it].w;
+                } else {
+                    const int r8 = q & 7, kc = (q >> 3) & 7, rg = q >> 6;
+                    off = (uint32_t)rg * S::SBO + (uint32_t)kc * S::LBO + (uint32_t)r8 * 16u;
+                    if (MODE == FWD) {
+                        v.x += ra2[it].x; v.y += ra2[it].y; v.z += ra2[it].z; v.w += ra2[it].w;
+                    } else {
+                        const int m = row0 + rg * 8 + r8, n = r0 + kc * 4;
+                        if (m < M && n < r_end) v = bn_fold4(v, ra2[it], m, false);
+                        if (blockIdx.x == 0) {                      // bias gradient = row sums of dz
+                            const float s = (v.x + v.y) + (v.z + v.w);
+                            if (s != 0.f) atomicAdd(&rowsum[rg * 8 + r8], s);
+                        }
+                    }
+                }
+                put_chunk<X3>(a_hi, a_lo, off, v);
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < QB; ++it) {
+            const int q = it * TCT + tid;
+            if (q < BN * (KC / 4)) {
+                uint32_t off;
+                float4 v = rb[it];
+                if (MODE == WGRAD) {
+                    const int r8 = q & 7, kc = (q >> 3) & 7, rg = q >> 6;
+                    off = (uint32_t)rg * S::SBO + (uint32_t)kc * S::LBO + (uint32_t)r8 * 16u;
+                } else {
+                    const int nl = q % BN, kc = q / BN;
+                    off = (uint32_t)(nl >> 3) * S::SBO + (uint32_t)kc * S::LBO + (uint32_t)(nl & 7) * 16u;
+                    if (MODE == DGRAD && col0 + nl < N) v = bn_fold4(v, rb2[it], r0 + kc * 4, true);
+                }
+                put_chunk<X3>(b_hi, b_lo, off, v);
+            }
+        }
+    };
+
+    // ---- main loop: stage slab c, then one thread issues its MMAs; slab c+1's loads are already in flight
+    constexpr uint32_t IDESC = idesc_tf32(TCM, BN);
+    if (n_chunks > 0) load_stage(r_beg);
+    for (int c = 0; c < n_chunks; ++c) {
+        const int stage = c % NST;
+        if (c >= NST) mbar_wait(&bar_free[stage], (uint32_t)((c / NST) - 1) & 1u);   // MMAs that read this slot are done
+        if (use_img && tid == 0) {
+            const int t = c + LA;                     // keep the weight TMA LA slabs ahead
+            if (t < n_chunks) {
+                if (t >= NST) mbar_wait(&bar_free[t % NST], (uint32_t)((t / NST) - 1) & 1u);
+                tma_slab(t);
+            }
+        }
+        store_stage(stage, r_beg + c * KC);
+        if (c + 1 < n_chunks) load_stage(r_beg + (c + 1) * KC);
+        fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+        __syncthreads();
+        if (tid == 0) {
+            if (use_img) mbar_wait(&bar_full[stage], (uint32_t)(c / NST) & 1u);      // weight slab has landed
+            tc_fence_after();
+            const uint32_t base = s32(smem + (size_t)stage * S::STAGE);
+            const uint32_t a_hi = base, a_lo = base + S::A_BYTES;
+            const uint32_t b_hi = base + (X3 ? 2u : 1u) * S::A_BYTES, b_lo = b_hi + S::B_BYTES;
+#pragma unroll
+            for (int ks = 0; ks < KC / 8; ++ks) {
+                const uint32_t ko = (uint32_t)ks * 2u * S::LBO;      // 8 tf32 = two 16-byte chunks
+                const uint32_t first = (c == 0 && ks == 0) ? 0u : 1u;
+                if (X3) {
+                    umma_tf32(tmem_d, kdesc(a_lo + ko, S::LBO, S::SBO), kdesc(b_hi + ko, S::LBO, S::SBO), IDESC, first);
+                    umma_tf32(tmem_d, kdesc(a_hi + ko, S::LBO, S::SBO), kdesc(b_lo + ko, S::LBO, S::SBO), IDESC, 1u);
+                    umma_tf32(tmem_d, kdesc(a_hi + ko, S::LBO, S::SBO), kdesc(b_hi + ko, S::LBO, S::SBO), IDESC, 1u);
+                } else {
+                    umma_tf32(tmem_d, kdesc(a_hi + ko, S::LBO, S::SBO), kdesc(b_hi + ko, S::LBO, S::SBO), IDESC, first);
+                }
+            }
+            umma_commit(&bar_free[stage]);                   // slot reusable once these MMAs have read it
+            if (c + 1 == n_chunks) umma_commit(bar_done);    // accumulator complete
+        }
+    }
+
+    // ---- epilogue: TMEM -> registers; thread t of warp w owns accumulator row (w & 3) * 32 + t and the
+    //      column half (w >> 2)
+    if (n_chunks > 0) mbar_wait(bar_done, 0u);
+    tc_fence_after();
+    const int row = (warp & 3) * 32 + lane;
+    const int half = warp >> 2;
+    constexpr int HC = BN / 2;                           // columns per thread
+    const uint32_t t_row = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
+    const int gr = row0 + row;                           // global row (m for FWD/WGRAD, k for DGRAD)
+    const bool row_ok = gr < n_rows;
+
+    if (MODE == FWD) {
+        float bias = 0.f;
+        int seg = 0, ml = 0;
+        if (row_ok) {
+            w_row(p, gr, ldw, &seg, &ml);
+            if (p.bias[seg]) bias = __ldg(p.bias[seg] + ml);
+        }
+        float sum = 0.f, m2 = 0.f;
+        int cnt = 0;
+        float vals[HC];
+#pragma unroll
+        for (int g = 0; g < HC / 16; ++g) {
+            float v[16];
+            tmem_ld16(t_row + (uint32_t)(half * HC + g * 16), v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) vals[g * 16 + j] = (n_chunks > 0 ? v[j] : 0.f) + bias;
+        }
+#pragma unroll
+        for (int j4 = 0; j4 < HC / 4; ++j4) {
+            const int n = col0 + half * HC + j4 * 4;
+            if (n < N) {                                  // N % 4 == 0 and L % 4 == 0: a 4-group is whole and in one sample
+                if (row_ok) {
+                    *reinterpret_cast<float4*>(p.Z + ((long long)(n / L) * M + gr) * L + (n % L)) =
+                        make_float4(vals[j4 * 4], vals[j4 * 4 + 1], vals[j4 * 4 + 2], vals[j4 * 4 + 3]);
+                }
+                sum += (vals[j4 * 4] + vals[j4 * 4 + 1]) + (vals[j4 * 4 + 2] + vals[j4 * 4 + 3]);
+                cnt += 4;
+            }
+        }
+        if (p.bn_mode == 1) {
+            const float mean = cnt ? sum / (float)cnt : 0.f;
+#pragma unroll
+            for (int j4 = 0; j4 < HC / 4; ++j4) {
+                if (col0 + half * HC + j4 * 4 < N) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float d = vals[j4 * 4 + j] - mean;
+                        m2 = fmaf(d, d, m2);
+                    }
+                }
+            }
+            // merge the two column halves of this row (Chan), then one (mean, M2) per (column tile, row)
+            if (half == 1) halfstat[row] = make_float2(mean, m2);
+            __syncthreads();
+            if (half == 0 && row_ok) {
+                const int cnt1 = max(0, min(HC, N - (col0 + HC)));
+                Wf a = {(float)cnt, mean, m2};
+                Wf b = {(float)cnt1, halfstat[row].x, halfstat[row].y};
+                const Wf w = wf_merge(a, b);
+                float* q = p.stat_part + ((long long)blockIdx.x * M + gr) * 2;
+                q[0] = w.mean;
+                q[1] = w.m2;
+            }
+        }
+    } else if (MODE == DGRAD) {
+        int s = 0, kl = 0;
+        if (row_ok) src_of(p, gr, &s, &kl);
+        float* dst = row_ok ? p.gsrc[s] : nullptr;
+        const bool accum = row_ok && p.gsrc_accum[s] != 0;
+#pragma unroll
+        for (int g = 0; g < HC / 16; ++g) {
+            float v[16];
+            tmem_ld16(t_row + (uint32_t)(half * HC + g * 16), v);
+            if (dst) {
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const int n = col0 + half * HC + g * 16 + j4 * 4;
+                    if (n < N) {
+                        float4* d = reinterpret_cast<float4*>(dst + ((long long)(n / L) * p.src_C[s] + kl) * L + (n % L));
+                        float4 o = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                        if (n_chunks == 0) o = z4;
+                        if (accum) {
+                            const float4 c_ = *d;
+                            o.x += c_.x; o.y += c_.y; o.z += c_.z; o.w += c_.w;
+                        }
+                        *d = o;
+                    }
+                }
+            }
+        }
+    } else {
+        int seg = 0, ml = 0;
+        if (row_ok) w_row(p, gr, ldw, &seg, &ml);
+        float* grow = (row_ok && p.gW[seg]) ? p.gW[seg] + (long long)ml * ldw : nullptr;
+#pragma unroll
+        for (int g = 0; g < HC / 16; ++g) {
+            float v[16];
+            tmem_ld16(t_row + (uint32_t)(half * HC + g * 16), v);
+            if (grow && n_chunks > 0) {
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const int k = col0 + half * HC + g * 16 + j4 * 4;
+                    if (k < K) {
+                        const float4 o = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                        red_add_v4(grow + k, o);
+                        if (p.w_fold == 2) red_add_v4(grow + K + k, o);
+                    }
+                }
+            }
+        }
+        if (blockIdx.x == 0 && half == 0 && row_ok && p.gbias[seg] && n_chunks > 0) atomicAdd(p.gbias[seg] + ml, rowsum[row]);
+    }
+
+    // ---- teardown (+ FWD: BatchNorm statistics finalize by the last CTA of this row tile)
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);
+    if (MODE == FWD) {
+        if (p.bn_mode == 2) {
+            if (blockIdx.x == 0 && tid < TCM) bn_eval_stats(p, row0 + tid, ldw);
+            return;
+        }
+        if (p.bn_mode != 1) return;
+        if (!last_block(p.counter + blockIdx.y, gridDim.x)) return;
+        bn_finalize_rows(p, N, aux /* n_col_tiles */, BN, row0, TCM, ldw);
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
+// Weight images.  For every conv: forward image (rows m, reduction k) and dgrad image (rows k, reduction
+// m) of Weff[m,k] = sum_f W[m, f*K + k], zero padded to 128-row tiles x 32-element slabs, each slab stored
+// as the exact shared-memory picture the MMA descriptors expect: [hi: 16 row-groups x 8 chunks x 128 B |
+// lo: same].  One thread produces one 16-byte chunk (hi and lo).
+// --------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_wprep(const bmnas_wprep_params p) {
+    pdl_prologue();
+    const long long q = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (q >= p.q_start[p.n]) return;
+    int i = 0;
+    while (i + 1 < p.n && q >= p.q_start[i + 1]) ++i;
+    long long ql = q - p.q_start[i];
+    const int M = p.M[i], K = p.K[i], fold = p.w_fold[i], nseg = p.n_seg[i], ldw = fold * K;
+    auto wrow = [&](int m) -> const float* {
+        int s = 0;
+        while (s + 1 < nseg && m >= p.seg_M[i * BMNAS_MAX_SEG + s]) {
+            m -= p.seg_M[i * BMNAS_MAX_SEG + s];
+            ++s;
+        }
+        return p.W[i * BMNAS_MAX_SEG + s] + (long long)m * ldw;
+    };
+    const int KSf = (K + KC - 1) / KC, RTf = (M + TCM - 1) / TCM;
+    const long long nf = (long long)RTf * KSf * 1024;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    float* dst;
+    if (ql < nf) {
+        const long long slab = ql >> 10;
+        const int w = (int)(ql & 1023), rt = (int)(slab / KSf), ks = (int)(slab % KSf);
+        const int r8 = w & 7, kc = (w >> 3) & 7, rg = w >> 6;
+        const int m = rt * TCM + rg * 8 + r8, k = ks * KC + kc * 4;
+        if (m < M && k < K) {
+            const float* r = wrow(m) + k;
+            v = __ldg(reinterpret_cast<const float4*>(r));
+            if (fold == 2) {
+                const float4 u = __ldg(reinterpret_cast<const float4*>(r + K));
+                v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+            }
+        }
+        dst = p.img_fwd[i] + slab * (2 * TCM * KC) + (rg * 1024 + kc * 128 + r8 * 16) / 4;
+    } else {
+        ql -= nf;
+        const int MSd = (M + KC - 1) / KC;
+        const long long slab = ql >> 10;
+        const int w = (int)(ql & 1023), rt = (int)(slab / MSd), ms = (int)(slab % MSd);
+        const int row = w & (TCM - 1), mc = w >> 7;
+        const int k = rt * TCM + row, m = ms * KC + mc * 4;
+        if (k < K) {
+            float e[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                e[j] = 0.f;
+                if (m + j < M) {
+                    const float* r = wrow(m + j) + k;
+                    e[j] = __ldg(r);
+                    if (fold == 2) e[j] += __ldg(r + K);
+                }
+            }
+            v = make_float4(e[0], e[1], e[2], e[3]);
+        }
+        dst = p.img_dgrad[i] + slab * (2 * TCM * KC) + ((row >> 3) * 1024 + mc * 128 + (row & 7) * 16) / 4;
+    }
+    const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    *reinterpret_cast<float4*>(dst) = h;
+    *reinterpret_cast<float4*>(dst + TCM * KC) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+}
+
+template <int MODE, int BN, bool X3>
+static int launch_tc(const bmnas_conv_params* p, dim3 grid, int N, int aux, cudaStream_t stream) {
+    using S = Smem<BN, X3>;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_gemm_tc<MODE, BN, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL) !=
+            cudaSuccess)
+            return BMNAS_ELAUNCH;
+        configured = true;
+    }
+    launch_k(k_gemm_tc<MODE, BN, X3>, grid, TCT, S::TOTAL, stream, *p, N, aux);
+    BMNAS_LAUNCH_CHECK();
+    return BMNAS_OK;
+}
+
+static bool al16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
+
+}  // namespace tc
+
+// The tensor-core path needs whole 16-byte groups everywhere: L % 4 == 0, K % 4 == 0, every channel
+// count of the virtual concat % 4 == 0, 16-byte aligned tensors.  Otherwise the caller keeps the FFMA path.
+bool tc_eligible(const bmnas_conv_params* p, int mode) {
+    using namespace tc;
+    if ((p->L & 3) || (p->K & 3)) return false;
+    for (int i = 0; i < p->n_src; ++i)
+        if ((p->src_C[i] & 3) || (mode != DGRAD && !al16(p->src[i])) || (mode == DGRAD && p->gsrc[i] && !al16(p->gsrc[i])))
+            return false;
+    for (int i = 0; i < p->n_seg; ++i) {
+        if (mode != WGRAD && !al16(p->W[i])) return false;
+        if (mode == WGRAD && p->gW[i] && !al16(p->gW[i])) return false;
+    }
+    if (mode == FWD && !al16(p->Z)) return false;
+    if (mode != FWD && (!al16(p->GV) || (p->coef_a && !al16(p->Z)))) return false;
+    return true;
+}
+
+int tc_conv_fwd(const bmnas_conv_params* p, int x3, cudaStream_t stream) {
+    using namespace tc;
+    const int N = p->B * p->L;
+    const int row_tiles = (p->M + TCM - 1) / TCM;
+    // enough CTAs to spread the operand staging over the machine, wide tiles once the batch is large
+    const int bn = (long long)row_tiles * ((N + 127) / 128) >= 2 * kNumSMs ? 128 : ((long long)row_tiles * ((N + 63) / 64) >= kNumSMs ? 64 : 32);
+    dim3 grid((N + bn - 1) / bn, row_tiles);
+    const int aux = (int)grid.x;
+    if (bn == 128) return x3 ? launch_tc<FWD, 128, true>(p, grid, N, aux, stream) : launch_tc<FWD, 128, false>(p, grid, N, aux, stream);
+    if (bn == 64) return x3 ? launch_tc<FWD, 64, true>(p, grid, N, aux, stream) : launch_tc<FWD, 64, false>(p, grid, N, aux, stream);
+    return x3 ? launch_tc<FWD, 32, true>(p, grid, N, aux, stream) : launch_tc<FWD, 32, false>(p, grid, N, aux, stream);
+}
+
+int tc_conv_dgrad(const bmnas_conv_params* p, int x3, cudaStream_t stream) {
+    using namespace tc;
+    const int N = p->B * p->L;
+    const int row_tiles = (p->K + TCM - 1) / TCM;
+    const int bn = (long long)row_tiles * ((N + 127) / 128) >= 2 * kNumSMs ? 128 : ((long long)row_tiles * ((N + 63) / 64) >= kNumSMs ? 64 : 32);
+    dim3 grid((N + bn - 1) / bn, row_tiles);
+    if (bn == 128) return x3 ? launch_tc<DGRAD, 128, true>(p, grid, N, 0, stream) : launch_tc<DGRAD, 128, false>(p, grid, N, 0, stream);
+    if (bn == 64) return x3 ? launch_tc<DGRAD, 64, true>(p, grid, N, 0, stream) : launch_tc<DGRAD, 64, false>(p, grid, N, 0, stream);
+    return x3 ? launch_tc<DGRAD, 32, true>(p, grid, N, 0, stream) : launch_tc<DGRAD, 32, false>(p, grid, N, 0, stream);
+}
+
+int tc_conv_wgrad(const bmnas_conv_params* p, int x3, cudaStream_t stream) {
+    using namespace tc;
+    const int N = p->B * p->L;
+    const int row_tiles = (p->M + TCM - 1) / TCM;
+    const int bn = p->K >= 128 ? 128 : (p->K > 32 ? 64 : 32);
+    const int col_tiles = (p->K + bn - 1) / bn;
+    const int tiles = row_tiles * col_tiles;
+    int splits = p->splits;
+    if (splits <= 0) {
+        splits = (kNumSMs + tiles - 1) / tiles;
+        const int maxs = (N + 4 * KC - 1) / (4 * KC);     // at least 4 ring stages of reduction per split
+        if (splits > maxs) splits = maxs;
+        if (splits < 1) splits = 1;
+    }
+    int chunkN = ((N + splits - 1) / splits + KC - 1) / KC * KC;
+    splits = (N + chunkN - 1) / chunkN;
+    dim3 grid(col_tiles, row_tiles, splits);
+    if (bn == 128) return x3 ? launch_tc<WGRAD, 128, true>(p, grid, N, chunkN, stream) : launch_tc<WGRAD, 128, false>(p, grid, N, chunkN, stream);
+    if (bn == 64) return x3 ? launch_tc<WGRAD, 64, true>(p, grid, N, chunkN, stream) : launch_tc<WGRAD, 64, false>(p, grid, N, chunkN, stream);
+    return x3 ? launch_tc<WGRAD, 32, true>(p, grid, N, chunkN, stream) : launch_tc<WGRAD, 32, false>(p, grid, N, chunkN, stream);
+}
+
+}  // namespace bmnas
+
+using namespace bmnas;
+
+extern "C" long long bmnas_wimg_floats(int M, int K, int which) {
+    const long long slab = 2LL * tc::TCM * tc::KC;
+    if (which == 0) return (long long)((M + tc::TCM - 1) / tc::TCM) * ((K + tc::KC - 1) / tc::KC) * slab;
+    return (long long)((K + tc::TCM - 1) / tc::TCM) * ((M + tc::KC - 1) / tc::KC) * slab;
+}
+
+extern "C" int bmnas_wprep(const bmnas_wprep_params* p, void* stream) {
+    if (!p || p->n < 1 || p->n > BMNAS_MAX_PREP) return BMNAS_EINVAL;
+    long long q = 0;
+    for (int i = 0; i < p->n; ++i) {
+        if (p->M[i] < 1 || p->K[i] < 4 || (p->K[i] & 3) || p->n_seg[i] < 1 || p->n_seg[i] > BMNAS_MAX_SEG) return BMNAS_EINVAL;
+        if (p->w_fold[i] != 1 && p->w_fold[i] != 2) return BMNAS_EINVAL;
+        if (!p->img_fwd[i] || !p->img_dgrad[i]) return BMNAS_EINVAL;
+        int m = 0;
+        for (int s = 0; s < p->n_seg[i]; ++s) {
+            if (!p->W[i * BMNAS_MAX_SEG + s] || (reinterpret_cast<uintptr_t>(p->W[i * BMNAS_MAX_SEG + s]) & 15u)) return BMNAS_EINVAL;
+            m += p->seg_M[i * BMNAS_MAX_SEG + s];
+        }
+        if (m != p->M[i]) return BMNAS_EINVAL;
+        if (p->q_start[i] != q) return BMNAS_EINVAL;
+        q += (bmnas_wimg_floats(p->M[i], p->K[i], 0) + bmnas_wimg_floats(p->M[i], p->K[i], 1)) / 8;   // 8 floats (hi+lo) per chunk
+    }
+    if (p->q_start[p->n] != q) return BMNAS_EINVAL;
+    BMNAS_DRY_RETURN();
+    launch_k(tc::k_wprep, (unsigned)((q + 255) / 256), 256, 0, (cudaStream_t)stream, *p);
+    BMNAS_LAUNCH_CHECK();
+    return BMNAS_OK;
+}

@@ -156,6 +156,7 @@ __device__ __forceinline__ void ln_stats(const float* vs, int E, float* red, flo
 
 template <int G>
 __global__ void __launch_bounds__(LTH) k_ln_fwd(const bmnas_ln_params p) {
+    pdl_prologue();
     extern __shared__ __align__(16) float smem[];
     const int E = p.Ctot * p.L;
     float* vs = smem;
@@ -200,6 +201,7 @@ __device__ __forceinline__ void ln_chan_add(float* acc, int m, float v, int lane
 
 template <int G, bool SEG>
 __global__ void __launch_bounds__(LTH) k_ln_bwd(const bmnas_ln_params p) {
+    pdl_prologue();
     extern __shared__ __align__(16) float smem[];
     const int L = p.L, Ctot = p.Ctot, E = Ctot * L, NG = E / G;
     const size_t Er = lrnd4((size_t)E), Cr = lrnd4((size_t)Ctot);
@@ -425,10 +427,10 @@ extern "C" int bmnas_ln_fwd(const bmnas_ln_params* p, void* stream) {
     const int blocks = p->B < kLnMaxBlocksFwd ? p->B : kLnMaxBlocksFwd;
     if (vec) {
         if ((e = ln_smem_attr(k_ln_fwd<4>, smem, &configured[1]))) return e;
-        k_ln_fwd<4><<<blocks, LTH, smem, (cudaStream_t)stream>>>(*p);
+        launch_k(k_ln_fwd<4>, blocks, LTH, smem, (cudaStream_t)stream, *p);
     } else {
         if ((e = ln_smem_attr(k_ln_fwd<1>, smem, &configured[0]))) return e;
-        k_ln_fwd<1><<<blocks, LTH, smem, (cudaStream_t)stream>>>(*p);
+        launch_k(k_ln_fwd<1>, blocks, LTH, smem, (cudaStream_t)stream, *p);
     }
     BMNAS_LAUNCH_CHECK();
     return BMNAS_OK;
@@ -447,13 +449,13 @@ extern "C" int bmnas_ln_bwd(const bmnas_ln_params* p, void* stream) {
     const int blocks = p->B < kLnMaxBlocksBwd ? p->B : kLnMaxBlocksBwd;
     if (vec && seg) {
         if ((e = ln_smem_attr(k_ln_bwd<4, true>, smem, &configured[0]))) return e;
-        k_ln_bwd<4, true><<<blocks, LTH, smem, (cudaStream_t)stream>>>(*p);
+        launch_k(k_ln_bwd<4, true>, blocks, LTH, smem, (cudaStream_t)stream, *p);
     } else if (vec) {
         if ((e = ln_smem_attr(k_ln_bwd<4, false>, smem, &configured[1]))) return e;
-        k_ln_bwd<4, false><<<blocks, LTH, smem, (cudaStream_t)stream>>>(*p);
+        launch_k(k_ln_bwd<4, false>, blocks, LTH, smem, (cudaStream_t)stream, *p);
     } else {
         if ((e = ln_smem_attr(k_ln_bwd<1, false>, smem, &configured[2]))) return e;
-        k_ln_bwd<1, false><<<blocks, LTH, smem, (cudaStream_t)stream>>>(*p);
+        launch_k(k_ln_bwd<1, false>, blocks, LTH, smem, (cudaStream_t)stream, *p);
     }
     BMNAS_LAUNCH_CHECK();
     return BMNAS_OK;

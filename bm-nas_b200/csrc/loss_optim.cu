@@ -9,6 +9,7 @@ constexpr int kLossMaxBlocks = kNumSMs * 2;
 
 // one warp per row (CE) -- row = sample
 __global__ void __launch_bounds__(OTH) k_loss_fwd(const bmnas_loss_params p) {
+    pdl_prologue();
     __shared__ float red[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = OTH / 32;
     const int n = p.n_classes;
@@ -51,6 +52,7 @@ __global__ void __launch_bounds__(OTH) k_loss_fwd(const bmnas_loss_params p) {
 }
 
 __global__ void __launch_bounds__(OTH) k_loss_bwd(const bmnas_loss_params p) {
+    pdl_prologue();
     const long long tot = (long long)p.B * p.n_classes;
     const float sc = p.gscale ? p.gscale[0] : 1.f;
     for (long long i = (long long)blockIdx.x * OTH + threadIdx.x; i < tot; i += (long long)gridDim.x * OTH)
@@ -58,12 +60,14 @@ __global__ void __launch_bounds__(OTH) k_loss_bwd(const bmnas_loss_params p) {
 }
 
 __global__ void __launch_bounds__(OTH) k_bias_rows(float* out, const float* bias, long long tot, int n) {
+    pdl_prologue();
     for (long long i = (long long)blockIdx.x * OTH + threadIdx.x; i < tot; i += (long long)gridDim.x * OTH)
         out[i] = bias ? bias[i % n] : 0.f;
 }
 
 // out[j] = sum_r in[r][j]; one block per column, fixed-order reduction
 __global__ void __launch_bounds__(OTH) k_colsum(float* out, const float* in, int rows, int n) {
+    pdl_prologue();
     __shared__ float red[32];
     const int j = blockIdx.x;
     float s[1] = {0.f};
@@ -73,6 +77,7 @@ __global__ void __launch_bounds__(OTH) k_colsum(float* out, const float* in, int
 }
 
 __global__ void __launch_bounds__(OTH) k_adam(const bmnas_adam_params p) {
+    pdl_prologue();
     __shared__ float s_c[4];
     // locate this block's tensor (block_start is ascending)
     int lo = 0, hi = p.n_tensors - 1;
@@ -113,7 +118,10 @@ __global__ void __launch_bounds__(OTH) k_adam(const bmnas_adam_params p) {
     }
 }
 
-__global__ void k_rng_advance(unsigned long long* st) { st[1] += 1ull; }
+__global__ void k_rng_advance(unsigned long long* st) {
+    pdl_prologue();
+    st[1] += 1ull;
+}
 
 }  // namespace bmnas
 
@@ -139,7 +147,7 @@ extern "C" int bmnas_loss_fwd(const bmnas_loss_params* p, void* stream) {
     BMNAS_DRY_RETURN();
     long long work = p->kind == 0 ? ((long long)p->B + 7) / 8 : ((long long)p->B * p->n_classes + OTH - 1) / OTH;
     int blocks = (int)(work < 1 ? 1 : (work > kLossMaxBlocks ? kLossMaxBlocks : work));
-    k_loss_fwd<<<blocks, OTH, 0, (cudaStream_t)stream>>>(*p);
+    launch_k(k_loss_fwd, blocks, OTH, 0, (cudaStream_t)stream, *p);
     BMNAS_LAUNCH_CHECK();
     return BMNAS_OK;
 }
@@ -147,7 +155,7 @@ extern "C" int bmnas_loss_fwd(const bmnas_loss_params* p, void* stream) {
 extern "C" int bmnas_loss_bwd(const bmnas_loss_params* p, void* stream) {
     if (!p || p->B < 1 || p->n_classes < 1 || !p->glogits || !p->gout_logits) return BMNAS_EINVAL;
     BMNAS_DRY_RETURN();
-    k_loss_bwd<<<grid_for((long long)p->B * p->n_classes), OTH, 0, (cudaStream_t)stream>>>(*p);
+    launch_k(k_loss_bwd, grid_for((long long)p->B * p->n_classes), OTH, 0, (cudaStream_t)stream, *p);
     BMNAS_LAUNCH_CHECK();
     return BMNAS_OK;
 }
@@ -156,7 +164,7 @@ extern "C" int bmnas_bias_rows(float* out, const float* bias, int rows, int n, v
     if (!out || rows < 1 || n < 1) return BMNAS_EINVAL;
     BMNAS_DRY_RETURN();
     const long long tot = (long long)rows * n;
-    k_bias_rows<<<grid_for(tot), OTH, 0, (cudaStream_t)stream>>>(out, bias, tot, n);
+    launch_k(k_bias_rows, grid_for(tot), OTH, 0, (cudaStream_t)stream, out, bias, tot, n);
     BMNAS_LAUNCH_CHECK();
     return BMNAS_OK;
 }
@@ -164,7 +172,7 @@ extern "C" int bmnas_bias_rows(float* out, const float* bias, int rows, int n, v
 extern "C" int bmnas_colsum(float* out, const float* in, int rows, int n, void* stream) {
     if (!out || !in || rows < 1 || n < 1) return BMNAS_EINVAL;
     BMNAS_DRY_RETURN();
-    k_colsum<<<n, OTH, 0, (cudaStream_t)stream>>>(out, in, rows, n);
+    launch_k(k_colsum, n, OTH, 0, (cudaStream_t)stream, out, in, rows, n);
     BMNAS_LAUNCH_CHECK();
     return BMNAS_OK;
 }
@@ -175,7 +183,7 @@ extern "C" int bmnas_adam_step(const bmnas_adam_params* p, void* stream) {
         return BMNAS_EINVAL;
     if (p->total_blocks > 0x7fffffffLL) return BMNAS_EINVAL;
     BMNAS_DRY_RETURN();
-    k_adam<<<(unsigned)p->total_blocks, OTH, 0, (cudaStream_t)stream>>>(*p);
+    launch_k(k_adam, (unsigned)p->total_blocks, OTH, 0, (cudaStream_t)stream, *p);
     BMNAS_LAUNCH_CHECK();
     return BMNAS_OK;
 }
@@ -183,7 +191,7 @@ extern "C" int bmnas_adam_step(const bmnas_adam_params* p, void* stream) {
 extern "C" int bmnas_rng_advance(unsigned long long* rng_state, void* stream) {
     if (!rng_state) return BMNAS_EINVAL;
     BMNAS_DRY_RETURN();
-    k_rng_advance<<<1, 1, 0, (cudaStream_t)stream>>>(rng_state);
+    launch_k(k_rng_advance, 1, 1, 0, (cudaStream_t)stream, rng_state);
     BMNAS_LAUNCH_CHECK();
     return BMNAS_OK;
 }
@@ -198,6 +206,11 @@ extern "C" const char* bmnas_strerror(int code) {
 }
 extern "C" int bmnas_abi_version(void) { return 1; }
 int bmnas_validate_only_flag = 0;
+int bmnas_pdl_flag = 0;
+extern "C" int bmnas_set_pdl(int on) {
+    bmnas_pdl_flag = on ? 1 : 0;
+    return BMNAS_OK;
+}
 extern "C" int bmnas_set_validate_only(int on) {
     bmnas_validate_only_flag = on ? 1 : 0;
     return BMNAS_OK;

@@ -26,6 +26,7 @@ __device__ __forceinline__ void mix_weights(const bmnas_mix_params& p, float* ws
 
 template <int VEC>
 __global__ void __launch_bounds__(kMixThreads) k_mix_fwd(const bmnas_mix_params p) {
+    pdl_prologue();
     __shared__ float ws[BMNAS_MAX_MIX], wn[BMNAS_MAX_MIX];
     mix_weights(p, ws, wn);
     const long long nvec = p.numel / VEC;
@@ -52,6 +53,7 @@ __global__ void __launch_bounds__(kMixThreads) k_mix_fwd(const bmnas_mix_params 
 
 template <int VEC>
 __global__ void __launch_bounds__(kMixThreads) k_mix_bwd(const bmnas_mix_params p) {
+    pdl_prologue();
     __shared__ float ws[BMNAS_MAX_MIX], wn[BMNAS_MAX_MIX];
     __shared__ float red[BMNAS_MAX_MIX * 32];
     mix_weights(p, ws, wn);
@@ -168,9 +170,9 @@ extern "C" int bmnas_mix_fwd(const bmnas_mix_params* p, void* stream) {
     const int vec = mix_vec(p, false);
     const int blocks = mix_blocks(p->numel / vec);
     if (vec == 4)
-        k_mix_fwd<4><<<blocks, kMixThreads, 0, s>>>(*p);
+        launch_k(k_mix_fwd<4>, blocks, kMixThreads, 0, s, *p);
     else
-        k_mix_fwd<1><<<blocks, kMixThreads, 0, s>>>(*p);
+        launch_k(k_mix_fwd<1>, blocks, kMixThreads, 0, s, *p);
     BMNAS_LAUNCH_CHECK();
     return BMNAS_OK;
 }
@@ -185,9 +187,9 @@ extern "C" int bmnas_mix_bwd(const bmnas_mix_params* p, void* stream) {
     const int vec = mix_vec(p, true);
     const int blocks = mix_blocks(p->numel / vec);
     if (vec == 4)
-        k_mix_bwd<4><<<blocks, kMixThreads, 0, s>>>(*p);
+        launch_k(k_mix_bwd<4>, blocks, kMixThreads, 0, s, *p);
     else
-        k_mix_bwd<1><<<blocks, kMixThreads, 0, s>>>(*p);
+        launch_k(k_mix_bwd<1>, blocks, kMixThreads, 0, s, *p);
     BMNAS_LAUNCH_CHECK();
     return BMNAS_OK;
 }

@@ -254,6 +254,7 @@ __device__ __forceinline__ void attn_forward(const bmnas_node_params& p, const N
 
 template <int G>
 __global__ void __launch_bounds__(NTH) k_node_fwd(const bmnas_node_params p) {
+    pdl_prologue();
     extern __shared__ __align__(16) float smem[];
     const int C = p.C, L = p.L, CL = C * L, M = p.M;
     NodeSmem sm = node_carve(smem, C, L, M, false);
@@ -341,6 +342,7 @@ __device__ __forceinline__ void chan_add(float* acc, int m, float v, int lanes, 
 
 template <int G, bool SEG>
 __global__ void __launch_bounds__(NTH) k_node_bwd(const bmnas_node_params p) {
+    pdl_prologue();
     extern __shared__ __align__(16) float smem[];
     const int C = p.C, L = p.L, CL = C * L, M = p.M;
     NodeSmem sm = node_carve(smem, C, L, M, true);
@@ -720,9 +722,9 @@ extern "C" int bmnas_node_fwd(const bmnas_node_params* p, void* stream) {
     if (e) return e;
     const int blocks = p->B < kNodeMaxBlocksFwd ? p->B : kNodeMaxBlocksFwd;
     if (vec)
-        k_node_fwd<4><<<blocks, NTH, smem, (cudaStream_t)stream>>>(*p);
+        launch_k(k_node_fwd<4>, blocks, NTH, smem, (cudaStream_t)stream, *p);
     else
-        k_node_fwd<1><<<blocks, NTH, smem, (cudaStream_t)stream>>>(*p);
+        launch_k(k_node_fwd<1>, blocks, NTH, smem, (cudaStream_t)stream, *p);
     BMNAS_LAUNCH_CHECK();
     return BMNAS_OK;
 }
@@ -740,13 +742,13 @@ extern "C" int bmnas_node_bwd(const bmnas_node_params* p, void* stream) {
     const int blocks = p->B < kNodeMaxBlocksBwd ? p->B : kNodeMaxBlocksBwd;
     if (vec && seg) {
         if ((e = node_smem_attr(k_node_bwd<4, true>, smem, &configured[0]))) return e;
-        k_node_bwd<4, true><<<blocks, NTH, smem, (cudaStream_t)stream>>>(*p);
+        launch_k(k_node_bwd<4, true>, blocks, NTH, smem, (cudaStream_t)stream, *p);
     } else if (vec) {
         if ((e = node_smem_attr(k_node_bwd<4, false>, smem, &configured[1]))) return e;
-        k_node_bwd<4, false><<<blocks, NTH, smem, (cudaStream_t)stream>>>(*p);
+        launch_k(k_node_bwd<4, false>, blocks, NTH, smem, (cudaStream_t)stream, *p);
     } else {
         if ((e = node_smem_attr(k_node_bwd<1, false>, smem, &configured[2]))) return e;
-        k_node_bwd<1, false><<<blocks, NTH, smem, (cudaStream_t)stream>>>(*p);
+        launch_k(k_node_bwd<1, false>, blocks, NTH, smem, (cudaStream_t)stream, *p);
     }
     BMNAS_LAUNCH_CHECK();
     return BMNAS_OK;

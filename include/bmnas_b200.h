@@ -33,6 +33,9 @@ extern "C" {
 #define BMNAS_MAX_SRC 4  /* tensors in a virtual channel concat               */
 #define BMNAS_MAX_SEG 4  /* stacked output-channel segments of one conv GEMM  */
 #define BMNAS_MAX_OPS 8  /* candidate primitives of one NodeMixedOp           */
+#define BMNAS_MAX_PREP 16     /* convs per bmnas_wprep launch                  */
+#define BMNAS_MAX_PREP_SEG 64 /* BMNAS_MAX_PREP * BMNAS_MAX_SEG                */
+#define BMNAS_MAX_PREP_P1 17  /* BMNAS_MAX_PREP + 1                            */
 
 #define BMNAS_OK 0
 #define BMNAS_EINVAL -1   /* bad shape / unsupported size / null pointer */
@@ -130,12 +133,43 @@ typedef struct bmnas_conv_params {
     int gsrc_accum[BMNAS_MAX_SRC];
     float* gW[BMNAS_MAX_SEG];
     float* gbias[BMNAS_MAX_SEG];
+    const float* wimg_fwd;
+    const float* wimg_dgrad;
 } bmnas_conv_params;
+/* wimg_fwd / wimg_dgrad (optional): tensor-core-ready images of the stacked, folded weight produced by
+ * bmnas_wprep (below).  When present the tcgen05 GEMMs fetch the weight operand with TMA bulk copies instead
+ * of staging it through registers; they must be refreshed (bmnas_wprep) whenever W changes. */
 int bmnas_conv_fwd(const bmnas_conv_params* p, void* stream);
 int bmnas_conv_dgrad(const bmnas_conv_params* p, void* stream);
 int bmnas_conv_wgrad(const bmnas_conv_params* p, void* stream);
 long long bmnas_conv_stat_part_size(const bmnas_conv_params* p); /* floats  */
 int bmnas_conv_num_counters(const bmnas_conv_params* p);         /* uints   */
+
+/* ------------------------------------------------------------------------
+ * Weight images for the tcgen05 GEMMs: for each of n convs (conv i: stacked segments
+ * W[i*BMNAS_MAX_SEG + s] of seg_M[...] rows, w_fold*K columns) write
+ *   img_fwd[i]   rows m, reduction k   (bmnas_wimg_floats(M, K, 0) floats)
+ *   img_dgrad[i] rows k, reduction m   (bmnas_wimg_floats(M, K, 1) floats)
+ * of Weff[m,k] = sum_f W[m, f*K + k], split into tf32 hi / lo parts, zero padded to 128-row x 32-element
+ * slabs and stored slab by slab as the K-major core-matrix shared-memory picture the MMA descriptors read.
+ * q_start is the exclusive prefix sum of (floats_fwd + floats_dgrad) / 8 over the convs (n + 1 entries).
+ * One launch per forward replaces the per-CTA fold / transpose / split of the weights
+ * (torch.cat([x, x]) + nn.Conv1d weight use in node_operations.py:30-34, 49-53, node_search.py:59-62).
+ * ---------------------------------------------------------------------- */
+typedef struct bmnas_wprep_params {
+    int n;
+    int M[BMNAS_MAX_PREP];
+    int K[BMNAS_MAX_PREP];
+    int w_fold[BMNAS_MAX_PREP];
+    int n_seg[BMNAS_MAX_PREP];
+    int seg_M[BMNAS_MAX_PREP_SEG];
+    const float* W[BMNAS_MAX_PREP_SEG];
+    float* img_fwd[BMNAS_MAX_PREP];
+    float* img_dgrad[BMNAS_MAX_PREP];
+    long long q_start[BMNAS_MAX_PREP_P1];
+} bmnas_wprep_params;
+int bmnas_wprep(const bmnas_wprep_params* p, void* stream);
+long long bmnas_wimg_floats(int M, int K, int which);
 
 /* ------------------------------------------------------------------------
  * Step-node mixed op: out = sum_k gamma~_k * op_k(x, y), evaluated per sample
@@ -324,6 +358,18 @@ int bmnas_sizeof_params(int which); /* 0 mix, 1 conv, 2 node, 3 ln, 4 loss, 5 ad
 /* validate-only mode: every entry point checks its parameter block and returns before launching
  * (lets host-side logic and bindings be tested on a machine without a GPU). */
 int bmnas_set_validate_only(int on);
+
+/* GEMM engine behind bmnas_conv_*: 0 = fp32 FFMA tiles, 1 = tcgen05 tensor cores with 3xTF32 operand
+ * splitting (fp32-class accuracy; default), 2 = tcgen05 single-pass TF32 (reduced precision).  Shapes the
+ * tensor-core path cannot take (L, K or a concat width not a multiple of 4, unaligned tensors) use mode 0. */
+int bmnas_set_gemm_mode(int mode);
+int bmnas_get_gemm_mode(void);
+
+/* programmatic dependent launch (off by default; measured slower on the B=96 step): every kernel is launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization and opens with griddepcontrol.launch_dependents +
+ * griddepcontrol.wait, so consecutive kernels overlap launch latency and prologue without changing any
+ * data dependency; under stream capture the attribute becomes a programmatic graph edge. */
+int bmnas_set_pdl(int on);
 
 /* rng_state = {seed, step}: advance the step counter on-device (one launch per search step) */
 int bmnas_rng_advance(unsigned long long* rng_state, void* stream);

@@ -1,0 +1,190 @@
+"""-m gpu: the conv GEMM family (bmnas_conv_fwd / dgrad / wgrad) through the C ABI, every GEMM engine
+(0 = fp32 FFMA, 1 = tcgen05 3xTF32, 2 = tcgen05 1xTF32) against a float64 torch restatement of
+  Z = Weff (x) cat(src) + bias  with train-mode BatchNorm statistics   (node_operations.py:30-34, 49-53)
+and its two backward GEMMs with BatchNorm-backward folded into the operand (dz = a*GV + b*Z + c).
+Tolerances: engines 0 and 1 are the fp32-parity engines (1e-5 of the tensor's max, the north_star fp32 gate);
+engine 2 is the reduced-precision engine (2e-2 class, north_star's bf16 gate; TF32 lands near 1e-3)."""
+import ctypes
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = {0: 1e-5, 1: 1e-5, 2: 5e-3}
+
+
+def _lib():
+    from bmnas import native as N
+    return N, N.lib()
+
+
+def _conv_case(B, L, src_C, seg_M, w_fold, seed, dev):
+    g = torch.Generator().manual_seed(seed)
+    K = sum(src_C)
+    srcs = [torch.randn(B, c, L, generator=g).to(dev) for c in src_C]
+    Ws = [(torch.randn(m, w_fold * K, generator=g) / (w_fold * K) ** 0.5).to(dev) for m in seg_M]
+    bias = [torch.randn(m, generator=g).to(dev) for m in seg_M]
+    return srcs, Ws, bias
+
+
+def _ref_fwd(srcs, Ws, bias, w_fold):
+    U = torch.cat([s.double() for s in srcs], 1)                       # (B, K, L)
+    K = U.shape[1]
+    W = torch.cat([w.double() for w in Ws], 0)
+    Weff = W[:, :K] + (W[:, K:] if w_fold == 2 else 0)
+    Z = torch.einsum('mk,bkl->bml', Weff, U) + torch.cat([b.double() for b in bias])[None, :, None]
+    mean = Z.mean(dim=(0, 2))
+    var = Z.var(dim=(0, 2), unbiased=False)
+    return Z, mean, 1.0 / torch.sqrt(var + 1e-5), Weff, U
+
+
+def _params(N, B, L, src_C, seg_M, w_fold, srcs, Ws):
+    st = N.bmnas_conv_params()
+    st.B, st.L, st.K, st.w_fold, st.n_src, st.n_seg, st.M = B, L, sum(src_C), w_fold, len(src_C), len(seg_M), sum(seg_M)
+    st.momentum, st.eps = 0.1, 1e-5
+    for i, (s, c) in enumerate(zip(srcs, src_C)):
+        st.src[i] = s.data_ptr()
+        st.src_C[i] = c
+    for i, (w, m) in enumerate(zip(Ws, seg_M)):
+        st.W[i] = w.data_ptr()
+        st.seg_M[i] = m
+    return st
+
+
+def _images(N, lib, Ws, seg_M, K, w_fold, dev):
+    """tensor-core-ready weight images through bmnas_wprep (TMA-fed weight operand of the tcgen05 GEMMs)"""
+    M = sum(seg_M)
+    img_f = torch.full((int(lib.bmnas_wimg_floats(M, K, 0)),), float('nan'), device=dev)
+    img_d = torch.full((int(lib.bmnas_wimg_floats(M, K, 1)),), float('nan'), device=dev)
+    st = N.bmnas_wprep_params()
+    st.n = 1
+    st.M[0], st.K[0], st.w_fold[0], st.n_seg[0] = M, K, w_fold, len(seg_M)
+    for j, (w, m) in enumerate(zip(Ws, seg_M)):
+        st.seg_M[j] = m
+        st.W[j] = w.data_ptr()
+    st.img_fwd[0], st.img_dgrad[0] = img_f.data_ptr(), img_d.data_ptr()
+    st.q_start[0], st.q_start[1] = 0, (img_f.numel() + img_d.numel()) // 8
+    N.launch('bmnas_wprep', ctypes.byref(st), N.current_stream())
+    return img_f, img_d
+
+
+CASES = [
+    # B, L, src_C, seg_M, w_fold      (NTU node conv, NTU out_conv, MM-IMDB node conv, ragged sizes)
+    (96, 8, [128], [256, 128], 2),
+    (96, 8, [128, 128], [128], 1),
+    (32, 16, [192], [384, 192], 2),
+    (5, 8, [24, 40], [72], 1),
+    (7, 4, [36], [20, 44], 2),
+    (300, 8, [128], [256, 128], 2),
+]
+
+
+def _rel(a, b):
+    return ((a.double() - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize('mode,img', [(0, False), (1, False), (2, False), (1, True), (2, True)])
+@pytest.mark.parametrize('case', range(len(CASES)))
+def test_conv_fwd_engines(mode, img, case):
+    N, lib = _lib()
+    dev = torch.device('cuda:0')
+    B, L, src_C, seg_M, w_fold = CASES[case]
+    srcs, Ws, bias = _conv_case(B, L, src_C, seg_M, w_fold, 10 + case, dev)
+    M = sum(seg_M)
+    st = _params(N, B, L, src_C, seg_M, w_fold, srcs, Ws)
+    Z = torch.full((B, M, L), float('nan'), device=dev)
+    mean, rstd = torch.zeros(M, device=dev), torch.zeros(M, device=dev)
+    rm = [torch.zeros(m, device=dev) for m in seg_M]
+    rv = [torch.ones(m, device=dev) for m in seg_M]
+    nbt = [torch.zeros((), dtype=torch.int64, device=dev) for _ in seg_M]
+    st.bn_mode = 1
+    for i in range(len(seg_M)):
+        st.bias[i] = bias[i].data_ptr()
+        st.running_mean[i], st.running_var[i], st.num_batches_tracked[i] = rm[i].data_ptr(), rv[i].data_ptr(), nbt[i].data_ptr()
+    part = torch.zeros(int(lib.bmnas_conv_stat_part_size(ctypes.byref(st))), device=dev)
+    cnt = torch.zeros(int(lib.bmnas_conv_num_counters(ctypes.byref(st))), dtype=torch.int32, device=dev)
+    st.Z, st.mean, st.rstd, st.stat_part, st.counter = Z.data_ptr(), mean.data_ptr(), rstd.data_ptr(), part.data_ptr(), cnt.data_ptr()
+    if img:
+        imgs = _images(N, lib, Ws, seg_M, sum(src_C), w_fold, dev)
+        st.wimg_fwd = imgs[0].data_ptr()
+    old = lib.bmnas_get_gemm_mode()
+    try:
+        lib.bmnas_set_gemm_mode(mode)
+        for _ in range(2):      # twice: the self-cleaning counters must be back at zero
+            N.launch('bmnas_conv_fwd', ctypes.byref(st), N.current_stream())
+        torch.cuda.synchronize()
+    finally:
+        lib.bmnas_set_gemm_mode(old)
+    Zr, mr, rr, _, _ = _ref_fwd(srcs, Ws, bias, w_fold)
+    tol = TOL[mode]
+    assert _rel(Z, Zr) < tol, ('Z', _rel(Z, Zr))
+    assert _rel(mean, mr) < max(tol, 2e-6) * 10 or (mean.double() - mr).abs().max() < tol
+    assert _rel(rstd, rr) < tol * 10
+    assert int(cnt.abs().sum()) == 0
+    assert all(int(n) == 2 for n in nbt)
+    nn_ = B * L
+    unb = (Zr.var(dim=(0, 2), unbiased=False) * nn_ / max(nn_ - 1, 1))
+    rv_ref = 0.9 * (0.9 * 1.0 + 0.1 * unb) + 0.1 * unb
+    assert _rel(torch.cat(rv), rv_ref) < tol * 10
+
+
+@pytest.mark.parametrize('mode,img', [(0, False), (1, False), (2, False), (1, True), (2, True)])
+@pytest.mark.parametrize('case', range(len(CASES)))
+@pytest.mark.parametrize('coef', [False, True])
+def test_conv_backward_engines(mode, img, case, coef):
+    N, lib = _lib()
+    dev = torch.device('cuda:0')
+    B, L, src_C, seg_M, w_fold = CASES[case]
+    srcs, Ws, bias = _conv_case(B, L, src_C, seg_M, w_fold, 40 + case, dev)
+    M, K = sum(seg_M), sum(src_C)
+    g = torch.Generator().manual_seed(70 + case)
+    GV = torch.randn(B, M, L, generator=g).to(dev)
+    Zt = torch.randn(B, M, L, generator=g).to(dev)
+    ca, cb, cc = (torch.randn(M, generator=g).to(dev) for _ in range(3))
+    dz = GV.double()
+    if coef:
+        dz = ca.double()[None, :, None] * GV.double() + cb.double()[None, :, None] * Zt.double() + cc.double()[None, :, None]
+    _, _, _, Weff, U = _ref_fwd(srcs, Ws, bias, w_fold)
+    dU = torch.einsum('mk,bml->bkl', Weff, dz)
+    dW = torch.einsum('bml,bkl->mk', dz, U)
+    db = dz.sum(dim=(0, 2))
+    tol = TOL[mode]
+    old = lib.bmnas_get_gemm_mode()
+    try:
+        lib.bmnas_set_gemm_mode(mode)
+        # ---- dgrad (first source overwritten, later ones accumulated onto a known value)
+        st = _params(N, B, L, src_C, seg_M, w_fold, srcs, Ws)
+        st.GV, st.Z = GV.data_ptr(), Zt.data_ptr()
+        if coef:
+            st.coef_a, st.coef_b, st.coef_c = ca.data_ptr(), cb.data_ptr(), cc.data_ptr()
+        if img:
+            imgs = _images(N, lib, Ws, seg_M, K, w_fold, dev)
+            st.wimg_dgrad = imgs[1].data_ptr()
+        gs = [torch.full((B, c, L), 0.5, device=dev) for c in src_C]
+        for i in range(len(src_C)):
+            st.gsrc[i] = gs[i].data_ptr()
+            st.gsrc_accum[i] = 1 if i > 0 else 0
+        N.launch('bmnas_conv_dgrad', ctypes.byref(st), N.current_stream())
+        # ---- wgrad (atomically accumulated onto zeros)
+        sw = _params(N, B, L, src_C, seg_M, w_fold, srcs, Ws)
+        sw.GV, sw.Z = GV.data_ptr(), Zt.data_ptr()
+        if coef:
+            sw.coef_a, sw.coef_b, sw.coef_c = ca.data_ptr(), cb.data_ptr(), cc.data_ptr()
+        gW = [torch.zeros(m, w_fold * K, device=dev) for m in seg_M]
+        gb = [torch.zeros(m, device=dev) for m in seg_M]
+        for i in range(len(seg_M)):
+            sw.gW[i], sw.gbias[i] = gW[i].data_ptr(), gb[i].data_ptr()
+        N.launch('bmnas_conv_wgrad', ctypes.byref(sw), N.current_stream())
+        torch.cuda.synchronize()
+    finally:
+        lib.bmnas_set_gemm_mode(old)
+    off = 0
+    for i, c in enumerate(src_C):
+        ref = dU[:, off:off + c] + (0.5 if i > 0 else 0.0)
+        assert _rel(gs[i], ref) < tol, ('dgrad', i, _rel(gs[i], ref))
+        off += c
+    dWc = torch.cat(gW, 0).double()
+    for f in range(w_fold):
+        assert _rel(dWc[:, f * K:(f + 1) * K], dW) < tol * 4, ('wgrad', f, _rel(dWc[:, f * K:(f + 1) * K], dW))
+    assert _rel(torch.cat(gb), db) < tol * 4, ('bias', _rel(torch.cat(gb), db))
