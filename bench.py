@@ -151,26 +151,43 @@ def make_pool(c, n_batches, seed, device, pinned=False):
     return pool
 
 
+def graph_time_us(call, R=50, reps=4):
+    """device time per launch of one prepared C-ABI call: R launches captured into a CUDA graph and replayed
+    (CUDA events on the replay stream; no host launch overhead inside the number)"""
+    import ctypes
+    side = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        sp = ctypes.c_void_p(side.cuda_stream)
+        for _ in range(3):
+            call(sp)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=side):
+            sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            for _ in range(R):
+                call(sp)
+    torch.cuda.current_stream().wait_stream(side)
+    g.replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / (reps * R)
+
+
 def kernel_roofline(head, ss, c, pk):
     """average duration of the dominant fused MixedOp kernels (bmnas_node_fwd / bmnas_node_bwd), timed live with
-    CUDA events around R back-to-back launches of the prepared parameter blocks on the launching stream."""
+    CUDA events around graph-replayed back-to-back launches of the prepared parameter blocks."""
     from bmnas import native as N
     runner = [r for r in head.fusion_net._bm_cache.values() if r.prog.training][0]
     prog = runner.prog
-    s = N.current_stream()
     res = {}
-    R = 200
     for name, calls in (('bmnas_node_fwd', prog.fwd), ('bmnas_node_bwd', prog.bwd)):
         call = [x for x in calls if x.name == name][0]
-        for _ in range(20):
-            call(s)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(R):
-            call(s)
-        e1.record()
-        torch.cuda.synchronize()
-        res[name] = e0.elapsed_time(e1) * 1e3 / R      # us per launch
+        res[name] = graph_time_us(call)                # us per launch
     T1 = c['C'] * c['L'] * 4
     M = 3 * c['C']
     # algorithmic bytes per sample of the fused node kernel (DESIGN.md): x (aliased with y) + Z (3C rows) in, out
@@ -184,28 +201,21 @@ def kernel_roofline(head, ss, c, pk):
             'note': 'B=%d working set is L2-resident and the kernel is latency-bound at this size; see DESIGN.md' % c['B']}
 
 
-def profile_kernels(head, R=100):
-    """warm per-launch time of every prepared call of the training plan (back-to-back replays, CUDA events)"""
+def profile_kernels(head, R=50):
+    """device time of every prepared call of the training plan: R back-to-back launches of the SAME call captured
+    into one CUDA graph and replayed (no host launch overhead in the number; stream launches through ctypes are
+    host-bound at ~3 us and hide anything shorter)"""
     from bmnas import native as N
     import ctypes
     runner = [r for r in head.fusion_net._bm_cache.values() if r.prog.training][0]
     prog = runner.prog
-    s = N.current_stream()
     rows = []
     for phase, calls in (('fwd', prog.fwd), ('bwd', prog.bwd)):
         for i, call in enumerate(calls):
-            for _ in range(5):
-                call(s)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(R):
-                call(s)
-            e1.record()
-            torch.cuda.synchronize()
             st = call.st
             dims = {k: getattr(st, k) for k in ('B', 'L', 'K', 'M', 'C', 'n', 'Ctot', 'n_src', 'w_fold', 'mode', 'n_ops')
                     if hasattr(st, k)}
-            rows.append((phase, i, call.name, round(e0.elapsed_time(e1) * 1e3 / R, 2), dims))
+            rows.append((phase, i, call.name, round(graph_time_us(call), 2), dims))
     return rows
 
 

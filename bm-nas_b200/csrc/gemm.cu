@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(GT, 1) k_conv_fwd(const bmnas_conv_params p, c
     if (p.bn_mode != 1) return;
     // ---- last CTA of this row-tile merges the per-column-tile statistics (Chan), fixed order
     if (!last_block(p.counter + blockIdx.y, gridDim.x)) return;
-    bn_finalize_rows(p, N, n_col_tiles, TN, m0, TM, ldw);
+    bn_finalize_rows(p, N, n_col_tiles, [=](int t) { return min(TN, N - t * TN); }, m0, TM, ldw);
 }
 
 // ------------------------------------------------------------------ dgrad

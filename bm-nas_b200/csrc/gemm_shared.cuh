@@ -40,9 +40,9 @@ __device__ __forceinline__ Wf wf_merge(Wf a, Wf b) {
         r.m2 = 0.f;
         return r;
     }
-    const float d = b.mean - a.mean;
-    r.mean = a.mean + d * (b.n / r.n);
-    r.m2 = a.m2 + b.m2 + d * d * (a.n * b.n / r.n);
+    const float d = b.mean - a.mean, inv = 1.f / r.n;
+    r.mean = a.mean + d * (b.n * inv);
+    r.m2 = a.m2 + b.m2 + d * d * (a.n * b.n * inv);
     return r;
 }
 
@@ -74,59 +74,70 @@ __device__ __forceinline__ void bn_eval_stats(const bmnas_conv_params& p, int m,
     p.rstd[m] = 1.f / sqrtf(p.running_var[s][ml] + p.eps);
 }
 
-// Train-mode BatchNorm finalize for rows [m0, m0+rows): merge the per-column-tile (mean, M2) partials in
-// stat_part (tile width tile_w columns, Chan's parallel update in a fixed order: 8 lanes per row walk
-// interleaved tiles, then a lane-symmetric butterfly), write mean / rstd, update the running statistics
-// (momentum, unbiased variance) and num_batches_tracked.  Called by every thread of ONE CTA (>= 256 threads
-// used as 32 rows x 8 lanes per pass).
-__device__ __forceinline__ void bn_finalize_rows(const bmnas_conv_params& p, int N, int n_col_tiles, int tile_w, int m0,
+// Train-mode BatchNorm finalize for rows [m0, m0+rows): merge the per-CTA (mean, M2) partials in stat_part
+// ([part][M][2]; part t covers cnt_of(t) columns) with Chan's parallel update in a fixed order, write
+// mean / rstd, update the running statistics (momentum, unbiased variance) and num_batches_tracked.
+// Called by every thread of ONE CTA.  All rows are handled in ONE pass: blockDim.x / rows lanes per row walk
+// interleaved partials (12 independent loads in flight per lane) and finish with a lane-symmetric butterfly,
+// and the running statistics are fetched while the partials are still in flight.
+template <class CntFn>
+__device__ __forceinline__ void bn_finalize_rows(const bmnas_conv_params& p, int N, int n_parts, CntFn cnt_of, int m0,
                                                  int rows, int ldw) {
     const int tid = threadIdx.x;
     const int M = p.M;
-    for (int rb = 0; rb < rows; rb += 32) {
-        const int r = tid >> 3, q = tid & 7;
-        const int m = m0 + rb + r;
-        if (r >= 32) continue;
-        Wf w = {0.f, 0.f, 0.f};
-        if (m < M) {
-            for (int t0 = q; t0 < n_col_tiles; t0 += 8 * 4) {   // 4 independent loads in flight per lane
-                float2 v[4];
+    int tpr = (int)blockDim.x / rows;            // lanes per row: power of two, <= 32 (256 / 128 = 2, 256 / 32 = 8)
+    if (tpr > 32) tpr = 32;
+    const int r = tid / tpr, q = tid - r * tpr;
+    const int m = m0 + r;
+    const bool ok = r < rows && m < M;
+    int s = 0, ml = 0;
+    float rm_old = 0.f, rv_old = 0.f;
+    bool has_run = false;
+    if (ok && q == 0) {
+        w_row(p, m, ldw, &s, &ml);
+        has_run = p.running_mean[s] != nullptr;
+        if (has_run) {
+            rm_old = __ldcg(p.running_mean[s] + ml);
+            rv_old = __ldcg(p.running_var[s] + ml);
+        }
+    }
+    Wf w = {0.f, 0.f, 0.f};
+    if (ok) {
+        constexpr int FB = 12;                   // independent loads in flight per lane
+        for (int t0 = q; t0 < n_parts; t0 += tpr * FB) {
+            float2 v[FB];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int tix = t0 + 8 * j;
-                    v[j] = tix < n_col_tiles ? __ldcg(reinterpret_cast<const float2*>(p.stat_part + ((long long)tix * M + m) * 2))
-                                             : make_float2(0.f, 0.f);
-                }
+            for (int j = 0; j < FB; ++j) {
+                const int tix = t0 + tpr * j;
+                v[j] = tix < n_parts ? __ldcg(reinterpret_cast<const float2*>(p.stat_part + ((long long)tix * M + m) * 2))
+                                     : make_float2(0.f, 0.f);
+            }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int tix = t0 + 8 * j;
-                    if (tix < n_col_tiles) {
-                        Wf b = {(float)min(tile_w, N - tix * tile_w), v[j].x, v[j].y};
-                        w = wf_merge(w, b);
-                    }
+            for (int j = 0; j < FB; ++j) {
+                const int tix = t0 + tpr * j;
+                if (tix < n_parts) {
+                    Wf b = {(float)cnt_of(tix), v[j].x, v[j].y};
+                    w = wf_merge(w, b);
                 }
             }
         }
-#pragma unroll
-        for (int o = 1; o <= 4; o <<= 1) {
-            Wf b;
-            b.n = __shfl_xor_sync(0xffffffffu, w.n, o);
-            b.mean = __shfl_xor_sync(0xffffffffu, w.mean, o);
-            b.m2 = __shfl_xor_sync(0xffffffffu, w.m2, o);
-            w = ((q & o) == 0) ? wf_merge(w, b) : wf_merge(b, w);  // same operand order in both lanes
-        }
-        if (q == 0 && m < M) {
-            const float var = w.m2 / (float)N;
-            p.mean[m] = w.mean;
-            p.rstd[m] = 1.f / sqrtf(var + p.eps);
-            int s, ml;
-            w_row(p, m, ldw, &s, &ml);
-            if (p.running_mean[s]) {
-                const float unb = w.m2 / (float)max(N - 1, 1);
-                p.running_mean[s][ml] = (1.f - p.momentum) * p.running_mean[s][ml] + p.momentum * w.mean;
-                p.running_var[s][ml] = (1.f - p.momentum) * p.running_var[s][ml] + p.momentum * unb;
-                if (ml == 0 && p.num_batches_tracked[s]) *p.num_batches_tracked[s] += 1;
-            }
+    }
+    for (int o = 1; o < tpr; o <<= 1) {
+        Wf b;
+        b.n = __shfl_xor_sync(0xffffffffu, w.n, o);
+        b.mean = __shfl_xor_sync(0xffffffffu, w.mean, o);
+        b.m2 = __shfl_xor_sync(0xffffffffu, w.m2, o);
+        w = ((q & o) == 0) ? wf_merge(w, b) : wf_merge(b, w);  // same operand order in both lanes
+    }
+    if (ok && q == 0) {
+        const float var = w.m2 / (float)N;
+        p.mean[m] = w.mean;
+        p.rstd[m] = 1.f / sqrtf(var + p.eps);
+        if (has_run) {
+            const float unb = w.m2 / (float)max(N - 1, 1);
+            p.running_mean[s][ml] = (1.f - p.momentum) * rm_old + p.momentum * w.mean;
+            p.running_var[s][ml] = (1.f - p.momentum) * rv_old + p.momentum * unb;
+            if (ml == 0 && p.num_batches_tracked[s]) *p.num_batches_tracked[s] += 1;
         }
     }
 }

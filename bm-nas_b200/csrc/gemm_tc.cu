@@ -28,6 +28,23 @@
 #include "common.cuh"
 #include "gemm_shared.cuh"
 
+#ifdef BMNAS_TIMELINE
+__device__ unsigned long long g_tl[64];
+#define TL(i)                                                                                       \
+    do {                                                                                            \
+        if (blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) { \
+            unsigned long long t__;                                                                 \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                                 \
+            g_tl[MODE * 20 + (i)] = t__;                                                            \
+        }                                                                                           \
+    } while (0)
+extern "C" int bmnas_debug_timeline(unsigned long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, g_tl, sizeof(g_tl));
+}
+#else
+#define TL(i)
+#endif
+
 namespace bmnas {
 namespace tc {
 
@@ -152,6 +169,7 @@ struct Smem {
 // --------------------------------------------------------------------------------------------------
 template <int MODE, int BN, bool X3>
 __global__ void __launch_bounds__(TCT, 1) k_gemm_tc(const bmnas_conv_params p, const int N, const int aux) {
+    TL(0);
     pdl_prologue();
     using S = Smem<BN, X3>;
     constexpr int NST = S::NST;
@@ -180,6 +198,7 @@ __global__ void __launch_bounds__(TCT, 1) k_gemm_tc(const bmnas_conv_params p, c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = tmem_base_s;
+    TL(1);
 
     const int row0 = blockIdx.y * TCM;
     const int col0 = blockIdx.x * BN;
@@ -375,6 +394,7 @@ __global__ void __launch_bounds__(TCT, 1) k_gemm_tc(const bmnas_conv_params p, c
     // ---- main loop: stage slab c, then one thread issues its MMAs; slab c+1's loads are already in flight
     constexpr uint32_t IDESC = idesc_tf32(TCM, BN);
     if (n_chunks > 0) load_stage(r_beg);
+    TL(2);
     for (int c = 0; c < n_chunks; ++c) {
         const int stage = c % NST;
         if (c >= NST) mbar_wait(&bar_free[stage], (uint32_t)((c / NST) - 1) & 1u);   // MMAs that read this slot are done
@@ -386,11 +406,14 @@ __global__ void __launch_bounds__(TCT, 1) k_gemm_tc(const bmnas_conv_params p, c
             }
         }
         store_stage(stage, r_beg + c * KC);
+        if (c == 0) TL(3);
         if (c + 1 < n_chunks) load_stage(r_beg + (c + 1) * KC);
         fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor-core (async) proxy
         __syncthreads();
+        if (c == 0) TL(4);
         if (tid == 0) {
             if (use_img) mbar_wait(&bar_full[stage], (uint32_t)(c / NST) & 1u);      // weight slab has landed
+            if (c == 0) TL(5);
             tc_fence_after();
             const uint32_t base = s32(smem + (size_t)stage * S::STAGE);
             const uint32_t a_hi = base, a_lo = base + S::A_BYTES;
@@ -414,8 +437,10 @@ __global__ void __launch_bounds__(TCT, 1) k_gemm_tc(const bmnas_conv_params p, c
 
     // ---- epilogue: TMEM -> registers; thread t of warp w owns accumulator row (w & 3) * 32 + t and the
     //      column half (w >> 2)
+    TL(6);
     if (n_chunks > 0) mbar_wait(bar_done, 0u);
     tc_fence_after();
+    TL(7);
     const int row = (warp & 3) * 32 + lane;
     const int half = warp >> 2;
     constexpr int HC = BN / 2;                           // columns per thread
@@ -527,8 +552,10 @@ __global__ void __launch_bounds__(TCT, 1) k_gemm_tc(const bmnas_conv_params p, c
     }
 
     // ---- teardown (+ FWD: BatchNorm statistics finalize by the last CTA of this row tile)
+    TL(8);
     tc_fence_before();
     __syncthreads();
+    TL(9);
     if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);
     if (MODE == FWD) {
         if (p.bn_mode == 2) {
@@ -536,9 +563,402 @@ __global__ void __launch_bounds__(TCT, 1) k_gemm_tc(const bmnas_conv_params p, c
             return;
         }
         if (p.bn_mode != 1) return;
-        if (!last_block(p.counter + blockIdx.y, gridDim.x)) return;
-        bn_finalize_rows(p, N, aux /* n_col_tiles */, BN, row0, TCM, ldw);
+        TL(10);
+        const bool lastb = last_block(p.counter + blockIdx.y, gridDim.x);
+        TL(11);
+        if (!lastb) return;
+        bn_finalize_rows(p, N, aux /* n_col_tiles */, [=](int t) { return min(BN, N - t * BN); }, row0, TCM, ldw);
+        if (threadIdx.x == 0) {
+#ifdef BMNAS_TIMELINE
+            unsigned long long t__;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));
+            g_tl[MODE * 20 + 12] = t__;
+#endif
+        }
     }
+}
+
+// --------------------------------------------------------------------------------------------------
+// Panel kernel (FWD / DGRAD when bmnas_wprep images exist): the design for short reductions.
+//   * persistent over column tiles: CTA (x, y) owns row tile y and column tiles x, x+gridDim.x, ...; the TMEM
+//     allocation, barriers and (FWD) the running BatchNorm statistics of its rows live across tiles, so the
+//     number of statistics partials is gridDim.x, not the number of column tiles;
+//   * the ACTIVATION operand of a whole tile (all reduction chunks = one "panel") is staged in ONE burst:
+//     every thread issues all its 128-bit loads (4 reduction rows x 4 columns per block) before the first
+//     dependent instruction, transposes 4x4 in registers, applies BatchNorm-backward (DGRAD), splits hi/lo
+//     and writes K-major core matrices with a lane rotation that keeps the 128-bit shared stores conflict
+//     free -- one global round trip per tile instead of one per 32-element chunk;
+//   * the WEIGHT operand arrives by TMA bulk copies issued by the same elected thread that issues the MMAs,
+//     NSTA slabs ahead; when the whole reduction fits in the ring (K_red <= 32*NSTA) the weights are loaded
+//     once per CTA and stay resident across column tiles;
+//   * no block-wide barrier inside the reduction: one __syncthreads after staging, tcgen05.commit -> mbarrier
+//     for everything else.
+// --------------------------------------------------------------------------------------------------
+template <int BN, bool X3>
+struct PSmem {
+    static constexpr uint32_t A_ST = (X3 ? 2u : 1u) * TCM * KC * 4;   // one weight slab in the ring: [hi | lo]
+    static constexpr uint32_t B_HALF = BN * KC * 4;                    // one activation chunk, hi or lo
+    static constexpr uint32_t B_CH = (X3 ? 2u : 1u) * B_HALF;
+    static constexpr uint32_t SBO = (KC / 4) * 128, LBO = 128;
+};
+
+template <int MODE, int BN, bool X3>
+__global__ void __launch_bounds__(TCT, 1) k_gemm_panel(const bmnas_conv_params p, const int N, const int n_col_tiles,
+                                                        const int nsta, const int pcap) {
+    TL(0);
+    pdl_prologue();
+    using S = PSmem<BN, X3>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smA = smem;
+    uint8_t* smB = smem + (size_t)nsta * S::A_ST;
+    __shared__ uint64_t bars[2 * NST_MAX + 2];     // [0,4) slot free, [4,8) slab landed, 8: accumulator done, 9: panel consumed
+    __shared__ uint32_t tmem_base_s;
+    float4* halfstat = reinterpret_cast<float4*>(smB);   // the panel buffer is free once the last tile's MMAs are done
+    uint64_t* bar_free = bars;
+    uint64_t* bar_full = bars + NST_MAX;
+    uint64_t* bar_done = bars + 2 * NST_MAX;
+    uint64_t* bar_panel = bars + 2 * NST_MAX + 1;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int K = p.K, M = p.M, L = p.L, ldw = p.w_fold * p.K;
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    if (warp == 0) tmem_alloc(&tmem_base_s, TMEM_COLS);
+    if (tid == 32) {
+        for (int i = 0; i < 2 * NST_MAX + 2; ++i) mbar_init(&bars[i], 1);
+        fence_barrier_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base_s;
+    TL(1);
+
+    const int row0 = blockIdx.y * TCM;
+    const int n_rows = MODE == DGRAD ? K : M;                  // valid accumulator rows overall
+    const int r_end = MODE == FWD ? K : M;                     // reduction extent
+    const int n_chunks = (r_end + KC - 1) / KC;
+    const int my_tiles = ((int)blockIdx.x < n_col_tiles) ? (n_col_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const bool resident = n_chunks <= nsta;
+    const long long total_slabs = resident ? n_chunks : (long long)my_tiles * n_chunks;
+
+    constexpr uint32_t IMG_SLAB = 2u * TCM * KC * 4;           // image slab: [hi 16 KB | lo 16 KB]
+    const uint8_t* img_rt = reinterpret_cast<const uint8_t*>(MODE == FWD ? p.wimg_fwd : p.wimg_dgrad) +
+                            (size_t)blockIdx.y * (size_t)n_chunks * IMG_SLAB;
+    long long a_issued = 0, a_used = 0;                        // thread 0 only
+    auto produce = [&]() {                                      // thread 0: keep up to nsta weight slabs in flight
+        while (a_issued < total_slabs && a_issued < a_used + nsta) {
+            const int st = (int)(a_issued % nsta);
+            if (a_issued >= nsta) mbar_wait(&bar_free[st], (uint32_t)((a_issued / nsta) - 1) & 1u);
+            mbar_expect_tx(&bar_full[st], S::A_ST);
+            tma_bulk_g2s(smA + (size_t)st * S::A_ST, img_rt + (size_t)(a_issued % n_chunks) * IMG_SLAB, S::A_ST, &bar_full[st]);
+            ++a_issued;
+        }
+    };
+    if (tid == 0 && my_tiles > 0) produce();
+
+    const bool has_coef = MODE == DGRAD && p.coef_a != nullptr;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    // lane roles inside a staging unit (8 column groups x 4 k-blocks)
+    const int cgl = lane & 1, kbl = (lane >> 1) & 3, q8 = lane >> 3;
+    constexpr int UPC = 2 * (BN / 32);                          // units per chunk
+    constexpr int UB = 3;                                       // units in flight per warp
+    constexpr uint32_t IDESC = idesc_tf32(TCM, BN);
+
+    // running BatchNorm statistics of this thread's (row, column half) across the CTA's tiles
+    Wf run = {0.f, 0.f, 0.f};
+    const int erow = (warp & 3) * 32 + lane;                    // accumulator row of this thread in the epilogue
+    const int half = warp >> 2;
+    constexpr int HC = BN / 2;
+    const uint32_t t_row = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
+    const int gr = row0 + erow;
+    const bool row_ok = gr < n_rows;
+    float bias = 0.f;
+    if (MODE == FWD && row_ok) {
+        int seg, ml;
+        w_row(p, gr, ldw, &seg, &ml);
+        if (p.bias[seg]) bias = __ldg(p.bias[seg] + ml);
+    }
+    uint32_t ph_panel = 0;
+
+    for (int ti = 0; ti < my_tiles; ++ti) {
+        const int col0 = ((int)blockIdx.x + ti * (int)gridDim.x) * BN;
+        for (int pc0 = 0; pc0 < n_chunks; pc0 += pcap) {
+            const int npc = min(pcap, n_chunks - pc0);
+            if (pc0 > 0) {                                       // the MMAs that read the previous panel must be done
+                mbar_wait(bar_panel, ph_panel);
+                ph_panel ^= 1u;
+            }
+            // ---- stage the activation panel: units of (8 column groups x 4 k-blocks) per warp
+            const int units = npc * UPC;
+            for (int u0 = warp; u0 < units; u0 += 8 * UB) {
+                float4 g[UB][4], zz[UB][4];
+#pragma unroll
+                for (int ui = 0; ui < UB; ++ui) {
+                    const int u = u0 + ui * 8;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) g[ui][j] = zz[ui][j] = z4;
+                    if (u < units) {
+                        const int ch = u / UPC, rem = u - ch * UPC;
+                        const int kb = (rem & 1) * 4 + kbl, cg = (rem >> 1) * 8 + 2 * q8 + cgl;
+                        const int n = col0 + cg * 4, r = (pc0 + ch) * KC + kb * 4;
+                        if (n < N && r < r_end) {
+                            const int b = n / L, l0 = n - b * L;
+                            if (MODE == FWD) {
+                                int s, kl;
+                                src_of(p, r, &s, &kl);
+                                const float* u_ = p.src[s] + ((long long)b * p.src_C[s] + kl) * L + l0;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) g[ui][j] = __ldg(reinterpret_cast<const float4*>(u_ + (long long)j * L));
+                            } else {
+                                const long long idx = ((long long)b * M + r) * L + l0;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    if (r + j < M) {
+                                        g[ui][j] = __ldg(reinterpret_cast<const float4*>(p.GV + idx + (long long)j * L));
+                                        if (has_coef) zz[ui][j] = __ldg(reinterpret_cast<const float4*>(p.Z + idx + (long long)j * L));
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int ui = 0; ui < UB; ++ui) {
+                    const int u = u0 + ui * 8;
+                    if (u < units) {
+                        const int ch = u / UPC, rem = u - ch * UPC;
+                        const int kb = (rem & 1) * 4 + kbl, cg = (rem >> 1) * 8 + 2 * q8 + cgl;
+                        if (has_coef) {
+                            const int r = (pc0 + ch) * KC + kb * 4;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                if (r + j < M) {
+                                    const float a = __ldg(p.coef_a + r + j), bb = __ldg(p.coef_b + r + j), c = __ldg(p.coef_c + r + j);
+                                    g[ui][j].x = fmaf(a, g[ui][j].x, fmaf(bb, zz[ui][j].x, c));
+                                    g[ui][j].y = fmaf(a, g[ui][j].y, fmaf(bb, zz[ui][j].y, c));
+                                    g[ui][j].z = fmaf(a, g[ui][j].z, fmaf(bb, zz[ui][j].z, c));
+                                    g[ui][j].w = fmaf(a, g[ui][j].w, fmaf(bb, zz[ui][j].w, c));
+                                }
+                            }
+                            if (col0 + cg * 4 >= N) {            // padding columns stay exactly zero
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) g[ui][j] = z4;
+                            }
+                        }
+                        uint8_t* b_hi = smB + (size_t)ch * S::B_CH;
+                        uint8_t* b_lo = b_hi + S::B_HALF;
+                        // 4x4 transpose: column i of the block = (row0[i], row1[i], row2[i], row3[i]); store step s
+                        // handles column (s + kbl) & 3 so the 8 lanes of a quarter warp hit 8 distinct 16-byte slots
+#pragma unroll
+                        for (int s_ = 0; s_ < 4; ++s_) {
+                            const int i = (s_ + kbl) & 3;
+                            float4 v;
+                            v.x = i == 0 ? g[ui][0].x : i == 1 ? g[ui][0].y : i == 2 ? g[ui][0].z : g[ui][0].w;
+                            v.y = i == 0 ? g[ui][1].x : i == 1 ? g[ui][1].y : i == 2 ? g[ui][1].z : g[ui][1].w;
+                            v.z = i == 0 ? g[ui][2].x : i == 1 ? g[ui][2].y : i == 2 ? g[ui][2].z : g[ui][2].w;
+                            v.w = i == 0 ? g[ui][3].x : i == 1 ? g[ui][3].y : i == 2 ? g[ui][3].z : g[ui][3].w;
+                            const int nl = cg * 4 + i;
+                            const uint32_t off = (uint32_t)(nl >> 3) * S::SBO + (uint32_t)kb * S::LBO + (uint32_t)(nl & 7) * 16u;
+                            put_chunk<X3>(b_hi, b_lo, off, v);
+                        }
+                    }
+                }
+            }
+            fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+            tc_fence_before();         // this thread's TMEM reads of the previous tile are ordered before the sync
+            __syncthreads();
+            if (ti == 0 && pc0 == 0) TL(4);
+            if (tid == 0) {
+                tc_fence_after();
+                for (int c = 0; c < npc; ++c) {
+                    produce();
+                    const long long sidx = resident ? (pc0 + c) : a_used;
+                    const int st = (int)(sidx % nsta);
+                    if (!resident || ti == 0) mbar_wait(&bar_full[st], (uint32_t)(sidx / nsta) & 1u);
+                    if (ti == 0 && pc0 == 0 && c == 0) TL(5);
+                    if (ti == 0 && pc0 == 0 && c > 0 && c < 7) TL(12 + c);
+                    tc_fence_after();
+                    const uint32_t a_hi = s32(smA + (size_t)st * S::A_ST), a_lo = a_hi + TCM * KC * 4;
+                    const uint32_t b_hi = s32(smB + (size_t)c * S::B_CH), b_lo = b_hi + S::B_HALF;
+#pragma unroll
+                    for (int ks = 0; ks < KC / 8; ++ks) {
+                        const uint32_t ko = (uint32_t)ks * 2u * S::LBO;      // 8 tf32 = two 16-byte chunks
+                        const uint32_t first = (pc0 == 0 && c == 0 && ks == 0) ? 0u : 1u;
+                        if (X3) {
+                            umma_tf32(tmem_d, kdesc(a_lo + ko, S::LBO, S::SBO), kdesc(b_hi + ko, S::LBO, S::SBO), IDESC, first);
+                            umma_tf32(tmem_d, kdesc(a_hi + ko, S::LBO, S::SBO), kdesc(b_lo + ko, S::LBO, S::SBO), IDESC, 1u);
+                            umma_tf32(tmem_d, kdesc(a_hi + ko, S::LBO, S::SBO), kdesc(b_hi + ko, S::LBO, S::SBO), IDESC, 1u);
+                        } else {
+                            umma_tf32(tmem_d, kdesc(a_hi + ko, S::LBO, S::SBO), kdesc(b_hi + ko, S::LBO, S::SBO), IDESC, first);
+                        }
+                    }
+                    if (!resident) {
+                        umma_commit(&bar_free[st]);                  // slot reusable once these MMAs have read it
+                        ++a_used;
+                    }
+                }
+                if (pc0 + npc >= n_chunks) umma_commit(bar_done);    // accumulator complete
+                else umma_commit(bar_panel);                         // panel buffer reusable
+                if (!resident) produce();                            // next tile's first slabs fly during the epilogue
+            }
+        }
+        if (ti == 0) TL(6);
+        mbar_wait(bar_done, (uint32_t)ti & 1u);
+        tc_fence_after();
+        if (ti == 0) TL(7);
+
+        // ---- epilogue: thread = (accumulator row erow, column half)
+        if (MODE == FWD) {
+            float vals[HC];
+#pragma unroll
+            for (int g_ = 0; g_ < HC / 16; ++g_) {
+                float v[16];
+                tmem_ld16(t_row + (uint32_t)(half * HC + g_ * 16), v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) vals[g_ * 16 + j] = v[j] + bias;
+            }
+            float sum = 0.f;
+            int cnt = 0;
+#pragma unroll
+            for (int j4 = 0; j4 < HC / 4; ++j4) {
+                const int n = col0 + half * HC + j4 * 4;
+                if (n < N) {                                  // N % 4 == 0 and L % 4 == 0: a 4-group is whole and in one sample
+                    if (row_ok) {
+                        *reinterpret_cast<float4*>(p.Z + ((long long)(n / L) * M + gr) * L + (n % L)) =
+                            make_float4(vals[j4 * 4], vals[j4 * 4 + 1], vals[j4 * 4 + 2], vals[j4 * 4 + 3]);
+                    }
+                    sum += (vals[j4 * 4] + vals[j4 * 4 + 1]) + (vals[j4 * 4 + 2] + vals[j4 * 4 + 3]);
+                    cnt += 4;
+                }
+            }
+            if (p.bn_mode == 1 && cnt > 0) {
+                const float mean = sum / (float)cnt;
+                float m2 = 0.f;
+#pragma unroll
+                for (int j4 = 0; j4 < HC / 4; ++j4) {
+                    if (col0 + half * HC + j4 * 4 < N) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float d = vals[j4 * 4 + j] - mean;
+                            m2 = fmaf(d, d, m2);
+                        }
+                    }
+                }
+                const Wf t = {(float)cnt, mean, m2};
+                run = wf_merge(run, t);
+            }
+        } else {
+            int s = 0, kl = 0;
+            if (row_ok) src_of(p, gr, &s, &kl);
+            float* dst = row_ok ? p.gsrc[s] : nullptr;
+            const bool accum = row_ok && p.gsrc_accum[s] != 0;
+#pragma unroll
+            for (int g_ = 0; g_ < HC / 16; ++g_) {
+                float v[16];
+                tmem_ld16(t_row + (uint32_t)(half * HC + g_ * 16), v);
+                if (dst) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const int n = col0 + half * HC + g_ * 16 + j4 * 4;
+                        if (n < N) {
+                            float4* d = reinterpret_cast<float4*>(dst + ((long long)(n / L) * p.src_C[s] + kl) * L + (n % L));
+                            float4 o = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                            if (accum) {
+                                const float4 c_ = *d;
+                                o.x += c_.x; o.y += c_.y; o.z += c_.z; o.w += c_.w;
+                            }
+                            *d = o;
+                        }
+                    }
+                }
+            }
+        }
+        if (ti == 0) TL(8);
+    }
+
+    // ---- teardown (+ FWD: one statistics partial per CTA and row, finalize by the last CTA of the row tile)
+    if (MODE == FWD && p.bn_mode == 1) {
+        if (half == 1) halfstat[erow] = make_float4(run.n, run.mean, run.m2, 0.f);
+    }
+    tc_fence_before();
+    __syncthreads();
+    TL(9);
+    if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);
+    if (MODE == FWD) {
+        if (p.bn_mode == 2) {
+            if (blockIdx.x == 0 && tid < TCM) bn_eval_stats(p, row0 + tid, ldw);
+            return;
+        }
+        if (p.bn_mode != 1) return;
+        if (half == 0 && row_ok) {
+            const Wf b = {halfstat[erow].x, halfstat[erow].y, halfstat[erow].z};
+            const Wf w = wf_merge(run, b);
+            float* qd = p.stat_part + ((long long)blockIdx.x * M + gr) * 2;
+            qd[0] = w.mean;
+            qd[1] = w.m2;
+        }
+        TL(10);
+        const bool lastb = last_block(p.counter + blockIdx.y, gridDim.x);
+        TL(11);
+        if (!lastb) return;
+        const int GX = (int)gridDim.x, last_w = N - (n_col_tiles - 1) * BN;
+        bn_finalize_rows(p, N, min(GX, n_col_tiles),
+                         [=](int x) {
+                             const int nt = (n_col_tiles - x + GX - 1) / GX;
+                             const bool owns_last = ((n_col_tiles - 1) % GX) == x;
+                             return nt * BN - (owns_last ? BN - last_w : 0);
+                         },
+                         row0, TCM, ldw);
+#ifdef BMNAS_TIMELINE
+        if (threadIdx.x == 0) {
+            unsigned long long t__;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));
+            g_tl[MODE * 20 + 12] = t__;
+        }
+#endif
+    }
+}
+
+template <int MODE, int BN, bool X3>
+static int launch_panel(const bmnas_conv_params* p, int N, cudaStream_t stream) {
+    using S = PSmem<BN, X3>;
+    const int row_tiles = ((MODE == DGRAD ? p->K : p->M) + TCM - 1) / TCM;
+    const int n_col_tiles = (N + BN - 1) / BN;
+    const int n_chunks = ((MODE == FWD ? p->K : p->M) + KC - 1) / KC;
+    // shared-memory plan: weight ring (whole reduction resident when it fits in 4 slabs) + activation panel
+    const uint32_t budget = 225u * 1024u;
+    int nsta = n_chunks < NST_MAX ? n_chunks : NST_MAX;
+    int pcap = (int)((budget - (uint32_t)nsta * S::A_ST) / S::B_CH);
+    if (pcap >= n_chunks) pcap = n_chunks;
+    else if (n_chunks > nsta && nsta > 2) {          // streaming weights anyway: trade a ring slot for a wider panel
+        const int alt = (int)((budget - (uint32_t)(nsta - 1) * S::A_ST) / S::B_CH);
+        if ((n_chunks + alt - 1) / alt < (n_chunks + pcap - 1) / pcap) { --nsta; pcap = alt < n_chunks ? alt : n_chunks; }
+    }
+    if (pcap < 1) return BMNAS_EINVAL;
+    const size_t smem = (size_t)nsta * S::A_ST + (size_t)pcap * S::B_CH + 1024;
+    static size_t configured = 0;
+    if (smem > configured) {
+        if (cudaFuncSetAttribute(k_gemm_panel<MODE, BN, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return BMNAS_ELAUNCH;
+        configured = smem;
+    }
+    int gx = kNumSMs / row_tiles;
+    if (gx < 1) gx = 1;
+    if (gx > n_col_tiles) gx = n_col_tiles;
+    dim3 grid(gx, row_tiles);
+    launch_k(k_gemm_panel<MODE, BN, X3>, grid, TCT, smem, stream, *p, N, n_col_tiles, nsta, pcap);
+    BMNAS_LAUNCH_CHECK();
+    return BMNAS_OK;
+}
+
+template <int MODE>
+static int panel_dispatch(const bmnas_conv_params* p, int x3, cudaStream_t stream) {
+    const int N = p->B * p->L;
+    const int row_tiles = ((MODE == DGRAD ? p->K : p->M) + TCM - 1) / TCM;
+    const bool wide = (long long)row_tiles * ((N + 31) / 32) > 2LL * kNumSMs;
+    if (wide) return x3 ? launch_panel<MODE, 64, true>(p, N, stream) : launch_panel<MODE, 64, false>(p, N, stream);
+    return x3 ? launch_panel<MODE, 32, true>(p, N, stream) : launch_panel<MODE, 32, false>(p, N, stream);
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -646,6 +1066,7 @@ bool tc_eligible(const bmnas_conv_params* p, int mode) {
 
 int tc_conv_fwd(const bmnas_conv_params* p, int x3, cudaStream_t stream) {
     using namespace tc;
+    if (p->wimg_fwd) return panel_dispatch<FWD>(p, x3, stream);
     const int N = p->B * p->L;
     const int row_tiles = (p->M + TCM - 1) / TCM;
     // enough CTAs to spread the operand staging over the machine, wide tiles once the batch is large
@@ -659,6 +1080,7 @@ int tc_conv_fwd(const bmnas_conv_params* p, int x3, cudaStream_t stream) {
 
 int tc_conv_dgrad(const bmnas_conv_params* p, int x3, cudaStream_t stream) {
     using namespace tc;
+    if (p->wimg_dgrad) return panel_dispatch<DGRAD>(p, x3, stream);
     const int N = p->B * p->L;
     const int row_tiles = (p->K + TCM - 1) / TCM;
     const int bn = (long long)row_tiles * ((N + 127) / 128) >= 2 * kNumSMs ? 128 : ((long long)row_tiles * ((N + 63) / 64) >= kNumSMs ? 64 : 32);
