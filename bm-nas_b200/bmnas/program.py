@@ -179,8 +179,9 @@ class Program:
                     self.setp(st, 'W', W, i * N.BMNAS_MAX_SEG + j)
                 self.setp(st, 'img_fwd', c['img_f'], i)
                 self.setp(st, 'img_dgrad', c['img_d'], i)
+                st.fmt[i] = c['fmt']
                 st.q_start[i] = q
-                q += (c['img_f'].numel() + c['img_d'].numel()) // 8
+                q += int(N.lib().bmnas_wprep_items(c['M'], c['K'], c['fmt']))
             st.q_start[len(group)] = q
             self._prep_calls.append(N.Call('bmnas_wprep', st))
         self.n_fwd_launches = len(self.fwd) + len(self._prep_calls) + (1 if self.rng_state is not None else 0)
@@ -302,14 +303,17 @@ class Program:
                 self.setp(st, 'num_batches_tracked', sg['nbt'], i)
         Z = self.buf(self.B, M, self.L)
         self.setp(st, 'Z', Z)
-        # tensor-core-ready weight images (refreshed by ONE bmnas_wprep launch at the start of every forward)
+        # weight images (refreshed by ONE bmnas_wprep launch at the start of every forward): the library picks the
+        # format = GEMM engine for this problem size (plain fp32 for the small-N cp.async kernels, tcgen05 slabs beyond)
         img_f = img_d = None
-        if (N.lib().bmnas_get_gemm_mode() != 0 and K % 4 == 0 and self.L % 4 == 0 and all(c % 4 == 0 for c in src_C)
-                and all(sg['W'].data_ptr() % 16 == 0 for sg in segs)):
-            img_f = self.buf(int(N.lib().bmnas_wimg_floats(M, K, 0)))
-            img_d = self.buf(int(N.lib().bmnas_wimg_floats(M, K, 1)))
+        fmt = int(N.lib().bmnas_conv_image_fmt(self.B, self.L, K, M))
+        if fmt >= 0 and all(c % 4 == 0 for c in src_C) and all(sg['W'].data_ptr() % 16 == 0 for sg in segs):
+            img_f = self.buf(int(N.lib().bmnas_wimg_floats_fmt(M, K, 0, fmt)))
+            img_d = self.buf(int(N.lib().bmnas_wimg_floats_fmt(M, K, 1, fmt)))
             self.setp(st, 'wimg_fwd', img_f)
-            self._prep.append(dict(M=M, K=K, fold=w_fold, segs=[(sg['W'], sg['M']) for sg in segs], img_f=img_f, img_d=img_d))
+            st.wimg_fmt = fmt
+            self._prep.append(dict(M=M, K=K, fold=w_fold, segs=[(sg['W'], sg['M']) for sg in segs], img_f=img_f, img_d=img_d,
+                                   fmt=fmt))
         mean = rstd = None
         if bn:
             mean, rstd = self.buf(M), self.buf(M)
@@ -319,7 +323,8 @@ class Program:
                 self.setp(st, 'stat_part', self.buf(int(N.lib().bmnas_conv_stat_part_size(ctypes.byref(st)))))
                 self.setp(st, 'counter', self.counter(N.lib().bmnas_conv_num_counters(ctypes.byref(st))))
         self.emit('bmnas_conv_fwd', st)
-        return dict(Z=Z, mean=mean, rstd=rstd, M=M, K=K, srcs=srcs, src_C=src_C, segs=segs, w_fold=w_fold, img_d=img_d)
+        return dict(Z=Z, mean=mean, rstd=rstd, M=M, K=K, srcs=srcs, src_C=src_C, segs=segs, w_fold=w_fold, img_d=img_d,
+                    fmt=max(fmt, 0))
 
     def conv_backward(self, cv, GV, coef, need_src):
         """dgrad into the source grads + wgrad into the parameter grad views."""
@@ -338,6 +343,7 @@ class Program:
             self.setp(st, 'GV', GV)
             self.setp(st, 'Z', cv['Z'])
             self.setp(st, 'wimg_dgrad', cv.get('img_d'))
+            st.wimg_fmt = cv.get('fmt', 0)
             if coef is not None:
                 self.setp(st, 'coef_a', coef[0])
                 self.setp(st, 'coef_b', coef[1])

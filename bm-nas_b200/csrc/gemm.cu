@@ -443,6 +443,9 @@ bool tc_eligible(const bmnas_conv_params* p, int mode);
 int tc_conv_fwd(const bmnas_conv_params* p, int x3, cudaStream_t stream);
 int tc_conv_dgrad(const bmnas_conv_params* p, int x3, cudaStream_t stream);
 int tc_conv_wgrad(const bmnas_conv_params* p, int x3, cudaStream_t stream);
+bool sg_eligible(const bmnas_conv_params* p, int mode);
+int sg_conv_fwd(const bmnas_conv_params* p, cudaStream_t stream);
+int sg_conv_dgrad(const bmnas_conv_params* p, cudaStream_t stream);
 }  // namespace bmnas
 
 // GEMM engine: 0 = fp32 FFMA tiles, 1 = tcgen05 3xTF32 (fp32-class accuracy), 2 = tcgen05 1xTF32 (reduced precision)
@@ -453,6 +456,17 @@ extern "C" int bmnas_set_gemm_mode(int mode) {
     return BMNAS_OK;
 }
 extern "C" int bmnas_get_gemm_mode(void) { return bmnas_gemm_mode_flag; }
+
+// Which weight-image format (= which GEMM engine) serves a conv over B*L columns best.  Up to a few thousand
+// columns the problem is latency bound and the cp.async fp32 kernels win (see gemm_sg.cu); beyond that the
+// tcgen05 panel kernel amortises its per-instruction cost.  BMNAS_GEMM_MODE=0 keeps everything on fp32 FFMA.
+extern "C" int bmnas_conv_image_fmt(int B, int L, int K, int M) {
+    if ((L & 3) || (K & 3) || (M & 3)) return -1;
+    const long long N = (long long)B * L;
+    const bool sg_ok = (L & (L - 1)) == 0 && L <= 32;      // gemm_sg.cu: a 32-column tile is 32 / L whole samples
+    if (bmnas_gemm_mode_flag == 0) return sg_ok ? 1 : -1;
+    return (sg_ok && N <= 4096) ? 1 : 0;
+}
 
 extern "C" long long bmnas_conv_stat_part_size(const bmnas_conv_params* p) {
     const long long N = (long long)p->B * p->L;
@@ -488,6 +502,13 @@ extern "C" int bmnas_conv_fwd(const bmnas_conv_params* p, void* stream) {
             if (!p->running_mean[i] || !p->running_var[i]) return BMNAS_EINVAL;
     }
     BMNAS_DRY_RETURN();
+    bmnas_conv_params q_;
+    if (p->wimg_fwd && p->wimg_fmt == 1) {
+        if (sg_eligible(p, 0)) return sg_conv_fwd(p, (cudaStream_t)stream);
+        q_ = *p;                       // unaligned call-time tensor: the generic kernels below stage W themselves
+        q_.wimg_fwd = q_.wimg_dgrad = nullptr;
+        p = &q_;
+    }
     if (bmnas_gemm_mode_flag && tc_eligible(p, 0)) return tc_conv_fwd(p, bmnas_gemm_mode_flag == 1, (cudaStream_t)stream);
     const int N = p->B * p->L;
     const int KC = min(KC_MAX, round_up(p->K, 4));
@@ -513,6 +534,13 @@ extern "C" int bmnas_conv_dgrad(const bmnas_conv_params* p, void* stream) {
     for (int i = 0; i < p->n_seg; ++i)
         if (!p->W[i]) return BMNAS_EINVAL;
     BMNAS_DRY_RETURN();
+    bmnas_conv_params q_;
+    if (p->wimg_dgrad && p->wimg_fmt == 1) {
+        if (sg_eligible(p, 1)) return sg_conv_dgrad(p, (cudaStream_t)stream);
+        q_ = *p;
+        q_.wimg_fwd = q_.wimg_dgrad = nullptr;
+        p = &q_;
+    }
     if (bmnas_gemm_mode_flag && tc_eligible(p, 1)) return tc_conv_dgrad(p, bmnas_gemm_mode_flag == 1, (cudaStream_t)stream);
     const int N = p->B * p->L;
     const int KC = min(KC_MAX, round_up(p->M, 4));

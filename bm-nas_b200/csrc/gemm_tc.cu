@@ -119,16 +119,38 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// sum of the same 16 columns of the first `used` of NA accumulators (accumulator a starts BNC columns after a-1)
+template <int NA, int BNC>
+__device__ __forceinline__ void tmem_ld16_sum(uint32_t taddr, float (&v)[16], int used) {
+    tmem_ld16(taddr, v);
+#pragma unroll
+    for (int a = 1; a < NA; ++a) {
+        if (a < used) {
+            float w[16];
+            tmem_ld16(taddr + (uint32_t)(a * BNC), w);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += w[i];
+        }
+    }
+}
 __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                  : "memory");
 }
 
-// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-// [0,14) start>>4, [16,30) leading byte offset>>4, [32,46) stride byte offset>>4, [46,48) version=1
-__device__ __forceinline__ uint64_t kdesc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo >> 4) & 0x3fffu) << 16) |
-           ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46);
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4, [16,30) leading byte offset>>4 (unused for swizzled K-major, 1), [32,46) stride byte offset>>4
+// (8 rows x 128 B = 1024), [46,48) version=1, [61,64) layout type (2 = SWIZZLE_128B).  One operand row holds the
+// KC = 32 reduction elements of a slab in 128 contiguous bytes; inside each 8-row x 128 B atom the 16-byte chunk c
+// of row r sits at chunk position c ^ (r & 7) (sw_off below).  A k-step of 8 tf32 advances the start address by
+// 32 bytes inside the atom (the hardware applies the XOR to the address bits), atoms are 1024-byte aligned.
+// (The SWIZZLE_NONE "interleave" layout this replaced fed the tensor core at ~40 B/clk: 130 cycles per
+// 128x32x8 MMA, measured; see profiles/.)
+__device__ __forceinline__ uint64_t kdesc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | (1ull << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__host__ __device__ __forceinline__ uint32_t sw_off(int row, int kc) {
+    return (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((kc ^ (row & 7)) << 4);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6)=1, a=tf32 [7,10)=2, b=tf32 [10,13)=2,
 // a/b K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
@@ -353,11 +375,11 @@ __global__ void __launch_bounds__(TCT, 1) k_gemm_tc(const bmnas_conv_params p, c
                 float4 v = ra[it];
                 if (MODE == DGRAD) {
                     const int row = q & (TCM - 1), mc = q >> 7;
-                    off = (uint32_t)(row >> 3) * S::SBO + (uint32_t)mc * S::LBO + (uint32_t)(row & 7) * 16u;
+                    off = sw_off(row, mc);
                     v.x += ra2[it].x; v.y += ra2[it].y; v.z += ra2[it].z; v.w += ra2[it].w;
                 } else {
                     const int r8 = q & 7, kc = (q >> 3) & 7, rg = q >> 6;
-                    off = (uint32_t)rg * S::SBO + (uint32_t)kc * S::LBO + (uint32_t)r8 * 16u;
+                    off = sw_off(rg * 8 + r8, kc);
                     if (MODE == FWD) {
                         v.x += ra2[it].x; v.y += ra2[it].y; v.z += ra2[it].z; v.w += ra2[it].w;
                     } else {
@@ -380,10 +402,10 @@ __global__ void __launch_bounds__(TCT, 1) k_gemm_tc(const bmnas_conv_params p, c
                 float4 v = rb[it];
                 if (MODE == WGRAD) {
                     const int r8 = q & 7, kc = (q >> 3) & 7, rg = q >> 6;
-                    off = (uint32_t)rg * S::SBO + (uint32_t)kc * S::LBO + (uint32_t)r8 * 16u;
+                    off = sw_off(rg * 8 + r8, kc);
                 } else {
                     const int nl = q % BN, kc = q / BN;
-                    off = (uint32_t)(nl >> 3) * S::SBO + (uint32_t)kc * S::LBO + (uint32_t)(nl & 7) * 16u;
+                    off = sw_off(nl, kc);
                     if (MODE == DGRAD && col0 + nl < N) v = bn_fold4(v, rb2[it], r0 + kc * 4, true);
                 }
                 put_chunk<X3>(b_hi, b_lo, off, v);
@@ -420,14 +442,14 @@ __global__ void __launch_bounds__(TCT, 1) k_gemm_tc(const bmnas_conv_params p, c
             const uint32_t b_hi = base + (X3 ? 2u : 1u) * S::A_BYTES, b_lo = b_hi + S::B_BYTES;
 #pragma unroll
             for (int ks = 0; ks < KC / 8; ++ks) {
-                const uint32_t ko = (uint32_t)ks * 2u * S::LBO;      // 8 tf32 = two 16-byte chunks
+                const uint32_t ko = (uint32_t)ks * 32u;              // 8 tf32 = 32 bytes inside the 128-byte swizzled row
                 const uint32_t first = (c == 0 && ks == 0) ? 0u : 1u;
                 if (X3) {
-                    umma_tf32(tmem_d, kdesc(a_lo + ko, S::LBO, S::SBO), kdesc(b_hi + ko, S::LBO, S::SBO), IDESC, first);
-                    umma_tf32(tmem_d, kdesc(a_hi + ko, S::LBO, S::SBO), kdesc(b_lo + ko, S::LBO, S::SBO), IDESC, 1u);
-                    umma_tf32(tmem_d, kdesc(a_hi + ko, S::LBO, S::SBO), kdesc(b_hi + ko, S::LBO, S::SBO), IDESC, 1u);
+                    umma_tf32(tmem_d, kdesc(a_lo + ko), kdesc(b_hi + ko), IDESC, first);
+                    umma_tf32(tmem_d, kdesc(a_hi + ko), kdesc(b_lo + ko), IDESC, 1u);
+                    umma_tf32(tmem_d, kdesc(a_hi + ko), kdesc(b_hi + ko), IDESC, 1u);
                 } else {
-                    umma_tf32(tmem_d, kdesc(a_hi + ko, S::LBO, S::SBO), kdesc(b_hi + ko, S::LBO, S::SBO), IDESC, first);
+                    umma_tf32(tmem_d, kdesc(a_hi + ko), kdesc(b_hi + ko), IDESC, first);
                 }
             }
             umma_commit(&bar_free[stage]);                   // slot reusable once these MMAs have read it
@@ -622,7 +644,11 @@ __global__ void __launch_bounds__(TCT, 1) k_gemm_panel(const bmnas_conv_params p
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int K = p.K, M = p.M, L = p.L, ldw = p.w_fold * p.K;
-    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    // NACC independent accumulators, used round-robin by consecutive MMAs: back-to-back tcgen05.mma into the SAME
+    // TMEM accumulator serialise on the accumulate latency (~130 cycles per 128x32x8 MMA measured, vs 16 cycles of
+    // math); rotating over 4 accumulators overlaps them, the epilogue adds the 4 partial sums
+    constexpr int NACC = 4;
+    constexpr uint32_t TMEM_COLS = NACC * BN;
     if (warp == 0) tmem_alloc(&tmem_base_s, TMEM_COLS);
     if (tid == 32) {
         for (int i = 0; i < 2 * NST_MAX + 2; ++i) mbar_init(&bars[i], 1);
@@ -660,7 +686,7 @@ __global__ void __launch_bounds__(TCT, 1) k_gemm_panel(const bmnas_conv_params p
     const bool has_coef = MODE == DGRAD && p.coef_a != nullptr;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     // lane roles inside a staging unit (8 column groups x 4 k-blocks)
-    const int cgl = lane & 1, kbl = (lane >> 1) & 3, q8 = lane >> 3;
+    const int cgw = lane & 7, kbl = lane >> 3;                 // column group inside the unit, k-block inside the unit
     constexpr int UPC = 2 * (BN / 32);                          // units per chunk
     constexpr int UB = 3;                                       // units in flight per warp
     constexpr uint32_t IDESC = idesc_tf32(TCM, BN);
@@ -683,6 +709,7 @@ __global__ void __launch_bounds__(TCT, 1) k_gemm_panel(const bmnas_conv_params p
 
     for (int ti = 0; ti < my_tiles; ++ti) {
         const int col0 = ((int)blockIdx.x + ti * (int)gridDim.x) * BN;
+        uint32_t n_mma = 0;                                    // thread 0: MMAs issued for this tile
         for (int pc0 = 0; pc0 < n_chunks; pc0 += pcap) {
             const int npc = min(pcap, n_chunks - pc0);
             if (pc0 > 0) {                                       // the MMAs that read the previous panel must be done
@@ -700,7 +727,7 @@ __global__ void __launch_bounds__(TCT, 1) k_gemm_panel(const bmnas_conv_params p
                     for (int j = 0; j < 4; ++j) g[ui][j] = zz[ui][j] = z4;
                     if (u < units) {
                         const int ch = u / UPC, rem = u - ch * UPC;
-                        const int kb = (rem & 1) * 4 + kbl, cg = (rem >> 1) * 8 + 2 * q8 + cgl;
+                        const int kb = (rem & 1) * 4 + kbl, cg = (rem >> 1) * 8 + cgw;
                         const int n = col0 + cg * 4, r = (pc0 + ch) * KC + kb * 4;
                         if (n < N && r < r_end) {
                             const int b = n / L, l0 = n - b * L;
@@ -728,7 +755,7 @@ __global__ void __launch_bounds__(TCT, 1) k_gemm_panel(const bmnas_conv_params p
                     const int u = u0 + ui * 8;
                     if (u < units) {
                         const int ch = u / UPC, rem = u - ch * UPC;
-                        const int kb = (rem & 1) * 4 + kbl, cg = (rem >> 1) * 8 + 2 * q8 + cgl;
+                        const int kb = (rem & 1) * 4 + kbl, cg = (rem >> 1) * 8 + cgw;
                         if (has_coef) {
                             const int r = (pc0 + ch) * KC + kb * 4;
 #pragma unroll
@@ -749,18 +776,18 @@ __global__ void __launch_bounds__(TCT, 1) k_gemm_panel(const bmnas_conv_params p
                         uint8_t* b_hi = smB + (size_t)ch * S::B_CH;
                         uint8_t* b_lo = b_hi + S::B_HALF;
                         // 4x4 transpose: column i of the block = (row0[i], row1[i], row2[i], row3[i]); store step s
-                        // handles column (s + kbl) & 3 so the 8 lanes of a quarter warp hit 8 distinct 16-byte slots
+                        // handles column (s + cgw/2) & 3, so the 8 lanes of a quarter warp (same k-block, 8 column
+                        // groups) write 8 distinct rows mod 8 = 8 distinct swizzled 16-byte slots: conflict free
 #pragma unroll
                         for (int s_ = 0; s_ < 4; ++s_) {
-                            const int i = (s_ + kbl) & 3;
+                            const int i = (s_ + (cgw >> 1)) & 3;
                             float4 v;
                             v.x = i == 0 ? g[ui][0].x : i == 1 ? g[ui][0].y : i == 2 ? g[ui][0].z : g[ui][0].w;
                             v.y = i == 0 ? g[ui][1].x : i == 1 ? g[ui][1].y : i == 2 ? g[ui][1].z : g[ui][1].w;
                             v.z = i == 0 ? g[ui][2].x : i == 1 ? g[ui][2].y : i == 2 ? g[ui][2].z : g[ui][2].w;
                             v.w = i == 0 ? g[ui][3].x : i == 1 ? g[ui][3].y : i == 2 ? g[ui][3].z : g[ui][3].w;
                             const int nl = cg * 4 + i;
-                            const uint32_t off = (uint32_t)(nl >> 3) * S::SBO + (uint32_t)kb * S::LBO + (uint32_t)(nl & 7) * 16u;
-                            put_chunk<X3>(b_hi, b_lo, off, v);
+                            put_chunk<X3>(b_hi, b_lo, sw_off(nl, kb), v);
                         }
                     }
                 }
@@ -783,14 +810,17 @@ __global__ void __launch_bounds__(TCT, 1) k_gemm_panel(const bmnas_conv_params p
                     const uint32_t b_hi = s32(smB + (size_t)c * S::B_CH), b_lo = b_hi + S::B_HALF;
 #pragma unroll
                     for (int ks = 0; ks < KC / 8; ++ks) {
-                        const uint32_t ko = (uint32_t)ks * 2u * S::LBO;      // 8 tf32 = two 16-byte chunks
-                        const uint32_t first = (pc0 == 0 && c == 0 && ks == 0) ? 0u : 1u;
+                        const uint32_t ko = (uint32_t)ks * 32u;              // 8 tf32 = 32 bytes inside the swizzled row
                         if (X3) {
-                            umma_tf32(tmem_d, kdesc(a_lo + ko, S::LBO, S::SBO), kdesc(b_hi + ko, S::LBO, S::SBO), IDESC, first);
-                            umma_tf32(tmem_d, kdesc(a_hi + ko, S::LBO, S::SBO), kdesc(b_lo + ko, S::LBO, S::SBO), IDESC, 1u);
-                            umma_tf32(tmem_d, kdesc(a_hi + ko, S::LBO, S::SBO), kdesc(b_hi + ko, S::LBO, S::SBO), IDESC, 1u);
+                            umma_tf32(tmem_d + (n_mma % NACC) * BN, kdesc(a_lo + ko), kdesc(b_hi + ko), IDESC, n_mma >= NACC);
+                            ++n_mma;
+                            umma_tf32(tmem_d + (n_mma % NACC) * BN, kdesc(a_hi + ko), kdesc(b_lo + ko), IDESC, n_mma >= NACC);
+                            ++n_mma;
+                            umma_tf32(tmem_d + (n_mma % NACC) * BN, kdesc(a_hi + ko), kdesc(b_hi + ko), IDESC, n_mma >= NACC);
+                            ++n_mma;
                         } else {
-                            umma_tf32(tmem_d, kdesc(a_hi + ko, S::LBO, S::SBO), kdesc(b_hi + ko, S::LBO, S::SBO), IDESC, first);
+                            umma_tf32(tmem_d + (n_mma % NACC) * BN, kdesc(a_hi + ko), kdesc(b_hi + ko), IDESC, n_mma >= NACC);
+                            ++n_mma;
                         }
                     }
                     if (!resident) {
@@ -808,13 +838,14 @@ __global__ void __launch_bounds__(TCT, 1) k_gemm_panel(const bmnas_conv_params p
         tc_fence_after();
         if (ti == 0) TL(7);
 
-        // ---- epilogue: thread = (accumulator row erow, column half)
+        // ---- epilogue: thread = (accumulator row erow, column half); accumulators that received an MMA are summed
+        const int used_acc = min(NACC, n_chunks * (KC / 8) * (X3 ? 3 : 1));
         if (MODE == FWD) {
             float vals[HC];
 #pragma unroll
             for (int g_ = 0; g_ < HC / 16; ++g_) {
                 float v[16];
-                tmem_ld16(t_row + (uint32_t)(half * HC + g_ * 16), v);
+                tmem_ld16_sum<NACC, BN>(t_row + (uint32_t)(half * HC + g_ * 16), v, used_acc);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) vals[g_ * 16 + j] = v[j] + bias;
             }
@@ -856,7 +887,7 @@ __global__ void __launch_bounds__(TCT, 1) k_gemm_panel(const bmnas_conv_params p
 #pragma unroll
             for (int g_ = 0; g_ < HC / 16; ++g_) {
                 float v[16];
-                tmem_ld16(t_row + (uint32_t)(half * HC + g_ * 16), v);
+                tmem_ld16_sum<NACC, BN>(t_row + (uint32_t)(half * HC + g_ * 16), v, used_acc);
                 if (dst) {
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
@@ -983,6 +1014,43 @@ __global__ void __launch_bounds__(256) k_wprep(const bmnas_wprep_params p) {
         }
         return p.W[i * BMNAS_MAX_SEG + s] + (long long)m * ldw;
     };
+    if (p.fmt[i] == 1) {
+        // plain fp32 tile-major images for the small-N FFMA GEMMs (gemm_sg.cu): FWD [ceil(M/32)][K][32] then
+        // DGRAD [ceil(K/32)][M][32]; one work item = one float4 of output
+        const int MT32 = (M + 31) / 32, KT32 = (K + 31) / 32;
+        const long long nf = (long long)MT32 * K * 8;
+        if (ql < nf) {
+            const int c4 = (int)(ql & 7), k = (int)((ql >> 3) % K), t = (int)((ql >> 3) / K);
+            float e[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int m = t * 32 + c4 * 4 + j;
+                e[j] = 0.f;
+                if (m < M) {
+                    const float* r = wrow(m) + k;
+                    e[j] = __ldg(r);
+                    if (fold == 2) e[j] += __ldg(r + K);
+                }
+            }
+            *reinterpret_cast<float4*>(p.img_fwd[i] + ql * 4) = make_float4(e[0], e[1], e[2], e[3]);
+        } else {
+            ql -= nf;
+            const int c4 = (int)(ql & 7), m = (int)((ql >> 3) % M), t = (int)((ql >> 3) / M);
+            const int k4 = t * 32 + c4 * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k4 < K) {
+                const float* r = wrow(m) + k4;
+                v = __ldg(reinterpret_cast<const float4*>(r));
+                if (fold == 2) {
+                    const float4 u = __ldg(reinterpret_cast<const float4*>(r + K));
+                    v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+                }
+            }
+            *reinterpret_cast<float4*>(p.img_dgrad[i] + ql * 4) = v;
+        }
+        (void)KT32;
+        return;
+    }
     const int KSf = (K + KC - 1) / KC, RTf = (M + TCM - 1) / TCM;
     const long long nf = (long long)RTf * KSf * 1024;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1000,7 +1068,7 @@ __global__ void __launch_bounds__(256) k_wprep(const bmnas_wprep_params p) {
                 v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
             }
         }
-        dst = p.img_fwd[i] + slab * (2 * TCM * KC) + (rg * 1024 + kc * 128 + r8 * 16) / 4;
+        dst = p.img_fwd[i] + slab * (2 * TCM * KC) + sw_off(rg * 8 + r8, kc) / 4;
     } else {
         ql -= nf;
         const int MSd = (M + KC - 1) / KC;
@@ -1021,7 +1089,7 @@ __global__ void __launch_bounds__(256) k_wprep(const bmnas_wprep_params p) {
             }
             v = make_float4(e[0], e[1], e[2], e[3]);
         }
-        dst = p.img_dgrad[i] + slab * (2 * TCM * KC) + ((row >> 3) * 1024 + mc * 128 + (row & 7) * 16) / 4;
+        dst = p.img_dgrad[i] + slab * (2 * TCM * KC) + sw_off(row, mc) / 4;
     }
     const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
     *reinterpret_cast<float4*>(dst) = h;
@@ -1116,6 +1184,17 @@ int tc_conv_wgrad(const bmnas_conv_params* p, int x3, cudaStream_t stream) {
 
 using namespace bmnas;
 
+extern "C" long long bmnas_wimg_floats(int M, int K, int which);
+extern "C" long long bmnas_wimg_floats_fmt(int M, int K, int which, int fmt) {
+    if (fmt == 1) return which == 0 ? (long long)((M + 31) / 32) * K * 32 : (long long)((K + 31) / 32) * M * 32;
+    return bmnas_wimg_floats(M, K, which);
+}
+
+extern "C" long long bmnas_wprep_items(int M, int K, int fmt) {
+    const long long f = bmnas_wimg_floats_fmt(M, K, 0, fmt) + bmnas_wimg_floats_fmt(M, K, 1, fmt);
+    return fmt == 1 ? f / 4 : f / 8;      // one work item = one 16-byte chunk of output (fmt 0: hi and lo)
+}
+
 extern "C" long long bmnas_wimg_floats(int M, int K, int which) {
     const long long slab = 2LL * tc::TCM * tc::KC;
     if (which == 0) return (long long)((M + tc::TCM - 1) / tc::TCM) * ((K + tc::KC - 1) / tc::KC) * slab;
@@ -1136,7 +1215,8 @@ extern "C" int bmnas_wprep(const bmnas_wprep_params* p, void* stream) {
         }
         if (m != p->M[i]) return BMNAS_EINVAL;
         if (p->q_start[i] != q) return BMNAS_EINVAL;
-        q += (bmnas_wimg_floats(p->M[i], p->K[i], 0) + bmnas_wimg_floats(p->M[i], p->K[i], 1)) / 8;   // 8 floats (hi+lo) per chunk
+        if (p->fmt[i] != 0 && p->fmt[i] != 1) return BMNAS_EINVAL;
+        q += bmnas_wprep_items(p->M[i], p->K[i], p->fmt[i]);
     }
     if (p->q_start[p->n] != q) return BMNAS_EINVAL;
     BMNAS_DRY_RETURN();

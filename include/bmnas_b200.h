@@ -135,10 +135,12 @@ typedef struct bmnas_conv_params {
     float* gbias[BMNAS_MAX_SEG];
     const float* wimg_fwd;
     const float* wimg_dgrad;
+    int wimg_fmt;
 } bmnas_conv_params;
-/* wimg_fwd / wimg_dgrad (optional): tensor-core-ready images of the stacked, folded weight produced by
- * bmnas_wprep (below).  When present the tcgen05 GEMMs fetch the weight operand with TMA bulk copies instead
- * of staging it through registers; they must be refreshed (bmnas_wprep) whenever W changes. */
+/* wimg_fwd / wimg_dgrad (optional): images of the stacked, folded weight produced by bmnas_wprep (below), in
+ * format wimg_fmt: 0 = tcgen05 slabs (the tensor-core GEMMs fetch them with TMA bulk copies), 1 = plain fp32
+ * (tile major [row tile of 32][reduction][32], fold applied; the small-N cp.async FFMA GEMMs of gemm_sg.cu).  They must be
+ * refreshed (bmnas_wprep) whenever W changes.  bmnas_conv_image_fmt() picks the format for a problem size. */
 int bmnas_conv_fwd(const bmnas_conv_params* p, void* stream);
 int bmnas_conv_dgrad(const bmnas_conv_params* p, void* stream);
 int bmnas_conv_wgrad(const bmnas_conv_params* p, void* stream);
@@ -152,7 +154,8 @@ int bmnas_conv_num_counters(const bmnas_conv_params* p);         /* uints   */
  *   img_dgrad[i] rows k, reduction m   (bmnas_wimg_floats(M, K, 1) floats)
  * of Weff[m,k] = sum_f W[m, f*K + k], split into tf32 hi / lo parts, zero padded to 128-row x 32-element
  * slabs and stored slab by slab as the K-major core-matrix shared-memory picture the MMA descriptors read.
- * q_start is the exclusive prefix sum of (floats_fwd + floats_dgrad) / 8 over the convs (n + 1 entries).
+ * q_start is the exclusive prefix sum of bmnas_wprep_items(M, K, fmt) over the convs (n + 1 entries);
+ * fmt[i] selects the image format of conv i (see bmnas_conv_params.wimg_fmt).
  * One launch per forward replaces the per-CTA fold / transpose / split of the weights
  * (torch.cat([x, x]) + nn.Conv1d weight use in node_operations.py:30-34, 49-53, node_search.py:59-62).
  * ---------------------------------------------------------------------- */
@@ -167,9 +170,15 @@ typedef struct bmnas_wprep_params {
     float* img_fwd[BMNAS_MAX_PREP];
     float* img_dgrad[BMNAS_MAX_PREP];
     long long q_start[BMNAS_MAX_PREP_P1];
+    int fmt[BMNAS_MAX_PREP];
 } bmnas_wprep_params;
 int bmnas_wprep(const bmnas_wprep_params* p, void* stream);
-long long bmnas_wimg_floats(int M, int K, int which);
+long long bmnas_wimg_floats(int M, int K, int which);               /* fmt 0 */
+long long bmnas_wimg_floats_fmt(int M, int K, int which, int fmt);  /* floats of one image in format fmt */
+long long bmnas_wprep_items(int M, int K, int fmt);                 /* work items of one conv (q_start increments) */
+/* image format for a conv over B*L columns: -1 = none (shape not eligible), 0 = tcgen05 slabs, 1 = plain fp32
+ * (small column counts: the fp32 cp.async GEMMs beat 3xTF32 UMMA there; see gemm_sg.cu) */
+int bmnas_conv_image_fmt(int B, int L, int K, int M);
 
 /* ------------------------------------------------------------------------
  * Step-node mixed op: out = sum_k gamma~_k * op_k(x, y), evaluated per sample

@@ -17,7 +17,7 @@ head = SearchHead(a, c['classes'], criterion=crit).to(dev)
 ss = SearchStep(head, crit, c['B'], c['classes'], use_graphs=False)
 pool = bench.make_pool(c, 2, 1, dev)
 ss.load('dev', *pool[0]); ss.load('train', *pool[1])
-for _ in range(3): ss.step()
+for _ in range(600): ss.step()     # ~0.5 s of load: clocks at boost before the timelines are taken
 torch.cuda.synchronize()
 runner = [r for r in head.fusion_net._bm_cache.values() if r.prog.training][0]
 prog = runner.prog
@@ -29,7 +29,7 @@ for mode, cname in ((0, 'bmnas_conv_fwd'), (1, 'bmnas_conv_dgrad'), (2, 'bmnas_c
     calls = [x for x in (prog.fwd + prog.bwd) if x.name == cname and x.st.M == 3 * c['C']]
     call = calls[0]
     for rep in range(3):
-        for _ in range(3): call(s)
+        for _ in range(200): call(s)
         torch.cuda.synchronize()
         N.lib().bmnas_debug_timeline(buf)
     t = [buf[mode * 20 + i] for i in range(19)]
@@ -37,3 +37,17 @@ for mode, cname in ((0, 'bmnas_conv_fwd'), (1, 'bmnas_conv_dgrad'), (2, 'bmnas_c
     for i in range(19):
         if t[i] >= t[0] and t[i] - t[0] < 10**8:
             print('   %-26s +%6d ns' % (names[0][i], t[i] - t[0]))
+
+names_sg = ['entry', 'copies issued', 'copies landed', 'transform+sync', 'FFMA done', 'epilogue done / pre last_block', 'post last_block', 'finalize done', 'after pdl', 'after bias prefetch', 'A copies issued']
+for mode, cname in ((0, 'bmnas_conv_fwd'), (1, 'bmnas_conv_dgrad')):
+    calls = [x for x in (prog.fwd + prog.bwd) if x.name == cname and x.st.M == 3 * c['C']]
+    call = calls[0]
+    for rep in range(3):
+        for _ in range(200): call(s)
+        torch.cuda.synchronize()
+        N.lib().bmnas_debug_timeline_sg(buf)
+    t = [buf[mode * 20 + i] for i in range(11)]
+    print('sg', cname, 'K', call.st.K, 'M', call.st.M, 'fmt', call.st.wimg_fmt)
+    for i in range(11):
+        if t[i] >= t[0] and t[i] - t[0] < 10**8:
+            print('   %-32s +%6d ns' % (names_sg[i], t[i] - t[0]))

@@ -52,11 +52,12 @@ def _params(N, B, L, src_C, seg_M, w_fold, srcs, Ws):
     return st
 
 
-def _images(N, lib, Ws, seg_M, K, w_fold, dev):
-    """tensor-core-ready weight images through bmnas_wprep (TMA-fed weight operand of the tcgen05 GEMMs)"""
+def _images(N, lib, Ws, seg_M, K, w_fold, dev, fmt=0):
+    """weight images through bmnas_wprep: fmt 0 = tcgen05 slabs (TMA-fed weight operand of the tensor-core GEMMs),
+    fmt 1 = plain fp32 (cp.async-fed weight operand of the small-N FFMA GEMMs)"""
     M = sum(seg_M)
-    img_f = torch.full((int(lib.bmnas_wimg_floats(M, K, 0)),), float('nan'), device=dev)
-    img_d = torch.full((int(lib.bmnas_wimg_floats(M, K, 1)),), float('nan'), device=dev)
+    img_f = torch.full((int(lib.bmnas_wimg_floats_fmt(M, K, 0, fmt)),), float('nan'), device=dev)
+    img_d = torch.full((int(lib.bmnas_wimg_floats_fmt(M, K, 1, fmt)),), float('nan'), device=dev)
     st = N.bmnas_wprep_params()
     st.n = 1
     st.M[0], st.K[0], st.w_fold[0], st.n_seg[0] = M, K, w_fold, len(seg_M)
@@ -64,7 +65,8 @@ def _images(N, lib, Ws, seg_M, K, w_fold, dev):
         st.seg_M[j] = m
         st.W[j] = w.data_ptr()
     st.img_fwd[0], st.img_dgrad[0] = img_f.data_ptr(), img_d.data_ptr()
-    st.q_start[0], st.q_start[1] = 0, (img_f.numel() + img_d.numel()) // 8
+    st.fmt[0] = fmt
+    st.q_start[0], st.q_start[1] = 0, int(lib.bmnas_wprep_items(M, K, fmt))
     N.launch('bmnas_wprep', ctypes.byref(st), N.current_stream())
     return img_f, img_d
 
@@ -84,7 +86,7 @@ def _rel(a, b):
     return ((a.double() - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
 
 
-@pytest.mark.parametrize('mode,img', [(0, False), (1, False), (2, False), (1, True), (2, True)])
+@pytest.mark.parametrize('mode,img', [(0, False), (1, False), (2, False), (1, True), (2, True), (0, 'sg'), (1, 'sg')])
 @pytest.mark.parametrize('case', range(len(CASES)))
 def test_conv_fwd_engines(mode, img, case):
     N, lib = _lib()
@@ -106,8 +108,9 @@ def test_conv_fwd_engines(mode, img, case):
     cnt = torch.zeros(int(lib.bmnas_conv_num_counters(ctypes.byref(st))), dtype=torch.int32, device=dev)
     st.Z, st.mean, st.rstd, st.stat_part, st.counter = Z.data_ptr(), mean.data_ptr(), rstd.data_ptr(), part.data_ptr(), cnt.data_ptr()
     if img:
-        imgs = _images(N, lib, Ws, seg_M, sum(src_C), w_fold, dev)
+        imgs = _images(N, lib, Ws, seg_M, sum(src_C), w_fold, dev, fmt=1 if img == 'sg' else 0)
         st.wimg_fwd = imgs[0].data_ptr()
+        st.wimg_fmt = 1 if img == 'sg' else 0
     old = lib.bmnas_get_gemm_mode()
     try:
         lib.bmnas_set_gemm_mode(mode)
@@ -129,7 +132,7 @@ def test_conv_fwd_engines(mode, img, case):
     assert _rel(torch.cat(rv), rv_ref) < tol * 10
 
 
-@pytest.mark.parametrize('mode,img', [(0, False), (1, False), (2, False), (1, True), (2, True)])
+@pytest.mark.parametrize('mode,img', [(0, False), (1, False), (2, False), (1, True), (2, True), (0, 'sg'), (1, 'sg')])
 @pytest.mark.parametrize('case', range(len(CASES)))
 @pytest.mark.parametrize('coef', [False, True])
 def test_conv_backward_engines(mode, img, case, coef):
@@ -159,8 +162,9 @@ def test_conv_backward_engines(mode, img, case, coef):
         if coef:
             st.coef_a, st.coef_b, st.coef_c = ca.data_ptr(), cb.data_ptr(), cc.data_ptr()
         if img:
-            imgs = _images(N, lib, Ws, seg_M, K, w_fold, dev)
+            imgs = _images(N, lib, Ws, seg_M, K, w_fold, dev, fmt=1 if img == 'sg' else 0)
             st.wimg_dgrad = imgs[1].data_ptr()
+            st.wimg_fmt = 1 if img == 'sg' else 0
         gs = [torch.full((B, c, L), 0.5, device=dev) for c in src_C]
         for i in range(len(src_C)):
             st.gsrc[i] = gs[i].data_ptr()
