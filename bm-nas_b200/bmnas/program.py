@@ -167,6 +167,14 @@ class Program:
         while self._stack:
             self._stack.pop()()
         self._cur = None
+        # programmatic dependent launch: a conv may fetch its weight image before griddepcontrol.wait when at least
+        # one kernel sits between bmnas_wprep and it (include/bmnas_b200.h, early_ok)
+        for i, c in enumerate(self.fwd):
+            if c.name == 'bmnas_conv_fwd' and i >= 1:
+                c.st.early_ok = 1
+        for c in self.bwd:
+            if c.name == 'bmnas_conv_dgrad':
+                c.st.early_ok = 1
         for i0 in range(0, len(self._prep), N.BMNAS_MAX_PREP):
             group = self._prep[i0:i0 + N.BMNAS_MAX_PREP]
             st = N.bmnas_wprep_params()
@@ -425,6 +433,7 @@ class Program:
         st = N.bmnas_node_params()
         fill(st)
         self.setp(st, 'out', out)
+        st.early_ok = 1 if cv else 0      # the conv GEMM sits between the producers of x / y and this kernel
         self.emit('bmnas_node_fwd', st)
 
         def bwd():
@@ -432,6 +441,7 @@ class Program:
                 return
             sb = N.bmnas_node_params()
             fill(sb)
+            sb.early_ok = 1                   # backward: x, y, Z, mean, rstd are forward tensors
             self.setp(sb, 'gout', self.grad_of(out))
             if need_x:
                 gx = self.grad_of(x)

@@ -20,14 +20,22 @@ extern int bmnas_pdl_flag;
 
 namespace bmnas {
 
-// Programmatic dependent launch: every kernel is launched with the stream-serialization attribute and
-// opens with launch_dependents + wait, so the NEXT kernel's CTAs are scheduled (and run their
-// parameter/shared-memory prologue) while this one is still executing; griddepcontrol.wait blocks until the
-// preceding grid has completed and its writes are visible, so data dependencies are unchanged.  Under stream
-// capture the attribute becomes a programmatic edge of the CUDA graph.
+// Programmatic dependent launch.  Every kernel is launched with the stream-serialization attribute (a programmatic
+// edge of the CUDA graph under capture).  Protocol, in every kernel:
+//     [early section]  ->  pdl_wait()  ->  pdl_trigger()  ->  main body
+//   pdl_wait()    griddepcontrol.wait: blocks until the preceding grid has COMPLETED and its writes are visible;
+//   pdl_trigger() griddepcontrol.launch_dependents: lets the next kernel of the stream start (its CTAs are
+//                 scheduled as soon as every CTA of this grid has triggered).
+// Because a kernel only triggers after its own wait, the kernel that starts early knows that everything up to
+// the grid BEFORE its predecessor is complete.  Its early section may therefore read data produced two or more
+// kernels ago (weights, weight images, the x tile of a node op whose conv sits in between, forward tensors
+// during the backward pass) and overlaps the predecessor's whole body; anything the predecessor writes is only
+// touched after pdl_wait().  Kernels with no early section call pdl_prologue() first thing.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_prologue() {
-    asm volatile("griddepcontrol.launch_dependents;");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    pdl_wait();
+    pdl_trigger();
 }
 
 template <class... KArgs, class... Args>

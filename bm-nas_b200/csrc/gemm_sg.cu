@@ -81,7 +81,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32
 template <int MODE, int TM>
 __host__ __device__ inline size_t smem_floats(int kc, int L, bool coef) {
     const size_t bsz = (size_t)(TN / L) * ((size_t)kc * L + SPAD);
-    return (size_t)kc * TM + bsz * ((MODE == DGRAD && coef) ? 2 : 1);
+    return (size_t)kc * TM + bsz * ((MODE == DGRAD && coef) ? 2 : 1) + ((MODE == DGRAD && coef) ? 3 * (size_t)kc : 0);
 }
 
 // MODE FWD  : rows = output channels m, cols = n=(b,l), reduction k (channels of the virtual concat)
@@ -90,7 +90,10 @@ template <int MODE, int TM>
 __global__ void __launch_bounds__(ST) k_sg(const bmnas_conv_params p, const int N, const int n_col_tiles, const int KC,
                                            const int lshift) {
     TLS(0);
-    pdl_prologue();
+    // early section (p.early_ok: the weight image was written at least two kernels ago): barrier setup, bias fetch and
+    // the TMA copies of the weight tile are issued BEFORE pdl_wait() and overlap the preceding kernel
+    bool waited = !p.early_ok;
+    if (waited) pdl_prologue();
     TLS(8);
     constexpr int MT = TM / 16;                   // rows per thread
     constexpr int NH = TM / 32;                   // 32-row halves of the weight tile
@@ -107,6 +110,7 @@ __global__ void __launch_bounds__(ST) k_sg(const bmnas_conv_params p, const int 
     float* As = smem;                             // [NH][KC][32]
     float* Bs = smem + (size_t)KC * TM;           // [spt][sstr]
     float* Bz = Bs + (size_t)spt * sstr;          // DGRAD with coef only
+    float* cf = Bz + (size_t)spt * sstr;          // DGRAD with coef only: coef_a | coef_b | coef_c of the staged rows
     const float* img = MODE == FWD ? p.wimg_fwd : p.wimg_dgrad;   // [row tile of 32][R][32]
     if (tid == 0) mbar_init(&bar, 1);
     __syncthreads();
@@ -160,8 +164,13 @@ __global__ void __launch_bounds__(ST) k_sg(const bmnas_conv_params p, const int 
                 if ((int)(blockIdx.y * NH + h) * 32 < n_rows)
                     bulk_g2s(As + (size_t)h * KC * 32, img + ((long long)(blockIdx.y * NH + h) * R + k0) * 32, (uint32_t)kc * 128u, &bar);
             }
+        }
+        if (!waited) {       // everything below reads what the preceding kernel wrote
+            pdl_prologue();
+            waited = true;
+        }
+        if (tid < 16) {
             for (int si = tid; si < nsv; si += 16) {
-                if (tid >= 16) break;
                 const int b = b0 + si;
                 if (MODE == FWD) {
                     int kk = 0;                      // rows [k0, k0+kc) of the virtual concat, source by source
@@ -187,21 +196,33 @@ __global__ void __launch_bounds__(ST) k_sg(const bmnas_conv_params p, const int 
                 for (int u = tid; u < kc * 8; u += ST) *reinterpret_cast<float4*>(As + (size_t)h * KC * 32 + u * 4) = z4;
         for (int si = nsv; si < spt; ++si)
             for (int u = tid; u < (kc * L) >> 2; u += ST) *reinterpret_cast<float4*>(Bs + (size_t)si * sstr + u * 4) = z4;
+        if (coef) {
+            for (int u = tid; u < kc; u += ST) {
+                cf[u] = __ldg(p.coef_a + k0 + u);
+                cf[KC + u] = __ldg(p.coef_b + k0 + u);
+                cf[2 * KC + u] = __ldg(p.coef_c + k0 + u);
+            }
+        }
         if (k0 == 0) TLS(1);
         mbar_wait(&bar, phase);
         phase ^= 1u;
         if (k0 == 0) TLS(2);
+        if (coef) __syncthreads();                // cf[] staged by all threads
         if (coef) {
-            // dz = a*GV + b*Z + c in place (valid samples only: padding columns stay zero)
+            // dz = a*GV + b*Z + c in place (valid samples only: padding columns stay zero); the per-row coefficients
+            // were staged in shared memory while the copies were in flight
             const int per = (kc * L) >> 2;        // float4 per sample
-            for (int u = tid; u < nsv * per; u += ST) {
-                const int si = u / per, q = u - si * per;
-                const int kk = (q << 2) >> lshift;
-                const float ca = __ldg(p.coef_a + k0 + kk), cb = __ldg(p.coef_b + k0 + kk), cc = __ldg(p.coef_c + k0 + kk);
-                float4* d = reinterpret_cast<float4*>(Bs + (size_t)si * sstr + q * 4);
-                const float4 g = *d, z = *reinterpret_cast<const float4*>(Bz + (size_t)si * sstr + q * 4);
-                *d = make_float4(fmaf(ca, g.x, fmaf(cb, z.x, cc)), fmaf(ca, g.y, fmaf(cb, z.y, cc)), fmaf(ca, g.z, fmaf(cb, z.z, cc)),
-                                 fmaf(ca, g.w, fmaf(cb, z.w, cc)));
+            for (int si = 0; si < nsv; ++si) {
+                float* bs = Bs + (size_t)si * sstr;
+                const float* bz = Bz + (size_t)si * sstr;
+                for (int q = tid; q < per; q += ST) {
+                    const int kk = (q << 2) >> lshift;
+                    const float ca = cf[kk], cb = cf[KC + kk], cc = cf[2 * KC + kk];
+                    float4* d = reinterpret_cast<float4*>(bs + q * 4);
+                    const float4 g = *d, z = *reinterpret_cast<const float4*>(bz + q * 4);
+                    *d = make_float4(fmaf(ca, g.x, fmaf(cb, z.x, cc)), fmaf(ca, g.y, fmaf(cb, z.y, cc)), fmaf(ca, g.z, fmaf(cb, z.z, cc)),
+                                     fmaf(ca, g.w, fmaf(cb, z.w, cc)));
+                }
             }
         }
         __syncthreads();

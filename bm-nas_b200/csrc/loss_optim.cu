@@ -206,7 +206,7 @@ extern "C" const char* bmnas_strerror(int code) {
 }
 extern "C" int bmnas_abi_version(void) { return 1; }
 int bmnas_validate_only_flag = 0;
-int bmnas_pdl_flag = 0;
+int bmnas_pdl_flag = 1;
 extern "C" int bmnas_set_pdl(int on) {
     bmnas_pdl_flag = on ? 1 : 0;
     return BMNAS_OK;

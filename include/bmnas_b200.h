@@ -136,6 +136,7 @@ typedef struct bmnas_conv_params {
     const float* wimg_fwd;
     const float* wimg_dgrad;
     int wimg_fmt;
+    int early_ok;
 } bmnas_conv_params;
 /* wimg_fwd / wimg_dgrad (optional): images of the stacked, folded weight produced by bmnas_wprep (below), in
  * format wimg_fmt: 0 = tcgen05 slabs (the tensor-core GEMMs fetch them with TMA bulk copies), 1 = plain fp32
@@ -240,6 +241,7 @@ typedef struct bmnas_node_params {
     float* coef_c;
     float* partials;
     unsigned int* counter;
+    int early_ok;
 } bmnas_node_params;
 int bmnas_node_fwd(const bmnas_node_params* p, void* stream);
 int bmnas_node_bwd(const bmnas_node_params* p, void* stream);
@@ -374,10 +376,13 @@ int bmnas_set_validate_only(int on);
 int bmnas_set_gemm_mode(int mode);
 int bmnas_get_gemm_mode(void);
 
-/* programmatic dependent launch (off by default; measured slower on the B=96 step): every kernel is launched with
- * cudaLaunchAttributeProgrammaticStreamSerialization and opens with griddepcontrol.launch_dependents +
- * griddepcontrol.wait, so consecutive kernels overlap launch latency and prologue without changing any
- * data dependency; under stream capture the attribute becomes a programmatic graph edge. */
+/* programmatic dependent launch: every kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization
+ * (a programmatic graph edge under stream capture) and follows the protocol [early section] -> griddepcontrol.wait
+ * -> griddepcontrol.launch_dependents -> body (csrc/common.cuh).  early_ok in bmnas_conv_params / bmnas_node_params
+ * tells a kernel that its early inputs (weight images; the x / y tiles of a node op) were produced at least two
+ * kernels before it in the stream, so it may read them before the wait and overlap its predecessor: the conv
+ * kernels prefetch the weight tile, the node kernels run the whole attention primitive (forward) / its
+ * recomputation (backward) there.  The caller sets it; 0 is always safe. */
 int bmnas_set_pdl(int on);
 
 /* rng_state = {seed, step}: advance the step counter on-device (one launch per search step) */
