@@ -178,12 +178,84 @@ def graph_time_us(call, R=50, reps=4):
     return e0.elapsed_time(e1) * 1e3 / (reps * R)
 
 
+def algorithmic_bytes(call, c, B):
+    """HBM bytes one launch must move: tensors read once + tensors written once, fp32"""
+    st, T = call.st, B * c['C'] * c['L'] * 4
+    n = call.name
+    if n == 'bmnas_mix_fwd':
+        return (st.n + 1) * T
+    if n == 'bmnas_mix_bwd':
+        return (2 * st.n + 1) * T
+    if n == 'bmnas_node_fwd':
+        return (1 if st.alias_xy else 2) * T + st.M * c['L'] * 4 * B + T
+    if n == 'bmnas_node_bwd':
+        return (2 if st.alias_xy else 3) * T + 2 * st.M * c['L'] * 4 * B + (1 if st.alias_xy else 2) * T
+    if n == 'bmnas_conv_fwd':
+        return (st.K + st.M) * c['L'] * 4 * B + st.K * st.M * 4
+    if n == 'bmnas_conv_dgrad':
+        return (2 * st.M + st.K) * c['L'] * 4 * B + st.K * st.M * 4
+    if n == 'bmnas_conv_wgrad':
+        return (2 * st.M + st.K) * c['L'] * 4 * B + st.K * st.M * 4
+    if n == 'bmnas_ln_fwd':
+        return (st.Ctot + (st.Ctot if st.mode == 1 else 0) + st.Ctot) * c['L'] * 4 * B
+    if n == 'bmnas_ln_bwd':
+        return 4 * st.Ctot * c['L'] * 4 * B
+    return 0
+
+
+def large_batch_roofline(args, c, pk, device, B):
+    """the same kernels at a batch where they are bandwidth bound: per-kernel device time (graph-replayed
+    launches), algorithmic bytes and fraction of the HBM peak; heaviest instance of each kernel"""
+    import types
+    from bmnas.nn import SearchHead, CrossEntropyLoss, BCEWithLogitsLoss
+    from bmnas.search import SearchStep
+    c = dict(c, B=B)
+    a = types.SimpleNamespace(**{k: c[k] for k in ('C', 'L', 'num_input_nodes', 'steps', 'multiplier', 'node_steps',
+                                                    'node_multiplier', 'drpt')}, weight_decay=c['weight_decay'])
+    crit = CrossEntropyLoss() if c['loss'] == 'ce' else BCEWithLogitsLoss()
+    head = SearchHead(a, c['classes'], criterion=crit).to(device)
+    ss = SearchStep(head, crit, B, c['classes'], loss_kind=c['loss'], use_graphs=False)
+    pool = make_pool(c, 2, 77, device)
+    ss.load('dev', *pool[0]); ss.load('train', *pool[1])
+    for _ in range(2):
+        ss.step()
+    torch.cuda.synchronize()
+    runner = [r for r in head.fusion_net._bm_cache.values() if r.prog.training][0]
+    keep_gout = torch.zeros_like(runner.out)
+    runner.prog.bind('gout', keep_gout)        # the upstream-gradient slot pointed at a freed autograd temporary
+    best = {}
+    for call in runner.prog.fwd + runner.prog.bwd:
+        by = algorithmic_bytes(call, c, B)
+        if by and (call.name not in best or by > best[call.name][1]):
+            best[call.name] = (call, by)
+    out = {'B': B, 'peak_GBs': pk['hbm'], 'peak_source': pk['src'], 'kernels': {}}
+    for name, (call, by) in sorted(best.items()):
+        us = graph_time_us(call, R=10, reps=3)
+        gbs = by / (us * 1e-6) / 1e9
+        out['kernels'][name] = {'us': round(us, 1), 'algorithmic_MB': round(by / 1e6, 1), 'GBs': round(gbs, 1),
+                                'frac': round(gbs / pk['hbm'], 4)}
+    del ss, head, pool
+    torch.cuda.empty_cache()
+    return out
+
+
+def ncu_traffic(kernel, B):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (profiles/)"""
+    try:
+        d = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
+        return d.get(f'{kernel}@B{B}')
+    except Exception:
+        return None
+
+
 def kernel_roofline(head, ss, c, pk):
     """average duration of the dominant fused MixedOp kernels (bmnas_node_fwd / bmnas_node_bwd), timed live with
     CUDA events around graph-replayed back-to-back launches of the prepared parameter blocks."""
     from bmnas import native as N
     runner = [r for r in head.fusion_net._bm_cache.values() if r.prog.training][0]
     prog = runner.prog
+    keep_gout = torch.zeros_like(runner.out)
+    prog.bind('gout', keep_gout)
     res = {}
     for name, calls in (('bmnas_node_fwd', prog.fwd), ('bmnas_node_bwd', prog.bwd)):
         call = [x for x in calls if x.name == name][0]
@@ -196,9 +268,11 @@ def kernel_roofline(head, ss, c, pk):
     ach = fwd_bytes / t / 1e9
     return {'bound': 'hbm', 'kernel': 'bmnas_node_fwd (fused NodeMixedOp forward)', 'achieved': round(ach, 2),
             'peak': pk['hbm'], 'peak_source': pk['src'], 'unit': 'GB/s', 'frac': round(ach / pk['hbm'], 5),
-            'traffic': None, 'avg_launch_us': {k: round(v, 3) for k, v in res.items()},
+            'traffic': ncu_traffic('bmnas_node_fwd', c['B']), 'avg_launch_us': {k: round(v, 3) for k, v in res.items()},
             'algorithmic_bytes_per_launch': fwd_bytes,
-            'note': 'B=%d working set is L2-resident and the kernel is latency-bound at this size; see DESIGN.md' % c['B']}
+            'note': 'B=%d working set is L2-resident and the kernel is latency-bound at this size (graph-replayed launches, '
+                    'programmatic dependent launch overlaps the early section of launch i+1 with launch i); '
+                    'roofline_large_batch times the same kernels where they are bandwidth bound' % c['B']}
 
 
 def profile_kernels(head, R=50):
@@ -209,6 +283,8 @@ def profile_kernels(head, R=50):
     import ctypes
     runner = [r for r in head.fusion_net._bm_cache.values() if r.prog.training][0]
     prog = runner.prog
+    keep_gout = torch.zeros_like(runner.out)
+    prog.bind('gout', keep_gout)               # the upstream-gradient slot pointed at a freed autograd temporary
     rows = []
     for phase, calls in (('fwd', prog.fwd), ('bwd', prog.bwd)):
         for i, call in enumerate(calls):
@@ -305,6 +381,18 @@ def run_ours(args):
     e2e_value = gB * args.steps / (e2e_ms_wall * 1e-3)
     lab_bytes = c['B'] * (8 if c['loss'] == 'ce' else 4 * c['classes'])
     out = None
+    if rank == 0 and args.profile_kernels and ss.graphs:
+        for which in ('dev', 'train'):
+            g = ss.graphs[which]
+            for _ in range(5):
+                g.replay()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(100):
+                g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            print('# graph replay (%s half step, back to back, no input copies): %.1f us' % (which, e0.elapsed_time(e1) * 10))
     if rank == 0 and args.profile_kernels:
         rows = profile_kernels(head)
         tot = sum(r[3] for r in rows)
@@ -314,6 +402,9 @@ def run_ours(args):
     if rank == 0:
         pk = peaks()
         roof = kernel_roofline(head, ss, c, pk)
+        big = None
+        if world == 1 and args.roofline_batch > 0:
+            big = large_batch_roofline(args, c, pk, device, args.roofline_batch)
         cpu = None
         if world == 1 and not args.no_cpu:
             v, ms, cores, done = cpu_reference(args.config, 40, 3, max_seconds=20.0)
@@ -340,7 +431,7 @@ def run_ours(args):
                            'wall clock between barriers'},
             'gpu_launches': (ss.launches_per_step or 0) * args.steps,
             'launches_per_step': ss.launches_per_step,
-            'roofline': roof, 'cpu_baseline': cpu, 'clocks': clk,
+            'roofline': roof, 'roofline_large_batch': big, 'cpu_baseline': cpu, 'clocks': clk,
         }
         print(json.dumps(out), flush=True)
     if world > 1:
@@ -379,6 +470,8 @@ def main():
     ap.add_argument('--no-graphs', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--profile-kernels', action='store_true')
+    ap.add_argument('--roofline-batch', type=int, default=8192,
+                    help='also time the kernels at this per-GPU batch (bandwidth-bound regime); 0 = skip')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

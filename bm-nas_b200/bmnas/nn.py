@@ -1,8 +1,8 @@
 """Head of the search network: classifier GEMM and loss on the same C-ABI kernels.
 
 * Linear            -- nn.Linear drop-in (ntu_darts_searchable.py:100-101, central_classifier);
-                       forward = NT GEMM (bmnas_conv_wgrad as C += A B^T on a bias-initialised
-                       output), backward = bmnas_conv_fwd (dX) + bmnas_conv_dgrad (dW) + bmnas_colsum (db).
+                       bmnas_linear_fwd / bmnas_linear_bwd (csrc/linear.cu: three skinny single-launch GEMMs);
+                       shapes those cannot take fall back to the generic conv GEMM kernels.
 * CrossEntropyLoss / BCEWithLogitsLoss -- mean-reduced criteria of the search scripts
                        (ntu_darts_searchable.py:25, mmimdb_darts_searchable.py:22), fused
                        softmax/sigmoid + gradient kernel.
@@ -31,20 +31,29 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+def _lin_ok(x, weight):
+    return x.shape[1] % 4 == 0 and x.data_ptr() % 16 == 0 and weight.data_ptr() % 16 == 0 and weight.shape[0] <= 1024
+
+
 class _LinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, gw_view, gb_view):
         B, Kc = x.shape
         Nc = weight.shape[0]
         s = N.current_stream()
-        L = N.lib()
         out = torch.empty(B, Nc, device=x.device, dtype=torch.float32)
-        N.launch('bmnas_bias_rows', ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(_p(bias)), B, Nc, s)
-        st = _conv_struct(1, Kc, Nc, B)       # out[m=b][k=class] += sum_l x[b][l] * W[class][l]
-        st.GV = x.data_ptr()
-        st.src[0] = weight.data_ptr()
-        st.gW[0] = out.data_ptr()
-        N.launch('bmnas_conv_wgrad', ctypes.byref(st), s)
+        if _lin_ok(x, weight):
+            st = N.bmnas_linear_params()
+            st.B, st.K, st.N = B, Kc, Nc
+            st.x, st.W, st.bias, st.out = x.data_ptr(), weight.data_ptr(), _p(bias), out.data_ptr()
+            N.launch('bmnas_linear_fwd', ctypes.byref(st), s)
+        else:   # odd shapes: generic GEMM kernels (NT GEMM = bmnas_conv_wgrad on a bias-initialised output)
+            N.launch('bmnas_bias_rows', ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(_p(bias)), B, Nc, s)
+            st = _conv_struct(1, Kc, Nc, B)       # out[m=b][k=class] += sum_l x[b][l] * W[class][l]
+            st.GV = x.data_ptr()
+            st.src[0] = weight.data_ptr()
+            st.gW[0] = out.data_ptr()
+            N.launch('bmnas_conv_wgrad', ctypes.byref(st), s)
         ctx.save_for_backward(x, weight)
         ctx.views = (gw_view, gb_view)
         ctx.has_bias = bias is not None
@@ -58,8 +67,17 @@ class _LinearFn(torch.autograd.Function):
         B, Kc = x.shape
         Nc = weight.shape[0]
         s = N.current_stream()
-        L = N.lib()
         gx = None
+        if _lin_ok(x, weight) and (gw_view is None or gw_view.data_ptr() % 16 == 0):
+            st = N.bmnas_linear_params()
+            st.B, st.K, st.N = B, Kc, Nc
+            st.x, st.W, st.gout = x.data_ptr(), weight.data_ptr(), g.data_ptr()
+            if ctx.needs_input_grad[0]:
+                gx = torch.empty_like(x)
+                st.gx = gx.data_ptr()
+            st.gW, st.gbias = _p(gw_view), _p(gb_view)
+            N.launch('bmnas_linear_bwd', ctypes.byref(st), s)
+            return gx, None, None, None, None
         if ctx.needs_input_grad[0]:
             gx = torch.empty_like(x)
             st = _conv_struct(1, Kc, Nc, B)   # gx[b][l] = sum_class g[b][class] * W[class][l]

@@ -446,6 +446,8 @@ int tc_conv_wgrad(const bmnas_conv_params* p, int x3, cudaStream_t stream);
 bool sg_eligible(const bmnas_conv_params* p, int mode);
 int sg_conv_fwd(const bmnas_conv_params* p, cudaStream_t stream);
 int sg_conv_dgrad(const bmnas_conv_params* p, cudaStream_t stream);
+bool sgw_eligible(const bmnas_conv_params* p);
+int sg_conv_wgrad(const bmnas_conv_params* p, cudaStream_t stream);
 }  // namespace bmnas
 
 // GEMM engine: 0 = fp32 FFMA tiles, 1 = tcgen05 3xTF32 (fp32-class accuracy), 2 = tcgen05 1xTF32 (reduced precision)
@@ -567,6 +569,9 @@ extern "C" int bmnas_conv_wgrad(const bmnas_conv_params* p, void* stream) {
     for (int i = 0; i < p->n_src; ++i)
         if (!p->src[i]) return BMNAS_EINVAL;
     BMNAS_DRY_RETURN();
+    // fp32 parity engines: the transposing FFMA kernel (gemm_sg.cu) beats the 3xTF32 UMMA ring at every batch
+    // (21 us -> 6 us at B=96); the reduced-precision mode keeps the single-pass TF32 tensor-core kernel
+    if (bmnas_gemm_mode_flag != 2 && sgw_eligible(p)) return sg_conv_wgrad(p, (cudaStream_t)stream);
     if (bmnas_gemm_mode_flag && tc_eligible(p, 2)) return tc_conv_wgrad(p, bmnas_gemm_mode_flag == 1, (cudaStream_t)stream);
     const int N = p->B * p->L, L = p->L;
     const int tiles = ((p->K + TN - 1) / TN) * ((p->M + TM - 1) / TM);

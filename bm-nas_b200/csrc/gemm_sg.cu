@@ -334,6 +334,172 @@ __global__ void __launch_bounds__(ST) k_sg(const bmnas_conv_params p, const int 
 // plain-fp32 weight images (fmt 1), tile major: [output-row tile of 32][reduction][32]; which 0 = FWD (rows m,
 // reduction k), 1 = DGRAD (rows k, reduction m); the last tile is zero padded
 
+// --------------------------------------------------------------------------------------------------
+// WGRAD  dW[m,k] += sum_{b,l} dz[b,m,l] U[b,k,l],  dbias[m] += sum_{b,l} dz[b,m,l]       (red.add onto gW / gbias)
+// 64 (m) x 32 (k) output tile per CTA; the reduction runs over chunks of 128/L samples, blockIdx.z strides over
+// the chunks (split-K across the machine: 144 CTAs at the NTU batch) and the partial tiles are accumulated with
+// vector red.add.  Both operands are (sample, row, l) in memory with l fastest, but the FFMA loop wants
+// reduction-major rows, so the staging pass transposes: coalesced 128-bit loads (a row tile of one sample is one
+// contiguous block), BatchNorm-backward fold on the fly, conflict-free scalar stores to [r = (sample, l)][row].
+// --------------------------------------------------------------------------------------------------
+constexpr int WTM = 64, WTK = 32, WR = 128;          // tile rows (m), tile cols (k), reduction elements per chunk
+constexpr int WLDA = WTM + 4, WLDB = WTK + 4;
+
+__global__ void __launch_bounds__(ST) k_sgw(const bmnas_conv_params p, const int lshift) {
+    pdl_prologue();
+    extern __shared__ __align__(16) float smem[];
+    float* A2 = smem;                       // [WR][WLDA]
+    float* B2 = A2 + WR * WLDA;             // [WR][WLDB]
+    float* cf = B2 + WR * WLDB;             // coef_a | coef_b | coef_c of the 64 rows
+    const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
+    const int m0 = blockIdx.y * WTM, kt0 = blockIdx.x * WTK;
+    const int K = p.K, M = p.M, L = p.L, ldw = p.w_fold * p.K;
+    const int SB = WR >> lshift;            // samples per chunk
+    const int q4 = L >> 2, q4s = lshift - 2;   // float4 per row
+    const bool coef = p.coef_a != nullptr;
+    if (coef) {
+        for (int u = tid; u < WTM; u += ST) {
+            const bool ok = m0 + u < M;
+            cf[u] = ok ? __ldg(p.coef_a + m0 + u) : 0.f;
+            cf[WTM + u] = ok ? __ldg(p.coef_b + m0 + u) : 0.f;
+            cf[2 * WTM + u] = ok ? __ldg(p.coef_c + m0 + u) : 0.f;
+        }
+    }
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float rowsum = 0.f;                      // bias gradient of row m0 + tid (threads < 64 of the k-tile-0 CTAs)
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int n_chunks = (p.B + SB - 1) / SB;
+
+    for (int ch = blockIdx.z; ch < n_chunks; ch += gridDim.z) {
+        const int b0 = ch * SB, nsv = min(SB, p.B - b0);
+        __syncthreads();                     // previous chunk's FFMA loop (and cf[]) done
+        // ---- dz tile, transposed: unit u = (sample si, row m, l-group lq), lq fastest
+        constexpr int UB = 8;
+        const int unitsA = SB * WTM * q4;
+        for (int u0 = tid; u0 < unitsA; u0 += ST * UB) {
+            float4 g[UB], z[UB];
+#pragma unroll
+            for (int i = 0; i < UB; ++i) {
+                const int u = u0 + i * ST;
+                g[i] = z[i] = z4;
+                if (u < unitsA) {
+                    const int lq = u & (q4 - 1), m = (u >> q4s) & (WTM - 1), si = u >> (q4s + 6);
+                    if (si < nsv && m0 + m < M) {
+                        const long long idx = ((long long)(b0 + si) * M + m0 + m) * L + lq * 4;
+                        g[i] = __ldg(reinterpret_cast<const float4*>(p.GV + idx));
+                        if (coef) z[i] = __ldg(reinterpret_cast<const float4*>(p.Z + idx));
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < UB; ++i) {
+                const int u = u0 + i * ST;
+                if (u < unitsA) {
+                    const int lq = u & (q4 - 1), m = (u >> q4s) & (WTM - 1), si = u >> (q4s + 6);
+                    float4 v = g[i];
+                    if (coef && si < nsv && m0 + m < M) {
+                        const float a = cf[m], b = cf[WTM + m], c = cf[2 * WTM + m];
+                        v = make_float4(fmaf(a, v.x, fmaf(b, z[i].x, c)), fmaf(a, v.y, fmaf(b, z[i].y, c)), fmaf(a, v.z, fmaf(b, z[i].z, c)),
+                                        fmaf(a, v.w, fmaf(b, z[i].w, c)));
+                    }
+                    float* d = A2 + ((si << lshift) + lq * 4) * WLDA + m;
+                    d[0] = v.x; d[WLDA] = v.y; d[2 * WLDA] = v.z; d[3 * WLDA] = v.w;
+                }
+            }
+        }
+        // ---- activation tile, transposed: unit u = (sample si, channel kk, l-group lq)
+        const int unitsB = SB * WTK * q4;
+        for (int u0 = tid; u0 < unitsB; u0 += ST * UB) {
+            float4 g[UB];
+#pragma unroll
+            for (int i = 0; i < UB; ++i) {
+                const int u = u0 + i * ST;
+                g[i] = z4;
+                if (u < unitsB) {
+                    const int lq = u & (q4 - 1), kk = (u >> q4s) & (WTK - 1), si = u >> (q4s + 5);
+                    if (si < nsv && kt0 + kk < K) {
+                        int s, kl;
+                        src_of(p, kt0 + kk, &s, &kl);
+                        g[i] = __ldg(reinterpret_cast<const float4*>(p.src[s] + ((long long)(b0 + si) * p.src_C[s] + kl) * L + lq * 4));
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < UB; ++i) {
+                const int u = u0 + i * ST;
+                if (u < unitsB) {
+                    const int lq = u & (q4 - 1), kk = (u >> q4s) & (WTK - 1), si = u >> (q4s + 5);
+                    float* d = B2 + ((si << lshift) + lq * 4) * WLDB + kk;
+                    d[0] = g[i].x; d[WLDB] = g[i].y; d[2 * WLDB] = g[i].z; d[3 * WLDB] = g[i].w;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- FFMA: 4 x 4 micro-tile, register double buffering (see k_sg)
+        const float* ap = A2 + ty * 4;
+        const float* bp = B2 + tx * 4;
+        constexpr int KB = 4;
+        float4 a0[KB], a1[KB], b0v[KB], b1v[KB];
+        auto load_blk = [&](float4 (&a)[KB], float4 (&b)[KB], int r) {
+#pragma unroll
+            for (int j = 0; j < KB; ++j) {
+                a[j] = *reinterpret_cast<const float4*>(ap + (r + j) * WLDA);
+                b[j] = *reinterpret_cast<const float4*>(bp + (r + j) * WLDB);
+            }
+        };
+        auto fma_blk = [&](const float4 (&a)[KB], const float4 (&b)[KB]) {
+#pragma unroll
+            for (int j = 0; j < KB; ++j) {
+                const float av[4] = {a[j].x, a[j].y, a[j].z, a[j].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    acc[i][0] = fmaf(av[i], b[j].x, acc[i][0]);
+                    acc[i][1] = fmaf(av[i], b[j].y, acc[i][1]);
+                    acc[i][2] = fmaf(av[i], b[j].z, acc[i][2]);
+                    acc[i][3] = fmaf(av[i], b[j].w, acc[i][3]);
+                }
+            }
+        };
+        constexpr int NBLK = WR / KB;
+        load_blk(a0, b0v, 0);
+#pragma unroll 1
+        for (int blk = 0; blk + 2 <= NBLK; blk += 2) {
+            load_blk(a1, b1v, (blk + 1) * KB);
+            fma_blk(a0, b0v);
+            if (blk + 2 < NBLK) load_blk(a0, b0v, (blk + 2) * KB);
+            fma_blk(a1, b1v);
+        }
+        if (blockIdx.x == 0 && tid < WTM) {   // bias gradient = row sums of dz
+            float s_ = 0.f;
+            for (int r = 0; r < WR; ++r) s_ += A2[r * WLDA + tid];
+            rowsum += s_;
+        }
+    }
+
+    // ---- epilogue: vector red.add of the partial tile (both halves of a folded weight)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i, k = kt0 + tx * 4;
+        if (m >= M || k >= K) continue;
+        int sg_, ml;
+        w_row(p, m, ldw, &sg_, &ml);
+        if (!p.gW[sg_]) continue;
+        float* row = p.gW[sg_] + (long long)ml * ldw + k;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row), "f"(acc[i][0]), "f"(acc[i][1]), "f"(acc[i][2]), "f"(acc[i][3]) : "memory");
+        if (p.w_fold == 2)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + K), "f"(acc[i][0]), "f"(acc[i][1]), "f"(acc[i][2]), "f"(acc[i][3]) : "memory");
+    }
+    if (blockIdx.x == 0 && tid < WTM && m0 + tid < M) {
+        int sg_, ml;
+        w_row(p, m0 + tid, ldw, &sg_, &ml);
+        if (p.gbias[sg_]) atomicAdd(p.gbias[sg_] + ml, rowsum);
+    }
+}
+
 template <int MODE, int TM>
 static int launch_sg(const bmnas_conv_params* p, cudaStream_t stream) {
     const int N = p->B * p->L;
@@ -376,6 +542,39 @@ int sg_conv_fwd(const bmnas_conv_params* p, cudaStream_t stream) {
     const int N = p->B * p->L;
     const long long t64 = (long long)((p->M + 63) / 64) * ((N + TN - 1) / TN);
     return t64 >= 120 ? launch_sg<FWD, 64>(p, stream) : launch_sg<FWD, 32>(p, stream);
+}
+
+// wgrad: vector red.add needs K % 4 == 0 and 16-byte aligned weight-gradient rows
+bool sgw_eligible(const bmnas_conv_params* p) {
+    using namespace sg;
+    if ((p->L & 3) || (p->K & 3) || (p->L & (p->L - 1)) || p->L > 32) return false;
+    for (int i = 0; i < p->n_src; ++i)
+        if ((p->src_C[i] & 3) || !al16(p->src[i])) return false;
+    for (int i = 0; i < p->n_seg; ++i)
+        if (p->gW[i] && !al16(p->gW[i])) return false;
+    return al16(p->GV) && (!p->coef_a || al16(p->Z));
+}
+
+int sg_conv_wgrad(const bmnas_conv_params* p, cudaStream_t stream) {
+    using namespace sg;
+    int lshift = 0;
+    while ((1 << lshift) < p->L) ++lshift;
+    const int SB = WR >> lshift, n_chunks = (p->B + SB - 1) / SB;
+    const int tiles = ((p->K + WTK - 1) / WTK) * ((p->M + WTM - 1) / WTM);
+    int zs = (kNumSMs + tiles - 1) / tiles;
+    if (p->splits > 0) zs = p->splits;
+    if (zs > n_chunks) zs = n_chunks;
+    if (zs < 1) zs = 1;
+    const size_t smem = (size_t)(WR * (WLDA + WLDB) + 3 * WTM) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_sgw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return BMNAS_ELAUNCH;
+        configured = true;
+    }
+    dim3 grid((p->K + WTK - 1) / WTK, (p->M + WTM - 1) / WTM, zs);
+    launch_k(k_sgw, grid, ST, smem, stream, *p, lshift);
+    BMNAS_LAUNCH_CHECK();
+    return BMNAS_OK;
 }
 
 int sg_conv_dgrad(const bmnas_conv_params* p, cudaStream_t stream) {

@@ -330,6 +330,29 @@ int bmnas_bias_rows(float* out, const float* bias, int rows, int n, void* stream
 int bmnas_colsum(float* out, const float* in, int rows, int n, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Classifier head nn.Linear (central_classifier: ntu_darts_searchable.py:100-101, 176-178;
+ * mmimdb_darts_searchable.py / ego_darts_searchable.py likewise): x (B,K) row major, W (N,K), out (B,N).
+ *   fwd: out = x W^T + bias                      (bias may be NULL)
+ *   bwd: gx = gout W (if gx), gW = gout^T x (if gW), gbias = column sums of gout (if gbias);
+ *        every result OVERWRITES its destination.  K % 4 == 0, 16-byte aligned x / W / gx / gW.
+ * ---------------------------------------------------------------------- */
+typedef struct bmnas_linear_params {
+    int B;
+    int K;
+    int N;
+    const float* x;
+    const float* W;
+    const float* bias;
+    float* out;
+    const float* gout;
+    float* gx;
+    float* gW;
+    float* gbias;
+} bmnas_linear_params;
+int bmnas_linear_fwd(const bmnas_linear_params* p, void* stream);
+int bmnas_linear_bwd(const bmnas_linear_params* p, void* stream);
+
+/* ------------------------------------------------------------------------
  * Multi-tensor Adam, identical arithmetic to torch.optim.Adam (coupled L2 weight
  * decay, bias correction, eps outside the sqrt):
  *   weights  ntu_darts_searchable.py:42    arch  :46-47   (architect.py:24 step)

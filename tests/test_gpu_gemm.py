@@ -192,3 +192,28 @@ def test_conv_backward_engines(mode, img, case, coef):
     for f in range(w_fold):
         assert _rel(dWc[:, f * K:(f + 1) * K], dW) < tol * 4, ('wgrad', f, _rel(dWc[:, f * K:(f + 1) * K], dW))
     assert _rel(torch.cat(gb), db) < tol * 4, ('bias', _rel(torch.cat(gb), db))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('B,K,Nc,bias', [(96, 2048, 60, True), (32, 6144, 23, True), (7, 36, 5, False), (13, 260, 83, True)])
+def test_linear_head(B, K, Nc, bias):
+    """bmnas.nn.Linear (csrc/linear.cu) against torch.nn.functional.linear in float64: output, gx, gW, gb.
+    central_classifier of the search networks (ntu_darts_searchable.py:100-101)."""
+    from bmnas.nn import Linear
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(5)
+    lin = Linear(K, Nc, bias=bias).to(dev)
+    x = torch.randn(B, K, generator=g).to(dev).requires_grad_(True)
+    w = torch.randn(B, Nc, generator=g).to(dev)
+    out = lin(x)
+    (out * w).sum().backward()
+    xr = x.detach().double().requires_grad_(True)
+    Wr = lin.weight.detach().double().requires_grad_(True)
+    br = lin.bias.detach().double().requires_grad_(True) if bias else None
+    outr = torch.nn.functional.linear(xr, Wr, br)
+    (outr * w.double()).sum().backward()
+    assert _rel(out.detach(), outr.detach()) < 1e-5
+    assert _rel(x.grad, xr.grad) < 1e-5
+    assert _rel(lin.weight.grad, Wr.grad) < 1e-5
+    if bias:
+        assert _rel(lin.bias.grad, br.grad) < 1e-5
