@@ -46,6 +46,11 @@ class SearchStep:
         self.graphs = {}
         self.launches_per_step = None
         self.steps_done = 0
+        # input pipeline (prefetch()): a copy stream fills the static buffers of the NEXT half step while the
+        # current one computes; _ready[which] = copy finished, _done[which] = last reader of the buffers finished
+        self.copy_stream = None
+        self._ready = {'dev': None, 'train': None}
+        self._done = {'dev': None, 'train': None}
 
     # ------------------------------------------------------------------ one half step, eager
     def _half(self, which):
@@ -65,16 +70,45 @@ class SearchStep:
             torch.distributed.all_reduce(self.head._joint_arena(self.device).flat, group=self.group)
 
     def _run_half(self, which):
+        ev = self._ready[which]
+        if ev is not None:                   # a prefetch()ed batch: the compute stream waits for its copy
+            torch.cuda.current_stream().wait_event(ev)
+            self._ready[which] = None
         g = self.graphs.get(which)
         if g is not None:
             g.replay()
         else:
             self.loss[which] = self._half(which)
+        if self.copy_stream is not None:     # the next prefetch() into these buffers must wait for this reader
+            d = self._done[which]
+            if d is None:
+                d = self._done[which] = torch.cuda.Event()
+            d.record(torch.cuda.current_stream())
 
     def load(self, which, feats_flat, labels):
         """copy a batch (any device, e.g. pinned host memory) into the static buffers; async"""
         self.flat[which].copy_(feats_flat, non_blocking=True)
         self.labels[which].copy_(labels, non_blocking=True)
+
+    def prefetch(self, which, feats_flat, labels):
+        """load() for an input pipeline: the copy runs on a dedicated stream, ordered after the last half step that
+        read these buffers and before the next one that will, so the host->device transfer of the next batch
+        overlaps the half step in flight (the 'dev' batch of step i+1 travels during the weight half of step i,
+        the 'train' batch during the arch half of step i+1).  Source in pinned memory for a truly async copy."""
+        if self.copy_stream is None:
+            self.copy_stream = torch.cuda.Stream(device=self.device)
+        cs = self.copy_stream
+        d = self._done[which]
+        if d is not None:
+            cs.wait_event(d)
+        else:                                # no half step has run through the pipeline yet: order after everything queued
+            cs.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cs):
+            self.flat[which].copy_(feats_flat, non_blocking=True)
+            self.labels[which].copy_(labels, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(cs)
+        self._ready[which] = ev
 
     # ------------------------------------------------------------------ state snapshot (warm-up must not train)
     def _snapshot(self):

@@ -569,9 +569,13 @@ extern "C" int bmnas_conv_wgrad(const bmnas_conv_params* p, void* stream) {
     for (int i = 0; i < p->n_src; ++i)
         if (!p->src[i]) return BMNAS_EINVAL;
     BMNAS_DRY_RETURN();
-    // fp32 parity engines: the transposing FFMA kernel (gemm_sg.cu) beats the 3xTF32 UMMA ring at every batch
-    // (21 us -> 6 us at B=96); the reduced-precision mode keeps the single-pass TF32 tensor-core kernel
-    if (bmnas_gemm_mode_flag != 2 && sgw_eligible(p)) return sg_conv_wgrad(p, (cudaStream_t)stream);
+    // fp32 parity engines: the transposing FFMA kernel (gemm_sg.cu) beats the 3xTF32 UMMA ring while the problem is
+    // latency bound (B=96: 9 us vs 21 us); the UMMA ring wins from a few thousand reduction columns on (measured,
+    // profiles/r01_v6_kernel_times_B1024.txt: 65 us vs 33 us at B*L = 8192).  FFMA mode (0) has no tensor-core
+    // engine and the reduced-precision mode (2) keeps the single-pass TF32 kernel.
+    const long long Ncols = (long long)p->B * p->L;
+    const bool tc_ok = bmnas_gemm_mode_flag && tc_eligible(p, 2);
+    if (bmnas_gemm_mode_flag != 2 && sgw_eligible(p) && (Ncols <= 2560 || !tc_ok)) return sg_conv_wgrad(p, (cudaStream_t)stream);
     if (bmnas_gemm_mode_flag && tc_eligible(p, 2)) return tc_conv_wgrad(p, bmnas_gemm_mode_flag == 1, (cudaStream_t)stream);
     const int N = p->B * p->L, L = p->L;
     const int tiles = ((p->K + TN - 1) / TN) * ((p->M + TM - 1) / TM);

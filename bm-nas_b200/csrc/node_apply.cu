@@ -344,6 +344,272 @@ __global__ void __launch_bounds__(NTH) k_node_fwd(const bmnas_node_params p) {
     if (!waited) pdl_prologue();
 }
 
+// ----------------------------------------------------------------------------------------------------------
+// Warp-per-sample forward (large batch).  The CTA-per-sample kernel above is latency optimal when the batch is
+// smaller than the machine (B=96: one sample per SM, 256 threads cooperate on it, ~10 block barriers per sample);
+// once there are more samples than warp slots those barriers and the short dependent phases between them cap it
+// near 18 % of the HBM roofline (profiles/r01_v6_bench.json, B=8192).  Here ONE WARP owns a sample from load to
+// store: lane `lane` holds the channels c = t*32 + lane (t < T) with all L positions in registers (a channel row
+// is L*4 contiguous bytes, so a warp's loads and stores are contiguous kilobyte runs), the x / y tiles and the
+// L x L attention matrix live in a private shared-memory slab, and every reduction is a warp shuffle -- no block
+// barrier inside the sample loop.  Needs L in {4, 8, 16}, T*L <= 32 register slots per tensor, 128-bit alignment.
+// Dropout uses exactly the group-of-4 Philox stream of the kernels above, so a forward through this kernel and a
+// backward through k_node_bwd see the same masks.
+constexpr int WPC = 8;            // warps (= samples in flight) per CTA
+constexpr int WMAXZ = 3;          // conv-backed primitives per mixed op the warp kernel takes (at most one of them a GLU)
+
+struct WarpOps {
+    float wsum, wattn;
+    int has_sum, k_attn, nz;
+    int type[WMAXZ], zo[WMAXZ], k[WMAXZ];
+    float w[WMAXZ];
+};
+
+__host__ __device__ inline size_t node_warp_smem_floats(int C, int L, int M, bool alias) {
+    const size_t CLr = rnd4((size_t)C * L), Mr = rnd4((size_t)M);
+    return 4 * Mr + WPC * ((alias ? 1 : 2) * CLr + rnd4((size_t)L * L)) + 16;
+}
+
+__device__ __forceinline__ float4 lds4(const float* q) { return *reinterpret_cast<const float4*>(q); }
+__device__ __forceinline__ float4 ldg4(const float* q) { return __ldg(reinterpret_cast<const float4*>(q)); }
+
+template <int L, int T>
+__global__ void __launch_bounds__(WPC * 32, 2) k_node_fwd_warp(const bmnas_node_params p) {
+    pdl_prologue();
+    extern __shared__ __align__(16) float smem[];
+    __shared__ float s_gw[BMNAS_MAX_OPS];
+    __shared__ WarpOps s_ops;
+    constexpr int Q = L / 4, KS = 32 / L;     // float4 per channel row; lanes sharing one query row in the score pass
+    const int C = p.C, CL = C * L, M = p.M;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool alias = p.alias_xy != 0;
+    const size_t CLr = rnd4((size_t)CL), Mr = rnd4((size_t)M);
+    NodeSmem sm;
+    sm.rs = smem; sm.mr = sm.rs + Mr; sm.bw = sm.mr + Mr; sm.bb = sm.bw + Mr;
+    sm.gw = s_gw;
+    float* xs = sm.bb + Mr + (size_t)warp * ((alias ? 1 : 2) * CLr + rnd4((size_t)L * L));
+    float* ys = alias ? xs : xs + CLr;
+    float* Ps = xs + (alias ? 1 : 2) * CLr;
+    node_setup_gamma(p, sm);
+    if (threadIdx.x == 0) {                  // same thread that wrote gw: fold the op list into one descriptor
+        WarpOps o;
+        o.wsum = o.wattn = 0.f;
+        o.has_sum = 0; o.k_attn = -1; o.nz = 0;
+        for (int k = 0; k < p.n_ops; ++k) {
+            const int ty = p.op_type[k];
+            if (ty == BMNAS_OP_SUM) { o.wsum += s_gw[k]; o.has_sum = 1; }
+            else if (ty == BMNAS_OP_ATTN) { o.wattn = s_gw[k]; o.k_attn = k; }
+            else if (o.nz < WMAXZ) { o.type[o.nz] = ty; o.zo[o.nz] = p.z_off[k]; o.k[o.nz] = k; o.w[o.nz] = s_gw[k]; ++o.nz; }
+        }
+        s_ops = o;
+    }
+    node_setup_bn(p, sm);                    // ends with __syncthreads(): s_gw, s_ops and the BN constants are visible
+    const int k_attn = s_ops.k_attn, nz = s_ops.nz;
+    const float inv_sqrt_c = 1.f / sqrtf((float)C);
+    const int gwarp = blockIdx.x * WPC + warp, gstride = gridDim.x * WPC;
+
+    for (int b = gwarp; b < p.B; b += gstride) {
+        const long long base = (long long)b * CL;
+        const unsigned long long gbase = (unsigned long long)(p.sample_offset + b) * CL;
+        __syncwarp();                        // the previous sample's readers of xs / ys / Ps are done
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const int c = t * 32 + lane;
+            if (c < C) {
+                float4 vx[Q], vy[Q];
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    vx[q] = ldg4(p.x + base + c * L + 4 * q);
+                    if (!alias) vy[q] = ldg4(p.y + base + c * L + 4 * q);
+                }
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    *reinterpret_cast<float4*>(xs + c * L + 4 * q) = vx[q];
+                    if (!alias) *reinterpret_cast<float4*>(ys + c * L + 4 * q) = vy[q];
+                }
+            }
+        }
+        __syncwarp();
+
+        float O[T][L];
+        float a_mean = 0.f, a_rstd = 0.f;
+        if (k_attn >= 0) {
+            // ---- scores: lane = (query position i, channel slice qs); S[i][:] over the slice, then over the KS lanes
+            const int i = lane / KS, qs = lane % KS;
+            float sc[L];
+#pragma unroll
+            for (int j = 0; j < L; ++j) sc[j] = 0.f;
+#pragma unroll 4
+            for (int c = qs; c < C; c += KS) {
+                const float a = xs[c * L + i];
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const float4 v = lds4(ys + c * L + 4 * q);
+                    sc[4 * q] = fmaf(a, v.x, sc[4 * q]);
+                    sc[4 * q + 1] = fmaf(a, v.y, sc[4 * q + 1]);
+                    sc[4 * q + 2] = fmaf(a, v.z, sc[4 * q + 2]);
+                    sc[4 * q + 3] = fmaf(a, v.w, sc[4 * q + 3]);
+                }
+            }
+#pragma unroll
+            for (int o = KS / 2; o > 0; o >>= 1)
+#pragma unroll
+                for (int j = 0; j < L; ++j) sc[j] += __shfl_xor_sync(0xffffffffu, sc[j], o);
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < L; ++j) {
+                sc[j] *= inv_sqrt_c;
+                mx = fmaxf(mx, sc[j]);
+            }
+            float den = 0.f;
+#pragma unroll
+            for (int j = 0; j < L; ++j) {
+                sc[j] = expf(sc[j] - mx);
+                den += sc[j];
+            }
+            if (qs == 0) {
+#pragma unroll
+                for (int q = 0; q < Q; ++q)
+                    *reinterpret_cast<float4*>(Ps + i * L + 4 * q) =
+                        make_float4(sc[4 * q] / den, sc[4 * q + 1] / den, sc[4 * q + 2] / den, sc[4 * q + 3] / den);
+            }
+            __syncwarp();
+            // ---- O[c][i] = sum_j P[i][j] y[c][j] for the lane's own channels
+            float yr[T][L];
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const int c = t * 32 + lane;
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const float4 v = c < C ? lds4(ys + c * L + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    yr[t][4 * q] = v.x; yr[t][4 * q + 1] = v.y; yr[t][4 * q + 2] = v.z; yr[t][4 * q + 3] = v.w;
+                }
+            }
+#pragma unroll
+            for (int i2 = 0; i2 < L; ++i2) {
+                float pr[L];
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const float4 v = lds4(Ps + i2 * L + 4 * q);
+                    pr[4 * q] = v.x; pr[4 * q + 1] = v.y; pr[4 * q + 2] = v.z; pr[4 * q + 3] = v.w;
+                }
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    float a = 0.f;
+#pragma unroll
+                    for (int j = 0; j < L; ++j) a = fmaf(pr[j], yr[t][j], a);
+                    O[t][i2] = a;
+                }
+            }
+            // ---- dropout(0.1) on the attention output, LayerNorm statistics over the whole (C, L) sample
+            const bool drop = p.training && p.p_drop[k_attn] > 0.f;
+            float s0 = 0.f;
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const int c = t * 32 + lane;
+                if (c < C) {
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {
+                        float ds[4];
+                        const int e0 = c * L + 4 * q;
+                        drop_v<4>(drop, p.mask[k_attn], p.rng_state, p.op_uid[k_attn], base + e0, gbase + e0,
+                                  p.p_drop[k_attn], ds);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            O[t][4 * q + r] *= ds[r];
+                            s0 += O[t][4 * q + r];
+                        }
+                    }
+                }
+            }
+            a_mean = warp_sum(s0) / (float)CL;
+            float s1 = 0.f;
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                if (t * 32 + lane < C) {
+#pragma unroll
+                    for (int j = 0; j < L; ++j) {
+                        const float d = O[t][j] - a_mean;
+                        s1 = fmaf(d, d, s1);
+                    }
+                }
+            }
+            a_rstd = 1.f / sqrtf(warp_sum(s1) / (float)CL + kLnEps);
+        }
+
+        // ---- epilogue: every primitive at the lane's own elements, softmax(gamma)-weighted sum, one store
+        const float* Zb = p.Z ? p.Z + (long long)b * M * L : nullptr;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const int c = t * 32 + lane;
+            if (c >= C) continue;
+            // conv-backed primitives first issue all their Z loads for this channel row
+            float4 za[WMAXZ][Q], zg[Q];
+#pragma unroll
+            for (int zi = 0; zi < WMAXZ; ++zi) {
+                if (zi < nz) {
+                    const int zo = s_ops.zo[zi];
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {
+                        za[zi][q] = ldg4(Zb + (long long)(zo + c) * L + 4 * q);
+                        if (s_ops.type[zi] == BMNAS_OP_GLU) zg[q] = ldg4(Zb + (long long)(zo + C + c) * L + 4 * q);
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const int e0 = c * L + 4 * q;
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                if (s_ops.has_sum) {
+                    const float4 xv = lds4(xs + e0), yv = lds4(ys + e0);
+                    const float w = s_ops.wsum;
+                    acc[0] = w * (xv.x + yv.x); acc[1] = w * (xv.y + yv.y); acc[2] = w * (xv.z + yv.z); acc[3] = w * (xv.w + yv.w);
+                }
+                if (k_attn >= 0) {
+                    const float4 lw = ldg4(p.ln_w[k_attn] + e0), lb = ldg4(p.ln_b[k_attn] + e0);
+                    const float w = s_ops.wattn;
+                    acc[0] = fmaf(w, fmaf((O[t][4 * q] - a_mean) * a_rstd, lw.x, lb.x), acc[0]);
+                    acc[1] = fmaf(w, fmaf((O[t][4 * q + 1] - a_mean) * a_rstd, lw.y, lb.y), acc[1]);
+                    acc[2] = fmaf(w, fmaf((O[t][4 * q + 2] - a_mean) * a_rstd, lw.z, lb.z), acc[2]);
+                    acc[3] = fmaf(w, fmaf((O[t][4 * q + 3] - a_mean) * a_rstd, lw.w, lb.w), acc[3]);
+                }
+#pragma unroll
+                for (int zi = 0; zi < WMAXZ; ++zi) {
+                    if (zi < nz) {
+                        const int ty = s_ops.type[zi], k = s_ops.k[zi], m = s_ops.zo[zi] + c;
+                        const float wk = s_ops.w[zi];
+                        const bool drop = p.training && p.p_drop[k] > 0.f;
+                        float ds[4];
+                        drop_v<4>(drop, p.mask[k], p.rng_state, p.op_uid[k], base + e0, gbase + e0, p.p_drop[k], ds);
+                        const float z[4] = {za[zi][q].x, za[zi][q].y, za[zi][q].z, za[zi][q].w};
+                        const float r = sm.rs[m], mr = sm.mr[m], w = sm.bw[m], bb = sm.bb[m];
+                        if (ty == BMNAS_OP_GLU) {
+                            const float g[4] = {zg[q].x, zg[q].y, zg[q].z, zg[q].w};
+                            const float r2 = sm.rs[m + C], mr2 = sm.mr[m + C], w2 = sm.bw[m + C], bb2 = sm.bb[m + C];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float va = fmaf(fmaf(z[e], r, -mr), w, bb);
+                                const float vg = fmaf(fmaf(g[e], r2, -mr2), w2, bb2);
+                                acc[e] = fmaf(wk, va * sigmoidf_(vg) * ds[e], acc[e]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float va = fmaf(fmaf(z[e], r, -mr), w, bb);
+                                acc[e] = fmaf(wk, (ty == BMNAS_OP_FC_RELU ? fmaxf(va, 0.f) : mishf_(va)) * ds[e], acc[e]);
+                            }
+                        }
+                    }
+                }
+                *reinterpret_cast<float4*>(p.out + base + e0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            }
+        }
+    }
+}
+
+// 0 = by batch size (default), 1 = always the CTA-per-sample kernels, 2 = the warp-per-sample kernels whenever eligible
+int node_variant_flag = 0;
+
 // add v (already summed over the thread's group) into acc[m]; the L/G lanes that share channel m are
 // adjacent and aligned, so a segmented shuffle + one plain store per channel is race-free and deterministic
 template <bool SEG>
@@ -737,12 +1003,64 @@ extern "C" long long bmnas_node_partials_size(const bmnas_node_params* p) {
     return (long long)kNodeMaxBlocksBwd * (2LL * p->M + BMNAS_MAX_OPS);
 }
 
+// warp-per-sample kernels: shapes they take (see k_node_fwd_warp)
+static bool node_warp_ok(const bmnas_node_params* p, bool bwd) {
+    const int L = p->L, T = (p->C + 31) / 32;
+    if (!(L == 4 || L == 8 || L == 16) || T * L > 32 || !node_vec_ok(p, bwd)) return false;
+    int nz = 0, nglu = 0;
+    for (int k = 0; k < p->n_ops; ++k) {
+        const int ty = p->op_type[k];
+        if (ty == BMNAS_OP_GLU) ++nglu;
+        if (ty != BMNAS_OP_SUM && ty != BMNAS_OP_ATTN) ++nz;
+    }
+    if (nz > WMAXZ || nglu > 1) return false;
+    return node_warp_smem_floats(p->C, L, p->M, p->alias_xy != 0) * sizeof(float) <= 100 * 1024;
+}
+
+// the CTA-per-sample kernels win while the batch is smaller than the machine's warp slots (latency bound)
+static bool node_use_warp(const bmnas_node_params* p, bool bwd) {
+    if (node_variant_flag == 1) return false;
+    if (!node_warp_ok(p, bwd)) return false;
+    return node_variant_flag == 2 || p->B >= 2048;
+}
+
+template <int L, int T>
+static int launch_node_fwd_warp(const bmnas_node_params* p, size_t smem, cudaStream_t stream) {
+    static size_t configured = 0;
+    int e = node_smem_attr(k_node_fwd_warp<L, T>, smem, &configured);
+    if (e) return e;
+    const int want = (p->B + WPC - 1) / WPC, cap = kNumSMs * 2;
+    launch_k(k_node_fwd_warp<L, T>, want < cap ? want : cap, WPC * 32, smem, stream, *p);
+    BMNAS_LAUNCH_CHECK();
+    return BMNAS_OK;
+}
+
+static int node_fwd_warp_dispatch(const bmnas_node_params* p, cudaStream_t stream) {
+    const int L = p->L, T = (p->C + 31) / 32;
+    const size_t smem = node_warp_smem_floats(p->C, L, p->M, p->alias_xy != 0) * sizeof(float);
+    // the smallest instantiated T' >= T (channels beyond C are masked off inside the kernel)
+#define BMNAS_WCASE(l, t) if (L == l && T <= t) return launch_node_fwd_warp<l, t>(p, smem, stream)
+    BMNAS_WCASE(4, 1); BMNAS_WCASE(4, 2); BMNAS_WCASE(4, 4); BMNAS_WCASE(4, 8);
+    BMNAS_WCASE(8, 1); BMNAS_WCASE(8, 2); BMNAS_WCASE(8, 4);
+    BMNAS_WCASE(16, 1); BMNAS_WCASE(16, 2);
+#undef BMNAS_WCASE
+    return BMNAS_EINVAL;
+}
+
+extern "C" int bmnas_set_node_variant(int v) {
+    if (v < 0 || v > 2) return BMNAS_EINVAL;
+    node_variant_flag = v;
+    return BMNAS_OK;
+}
+extern "C" int bmnas_get_node_variant(void) { return node_variant_flag; }
+
 extern "C" int bmnas_node_fwd(const bmnas_node_params* p, void* stream) {
     int e = node_check(p, false);
     if (e) return e;
     const size_t smem = node_smem_floats(p->C, p->L, p->M, false) * sizeof(float);
     if (smem > 227 * 1024) return BMNAS_EINVAL;
     BMNAS_DRY_RETURN();
+    if (node_use_warp(p, false)) return node_fwd_warp_dispatch(p, (cudaStream_t)stream);
     const bool vec = node_vec_ok(p, false);
     static size_t configured[2] = {0, 0};
     e = vec ? node_smem_attr(k_node_fwd<4>, smem, &configured[1]) : node_smem_attr(k_node_fwd<1>, smem, &configured[0]);

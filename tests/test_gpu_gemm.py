@@ -79,6 +79,7 @@ CASES = [
     (5, 8, [24, 40], [72], 1),
     (7, 4, [36], [20, 44], 2),
     (300, 8, [128], [256, 128], 2),
+    (400, 8, [128], [256, 128], 2),     # B*L = 3200 > 2560: the 3xTF32 UMMA wgrad takes over from the FFMA kernel
 ]
 
 

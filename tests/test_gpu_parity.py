@@ -10,6 +10,19 @@ from helpers import O, load, sub, cfg_of, arch_of, unpickle_genotype, geno_plain
 import gpu_util as U
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True, params=[0, 2], ids=['node_auto', 'node_warp'])
+def node_variant(request):
+    """every parity test runs twice: with the default kernel choice (CTA per sample at these batch sizes) and with
+    the warp-per-sample node kernels forced wherever the shape is eligible (bmnas_set_node_variant)"""
+    from bmnas import native as N
+    lib = N.lib()
+    lib.bmnas_set_node_variant(request.param)
+    yield request.param
+    lib.bmnas_set_node_variant(0)
+
+
 TOL = 1e-5
 GTOL = 3e-5      # gradients: max-abs error relative to the largest entry of the tensor
 
@@ -365,3 +378,51 @@ def test_gradcheck_dropout_mask_reuse():
                 t.view(-1)[idx] += eps
             num.view(-1)[idx] = (lp - lm) / (2 * eps)
         assert_close(gt_, num, 5e-2, 'numeric grad', atol=2e-3)
+
+
+# ------------------------------------------------------------------ input pipeline: prefetch() == load()
+@pytest.mark.parametrize('graphs', [False, True])
+def test_prefetch_pipeline_matches_serial_loads(graphs):
+    """SearchStep.prefetch() (copy stream, batch i+1 in flight while step i computes) must feed every half step
+    exactly the batch load() would have: the same loss trajectory and architecture (dropout off; the split
+    reductions use float atomics, so the comparison is to 1e-5, far below the step-to-step differences)."""
+    from bmnas.search import SearchStep
+    from bmnas.nn import CrossEntropyLoss
+    cfg = O.Cfg(32, 8, 4, 2, 2, 2, 2, 0.0)
+    B, ncls, K = 16, 7, 6
+    P = O.init_params(cfg, ncls, seed=11, prefix='cell')
+    arch = O.init_arch(cfg, seed=11, scale=0.3)
+    batches = []
+    for i in range(2 * K):
+        f, y = O.synthetic_batch(cfg, B, ncls, seed=100 + i)
+        batches.append((torch.stack(f).pin_memory(), y.pin_memory()))
+
+    def run(pipelined):
+        head = U.build_head(cfg, ncls, P, arch)
+        head.train()
+        for m in head.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+        ss = SearchStep(head, CrossEntropyLoss(), B, ncls, use_graphs=graphs)
+        ss.load('dev', *batches[0]); ss.load('train', *batches[1])
+        ss.prepare(warmup=2, restore=True)
+        losses = []
+        if pipelined:
+            ss.prefetch('dev', *batches[0]); ss.prefetch('train', *batches[1])
+        for i in range(K):
+            if not pipelined:
+                ss.load('dev', *batches[2 * i]); ss.load('train', *batches[2 * i + 1])
+            la, lw = ss.step()
+            if pipelined and i + 1 < K:
+                ss.prefetch('dev', *batches[2 * i + 2]); ss.prefetch('train', *batches[2 * i + 3])
+            losses.append((la.item(), lw.item()))
+        torch.cuda.synchronize()
+        return losses, [a.detach().cpu().clone() for a in head.arch_parameters()]
+
+    l0, a0 = run(False)
+    l1, a1 = run(True)
+    for (xa, xw), (ya, yw) in zip(l0, l1):
+        assert abs(xa - ya) <= 1e-5 * max(1.0, abs(xa)) and abs(xw - yw) <= 1e-5 * max(1.0, abs(xw)), (l0, l1)
+    for x, y in zip(a0, a1):
+        assert_close(y, x, 1e-4, 'arch after pipelined loop')
+    assert len({round(v[1], 6) for v in l0}) > 1      # the batches really differ step to step
