@@ -107,11 +107,14 @@ __device__ __forceinline__ bool last_block(unsigned int* counter, unsigned int e
 
 __device__ __forceinline__ float ld_cg(const float* p) { return __ldcg(p); }
 
-// ---------------------------------------------------------------- Philox4x32-10
+// ---------------------------------------------------------------- Philox4x32-7
+// Seven rounds is the smallest Philox4x32 variant that passes BigCrush (Salmon et al., SC'11, table 2); dropout
+// masks need no more, and the generator is a third of the fused node kernels' instruction stream at large batch.
+constexpr int kPhiloxRounds = 7;
 static __device__ __noinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < kPhiloxRounds; ++r) {
         uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
         uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
         ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);

@@ -358,20 +358,85 @@ __global__ void __launch_bounds__(NTH) k_node_fwd(const bmnas_node_params p) {
 constexpr int WPC = 8;            // warps (= samples in flight) per CTA
 constexpr int WMAXZ = 3;          // conv-backed primitives per mixed op the warp kernel takes (at most one of them a GLU)
 
-struct WarpOps {
-    float wsum, wattn;
-    int has_sum, k_attn, nz;
-    int type[WMAXZ], zo[WMAXZ], k[WMAXZ];
-    float w[WMAXZ];
+// one dropout site, everything that does not depend on the element folded once per kernel
+struct DropSite {
+    uint2 key;                   // Philox key of (seed, op uid)
+    uint32_t step_lo, step_hi;   // rng_state[1]
+    uint32_t thr;                // keep iff (bits >> 8) >= thr, thr = ceil(p * 2^24): the same decision as
+                                 // (float)(bits >> 8) * 2^-24 >= p in drop_v / philox_keep (both sides exact)
+    float keep;                  // 1 / (1 - p)
+    int mode;                    // 0 inactive, 1 Philox, 2 injected uint8 mask
+    const unsigned char* mask;
 };
 
+struct WarpOps {
+    float wsum, wattn;
+    int has_sum, k_attn, nz, glu_zo;
+    int type[WMAXZ], zo[WMAXZ];
+    float w[WMAXZ];
+    DropSite attn_drop, zdrop[WMAXZ];
+};
+
+__device__ __forceinline__ DropSite make_drop_site(const bmnas_node_params& p, int k) {
+    DropSite d;
+    const float pd = p.p_drop[k];
+    d.mode = (p.training && pd > 0.f) ? (p.mask[k] ? 2 : 1) : 0;
+    d.mask = p.mask[k];
+    d.keep = 1.f / (1.f - pd);
+    d.thr = (uint32_t)ceilf(pd * 16777216.0f);
+    d.key = make_uint2(0u, 0u);
+    d.step_lo = d.step_hi = 0u;
+    if (d.mode == 1) {
+        const unsigned long long seed = p.rng_state[0], step = p.rng_state[1];
+        const uint32_t uid = p.op_uid[k];
+        d.key = make_uint2((uint32_t)seed ^ (uid * 0x9E3779B1u), (uint32_t)(seed >> 32) + uid);
+        d.step_lo = (uint32_t)step;
+        d.step_hi = (uint32_t)(step >> 32);
+    }
+    return d;
+}
+
+// dropout scales of the 4 consecutive elements starting at local index li / global index gi (gi % 4 == 0)
+__device__ __forceinline__ void drop4(const DropSite& d, long long li, unsigned long long gi, float (&ds)[4]) {
+    if (d.mode == 0) {
+        ds[0] = ds[1] = ds[2] = ds[3] = 1.f;
+    } else if (d.mode == 1) {
+        const uint4 r = philox4x32(make_uint4((uint32_t)(gi >> 2), (uint32_t)(gi >> 34), d.step_lo, d.step_hi), d.key);
+        ds[0] = (r.x >> 8) >= d.thr ? d.keep : 0.f;
+        ds[1] = (r.y >> 8) >= d.thr ? d.keep : 0.f;
+        ds[2] = (r.z >> 8) >= d.thr ? d.keep : 0.f;
+        ds[3] = (r.w >> 8) >= d.thr ? d.keep : 0.f;
+    } else {
+        const uchar4 m = *reinterpret_cast<const uchar4*>(d.mask + li);
+        ds[0] = m.x ? d.keep : 0.f; ds[1] = m.y ? d.keep : 0.f; ds[2] = m.z ? d.keep : 0.f; ds[3] = m.w ? d.keep : 0.f;
+    }
+}
+
+// sigmoid on the fast paths (ex2.approx / rcp.approx: ~2 ulp, three orders below the 1e-5 parity gate)
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+
+__host__ __device__ inline size_t node_warp_slab_floats(int C, int L, bool alias) {
+    // per warp: x (and y) tile, double buffered (cp.async prefetch of the warp's next sample), the attention output
+    // tile, the L x L probability matrix
+    return (alias ? 2 : 4) * rnd4((size_t)C * L) + rnd4((size_t)C * L) + rnd4((size_t)L * L);
+}
 __host__ __device__ inline size_t node_warp_smem_floats(int C, int L, int M, bool alias) {
-    const size_t CLr = rnd4((size_t)C * L), Mr = rnd4((size_t)M);
-    return 4 * Mr + WPC * ((alias ? 1 : 2) * CLr + rnd4((size_t)L * L)) + 16;
+    return 2 * rnd4((size_t)M) + WPC * node_warp_slab_floats(C, L, alias) + 16;
 }
 
 __device__ __forceinline__ float4 lds4(const float* q) { return *reinterpret_cast<const float4*>(q); }
 __device__ __forceinline__ float4 ldg4(const float* q) { return __ldg(reinterpret_cast<const float4*>(q)); }
+__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Z rows of one channel for the conv-backed primitives (register prefetch buffer)
+template <int Q>
+struct ZRows {
+    float4 a[WMAXZ][Q];
+    float4 g[Q];
+};
 
 template <int L, int T>
 __global__ void __launch_bounds__(WPC * 32, 2) k_node_fwd_warp(const bmnas_node_params p) {
@@ -384,54 +449,92 @@ __global__ void __launch_bounds__(WPC * 32, 2) k_node_fwd_warp(const bmnas_node_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool alias = p.alias_xy != 0;
     const size_t CLr = rnd4((size_t)CL), Mr = rnd4((size_t)M);
-    NodeSmem sm;
-    sm.rs = smem; sm.mr = sm.rs + Mr; sm.bw = sm.mr + Mr; sm.bb = sm.bw + Mr;
-    sm.gw = s_gw;
-    float* xs = sm.bb + Mr + (size_t)warp * ((alias ? 1 : 2) * CLr + rnd4((size_t)L * L));
-    float* ys = alias ? xs : xs + CLr;
-    float* Ps = xs + (alias ? 1 : 2) * CLr;
-    node_setup_gamma(p, sm);
+    float2* bnc = reinterpret_cast<float2*>(smem);      // BatchNorm + affine folded per channel: v = z * A + Bc
+    float* slab = smem + 2 * Mr + (size_t)warp * node_warp_slab_floats(C, L, alias);
+    const size_t xstride = (alias ? 1 : 2) * CLr;                   // [x | y] per buffer, two buffers
+    float* os = slab + (alias ? 2 : 4) * CLr;
+    float* Ps = os + CLr;
+    {
+        NodeSmem sm;
+        sm.gw = s_gw;
+        node_setup_gamma(p, sm);
+    }
     if (threadIdx.x == 0) {                  // same thread that wrote gw: fold the op list into one descriptor
-        WarpOps o;
+        WarpOps& o = s_ops;
         o.wsum = o.wattn = 0.f;
-        o.has_sum = 0; o.k_attn = -1; o.nz = 0;
+        o.has_sum = 0; o.k_attn = -1; o.nz = 0; o.glu_zo = -1;
+        o.attn_drop.mode = 0;
         for (int k = 0; k < p.n_ops; ++k) {
             const int ty = p.op_type[k];
             if (ty == BMNAS_OP_SUM) { o.wsum += s_gw[k]; o.has_sum = 1; }
-            else if (ty == BMNAS_OP_ATTN) { o.wattn = s_gw[k]; o.k_attn = k; }
-            else if (o.nz < WMAXZ) { o.type[o.nz] = ty; o.zo[o.nz] = p.z_off[k]; o.k[o.nz] = k; o.w[o.nz] = s_gw[k]; ++o.nz; }
+            else if (ty == BMNAS_OP_ATTN) { o.wattn = s_gw[k]; o.k_attn = k; o.attn_drop = make_drop_site(p, k); }
+            else if (o.nz < WMAXZ) {
+                const int z = o.nz++;
+                o.type[z] = ty; o.zo[z] = p.z_off[k]; o.w[z] = s_gw[k]; o.zdrop[z] = make_drop_site(p, k);
+                if (ty == BMNAS_OP_GLU) o.glu_zo = p.z_off[k];
+            }
         }
-        s_ops = o;
     }
-    node_setup_bn(p, sm);                    // ends with __syncthreads(): s_gw, s_ops and the BN constants are visible
-    const int k_attn = s_ops.k_attn, nz = s_ops.nz;
+    for (int k = 0; k < p.n_ops; ++k) {
+        const int ty = p.op_type[k];
+        if (ty == BMNAS_OP_SUM || ty == BMNAS_OP_ATTN) continue;
+        const int rows = ty == BMNAS_OP_GLU ? 2 * C : C, zo = p.z_off[k];
+        for (int ml = threadIdx.x; ml < rows; ml += WPC * 32) {
+            const float a = __ldg(p.rstd + zo + ml) * __ldg(p.bn_w[k] + ml);
+            bnc[zo + ml] = make_float2(a, fmaf(-__ldg(p.mean + zo + ml), a, __ldg(p.bn_b[k] + ml)));
+        }
+    }
+    __syncthreads();
+    const int k_attn = s_ops.k_attn, nz = s_ops.nz, glu_zo = s_ops.glu_zo;
+    const bool has_sum = s_ops.has_sum != 0;
+    const float wsum = s_ops.wsum, wattn = s_ops.wattn;
     const float inv_sqrt_c = 1.f / sqrtf((float)C);
     const int gwarp = blockIdx.x * WPC + warp, gstride = gridDim.x * WPC;
+    const float* lnw = k_attn >= 0 ? p.ln_w[k_attn] : nullptr;
+    const float* lnb = k_attn >= 0 ? p.ln_b[k_attn] : nullptr;
 
-    for (int b = gwarp; b < p.B; b += gstride) {
+    auto stage = [&](int b, float* dst) {    // the warp's next sample: global -> shared, no registers, no wait
         const long long base = (long long)b * CL;
-        const unsigned long long gbase = (unsigned long long)(p.sample_offset + b) * CL;
-        __syncwarp();                        // the previous sample's readers of xs / ys / Ps are done
 #pragma unroll
         for (int t = 0; t < T; ++t) {
             const int c = t * 32 + lane;
             if (c < C) {
-                float4 vx[Q], vy[Q];
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
-                    vx[q] = ldg4(p.x + base + c * L + 4 * q);
-                    if (!alias) vy[q] = ldg4(p.y + base + c * L + 4 * q);
-                }
-#pragma unroll
-                for (int q = 0; q < Q; ++q) {
-                    *reinterpret_cast<float4*>(xs + c * L + 4 * q) = vx[q];
-                    if (!alias) *reinterpret_cast<float4*>(ys + c * L + 4 * q) = vy[q];
+                    cp_async16(dst + c * L + 4 * q, p.x + base + c * L + 4 * q);
+                    if (!alias) cp_async16(dst + CLr + c * L + 4 * q, p.y + base + c * L + 4 * q);
                 }
             }
         }
-        __syncwarp();
+    };
+    auto load_z = [&](const float* Zb, int c, ZRows<Q>& z) {
+#pragma unroll
+        for (int zi = 0; zi < WMAXZ; ++zi) {
+            if (zi < nz) {
+                const int zo = s_ops.zo[zi];
+#pragma unroll
+                for (int q = 0; q < Q; ++q) z.a[zi][q] = ldg4(Zb + (long long)(zo + c) * L + 4 * q);
+            }
+        }
+        if (glu_zo >= 0) {                   // the gate rows of the (single) LinearGLU
+#pragma unroll
+            for (int q = 0; q < Q; ++q) z.g[q] = ldg4(Zb + (long long)(glu_zo + C + c) * L + 4 * q);
+        }
+    };
 
-        float O[T][L];
+    int buf = 0;
+    if (gwarp < p.B) stage(gwarp, slab);
+    for (int b = gwarp; b < p.B; b += gstride, buf ^= 1) {
+        const long long base = (long long)b * CL;
+        const unsigned long long gbase = (unsigned long long)(p.sample_offset + b) * CL;
+        const float* xs = slab + buf * xstride;
+        const float* ys = alias ? xs : xs + CLr;
+        const float* Zb = p.Z ? p.Z + (long long)b * M * L : nullptr;
+        cp_async_wait_all();
+        __syncwarp();                        // this sample's tiles are visible to every lane; the other buffer is free
+        if (b + gstride < p.B) stage(b + gstride, slab + (buf ^ 1) * xstride);
+
+        ZRows<Q> zn;                          // Z rows of the lane's first channel: in flight across the attention tail
         float a_mean = 0.f, a_rstd = 0.f;
         if (k_attn >= 0) {
             // ---- scores: lane = (query position i, channel slice qs); S[i][:] over the slice, then over the KS lanes
@@ -468,41 +571,46 @@ __global__ void __launch_bounds__(WPC * 32, 2) k_node_fwd_warp(const bmnas_node_
                 den += sc[j];
             }
             if (qs == 0) {
+                const float inv = 1.f / den;
 #pragma unroll
                 for (int q = 0; q < Q; ++q)
                     *reinterpret_cast<float4*>(Ps + i * L + 4 * q) =
-                        make_float4(sc[4 * q] / den, sc[4 * q + 1] / den, sc[4 * q + 2] / den, sc[4 * q + 3] / den);
+                        make_float4(sc[4 * q] * inv, sc[4 * q + 1] * inv, sc[4 * q + 2] * inv, sc[4 * q + 3] * inv);
             }
             __syncwarp();
             // ---- O[c][i] = sum_j P[i][j] y[c][j] for the lane's own channels
-            float yr[T][L];
-#pragma unroll
-            for (int t = 0; t < T; ++t) {
-                const int c = t * 32 + lane;
-#pragma unroll
-                for (int q = 0; q < Q; ++q) {
-                    const float4 v = c < C ? lds4(ys + c * L + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    yr[t][4 * q] = v.x; yr[t][4 * q + 1] = v.y; yr[t][4 * q + 2] = v.z; yr[t][4 * q + 3] = v.w;
-                }
-            }
-#pragma unroll
-            for (int i2 = 0; i2 < L; ++i2) {
-                float pr[L];
-#pragma unroll
-                for (int q = 0; q < Q; ++q) {
-                    const float4 v = lds4(Ps + i2 * L + 4 * q);
-                    pr[4 * q] = v.x; pr[4 * q + 1] = v.y; pr[4 * q + 2] = v.z; pr[4 * q + 3] = v.w;
-                }
+            float O[T][L];
+            {
+                float yr[T][L];
 #pragma unroll
                 for (int t = 0; t < T; ++t) {
-                    float a = 0.f;
+                    const int c = t * 32 + lane;
 #pragma unroll
-                    for (int j = 0; j < L; ++j) a = fmaf(pr[j], yr[t][j], a);
-                    O[t][i2] = a;
+                    for (int q = 0; q < Q; ++q) {
+                        const float4 v = c < C ? lds4(ys + c * L + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        yr[t][4 * q] = v.x; yr[t][4 * q + 1] = v.y; yr[t][4 * q + 2] = v.z; yr[t][4 * q + 3] = v.w;
+                    }
+                }
+#pragma unroll
+                for (int i2 = 0; i2 < L; ++i2) {
+                    float pr[L];
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {
+                        const float4 v = lds4(Ps + i2 * L + 4 * q);
+                        pr[4 * q] = v.x; pr[4 * q + 1] = v.y; pr[4 * q + 2] = v.z; pr[4 * q + 3] = v.w;
+                    }
+#pragma unroll
+                    for (int t = 0; t < T; ++t) {
+                        float a = 0.f;
+#pragma unroll
+                        for (int j = 0; j < L; ++j) a = fmaf(pr[j], yr[t][j], a);
+                        O[t][i2] = a;
+                    }
                 }
             }
+            if (nz > 0 && lane < C) load_z(Zb, lane, zn);
             // ---- dropout(0.1) on the attention output, LayerNorm statistics over the whole (C, L) sample
-            const bool drop = p.training && p.p_drop[k_attn] > 0.f;
+            const DropSite dsite = s_ops.attn_drop;
             float s0 = 0.f;
 #pragma unroll
             for (int t = 0; t < T; ++t) {
@@ -512,13 +620,14 @@ __global__ void __launch_bounds__(WPC * 32, 2) k_node_fwd_warp(const bmnas_node_
                     for (int q = 0; q < Q; ++q) {
                         float ds[4];
                         const int e0 = c * L + 4 * q;
-                        drop_v<4>(drop, p.mask[k_attn], p.rng_state, p.op_uid[k_attn], base + e0, gbase + e0,
-                                  p.p_drop[k_attn], ds);
+                        drop4(dsite, base + e0, gbase + e0, ds);
 #pragma unroll
                         for (int r = 0; r < 4; ++r) {
                             O[t][4 * q + r] *= ds[r];
                             s0 += O[t][4 * q + r];
                         }
+                        *reinterpret_cast<float4*>(os + e0) =
+                            make_float4(O[t][4 * q], O[t][4 * q + 1], O[t][4 * q + 2], O[t][4 * q + 3]);
                     }
                 }
             }
@@ -535,68 +644,58 @@ __global__ void __launch_bounds__(WPC * 32, 2) k_node_fwd_warp(const bmnas_node_
                 }
             }
             a_rstd = 1.f / sqrtf(warp_sum(s1) / (float)CL + kLnEps);
+        } else if (nz > 0 && lane < C) {
+            load_z(Zb, lane, zn);
         }
 
-        // ---- epilogue: every primitive at the lane's own elements, softmax(gamma)-weighted sum, one store
-        const float* Zb = p.Z ? p.Z + (long long)b * M * L : nullptr;
-#pragma unroll
+        // ---- epilogue: every primitive at the lane's own elements (the lane wrote os[] itself: no sync needed),
+        //      softmax(gamma)-weighted sum, one store.  Rolled over the lane's channels; the Z rows of the next
+        //      channel are requested before the current one is evaluated.
+#pragma unroll 1
         for (int t = 0; t < T; ++t) {
             const int c = t * 32 + lane;
-            if (c >= C) continue;
-            // conv-backed primitives first issue all their Z loads for this channel row
-            float4 za[WMAXZ][Q], zg[Q];
-#pragma unroll
-            for (int zi = 0; zi < WMAXZ; ++zi) {
-                if (zi < nz) {
-                    const int zo = s_ops.zo[zi];
-#pragma unroll
-                    for (int q = 0; q < Q; ++q) {
-                        za[zi][q] = ldg4(Zb + (long long)(zo + c) * L + 4 * q);
-                        if (s_ops.type[zi] == BMNAS_OP_GLU) zg[q] = ldg4(Zb + (long long)(zo + C + c) * L + 4 * q);
-                    }
-                }
-            }
+            if (c >= C) break;
+            ZRows<Q> z = zn;
+            if (nz > 0 && t + 1 < T && c + 32 < C) load_z(Zb, c + 32, zn);
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
                 const int e0 = c * L + 4 * q;
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                if (s_ops.has_sum) {
+                if (has_sum) {
                     const float4 xv = lds4(xs + e0), yv = lds4(ys + e0);
-                    const float w = s_ops.wsum;
-                    acc[0] = w * (xv.x + yv.x); acc[1] = w * (xv.y + yv.y); acc[2] = w * (xv.z + yv.z); acc[3] = w * (xv.w + yv.w);
+                    acc[0] = wsum * (xv.x + yv.x); acc[1] = wsum * (xv.y + yv.y);
+                    acc[2] = wsum * (xv.z + yv.z); acc[3] = wsum * (xv.w + yv.w);
                 }
                 if (k_attn >= 0) {
-                    const float4 lw = ldg4(p.ln_w[k_attn] + e0), lb = ldg4(p.ln_b[k_attn] + e0);
-                    const float w = s_ops.wattn;
-                    acc[0] = fmaf(w, fmaf((O[t][4 * q] - a_mean) * a_rstd, lw.x, lb.x), acc[0]);
-                    acc[1] = fmaf(w, fmaf((O[t][4 * q + 1] - a_mean) * a_rstd, lw.y, lb.y), acc[1]);
-                    acc[2] = fmaf(w, fmaf((O[t][4 * q + 2] - a_mean) * a_rstd, lw.z, lb.z), acc[2]);
-                    acc[3] = fmaf(w, fmaf((O[t][4 * q + 3] - a_mean) * a_rstd, lw.w, lb.w), acc[3]);
+                    const float4 lw = ldg4(lnw + e0), lb = ldg4(lnb + e0), ov = lds4(os + e0);
+                    acc[0] = fmaf(wattn, fmaf((ov.x - a_mean) * a_rstd, lw.x, lb.x), acc[0]);
+                    acc[1] = fmaf(wattn, fmaf((ov.y - a_mean) * a_rstd, lw.y, lb.y), acc[1]);
+                    acc[2] = fmaf(wattn, fmaf((ov.z - a_mean) * a_rstd, lw.z, lb.z), acc[2]);
+                    acc[3] = fmaf(wattn, fmaf((ov.w - a_mean) * a_rstd, lw.w, lb.w), acc[3]);
                 }
 #pragma unroll
                 for (int zi = 0; zi < WMAXZ; ++zi) {
                     if (zi < nz) {
-                        const int ty = s_ops.type[zi], k = s_ops.k[zi], m = s_ops.zo[zi] + c;
+                        const int ty = s_ops.type[zi], m = s_ops.zo[zi] + c;
                         const float wk = s_ops.w[zi];
-                        const bool drop = p.training && p.p_drop[k] > 0.f;
                         float ds[4];
-                        drop_v<4>(drop, p.mask[k], p.rng_state, p.op_uid[k], base + e0, gbase + e0, p.p_drop[k], ds);
-                        const float z[4] = {za[zi][q].x, za[zi][q].y, za[zi][q].z, za[zi][q].w};
-                        const float r = sm.rs[m], mr = sm.mr[m], w = sm.bw[m], bb = sm.bb[m];
+                        drop4(s_ops.zdrop[zi], base + e0, gbase + e0, ds);
+                        const float zv[4] = {z.a[zi][q].x, z.a[zi][q].y, z.a[zi][q].z, z.a[zi][q].w};
+                        const float2 ab = bnc[m];
                         if (ty == BMNAS_OP_GLU) {
-                            const float g[4] = {zg[q].x, zg[q].y, zg[q].z, zg[q].w};
-                            const float r2 = sm.rs[m + C], mr2 = sm.mr[m + C], w2 = sm.bw[m + C], bb2 = sm.bb[m + C];
+                            const float g[4] = {z.g[q].x, z.g[q].y, z.g[q].z, z.g[q].w};
+                            const float2 ab2 = bnc[m + C];
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                const float va = fmaf(fmaf(z[e], r, -mr), w, bb);
-                                const float vg = fmaf(fmaf(g[e], r2, -mr2), w2, bb2);
-                                acc[e] = fmaf(wk, va * sigmoidf_(vg) * ds[e], acc[e]);
+                                const float va = fmaf(zv[e], ab.x, ab.y);
+                                const float vg = fmaf(g[e], ab2.x, ab2.y);
+                                acc[e] = fmaf(wk * ds[e], va * sigmoid_fast(vg), acc[e]);
                             }
                         } else {
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                const float va = fmaf(fmaf(z[e], r, -mr), w, bb);
-                                acc[e] = fmaf(wk, (ty == BMNAS_OP_FC_RELU ? fmaxf(va, 0.f) : mishf_(va)) * ds[e], acc[e]);
+                                const float va = fmaf(zv[e], ab.x, ab.y);
+                                acc[e] = fmaf(wk * ds[e], ty == BMNAS_OP_FC_RELU ? fmaxf(va, 0.f) : mishf_(va), acc[e]);
                             }
                         }
                     }
@@ -605,6 +704,7 @@ __global__ void __launch_bounds__(WPC * 32, 2) k_node_fwd_warp(const bmnas_node_
             }
         }
     }
+    cp_async_wait_all();
 }
 
 // 0 = by batch size (default), 1 = always the CTA-per-sample kernels, 2 = the warp-per-sample kernels whenever eligible
@@ -1014,7 +1114,7 @@ static bool node_warp_ok(const bmnas_node_params* p, bool bwd) {
         if (ty != BMNAS_OP_SUM && ty != BMNAS_OP_ATTN) ++nz;
     }
     if (nz > WMAXZ || nglu > 1) return false;
-    return node_warp_smem_floats(p->C, L, p->M, p->alias_xy != 0) * sizeof(float) <= 100 * 1024;
+    return node_warp_smem_floats(p->C, L, p->M, p->alias_xy != 0) * sizeof(float) <= 200 * 1024;
 }
 
 // the CTA-per-sample kernels win while the batch is smaller than the machine's warp slots (latency bound)
