@@ -421,7 +421,8 @@ __host__ __device__ inline size_t node_warp_slab_floats(int C, int L, bool alias
     return (alias ? 2 : 4) * rnd4((size_t)C * L) + rnd4((size_t)C * L) + rnd4((size_t)L * L);
 }
 __host__ __device__ inline size_t node_warp_smem_floats(int C, int L, int M, bool alias) {
-    return 2 * rnd4((size_t)M) + WPC * node_warp_slab_floats(C, L, alias) + 16;
+    // folded BatchNorm constants (2 per conv row), the attention LayerNorm affine (2 x C*L), the per-warp slabs
+    return 2 * rnd4((size_t)M) + 2 * rnd4((size_t)C * L) + WPC * node_warp_slab_floats(C, L, alias) + 16;
 }
 
 __device__ __forceinline__ float4 lds4(const float* q) { return *reinterpret_cast<const float4*>(q); }
@@ -450,7 +451,9 @@ __global__ void __launch_bounds__(WPC * 32, 2) k_node_fwd_warp(const bmnas_node_
     const bool alias = p.alias_xy != 0;
     const size_t CLr = rnd4((size_t)CL), Mr = rnd4((size_t)M);
     float2* bnc = reinterpret_cast<float2*>(smem);      // BatchNorm + affine folded per channel: v = z * A + Bc
-    float* slab = smem + 2 * Mr + (size_t)warp * node_warp_slab_floats(C, L, alias);
+    float* lnw = smem + 2 * Mr;                         // LayerNorm affine of the attention primitive, staged once
+    float* lnb = lnw + CLr;
+    float* slab = lnb + CLr + (size_t)warp * node_warp_slab_floats(C, L, alias);
     const size_t xstride = (alias ? 1 : 2) * CLr;                   // [x | y] per buffer, two buffers
     float* os = slab + (alias ? 2 : 4) * CLr;
     float* Ps = os + CLr;
@@ -484,14 +487,19 @@ __global__ void __launch_bounds__(WPC * 32, 2) k_node_fwd_warp(const bmnas_node_
             bnc[zo + ml] = make_float2(a, fmaf(-__ldg(p.mean + zo + ml), a, __ldg(p.bn_b[k] + ml)));
         }
     }
+    for (int k = 0; k < p.n_ops; ++k) {
+        if (p.op_type[k] != BMNAS_OP_ATTN) continue;
+        for (int e = threadIdx.x * 4; e < CL; e += WPC * 32 * 4) {
+            *reinterpret_cast<float4*>(lnw + e) = ldg4(p.ln_w[k] + e);
+            *reinterpret_cast<float4*>(lnb + e) = ldg4(p.ln_b[k] + e);
+        }
+    }
     __syncthreads();
     const int k_attn = s_ops.k_attn, nz = s_ops.nz, glu_zo = s_ops.glu_zo;
     const bool has_sum = s_ops.has_sum != 0;
     const float wsum = s_ops.wsum, wattn = s_ops.wattn;
     const float inv_sqrt_c = 1.f / sqrtf((float)C);
     const int gwarp = blockIdx.x * WPC + warp, gstride = gridDim.x * WPC;
-    const float* lnw = k_attn >= 0 ? p.ln_w[k_attn] : nullptr;
-    const float* lnb = k_attn >= 0 ? p.ln_b[k_attn] : nullptr;
 
     auto stage = [&](int b, float* dst) {    // the warp's next sample: global -> shared, no registers, no wait
         const long long base = (long long)b * CL;
@@ -667,7 +675,7 @@ __global__ void __launch_bounds__(WPC * 32, 2) k_node_fwd_warp(const bmnas_node_
                     acc[2] = wsum * (xv.z + yv.z); acc[3] = wsum * (xv.w + yv.w);
                 }
                 if (k_attn >= 0) {
-                    const float4 lw = ldg4(lnw + e0), lb = ldg4(lnb + e0), ov = lds4(os + e0);
+                    const float4 lw = lds4(lnw + e0), lb = lds4(lnb + e0), ov = lds4(os + e0);
                     acc[0] = fmaf(wattn, fmaf((ov.x - a_mean) * a_rstd, lw.x, lb.x), acc[0]);
                     acc[1] = fmaf(wattn, fmaf((ov.y - a_mean) * a_rstd, lw.y, lb.y), acc[1]);
                     acc[2] = fmaf(wattn, fmaf((ov.z - a_mean) * a_rstd, lw.z, lb.z), acc[2]);
@@ -705,6 +713,543 @@ __global__ void __launch_bounds__(WPC * 32, 2) k_node_fwd_warp(const bmnas_node_
         }
     }
     cp_async_wait_all();
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// Warp-per-sample backward (large batch, searchable cell: x is y).  Same ownership as the forward: lane holds the
+// channels c = t*32 + lane.  Per sample the warp (A) stages x and gout in its slab, (B) recomputes the attention
+// primitive exactly as the forward did (P, dropped output, LayerNorm statistics; the keep bits of its 32 own
+// elements stay in one register), (C) walks its own elements once: d(gamma) partials, GV rows for the conv
+// backward, per-channel BatchNorm sums and the LayerNorm affine gradients (shared-memory atomics on CTA-wide
+// accumulators: the lane owns the address within its warp, warps collide rarely), (D) LayerNorm backward ->
+// dO, dP = dO^T y, dS, (E) dx + dy for its channel rows and the single gx store.  CTA-level sums go to the global
+// accumulator with one atomic per value, the last CTA finalises exactly like k_node_bwd.
+constexpr int WPCB = 12;          // warps per CTA of the backward (one CTA per SM: 12.6 KB slab per warp at NTU shapes)
+
+__host__ __device__ inline size_t node_bwarp_slab_floats(int C, int L) {
+    return 3 * rnd4((size_t)C * L) + 2 * rnd4((size_t)L * L);            // x, gout, a/dO tiles; P, dS
+}
+__host__ __device__ inline size_t node_bwarp_smem_floats(int C, int L, int M) {
+    // (rstd, mean*rstd) and (w, b) per conv row; S1 | S2 sums; LN weight; LN affine gradient accumulators; slabs
+    return 6 * rnd4((size_t)M) + 3 * rnd4((size_t)C * L) + WPCB * node_bwarp_slab_floats(C, L) + 16;
+}
+
+template <int L, int T>
+__global__ void __launch_bounds__(WPCB * 32, 1) k_node_bwd_warp(const bmnas_node_params p) {
+    pdl_prologue();
+    extern __shared__ __align__(16) float smem[];
+    __shared__ float s_gw[BMNAS_MAX_OPS];
+    __shared__ float s_dg[BMNAS_MAX_OPS];
+    __shared__ WarpOps s_ops;
+    constexpr int Q = L / 4, KS = 32 / L;
+    const int C = p.C, CL = C * L, M = p.M;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t CLr = rnd4((size_t)CL), Mr = rnd4((size_t)M), LLr = rnd4((size_t)L * L);
+    float2* bnr = reinterpret_cast<float2*>(smem);            // (rstd, mean * rstd)
+    float2* bnw = bnr + Mr;                                   // (weight, bias)
+    float* S1s = smem + 4 * Mr;
+    float* S2s = S1s + Mr;
+    float* lnw = S2s + Mr;
+    float* accG = lnw + CLr;
+    float* accH = accG + CLr;
+    float* slab = accH + CLr + (size_t)warp * node_bwarp_slab_floats(C, L);
+    float* xs = slab;
+    float* gs = xs + CLr;
+    float* os = gs + CLr;
+    float* Ps = os + CLr;
+    float* dSs = Ps + LLr;
+    {
+        NodeSmem sm;
+        sm.gw = s_gw;
+        node_setup_gamma(p, sm);
+    }
+    if (threadIdx.x == 0) {
+        WarpOps& o = s_ops;
+        o.wsum = o.wattn = 0.f;
+        o.has_sum = 0; o.k_attn = -1; o.nz = 0; o.glu_zo = -1;
+        o.attn_drop.mode = 0;
+        for (int k = 0; k < p.n_ops; ++k) {
+            const int ty = p.op_type[k];
+            if (ty == BMNAS_OP_SUM) { o.wsum += s_gw[k]; o.has_sum = 1; }
+            else if (ty == BMNAS_OP_ATTN) { o.wattn = s_gw[k]; o.k_attn = k; o.attn_drop = make_drop_site(p, k); }
+            else if (o.nz < WMAXZ) {
+                const int z = o.nz++;
+                o.type[z] = ty; o.zo[z] = p.z_off[k]; o.w[z] = s_gw[k]; o.zdrop[z] = make_drop_site(p, k);
+                if (ty == BMNAS_OP_GLU) o.glu_zo = p.z_off[k];
+            }
+        }
+    }
+    if (threadIdx.x < BMNAS_MAX_OPS) s_dg[threadIdx.x] = 0.f;
+    for (int k = 0; k < p.n_ops; ++k) {
+        const int ty = p.op_type[k];
+        if (ty == BMNAS_OP_ATTN) {
+            for (int e = threadIdx.x * 4; e < CL; e += WPCB * 32 * 4)
+                *reinterpret_cast<float4*>(lnw + e) = ldg4(p.ln_w[k] + e);
+            continue;
+        }
+        if (ty == BMNAS_OP_SUM) continue;
+        const int rows = ty == BMNAS_OP_GLU ? 2 * C : C, zo = p.z_off[k];
+        for (int ml = threadIdx.x; ml < rows; ml += WPCB * 32) {
+            const float r = __ldg(p.rstd + zo + ml);
+            bnr[zo + ml] = make_float2(r, __ldg(p.mean + zo + ml) * r);
+            bnw[zo + ml] = make_float2(__ldg(p.bn_w[k] + ml), __ldg(p.bn_b[k] + ml));
+        }
+    }
+    for (int i = threadIdx.x; i < M; i += WPCB * 32) {
+        S1s[i] = 0.f;
+        S2s[i] = 0.f;
+    }
+    for (int i = threadIdx.x; i < CL; i += WPCB * 32) {
+        accG[i] = 0.f;
+        accH[i] = 0.f;
+    }
+    __syncthreads();
+    const int k_attn = s_ops.k_attn, nz = s_ops.nz, glu_zo = s_ops.glu_zo;
+    const bool has_sum = s_ops.has_sum != 0;
+    const float wsum = s_ops.wsum, wattn = s_ops.wattn;
+    const float inv_sqrt_c = 1.f / sqrtf((float)C);
+    const int gwarp = blockIdx.x * WPCB + warp, gstride = gridDim.x * WPCB;
+    const float* lnb_g = k_attn >= 0 ? p.ln_b[k_attn] : nullptr;
+    float dg_sum = 0.f, dg_attn = 0.f, dg_z[WMAXZ];
+#pragma unroll
+    for (int zi = 0; zi < WMAXZ; ++zi) dg_z[zi] = 0.f;
+
+    auto load_z = [&](const float* Zb, int c, ZRows<Q>& z) {
+#pragma unroll
+        for (int zi = 0; zi < WMAXZ; ++zi) {
+            if (zi < nz) {
+                const int zo = s_ops.zo[zi];
+#pragma unroll
+                for (int q = 0; q < Q; ++q) z.a[zi][q] = ldg4(Zb + (long long)(zo + c) * L + 4 * q);
+            }
+        }
+        if (glu_zo >= 0) {
+#pragma unroll
+            for (int q = 0; q < Q; ++q) z.g[q] = ldg4(Zb + (long long)(glu_zo + C + c) * L + 4 * q);
+        }
+    };
+
+    for (int b = gwarp; b < p.B; b += gstride) {
+        const long long base = (long long)b * CL;
+        const unsigned long long gbase = (unsigned long long)(p.sample_offset + b) * CL;
+        const float* Zb = p.Z ? p.Z + (long long)b * M * L : nullptr;
+        float* GVb = p.GV ? p.GV + (long long)b * M * L : nullptr;
+        __syncwarp();                        // the previous sample's readers of the slab are done
+        // ---- (A) stage x and gout
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const int c = t * 32 + lane;
+            if (c < C) {
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    cp_async16(xs + c * L + 4 * q, p.x + base + c * L + 4 * q);
+                    cp_async16(gs + c * L + 4 * q, p.gout + base + c * L + 4 * q);
+                }
+            }
+        }
+        ZRows<Q> zn;
+        if (nz > 0 && lane < C) load_z(Zb, lane, zn);
+        cp_async_wait_all();
+        __syncwarp();
+
+        // ---- (B) attention primitive, recomputed as in the forward
+        float a_mean = 0.f, a_rstd = 0.f;
+        uint32_t keepbits = 0xffffffffu;     // bit (t*L + l): element kept by the attention dropout
+        if (k_attn >= 0) {
+            const int i = lane / KS, qs = lane % KS;
+            float sc[L];
+#pragma unroll
+            for (int j = 0; j < L; ++j) sc[j] = 0.f;
+#pragma unroll 4
+            for (int c = qs; c < C; c += KS) {
+                const float a = xs[c * L + i];
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const float4 v = lds4(xs + c * L + 4 * q);
+                    sc[4 * q] = fmaf(a, v.x, sc[4 * q]);
+                    sc[4 * q + 1] = fmaf(a, v.y, sc[4 * q + 1]);
+                    sc[4 * q + 2] = fmaf(a, v.z, sc[4 * q + 2]);
+                    sc[4 * q + 3] = fmaf(a, v.w, sc[4 * q + 3]);
+                }
+            }
+#pragma unroll
+            for (int o = KS / 2; o > 0; o >>= 1)
+#pragma unroll
+                for (int j = 0; j < L; ++j) sc[j] += __shfl_xor_sync(0xffffffffu, sc[j], o);
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < L; ++j) {
+                sc[j] *= inv_sqrt_c;
+                mx = fmaxf(mx, sc[j]);
+            }
+            float den = 0.f;
+#pragma unroll
+            for (int j = 0; j < L; ++j) {
+                sc[j] = expf(sc[j] - mx);
+                den += sc[j];
+            }
+            if (qs == 0) {
+                const float inv = 1.f / den;
+#pragma unroll
+                for (int q = 0; q < Q; ++q)
+                    *reinterpret_cast<float4*>(Ps + i * L + 4 * q) =
+                        make_float4(sc[4 * q] * inv, sc[4 * q + 1] * inv, sc[4 * q + 2] * inv, sc[4 * q + 3] * inv);
+            }
+            __syncwarp();
+            float O[T][L];
+            {
+                float yr[T][L];
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    const int c = t * 32 + lane;
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {
+                        const float4 v = c < C ? lds4(xs + c * L + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        yr[t][4 * q] = v.x; yr[t][4 * q + 1] = v.y; yr[t][4 * q + 2] = v.z; yr[t][4 * q + 3] = v.w;
+                    }
+                }
+#pragma unroll
+                for (int i2 = 0; i2 < L; ++i2) {
+                    float pr[L];
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {
+                        const float4 v = lds4(Ps + i2 * L + 4 * q);
+                        pr[4 * q] = v.x; pr[4 * q + 1] = v.y; pr[4 * q + 2] = v.z; pr[4 * q + 3] = v.w;
+                    }
+#pragma unroll
+                    for (int t = 0; t < T; ++t) {
+                        float a = 0.f;
+#pragma unroll
+                        for (int j = 0; j < L; ++j) a = fmaf(pr[j], yr[t][j], a);
+                        O[t][i2] = a;
+                    }
+                }
+            }
+            const DropSite dsite = s_ops.attn_drop;
+            float s0 = 0.f;
+            keepbits = 0u;
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const int c = t * 32 + lane;
+                if (c < C) {
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {
+                        float ds[4];
+                        const int e0 = c * L + 4 * q;
+                        drop4(dsite, base + e0, gbase + e0, ds);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            O[t][4 * q + r] *= ds[r];
+                            s0 += O[t][4 * q + r];
+                            if (ds[r] != 0.f) keepbits |= 1u << (t * L + 4 * q + r);
+                        }
+                        *reinterpret_cast<float4*>(os + e0) =
+                            make_float4(O[t][4 * q], O[t][4 * q + 1], O[t][4 * q + 2], O[t][4 * q + 3]);
+                    }
+                }
+            }
+            a_mean = warp_sum(s0) / (float)CL;
+            float s1 = 0.f;
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                if (t * 32 + lane < C) {
+#pragma unroll
+                    for (int j = 0; j < L; ++j) {
+                        const float d = O[t][j] - a_mean;
+                        s1 = fmaf(d, d, s1);
+                    }
+                }
+            }
+            a_rstd = 1.f / sqrtf(warp_sum(s1) / (float)CL + kLnEps);
+        }
+
+        // ---- (C) own elements: d(gamma) partials, GV rows, BatchNorm sums, LayerNorm affine gradients
+        float lnsum0 = 0.f, lnsum1 = 0.f;
+#pragma unroll 1
+        for (int t = 0; t < T; ++t) {
+            const int c = t * 32 + lane;
+            if (c >= C) break;
+            ZRows<Q> z = zn;
+            if (nz > 0 && t + 1 < T && c + 32 < C) load_z(Zb, c + 32, zn);
+            float s1r[WMAXZ], s2r[WMAXZ], s1g = 0.f, s2g = 0.f;
+#pragma unroll
+            for (int zi = 0; zi < WMAXZ; ++zi) s1r[zi] = s2r[zi] = 0.f;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const int e0 = c * L + 4 * q;
+                const float4 g4 = lds4(gs + e0);
+                const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+                if (has_sum) {
+                    const float4 xv = lds4(xs + e0);
+                    dg_sum += 2.f * (gv[0] * xv.x + gv[1] * xv.y + gv[2] * xv.z + gv[3] * xv.w);
+                }
+                if (k_attn >= 0) {
+                    const float4 a4 = lds4(os + e0), w4 = lds4(lnw + e0), b4 = ldg4(lnb_g + e0);
+                    const float av[4] = {a4.x, a4.y, a4.z, a4.w}, wv[4] = {w4.x, w4.y, w4.z, w4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float oh = (av[e] - a_mean) * a_rstd;
+                        dg_attn += gv[e] * fmaf(oh, wv[e], bv[e]);
+                        const float go = wattn * gv[e];
+                        atomicAdd(accG + e0 + e, go * oh);
+                        atomicAdd(accH + e0 + e, go);
+                        const float qq = go * wv[e];
+                        lnsum0 += qq;
+                        lnsum1 = fmaf(qq, oh, lnsum1);
+                    }
+                }
+#pragma unroll
+                for (int zi = 0; zi < WMAXZ; ++zi) {
+                    if (zi < nz) {
+                        const int ty = s_ops.type[zi], zo = s_ops.zo[zi], m = zo + c;
+                        const float wk = s_ops.w[zi];
+                        float ds[4];
+                        drop4(s_ops.zdrop[zi], base + e0, gbase + e0, ds);
+                        const float zv[4] = {z.a[zi][q].x, z.a[zi][q].y, z.a[zi][q].z, z.a[zi][q].w};
+                        const float2 rm = bnr[m], wb = bnw[m];
+                        float gva[4];
+                        if (ty == BMNAS_OP_GLU) {
+                            const float g[4] = {z.g[q].x, z.g[q].y, z.g[q].z, z.g[q].w};
+                            const float2 rm2 = bnr[m + C], wb2 = bnw[m + C];
+                            float gvg[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float zha = fmaf(zv[e], rm.x, -rm.y), zhg = fmaf(g[e], rm2.x, -rm2.y);
+                                const float va = fmaf(zha, wb.x, wb.y), vg = fmaf(zhg, wb2.x, wb2.y);
+                                const float sg = sigmoid_fast(vg);
+                                dg_z[zi] += gv[e] * (va * sg * ds[e]);
+                                const float go = wk * gv[e] * ds[e];
+                                gva[e] = go * sg;
+                                gvg[e] = go * va * sg * (1.f - sg);
+                                s1r[zi] += gva[e]; s2r[zi] = fmaf(gva[e], zha, s2r[zi]);
+                                s1g += gvg[e]; s2g = fmaf(gvg[e], zhg, s2g);
+                            }
+                            *reinterpret_cast<float4*>(GVb + (long long)(zo + C + c) * L + 4 * q) = make_float4(gvg[0], gvg[1], gvg[2], gvg[3]);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float zha = fmaf(zv[e], rm.x, -rm.y);
+                                const float va = fmaf(zha, wb.x, wb.y);
+                                float o, d;
+                                if (ty == BMNAS_OP_FC_RELU) {
+                                    o = fmaxf(va, 0.f);
+                                    d = va > 0.f ? 1.f : 0.f;
+                                } else {
+                                    o = mishf_(va);
+                                    d = mish_grad(va);
+                                }
+                                dg_z[zi] += gv[e] * (o * ds[e]);
+                                gva[e] = wk * gv[e] * ds[e] * d;
+                                s1r[zi] += gva[e]; s2r[zi] = fmaf(gva[e], zha, s2r[zi]);
+                            }
+                        }
+                        *reinterpret_cast<float4*>(GVb + (long long)m * L + 4 * q) = make_float4(gva[0], gva[1], gva[2], gva[3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int zi = 0; zi < WMAXZ; ++zi) {
+                if (zi < nz) {
+                    atomicAdd(S1s + s_ops.zo[zi] + c, s1r[zi]);
+                    atomicAdd(S2s + s_ops.zo[zi] + c, s2r[zi]);
+                }
+            }
+            if (glu_zo >= 0) {
+                atomicAdd(S1s + glu_zo + C + c, s1g);
+                atomicAdd(S2s + glu_zo + C + c, s2g);
+            }
+        }
+
+        // ---- (D) LayerNorm backward -> dO (into os), dP, dS
+        if (k_attn >= 0) {
+            const float mq = warp_sum(lnsum0) / (float)CL, mqo = warp_sum(lnsum1) / (float)CL;
+            const float keep = s_ops.attn_drop.mode ? s_ops.attn_drop.keep : 1.f;
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const int c = t * 32 + lane;
+                if (c < C) {
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {
+                        const int e0 = c * L + 4 * q;
+                        const float4 a4 = lds4(os + e0), w4 = lds4(lnw + e0), g4 = lds4(gs + e0);
+                        const float av[4] = {a4.x, a4.y, a4.z, a4.w}, wv[4] = {w4.x, w4.y, w4.z, w4.w}, gv[4] = {g4.x, g4.y, g4.z, g4.w};
+                        float dd[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float oh = (av[e] - a_mean) * a_rstd;
+                            const float sc_ = ((keepbits >> (t * L + 4 * q + e)) & 1u) ? keep : 0.f;
+                            dd[e] = a_rstd * (wattn * gv[e] * wv[e] - mq - oh * mqo) * sc_;
+                        }
+                        *reinterpret_cast<float4*>(os + e0) = make_float4(dd[0], dd[1], dd[2], dd[3]);
+                    }
+                }
+            }
+            __syncwarp();
+            const int i = lane / KS, qs = lane % KS;
+            float dp[L];
+#pragma unroll
+            for (int j = 0; j < L; ++j) dp[j] = 0.f;
+#pragma unroll 4
+            for (int c = qs; c < C; c += KS) {        // dP[i][j] = sum_c dO[c,i] y[c,j]
+                const float a = os[c * L + i];
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const float4 v = lds4(xs + c * L + 4 * q);
+                    dp[4 * q] = fmaf(a, v.x, dp[4 * q]);
+                    dp[4 * q + 1] = fmaf(a, v.y, dp[4 * q + 1]);
+                    dp[4 * q + 2] = fmaf(a, v.z, dp[4 * q + 2]);
+                    dp[4 * q + 3] = fmaf(a, v.w, dp[4 * q + 3]);
+                }
+            }
+#pragma unroll
+            for (int o = KS / 2; o > 0; o >>= 1)
+#pragma unroll
+                for (int j = 0; j < L; ++j) dp[j] += __shfl_xor_sync(0xffffffffu, dp[j], o);
+            if (qs == 0) {                            // dS = P o (dP - <dP, P>_row) / sqrt(C)
+                float pr[L];
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const float4 v = lds4(Ps + i * L + 4 * q);
+                    pr[4 * q] = v.x; pr[4 * q + 1] = v.y; pr[4 * q + 2] = v.z; pr[4 * q + 3] = v.w;
+                }
+                float rd = 0.f;
+#pragma unroll
+                for (int j = 0; j < L; ++j) rd = fmaf(dp[j], pr[j], rd);
+#pragma unroll
+                for (int q = 0; q < Q; ++q)
+                    *reinterpret_cast<float4*>(dSs + i * L + 4 * q) =
+                        make_float4(pr[4 * q] * (dp[4 * q] - rd) * inv_sqrt_c, pr[4 * q + 1] * (dp[4 * q + 1] - rd) * inv_sqrt_c,
+                                    pr[4 * q + 2] * (dp[4 * q + 2] - rd) * inv_sqrt_c, pr[4 * q + 3] * (dp[4 * q + 3] - rd) * inv_sqrt_c);
+            }
+            __syncwarp();
+        }
+
+        // ---- (E) gx = d/dx + d/dy for the lane's channel rows
+        if (p.gx) {
+#pragma unroll 1
+            for (int t = 0; t < T; ++t) {
+                const int c = t * 32 + lane;
+                if (c >= C) break;
+                float out[L];
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const float4 g4 = lds4(gs + c * L + 4 * q);
+                    const float w2 = has_sum ? 2.f * wsum : 0.f;
+                    out[4 * q] = w2 * g4.x; out[4 * q + 1] = w2 * g4.y; out[4 * q + 2] = w2 * g4.z; out[4 * q + 3] = w2 * g4.w;
+                }
+                if (k_attn >= 0) {
+                    float xr[L], dor[L];
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {
+                        const float4 v = lds4(xs + c * L + 4 * q), d = lds4(os + c * L + 4 * q);
+                        xr[4 * q] = v.x; xr[4 * q + 1] = v.y; xr[4 * q + 2] = v.z; xr[4 * q + 3] = v.w;
+                        dor[4 * q] = d.x; dor[4 * q + 1] = d.y; dor[4 * q + 2] = d.z; dor[4 * q + 3] = d.w;
+                    }
+#pragma unroll
+                    for (int r = 0; r < L; ++r) {
+                        float pr[L], dsr[L];
+#pragma unroll
+                        for (int q = 0; q < Q; ++q) {
+                            const float4 v = lds4(Ps + r * L + 4 * q), d = lds4(dSs + r * L + 4 * q);
+                            pr[4 * q] = v.x; pr[4 * q + 1] = v.y; pr[4 * q + 2] = v.z; pr[4 * q + 3] = v.w;
+                            dsr[4 * q] = d.x; dsr[4 * q + 1] = d.y; dsr[4 * q + 2] = d.z; dsr[4 * q + 3] = d.w;
+                        }
+                        float dxr = 0.f;
+#pragma unroll
+                        for (int j = 0; j < L; ++j) {
+                            dxr = fmaf(dsr[j], xr[j], dxr);                       // dx[c,r] = sum_j dS[r][j] y[c,j]
+                            out[j] = fmaf(dor[r], pr[j], out[j]);                 // dy[c,j] += dO[c,r] P[r][j]
+                            out[j] = fmaf(xr[r], dsr[j], out[j]);                 //          + x[c,r] dS[r][j]
+                        }
+                        out[r] += dxr;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    float* dst = p.gx + base + c * L + 4 * q;
+                    float4 o4 = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+                    if (p.gx_accum) {
+                        const float4 cur = *reinterpret_cast<const float4*>(dst);
+                        o4.x += cur.x; o4.y += cur.y; o4.z += cur.z; o4.w += cur.w;
+                    }
+                    *reinterpret_cast<float4*>(dst) = o4;
+                }
+            }
+        }
+    }
+
+    // ---- CTA sums -> global accumulator (one atomic per value), last CTA finalises (as k_node_bwd)
+    dg_sum = warp_sum(dg_sum);
+    dg_attn = warp_sum(dg_attn);
+#pragma unroll
+    for (int zi = 0; zi < WMAXZ; ++zi) dg_z[zi] = warp_sum(dg_z[zi]);
+    if (lane == 0) {
+        int zi = 0;
+        for (int k = 0; k < p.n_ops; ++k) {
+            const int ty = p.op_type[k];
+            float v;
+            if (ty == BMNAS_OP_SUM) v = dg_sum;
+            else if (ty == BMNAS_OP_ATTN) v = dg_attn;
+            else { v = zi == 0 ? dg_z[0] : (zi == 1 ? dg_z[1] : dg_z[2]); ++zi; }
+            atomicAdd(s_dg + k, v);
+        }
+    }
+    __syncthreads();
+    float* gacc = p.partials;
+    for (int i = threadIdx.x; i < M; i += WPCB * 32) {
+        atomicAdd(gacc + i, S1s[i]);
+        atomicAdd(gacc + M + i, S2s[i]);
+    }
+    if (threadIdx.x < p.n_ops) atomicAdd(gacc + 2 * M + threadIdx.x, s_dg[threadIdx.x]);
+    if (k_attn >= 0 && p.g_ln_w[k_attn]) {
+        for (int e = threadIdx.x; e < CL; e += WPCB * 32) {
+            atomicAdd(p.g_ln_w[k_attn] + e, accG[e]);
+            atomicAdd(p.g_ln_b[k_attn] + e, accH[e]);
+        }
+    }
+    if (!last_block(p.counter, gridDim.x)) return;
+    const int PW = 2 * M + BMNAS_MAX_OPS;
+    float* tot = S1s;                                  // S1s | S2s are contiguous (2 * Mr); totals for gamma in s_dg
+    for (int v = threadIdx.x; v < PW; v += WPCB * 32) {
+        const float x = ld_cg(gacc + v);
+        gacc[v] = 0.f;
+        if (v < M) S1s[v] = x;
+        else if (v < 2 * M) S2s[v - M] = x;
+        else s_dg[v - 2 * M] = x;
+    }
+    (void)tot;
+    __syncthreads();
+    const float n = (float)p.B * (float)L;
+    for (int k = 0; k < p.n_ops; ++k) {
+        const int ty = p.op_type[k];
+        if (ty == BMNAS_OP_SUM || ty == BMNAS_OP_ATTN) continue;
+        const int rows = ty == BMNAS_OP_GLU ? 2 * C : C, zo = p.z_off[k];
+        for (int ml = threadIdx.x; ml < rows; ml += WPCB * 32) {
+            const int m = zo + ml;
+            const float s1 = S1s[m], s2 = S2s[m];
+            if (p.g_bn_w[k]) {
+                p.g_bn_w[k][ml] = s2;
+                p.g_bn_b[k][ml] = s1;
+            }
+            const float rs = bnr[m].x, mur = bnr[m].y, w = bnw[m].x;
+            if (p.training) {
+                const float a = w * rs, m1 = s1 / n, m2 = s2 / n;
+                p.coef_a[m] = a;
+                p.coef_b[m] = -a * rs * m2;
+                p.coef_c[m] = a * (mur * m2 - m1);
+            } else {
+                p.coef_a[m] = w * rs;
+                p.coef_b[m] = 0.f;
+                p.coef_c[m] = 0.f;
+            }
+        }
+    }
+    if (p.g_gamma && threadIdx.x == 0) {
+        float dot = 0.f;
+        for (int k = 0; k < p.n_ops; ++k) dot += s_gw[k] * s_dg[k];
+        for (int k = 0; k < p.n_ops; ++k)
+            p.g_gamma[k] = p.gamma_is_logits ? s_gw[k] * (s_dg[k] - dot) : s_dg[k];
+    }
 }
 
 // 0 = by batch size (default), 1 = always the CTA-per-sample kernels, 2 = the warp-per-sample kernels whenever eligible
@@ -1147,6 +1692,33 @@ static int node_fwd_warp_dispatch(const bmnas_node_params* p, cudaStream_t strea
     return BMNAS_EINVAL;
 }
 
+template <int L, int T>
+static int launch_node_bwd_warp(const bmnas_node_params* p, size_t smem, cudaStream_t stream) {
+    static size_t configured = 0;
+    int e = node_smem_attr(k_node_bwd_warp<L, T>, smem, &configured);
+    if (e) return e;
+    const int want = (p->B + WPCB - 1) / WPCB;
+    launch_k(k_node_bwd_warp<L, T>, want < kNumSMs ? want : kNumSMs, WPCB * 32, smem, stream, *p);
+    BMNAS_LAUNCH_CHECK();
+    return BMNAS_OK;
+}
+
+static bool node_bwd_warp_ok(const bmnas_node_params* p) {
+    if (!p->alias_xy || !node_warp_ok(p, true)) return false;    // searchable cell only (x is y)
+    return node_bwarp_smem_floats(p->C, p->L, p->M) * sizeof(float) <= 220 * 1024;
+}
+
+static int node_bwd_warp_dispatch(const bmnas_node_params* p, cudaStream_t stream) {
+    const int L = p->L, T = (p->C + 31) / 32;
+    const size_t smem = node_bwarp_smem_floats(p->C, L, p->M) * sizeof(float);
+#define BMNAS_WCASE(l, t) if (L == l && T <= t) return launch_node_bwd_warp<l, t>(p, smem, stream)
+    BMNAS_WCASE(4, 1); BMNAS_WCASE(4, 2); BMNAS_WCASE(4, 4); BMNAS_WCASE(4, 8);
+    BMNAS_WCASE(8, 1); BMNAS_WCASE(8, 2); BMNAS_WCASE(8, 4);
+    BMNAS_WCASE(16, 1); BMNAS_WCASE(16, 2);
+#undef BMNAS_WCASE
+    return BMNAS_EINVAL;
+}
+
 extern "C" int bmnas_set_node_variant(int v) {
     if (v < 0 || v > 2) return BMNAS_EINVAL;
     node_variant_flag = v;
@@ -1180,6 +1752,8 @@ extern "C" int bmnas_node_bwd(const bmnas_node_params* p, void* stream) {
     const size_t smem = node_smem_floats(p->C, p->L, p->M, true) * sizeof(float);
     if (smem > 227 * 1024) return BMNAS_EINVAL;
     BMNAS_DRY_RETURN();
+    if (node_variant_flag != 1 && node_bwd_warp_ok(p) && (node_variant_flag == 2 || p->B >= 2048))
+        return node_bwd_warp_dispatch(p, (cudaStream_t)stream);
     const bool vec = node_vec_ok(p, true);
     const int lanes = p->L / 4;
     const bool seg = vec && lanes >= 1 && lanes <= 32 && (lanes & (lanes - 1)) == 0;
