@@ -111,7 +111,7 @@ __device__ __forceinline__ float ld_cg(const float* p) { return __ldcg(p); }
 // Seven rounds is the smallest Philox4x32 variant that passes BigCrush (Salmon et al., SC'11, table 2); dropout
 // masks need no more, and the generator is a third of the fused node kernels' instruction stream at large batch.
 constexpr int kPhiloxRounds = 7;
-static __device__ __noinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+__device__ __forceinline__ uint4 philox4x32_inl(uint4 ctr, uint2 key) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
     for (int r = 0; r < kPhiloxRounds; ++r) {
@@ -123,6 +123,8 @@ static __device__ __noinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
     }
     return ctr;
 }
+// out-of-line copy for the latency-bound kernels (keeps their code small)
+static __device__ __noinline__ uint4 philox4x32(uint4 ctr, uint2 key) { return philox4x32_inl(ctr, key); }
 
 // keep-decision of dropout for one element. idx = global element index (sample
 // index already offset by the rank's first sample, so masks do not depend on the

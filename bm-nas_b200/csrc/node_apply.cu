@@ -401,7 +401,8 @@ __device__ __forceinline__ void drop4(const DropSite& d, long long li, unsigned 
     if (d.mode == 0) {
         ds[0] = ds[1] = ds[2] = ds[3] = 1.f;
     } else if (d.mode == 1) {
-        const uint4 r = philox4x32(make_uint4((uint32_t)(gi >> 2), (uint32_t)(gi >> 34), d.step_lo, d.step_hi), d.key);
+        // inlined: a CALL would first wait for every load in flight (the Z-row prefetch) to land
+        const uint4 r = philox4x32_inl(make_uint4((uint32_t)(gi >> 2), (uint32_t)(gi >> 34), d.step_lo, d.step_hi), d.key);
         ds[0] = (r.x >> 8) >= d.thr ? d.keep : 0.f;
         ds[1] = (r.y >> 8) >= d.thr ? d.keep : 0.f;
         ds[2] = (r.z >> 8) >= d.thr ? d.keep : 0.f;
@@ -724,14 +725,16 @@ __global__ void __launch_bounds__(WPC * 32, 2) k_node_fwd_warp(const bmnas_node_
 // accumulators: the lane owns the address within its warp, warps collide rarely), (D) LayerNorm backward ->
 // dO, dP = dO^T y, dS, (E) dx + dy for its channel rows and the single gx store.  CTA-level sums go to the global
 // accumulator with one atomic per value, the last CTA finalises exactly like k_node_bwd.
-constexpr int WPCB = 12;          // warps per CTA of the backward (one CTA per SM: 12.6 KB slab per warp at NTU shapes)
+constexpr int WPCB = 8;           // warps per CTA of the backward (one CTA per SM; 204 registers per thread for the 64 LN-affine accumulators)
 
-__host__ __device__ inline size_t node_bwarp_slab_floats(int C, int L) {
-    return 3 * rnd4((size_t)C * L) + 2 * rnd4((size_t)L * L);            // x, gout, a/dO tiles; P, dS
+__host__ __device__ inline size_t node_bwarp_slab_floats(int C, int L, int M) {
+    // x and gout tiles (double buffered: cp.async prefetch of the warp's next sample), a/dO tile; P, dS; the warp's
+    // private per-channel BatchNorm sums S1 | S2
+    return 5 * rnd4((size_t)C * L) + 2 * rnd4((size_t)L * L) + 2 * rnd4((size_t)M);
 }
 __host__ __device__ inline size_t node_bwarp_smem_floats(int C, int L, int M) {
-    // (rstd, mean*rstd) and (w, b) per conv row; S1 | S2 sums; LN weight; LN affine gradient accumulators; slabs
-    return 6 * rnd4((size_t)M) + 3 * rnd4((size_t)C * L) + WPCB * node_bwarp_slab_floats(C, L) + 16;
+    // (rstd, mean*rstd) and (w, b) per conv row; S1 | S2 totals (last CTA); LN weight; slabs
+    return 6 * rnd4((size_t)M) + rnd4((size_t)C * L) + WPCB * node_bwarp_slab_floats(C, L, M) + 16;
 }
 
 template <int L, int T>
@@ -750,14 +753,14 @@ __global__ void __launch_bounds__(WPCB * 32, 1) k_node_bwd_warp(const bmnas_node
     float* S1s = smem + 4 * Mr;
     float* S2s = S1s + Mr;
     float* lnw = S2s + Mr;
-    float* accG = lnw + CLr;
-    float* accH = accG + CLr;
-    float* slab = accH + CLr + (size_t)warp * node_bwarp_slab_floats(C, L);
-    float* xs = slab;
-    float* gs = xs + CLr;
-    float* os = gs + CLr;
+    float* slab0 = lnw + CLr;
+    const size_t slab_floats = node_bwarp_slab_floats(C, L, M);
+    float* slab = slab0 + (size_t)warp * slab_floats;    // [x0 | g0 | x1 | g1 | a/dO | P | dS | S1 | S2]
+    float* os = slab + 4 * CLr;
     float* Ps = os + CLr;
     float* dSs = Ps + LLr;
+    float* wS1 = dSs + LLr;                                   // this warp's S1 | S2 (lane-owned rows: no atomics)
+    float* wS2 = wS1 + Mr;
     {
         NodeSmem sm;
         sm.gw = s_gw;
@@ -799,10 +802,7 @@ __global__ void __launch_bounds__(WPCB * 32, 1) k_node_bwd_warp(const bmnas_node
         S1s[i] = 0.f;
         S2s[i] = 0.f;
     }
-    for (int i = threadIdx.x; i < CL; i += WPCB * 32) {
-        accG[i] = 0.f;
-        accH[i] = 0.f;
-    }
+    for (int i = lane; i < 2 * (int)Mr; i += 32) wS1[i] = 0.f;
     __syncthreads();
     const int k_attn = s_ops.k_attn, nz = s_ops.nz, glu_zo = s_ops.glu_zo;
     const bool has_sum = s_ops.has_sum != 0;
@@ -813,6 +813,12 @@ __global__ void __launch_bounds__(WPCB * 32, 1) k_node_bwd_warp(const bmnas_node
     float dg_sum = 0.f, dg_attn = 0.f, dg_z[WMAXZ];
 #pragma unroll
     for (int zi = 0; zi < WMAXZ; ++zi) dg_z[zi] = 0.f;
+    // LayerNorm affine gradients of the lane's own elements, summed over the warp's samples in registers
+    float aG[T][L], aH[T][L];
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+#pragma unroll
+        for (int j = 0; j < L; ++j) aG[t][j] = aH[t][j] = 0.f;
 
     auto load_z = [&](const float* Zb, int c, ZRows<Q>& z) {
 #pragma unroll
@@ -829,28 +835,32 @@ __global__ void __launch_bounds__(WPCB * 32, 1) k_node_bwd_warp(const bmnas_node
         }
     };
 
-    for (int b = gwarp; b < p.B; b += gstride) {
-        const long long base = (long long)b * CL;
-        const unsigned long long gbase = (unsigned long long)(p.sample_offset + b) * CL;
-        const float* Zb = p.Z ? p.Z + (long long)b * M * L : nullptr;
-        float* GVb = p.GV ? p.GV + (long long)b * M * L : nullptr;
-        __syncwarp();                        // the previous sample's readers of the slab are done
-        // ---- (A) stage x and gout
+    auto stage = [&](int b, float* dst) {    // x and gout of one sample: global -> shared, asynchronously
+        const long long sb = (long long)b * CL;
 #pragma unroll
         for (int t = 0; t < T; ++t) {
             const int c = t * 32 + lane;
             if (c < C) {
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
-                    cp_async16(xs + c * L + 4 * q, p.x + base + c * L + 4 * q);
-                    cp_async16(gs + c * L + 4 * q, p.gout + base + c * L + 4 * q);
+                    cp_async16(dst + c * L + 4 * q, p.x + sb + c * L + 4 * q);
+                    cp_async16(dst + CLr + c * L + 4 * q, p.gout + sb + c * L + 4 * q);
                 }
             }
         }
-        ZRows<Q> zn;
-        if (nz > 0 && lane < C) load_z(Zb, lane, zn);
+    };
+    int buf = 0;
+    if (gwarp < p.B) stage(gwarp, slab);
+    for (int b = gwarp; b < p.B; b += gstride, buf ^= 1) {
+        const long long base = (long long)b * CL;
+        const unsigned long long gbase = (unsigned long long)(p.sample_offset + b) * CL;
+        const float* Zb = p.Z ? p.Z + (long long)b * M * L : nullptr;
+        float* GVb = p.GV ? p.GV + (long long)b * M * L : nullptr;
+        const float* xs = slab + buf * 2 * CLr;
+        const float* gs = xs + CLr;
         cp_async_wait_all();
-        __syncwarp();
+        __syncwarp();                        // this sample's tiles are visible; the other buffer and os / P / dS are free
+        if (b + gstride < p.B) stage(b + gstride, slab + (buf ^ 1) * 2 * CLr);
 
         // ---- (B) attention primitive, recomputed as in the forward
         float a_mean = 0.f, a_rstd = 0.f;
@@ -963,41 +973,57 @@ __global__ void __launch_bounds__(WPCB * 32, 1) k_node_bwd_warp(const bmnas_node
             a_rstd = 1.f / sqrtf(warp_sum(s1) / (float)CL + kLnEps);
         }
 
-        // ---- (C) own elements: d(gamma) partials, GV rows, BatchNorm sums, LayerNorm affine gradients
+        // ---- (C1) attention LayerNorm: d(gamma) partial, affine gradients (registers), the two LayerNorm-backward sums
         float lnsum0 = 0.f, lnsum1 = 0.f;
+        if (k_attn >= 0) {
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const int c = t * 32 + lane;
+                if (c < C) {
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {
+                        const int e0 = c * L + 4 * q;
+                        const float4 g4 = lds4(gs + e0), a4 = lds4(os + e0), w4 = lds4(lnw + e0), b4 = ldg4(lnb_g + e0);
+                        const float gv[4] = {g4.x, g4.y, g4.z, g4.w}, av[4] = {a4.x, a4.y, a4.z, a4.w};
+                        const float wv[4] = {w4.x, w4.y, w4.z, w4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float oh = (av[e] - a_mean) * a_rstd;
+                            dg_attn = fmaf(gv[e], fmaf(oh, wv[e], bv[e]), dg_attn);
+                            const float go = wattn * gv[e];
+                            aG[t][4 * q + e] = fmaf(go, oh, aG[t][4 * q + e]);
+                            aH[t][4 * q + e] += go;
+                            const float qq = go * wv[e];
+                            lnsum0 += qq;
+                            lnsum1 = fmaf(qq, oh, lnsum1);
+                        }
+                    }
+                }
+            }
+        }
+        // ---- (C2) conv-backed primitives and Sum: d(gamma) partials, GV rows, per-channel BatchNorm sums
 #pragma unroll 1
         for (int t = 0; t < T; ++t) {
             const int c = t * 32 + lane;
             if (c >= C) break;
-            ZRows<Q> z = zn;
-            if (nz > 0 && t + 1 < T && c + 32 < C) load_z(Zb, c + 32, zn);
+            ZRows<Q> z;
+            if (nz > 0) load_z(Zb, c, z);
             float s1r[WMAXZ], s2r[WMAXZ], s1g = 0.f, s2g = 0.f;
 #pragma unroll
             for (int zi = 0; zi < WMAXZ; ++zi) s1r[zi] = s2r[zi] = 0.f;
+            float4 g4q[Q];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                g4q[q] = lds4(gs + c * L + 4 * q);
+                if (has_sum) {
+                    const float4 xv = lds4(xs + c * L + 4 * q);
+                    dg_sum += 2.f * (g4q[q].x * xv.x + g4q[q].y * xv.y + g4q[q].z * xv.z + g4q[q].w * xv.w);
+                }
+            }
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
                 const int e0 = c * L + 4 * q;
-                const float4 g4 = lds4(gs + e0);
-                const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
-                if (has_sum) {
-                    const float4 xv = lds4(xs + e0);
-                    dg_sum += 2.f * (gv[0] * xv.x + gv[1] * xv.y + gv[2] * xv.z + gv[3] * xv.w);
-                }
-                if (k_attn >= 0) {
-                    const float4 a4 = lds4(os + e0), w4 = lds4(lnw + e0), b4 = ldg4(lnb_g + e0);
-                    const float av[4] = {a4.x, a4.y, a4.z, a4.w}, wv[4] = {w4.x, w4.y, w4.z, w4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float oh = (av[e] - a_mean) * a_rstd;
-                        dg_attn += gv[e] * fmaf(oh, wv[e], bv[e]);
-                        const float go = wattn * gv[e];
-                        atomicAdd(accG + e0 + e, go * oh);
-                        atomicAdd(accH + e0 + e, go);
-                        const float qq = go * wv[e];
-                        lnsum0 += qq;
-                        lnsum1 = fmaf(qq, oh, lnsum1);
-                    }
-                }
+                const float gv[4] = {g4q[q].x, g4q[q].y, g4q[q].z, g4q[q].w};
 #pragma unroll
                 for (int zi = 0; zi < WMAXZ; ++zi) {
                     if (zi < nz) {
@@ -1049,14 +1075,14 @@ __global__ void __launch_bounds__(WPCB * 32, 1) k_node_bwd_warp(const bmnas_node
             }
 #pragma unroll
             for (int zi = 0; zi < WMAXZ; ++zi) {
-                if (zi < nz) {
-                    atomicAdd(S1s + s_ops.zo[zi] + c, s1r[zi]);
-                    atomicAdd(S2s + s_ops.zo[zi] + c, s2r[zi]);
+                if (zi < nz) {                       // lane-owned rows of the warp's private sums
+                    wS1[s_ops.zo[zi] + c] += s1r[zi];
+                    wS2[s_ops.zo[zi] + c] += s2r[zi];
                 }
             }
             if (glu_zo >= 0) {
-                atomicAdd(S1s + glu_zo + C + c, s1g);
-                atomicAdd(S2s + glu_zo + C + c, s2g);
+                wS1[glu_zo + C + c] += s1g;
+                wS2[glu_zo + C + c] += s2g;
             }
         }
 
@@ -1195,16 +1221,46 @@ __global__ void __launch_bounds__(WPCB * 32, 1) k_node_bwd_warp(const bmnas_node
         }
     }
     __syncthreads();
+    // warp-private sums -> global accumulators: every warp parks its LayerNorm-affine registers in its (now idle)
+    // slab, then all threads sum the WPCB slabs element-wise and issue ONE global atomic per value
+    cp_async_wait_all();
+    if (k_attn >= 0) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const int c = t * 32 + lane;
+            if (c < C) {
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    *reinterpret_cast<float4*>(slab + c * L + 4 * q) = make_float4(aG[t][4 * q], aG[t][4 * q + 1], aG[t][4 * q + 2], aG[t][4 * q + 3]);
+                    *reinterpret_cast<float4*>(slab + CLr + c * L + 4 * q) = make_float4(aH[t][4 * q], aH[t][4 * q + 1], aH[t][4 * q + 2], aH[t][4 * q + 3]);
+                }
+            }
+        }
+    }
+    __syncthreads();
     float* gacc = p.partials;
+    const size_t s_off = 5 * CLr + 2 * LLr;            // S1 | S2 inside a slab
     for (int i = threadIdx.x; i < M; i += WPCB * 32) {
-        atomicAdd(gacc + i, S1s[i]);
-        atomicAdd(gacc + M + i, S2s[i]);
+        float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < WPCB; ++w) {
+            a1 += slab0[w * slab_floats + s_off + i];
+            a2 += slab0[w * slab_floats + s_off + Mr + i];
+        }
+        atomicAdd(gacc + i, a1);
+        atomicAdd(gacc + M + i, a2);
     }
     if (threadIdx.x < p.n_ops) atomicAdd(gacc + 2 * M + threadIdx.x, s_dg[threadIdx.x]);
     if (k_attn >= 0 && p.g_ln_w[k_attn]) {
         for (int e = threadIdx.x; e < CL; e += WPCB * 32) {
-            atomicAdd(p.g_ln_w[k_attn] + e, accG[e]);
-            atomicAdd(p.g_ln_b[k_attn] + e, accH[e]);
+            float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+            for (int w = 0; w < WPCB; ++w) {
+                a1 += slab0[w * slab_floats + e];
+                a2 += slab0[w * slab_floats + CLr + e];
+            }
+            atomicAdd(p.g_ln_w[k_attn] + e, a1);
+            atomicAdd(p.g_ln_b[k_attn] + e, a2);
         }
     }
     if (!last_block(p.counter, gridDim.x)) return;
