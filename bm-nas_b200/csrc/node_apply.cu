@@ -974,6 +974,8 @@ __global__ void __launch_bounds__(WPCB * 32, 1) k_node_bwd_warp(const bmnas_node
         }
 
         // ---- (C1) attention LayerNorm: d(gamma) partial, affine gradients (registers), the two LayerNorm-backward sums
+        ZRows<Q> zn;                          // Z rows of the lane's first channel travel while C1 runs
+        if (nz > 0 && lane < C) load_z(Zb, lane, zn);
         float lnsum0 = 0.f, lnsum1 = 0.f;
         if (k_attn >= 0) {
 #pragma unroll
@@ -1006,8 +1008,8 @@ __global__ void __launch_bounds__(WPCB * 32, 1) k_node_bwd_warp(const bmnas_node
         for (int t = 0; t < T; ++t) {
             const int c = t * 32 + lane;
             if (c >= C) break;
-            ZRows<Q> z;
-            if (nz > 0) load_z(Zb, c, z);
+            ZRows<Q> z = zn;
+            if (nz > 0 && t + 1 < T && c + 32 < C) load_z(Zb, c + 32, zn);
             float s1r[WMAXZ], s2r[WMAXZ], s1g = 0.f, s2g = 0.f;
 #pragma unroll
             for (int zi = 0; zi < WMAXZ; ++zi) s1r[zi] = s2r[zi] = 0.f;
@@ -1718,11 +1720,14 @@ static bool node_warp_ok(const bmnas_node_params* p, bool bwd) {
     return node_warp_smem_floats(p->C, L, p->M, p->alias_xy != 0) * sizeof(float) <= 200 * 1024;
 }
 
-// the CTA-per-sample kernels win while the batch is smaller than the machine's warp slots (latency bound)
+// the CTA-per-sample kernels win while the batch is smaller than the machine's warp slots (latency bound).
+// Measured crossover at NTU shapes (profiles/r01_v7_node_variants.txt): forward 10.8 vs 15.9 us at B=512 and
+// 19.9 vs 16.2 us at B=1024; backward 32.1 vs 32.8 us at B=512 and 61.1 vs 33.1 us at B=1024.
+constexpr int kWarpFwdMinB = 768, kWarpBwdMinB = 640;
 static bool node_use_warp(const bmnas_node_params* p, bool bwd) {
     if (node_variant_flag == 1) return false;
     if (!node_warp_ok(p, bwd)) return false;
-    return node_variant_flag == 2 || p->B >= 2048;
+    return node_variant_flag == 2 || p->B >= kWarpFwdMinB;
 }
 
 template <int L, int T>
@@ -1808,7 +1813,7 @@ extern "C" int bmnas_node_bwd(const bmnas_node_params* p, void* stream) {
     const size_t smem = node_smem_floats(p->C, p->L, p->M, true) * sizeof(float);
     if (smem > 227 * 1024) return BMNAS_EINVAL;
     BMNAS_DRY_RETURN();
-    if (node_variant_flag != 1 && node_bwd_warp_ok(p) && (node_variant_flag == 2 || p->B >= 2048))
+    if (node_variant_flag != 1 && node_bwd_warp_ok(p) && (node_variant_flag == 2 || p->B >= kWarpBwdMinB))
         return node_bwd_warp_dispatch(p, (cudaStream_t)stream);
     const bool vec = node_vec_ok(p, true);
     const int lanes = p->L / 4;

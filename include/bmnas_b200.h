@@ -408,10 +408,12 @@ int bmnas_get_gemm_mode(void);
  * recomputation (backward) there.  The caller sets it; 0 is always safe. */
 int bmnas_set_pdl(int on);
 
-/* Kernel variant behind bmnas_node_fwd: 0 = by batch size (default: one CTA per sample below B = 2048, where the
- * launch is latency bound; one warp per sample above, where it is throughput bound), 1 = always CTA per sample,
- * 2 = warp per sample whenever the shape is eligible (L in {4,8,16}, ceil(C/32)*L <= 32, 16-byte aligned tensors,
- * at most 3 conv-backed primitives of which at most one LinearGLU).  Both variants draw identical dropout masks. */
+/* Kernel variant behind bmnas_node_fwd / bmnas_node_bwd: 0 = by batch size (default: one CTA per sample while the
+ * launch is latency bound -- B < 768 forward, B < 640 backward -- one warp per sample beyond, where it is
+ * throughput bound), 1 = always CTA per sample, 2 = warp per sample whenever the shape is eligible (L in
+ * {4,8,16}, ceil(C/32)*L <= 32, 16-byte aligned tensors, at most 3 conv-backed primitives of which at most one
+ * LinearGLU; the backward additionally needs x is y, i.e. the searchable cell).  All variants draw identical
+ * dropout masks and agree to fp32 rounding. */
 int bmnas_set_node_variant(int v);
 int bmnas_get_node_variant(void);
 
