@@ -101,7 +101,7 @@ class Program:
         key = t.name if isinstance(t, Slot) else id(t)
         g = self._grads.get(key)
         if g is None:
-            g = self.buf(self.B, self.C, self.L)
+            g = self.buf(*t.shape) if torch.is_tensor(t) else self.buf(self.B, self.C, self.L)
             self._grads[key] = g
         return g
 
@@ -378,11 +378,17 @@ class Program:
 
     # ------------------------------------------------------------------ kernels: step-node mixed op
     def node_op(self, x, y, ops, P, G, prefix_of, gamma, gamma_off, logits, out, g_gamma=None,
-                need_x=True, need_y=True):
+                need_x=True, need_y=True, conv_srcs=None, conv_src_C=None, conv_need=None):
         """ops: list of primitive names; prefix_of(k) -> parameter prefix of op k.
-        x, y: tensors/Slots (x is y => aliased).  Emits conv (if any conv-backed op) + node kernels."""
+        x, y: tensors/Slots (x is y => aliased).  Emits conv (if any conv-backed op) + node kernels.
+        conv_srcs / conv_src_C / conv_need: the conv reads these sources (any channel counts) instead of cat(x, y)
+        -- the reshape layers, whose conv block is ConcatFC over one pooled source; x and y are then unused."""
         C, L = self.C, self.L
         alias = x is y
+        ext = conv_srcs is not None
+        if ext:
+            assert all(n in ('ConcatFC', 'CatConvMish', 'LinearGLU') for n in ops)
+            need_x = need_y = False
         segs, z_off, off = [], {}, 0
         for k, name in enumerate(ops):
             if name in ('LinearGLU', 'ConcatFC', 'CatConvMish'):
@@ -396,7 +402,11 @@ class Program:
                 off += rows
         assert len(segs) <= N.BMNAS_MAX_SEG
         cv = None
-        if segs:
+        if segs and ext:
+            cv = self.conv(list(conv_srcs), list(conv_src_C), segs, 1, bn=True)
+            x = y = cv['Z']               # placeholders: no primitive of an external-source op reads x / y
+            alias = True
+        elif segs:
             cv = self.conv([x] if alias else [x, y], [C] if alias else [C, C], segs, 2 if alias else 1, bn=True)
         M = cv['M'] if cv else 0
 
@@ -473,8 +483,38 @@ class Program:
             self.setp(sb, 'counter', self.counter())
             self.emit('bmnas_node_bwd', sb)
             if cv:
-                self.conv_backward(cv, GV, coef, [need_x] if alias else [need_x, need_y])
+                self.conv_backward(cv, GV, coef, list(conv_need) if ext else ([need_x] if alias else [need_x, need_y]))
         self.on_backward(bwd)
+
+    # ------------------------------------------------------------------ kernels: adaptive max pool (reshape layers)
+    def pool(self, x, Cin, H, W, OH, OW, need_x):
+        """pooled (B, Cin, OH*OW) = AdaptiveMaxPool2d((OH, OW)) of the raw feature x (B, Cin, H, W)
+        (aux_models.py:61-69, 102-110); registers the gather backward when the input wants a gradient."""
+        pooled = self.buf(self.B, Cin, OH * OW)
+        st = N.bmnas_pool_params()
+        st.B, st.C, st.H, st.W, st.OH, st.OW = self.B, Cin, H, W, OH, OW
+        self.setp(st, 'x', x)
+        self.setp(st, 'out', pooled)
+        idx = None
+        if need_x:
+            idx = self.buf(self.B, Cin, OH * OW, dtype=torch.int32)
+            self.setp(st, 'argmax', idx)
+        self.emit('bmnas_pool_fwd', st)
+
+        def bwd():
+            if not need_x or not self.has_grad(pooled):
+                return
+            sb = N.bmnas_pool_params()
+            sb.B, sb.C, sb.H, sb.W, sb.OH, sb.OW = self.B, Cin, H, W, OH, OW
+            gx = self.buf(self.B, Cin, H, W)
+            self._grads[x.name if isinstance(x, Slot) else id(x)] = gx
+            sb.gx_accum = self.acc(gx)
+            self.setp(sb, 'gout', self._grads[id(pooled)])
+            self.setp(sb, 'argmax', idx)
+            self.setp(sb, 'gx', gx)
+            self.emit('bmnas_pool_bwd', sb)
+        self.on_backward(bwd)
+        return pooled
 
     # ------------------------------------------------------------------ kernels: LayerNorm blocks
     def ln_cat(self, srcs, src_C, residual, ln_w, ln_b, g_ln_w, g_ln_b, relu, out, need_src=None, need_res=True):

@@ -182,6 +182,34 @@ long long bmnas_wprep_items(int M, int K, int fmt);                 /* work item
 int bmnas_conv_image_fmt(int B, int L, int K, int M);
 
 /* ------------------------------------------------------------------------
+ * Adaptive max pooling of a raw backbone feature map onto the (C_in, L) grid: the first stage of the reshape
+ * layers right upstream of the fusion cells.
+ * replaces nn.AdaptiveMaxPool2d((L, 1)) in ReshapeInputLayer.forward (models/auxiliary/aux_models.py:61-69;
+ * the F.interpolate(size=L) after it is the identity) and nn.AdaptiveMaxPool2d((sqrt L, sqrt L)) in
+ * ReshapeInputLayer_MMIMDB.forward (:102-110).  The Conv1d -> BatchNorm1d -> ReLU -> Dropout block that follows
+ * runs on bmnas_conv_* + bmnas_node_* (it is ConcatFC over a single source).
+ * x (B, C, H, W) contiguous -> out (B, C, OH*OW); bin (i, j) covers rows [floor(i*H/OH), ceil((i+1)*H/OH)) and
+ * columns likewise (ATen rule).  argmax (int32, flat h*W+w per bin) is optional in the forward and required by
+ * the backward, which gathers: gx[e] = sum of gout over the bins that elected e (+ gx if gx_accum).
+ * ---------------------------------------------------------------------- */
+typedef struct bmnas_pool_params {
+    int B;
+    int C;
+    int H;
+    int W;
+    int OH;
+    int OW;
+    int gx_accum;
+    const float* x;
+    float* out;
+    int* argmax;
+    const float* gout;
+    float* gx;
+} bmnas_pool_params;
+int bmnas_pool_fwd(const bmnas_pool_params* p, void* stream);
+int bmnas_pool_bwd(const bmnas_pool_params* p, void* stream);
+
+/* ------------------------------------------------------------------------
  * Step-node mixed op: out = sum_k gamma~_k * op_k(x, y), evaluated per sample
  * from the x / y tiles staged once in shared memory; per-op outputs are never
  * written to HBM.

@@ -107,6 +107,43 @@ def conv1x1(u, w, b):
     return torch.einsum('mk,bkl->bml', w[:, :, 0], u) + b[None, :, None]
 
 
+def adaptive_max_pool_2d(x4, out_h, out_w):
+    """nn.AdaptiveMaxPool2d over the last two dims of (B, C, H, W): output bin (i, j) covers rows
+    [floor(i*H/out_h), ceil((i+1)*H/out_h)) and columns likewise (ATen adaptive pooling start/end index rule);
+    bins overlap or repeat when H is not a multiple of out_h (also used to UP-sample: H < out_h)."""
+    B, C, H, W = x4.shape
+    rows = []
+    for i in range(out_h):
+        h0, h1 = (i * H) // out_h, -((-(i + 1) * H) // out_h)
+        cols = []
+        for j in range(out_w):
+            w0, w1 = (j * W) // out_w, -((-(j + 1) * W) // out_w)
+            cols.append(x4[:, :, h0:h1, w0:w1].amax(dim=(2, 3)))
+        rows.append(torch.stack(cols, dim=-1))
+    return torch.stack(rows, dim=-2)             # (B, C, out_h, out_w)
+
+
+def reshape_input(x, P, prefix, L, masks, training, drpt, mmimdb=False):
+    """ReshapeInputLayer.forward (models/auxiliary/aux_models.py:61-76) and ReshapeInputLayer_MMIMDB.forward
+    (:102-115): raw backbone feature (B, C_in[, d2[, ...]]) -> (B, C, L).
+      NTU/Ego: view (B, C_in, d2, rest) -> AdaptiveMaxPool2d((L, 1)) -> F.interpolate(size=L) (nearest, same
+               length: the identity) -> Conv1d(C_in, C, 1) -> BatchNorm1d -> ReLU -> Dropout(drpt)
+      MM-IMDB: view (B, C_in, d2, rest) -> AdaptiveMaxPool2d((sqrt L, sqrt L)) -> flatten -> the same conv block."""
+    B, Cin = x.shape[0], x.shape[1]
+    if mmimdb:
+        x4 = x.reshape(B, Cin, 1, 1) if x.dim() == 2 else x.reshape(B, Cin, x.shape[2], -1)
+        ps = int(math.sqrt(L))
+        assert ps * ps == L
+        pooled = adaptive_max_pool_2d(x4, ps, ps).reshape(B, Cin, L)
+    else:
+        x4 = x.reshape(B, Cin, 1, 1) if x.dim() == 2 else x.reshape(B, Cin, x.shape[2], -1)
+        pooled = adaptive_max_pool_2d(x4, L, 1).reshape(B, Cin, L)
+    z = conv1x1(pooled, P[prefix + '.conv.weight'], P[prefix + '.conv.bias'])
+    z = batchnorm(z, P, prefix + '.bn', training)
+    z = F.relu(z)
+    return _dropout(z, drpt, masks, prefix + '.dropout', training)
+
+
 def edge_mix(states, w):
     """Sum of FusionMixedOps over candidate input tensors, PRIMITIVES = [none, skip]
     (operations.py:104-106, Zero :18-20, Identity :92-93; python ``sum`` order

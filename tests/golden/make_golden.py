@@ -39,6 +39,7 @@ from models.search.darts import node_operations as ref_nops         # noqa: E402
 from models.search.darts import genotypes as ref_gt                 # noqa: E402
 from models.search.darts.genotypes import Genotype, StepGenotype    # noqa: E402
 import models.auxiliary.scheduler as ref_sc                         # noqa: E402
+import models.auxiliary.aux_models as ref_aux                       # noqa: E402
 
 MASKS = {}          # name -> mask, filled lazily by the patched dropout
 MASK_SEED = [0]
@@ -269,6 +270,58 @@ def found_case(tag, B, num_classes, genotype, seed, **cfg):
     save(tag, **out)
 
 
+# ---------------------------------------------------------------- reshape layers
+RESHAPE_CASES = [
+    # tag, class, raw feature shape, C, L          (shapes follow SURVEY App. B, channel counts scaled down)
+    ('ntu_5d', 'ReshapeInputLayer', (3, 12, 8, 3, 3), 16, 8),        # (B, C_in, T=L, H, W): pool the spatial dims only
+    ('ntu_skel', 'ReshapeInputLayer', (3, 10, 4, 4), 16, 8),         # d2 = 4 < L: adaptive bins repeat rows (up-sampling)
+    ('ntu_vec', 'ReshapeInputLayer', (3, 20), 16, 8),                # pooled (B, C_in) vector: replicated over L
+    ('ragged_down', 'ReshapeInputLayer', (4, 6, 11, 5), 8, 8),       # d2 = 11 -> 8 overlapping bins
+    ('ragged_up', 'ReshapeInputLayer', (4, 6, 5, 7), 8, 8),          # d2 = 5 -> 8
+    ('ego_5d', 'ReshapeInputLayer', (2, 9, 2, 4, 4), 16, 8),
+    ('mm_map', 'ReshapeInputLayer_MMIMDB', (3, 8, 7, 7), 24, 16),    # VGG feature map -> 4 x 4
+    ('mm_vec', 'ReshapeInputLayer_MMIMDB', (3, 9), 24, 16),          # Maxout vector -> replicated
+    ('mm_small', 'ReshapeInputLayer_MMIMDB', (3, 5, 3, 2), 12, 4),   # 3 x 2 -> 2 x 2
+]
+
+
+def reshape_cases():
+    """ReshapeInputLayer / ReshapeInputLayer_MMIMDB (models/auxiliary/aux_models.py:51-115): forward, all gradients
+    (input included), BatchNorm buffers after the step, eval-mode forward."""
+    out = {}
+    for ci, (tag, cls, shape, C, L) in enumerate(RESHAPE_CASES):
+        MASKS.clear()
+        MASK_SEED[0] = 900 + ci
+        g = torch.Generator().manual_seed(300 + ci)
+        args = Args(drpt=0.2)
+        mod = getattr(ref_aux, cls)(shape[1], C, L, args)
+        randomize(mod, 310 + ci)
+        name_dropouts(mod, prefix='op.')
+        mod.train()
+        for k, v in to_np(mod.state_dict()).items():
+            out[f'{tag}/sd0/op.{k}'] = v
+        x = torch.randn(*shape, generator=g).requires_grad_(True)
+        y = mod(x)
+        go = torch.randn(y.shape, generator=g)
+        y.backward(go)
+        out[f'{tag}/x'] = x.detach().numpy()
+        out[f'{tag}/out'] = y.detach().numpy()
+        out[f'{tag}/go'] = go.numpy()
+        out[f'{tag}/gx'] = x.grad.numpy().copy()
+        for n, p_ in mod.named_parameters():
+            out[f'{tag}/g/op.{n}'] = p_.grad.numpy().copy()
+        for k, v in MASKS.items():
+            out[f'{tag}/mask/{k}'] = v.numpy()
+        for k, v in to_np(mod.state_dict()).items():
+            if 'running' in k or 'num_batches' in k:
+                out[f'{tag}/sd1/op.{k}'] = v
+        mod.eval()
+        with torch.no_grad():
+            out[f'{tag}/eval_out'] = mod(x.detach()).numpy()
+        out[f'{tag}/meta'] = np.asarray([C, L, int(cls.endswith('MMIMDB'))])
+    save('reshape', **out)
+
+
 # ---------------------------------------------------------------- primitives
 def primitive_cases():
     """Each step-node primitive alone, x != y, train + eval, incl. the unregistered
@@ -433,6 +486,7 @@ if __name__ == '__main__':
     found_case('found_nm1', B=5, num_classes=4, genotype=FOUND_NM1, seed=80,
                C=24, L=16, num_input_nodes=4, steps=2, multiplier=2, node_steps=1, node_multiplier=1, drpt=0.1)
     primitive_cases()
+    reshape_cases()
     genotype_cases()
     scheduler_cases()
     adam_cases()

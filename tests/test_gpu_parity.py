@@ -426,3 +426,63 @@ def test_prefetch_pipeline_matches_serial_loads(graphs):
     for x, y in zip(a0, a1):
         assert_close(y, x, 1e-4, 'arch after pipelined loop')
     assert len({round(v[1], 6) for v in l0}) > 1      # the batches really differ step to step
+
+
+# ------------------------------------------------------------------ reshape layers upstream of the cells
+@pytest.mark.parametrize('tag', ['ntu_5d', 'ntu_skel', 'ntu_vec', 'ragged_down', 'ragged_up', 'ego_5d', 'mm_map', 'mm_vec',
+                                 'mm_small'])
+def test_reshape_layers_golden(tag):
+    """ReshapeInputLayer / ReshapeInputLayer_MMIMDB on the CUDA path (bmnas_pool_* + conv + node kernels) against the
+    reference's own modules: output, input gradient through the adaptive max pool, parameter gradients, BatchNorm
+    buffers, eval-mode output"""
+    import types
+    from models.auxiliary.aux_models import ReshapeInputLayer, ReshapeInputLayer_MMIMDB
+    d = load('reshape')
+    C, L, mm = (int(v) for v in d[f'{tag}/meta'])
+    x = torch.from_numpy(d[f'{tag}/x']).to(U.DEV).requires_grad_(True)
+    cls = ReshapeInputLayer_MMIMDB if mm else ReshapeInputLayer
+    mod = cls(x.shape[1], C, L, types.SimpleNamespace(drpt=0.2))
+    mod.load_state_dict({k[3:]: v for k, v in sub(d, f'{tag}/sd0/').items()}, strict=True)
+    mod.to(U.DEV).train()
+    U.inject_masks(mod, {k[3:]: v for k, v in sub(d, f'{tag}/mask/').items()})
+    out = mod(x)
+    out.backward(torch.from_numpy(d[f'{tag}/go']).to(U.DEV))
+    torch.cuda.synchronize()
+    assert_close(out, d[f'{tag}/out'], TOL, 'out')
+    assert_close(x.grad, d[f'{tag}/gx'], GTOL, 'gx')
+    for k, p in mod.named_parameters():
+        assert_close(p.grad, d[f'{tag}/g/op.{k}'], GTOL, k, atol=(1e-4 if k.endswith('conv.bias') else 1e-7))
+    sd = mod.state_dict()
+    for k, v in sub(d, f'{tag}/sd1/').items():
+        assert_close(sd[k[3:]], v, 1e-5, k)
+    mod.eval()
+    with torch.no_grad():
+        ev = mod(x.detach())
+    assert_close(ev, d[f'{tag}/eval_out'], TOL, 'eval')
+
+
+@pytest.mark.parametrize('shape,C_in', [((96, 512, 8, 8, 8), 512), ((96, 2048), 2048), ((32, 1024, 8, 4, 4), 1024)])
+def test_reshape_layer_full_size_vs_oracle(shape, C_in):
+    """NTU-sized reshape layers (C_in up to 2048: the one large-K GEMM next to the path) against the CPU oracle"""
+    import types
+    from models.auxiliary.aux_models import ReshapeInputLayer
+    C, L = 128, 8
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(*shape, generator=g)
+    mod = ReshapeInputLayer(C_in, C, L, types.SimpleNamespace(drpt=0.2))
+    P = {'op.' + k: v.detach().clone() for k, v in mod.state_dict().items()}
+    mask = (torch.rand(shape[0], C, L, generator=g) >= 0.2).to(torch.uint8)
+    go = torch.randn(shape[0], C, L, generator=g)
+    names = O.trainable_names(P)
+    leaves = {k: P[k].clone().requires_grad_(True) for k in names}
+    Pl = dict(P); Pl.update(leaves)
+    o = O.reshape_input(x, Pl, 'op', L, {'op.dropout': mask}, True, 0.2)
+    o.backward(go)
+    mod.to(U.DEV).train()
+    U.inject_masks(mod, {'dropout': mask})
+    out = mod(x.to(U.DEV))
+    out.backward(go.to(U.DEV))
+    torch.cuda.synchronize()
+    assert_close(out, o, TOL, 'out')
+    for k, p in mod.named_parameters():
+        assert_close(p.grad, leaves['op.' + k].grad, GTOL, k, atol=(2e-4 if k.endswith('conv.bias') else 1e-7))

@@ -208,3 +208,26 @@ def test_launch_plan_builds_in_validate_only_mode(name, validate_only):
         assert p.grad is not None and p.grad.data_ptr() == arena.view(p).data_ptr()
     lo, hi = arena.flat.data_ptr(), arena.flat.data_ptr() + arena.flat.numel() * 4
     assert all(lo <= p.grad.data_ptr() < hi for p in head.parameters())
+
+
+@pytest.mark.parametrize('tag', ['ntu_5d', 'ntu_vec', 'mm_map'])
+def test_reshape_layer_plan_and_state_dict(tag, validate_only):
+    """drop-in ReshapeInputLayer / ReshapeInputLayer_MMIMDB: reference state_dict loads by name, the launch plan is
+    pool -> conv -> node (and the mirrored backward incl. the pooling gather when the input wants a gradient)"""
+    from models.auxiliary.aux_models import ReshapeInputLayer, ReshapeInputLayer_MMIMDB
+    d = load('reshape')
+    C, L, mm = (int(v) for v in d[f'{tag}/meta'])
+    x = torch.from_numpy(d[f'{tag}/x']).requires_grad_(True)
+    cls = ReshapeInputLayer_MMIMDB if mm else ReshapeInputLayer
+    mod = cls(x.shape[1], C, L, types.SimpleNamespace(drpt=0.2))
+    mod.load_state_dict({k[3:]: v for k, v in sub(d, f'{tag}/sd0/').items()}, strict=True)
+    mod.train()
+    U.inject_masks(mod, {k[3:]: v for k, v in sub(d, f'{tag}/mask/').items()}, device=torch.device('cpu'))
+    out = mod(x)
+    assert out.shape == (x.shape[0], C, L)
+    out.backward(torch.from_numpy(d[f'{tag}/go']))
+    runner = list(mod._bm_cache.values())[0]
+    assert [c.name for c in runner.prog.fwd] == ['bmnas_pool_fwd', 'bmnas_conv_fwd', 'bmnas_node_fwd']
+    assert [c.name for c in runner.prog.bwd] == ['bmnas_node_bwd', 'bmnas_conv_wgrad', 'bmnas_conv_dgrad', 'bmnas_pool_bwd']
+    assert x.grad is not None and x.grad.shape == x.shape
+    assert all(p.grad is not None for p in mod.parameters())

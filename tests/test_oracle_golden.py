@@ -142,6 +142,36 @@ def test_primitives(op):
     assert_close(ev, d[f'{op}/eval_out'], TOL, 'eval')
 
 
+RESHAPE_TAGS = ['ntu_5d', 'ntu_skel', 'ntu_vec', 'ragged_down', 'ragged_up', 'ego_5d', 'mm_map', 'mm_vec', 'mm_small']
+
+
+@pytest.mark.parametrize('tag', RESHAPE_TAGS)
+def test_reshape_input_layer(tag):
+    """oracle restatement of ReshapeInputLayer / ReshapeInputLayer_MMIMDB (aux_models.py:51-115) against the
+    reference's own modules: output, input gradient (through the adaptive max pool), parameter gradients,
+    BatchNorm buffers, eval-mode output"""
+    d = load('reshape')
+    C, L, mm = (int(v) for v in d[f'{tag}/meta'])
+    P = sub(d, f'{tag}/sd0/')
+    x = torch.from_numpy(d[f'{tag}/x']).requires_grad_(True)
+    names = O.trainable_names(P)
+    leaves = {k: P[k].clone().requires_grad_(True) for k in names}
+    Pl = dict(P); Pl.update(leaves)
+    o = O.reshape_input(x, Pl, 'op', L, sub(d, f'{tag}/mask/'), True, 0.2, mmimdb=bool(mm))
+    o.backward(torch.from_numpy(d[f'{tag}/go']))
+    assert o.shape == (x.shape[0], C, L)
+    assert_close(o, d[f'{tag}/out'], TOL, 'out')
+    assert_close(x.grad, d[f'{tag}/gx'], 5e-5, 'gx')
+    for k in names:
+        # a conv bias feeding a train-mode BatchNorm has an analytically zero gradient: rounding noise on both sides
+        assert_close(leaves[k].grad, d[f'{tag}/g/' + k], 5e-5, k, atol=(1e-4 if k.endswith('conv.bias') else 2e-7))
+    for k, v in sub(d, f'{tag}/sd1/').items():
+        assert_close(P[k], v, 1e-5, k)
+    with torch.no_grad():
+        ev = O.reshape_input(x.detach(), P, 'op', L, None, False, 0.2, mmimdb=bool(mm))
+    assert_close(ev, d[f'{tag}/eval_out'], TOL, 'eval')
+
+
 def test_mixed5_with_catconvmish():
     d = load('primitives')
     P = sub(d, 'Mixed5/sd0/')
