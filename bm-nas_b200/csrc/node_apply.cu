@@ -717,7 +717,8 @@ __global__ void __launch_bounds__(WPC * 32, 2) k_node_fwd_warp(const bmnas_node_
 }
 
 // ----------------------------------------------------------------------------------------------------------
-// Warp-per-sample backward (large batch, searchable cell: x is y).  Same ownership as the forward: lane holds the
+// Warp-per-sample backward (large batch; x is y in the searchable cell, x != y in the found cell).  Same ownership
+// as the forward: lane holds the
 // channels c = t*32 + lane.  Per sample the warp (A) stages x and gout in its slab, (B) recomputes the attention
 // primitive exactly as the forward did (P, dropped output, LayerNorm statistics; the keep bits of its 32 own
 // elements stay in one register), (C) walks its own elements once: d(gamma) partials, GV rows for the conv
@@ -747,6 +748,7 @@ __global__ void __launch_bounds__(WPCB * 32, 1) k_node_bwd_warp(const bmnas_node
     constexpr int Q = L / 4, KS = 32 / L;
     const int C = p.C, CL = C * L, M = p.M;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool alias = p.alias_xy != 0;
     const size_t CLr = rnd4((size_t)CL), Mr = rnd4((size_t)M), LLr = rnd4((size_t)L * L);
     float2* bnr = reinterpret_cast<float2*>(smem);            // (rstd, mean * rstd)
     float2* bnw = bnr + Mr;                                   // (weight, bias)
@@ -755,7 +757,9 @@ __global__ void __launch_bounds__(WPCB * 32, 1) k_node_bwd_warp(const bmnas_node
     float* lnw = S2s + Mr;
     float* slab0 = lnw + CLr;
     const size_t slab_floats = node_bwarp_slab_floats(C, L, M);
-    float* slab = slab0 + (size_t)warp * slab_floats;    // [x0 | g0 | x1 | g1 | a/dO | P | dS | S1 | S2]
+    // x is y (searchable cell): [x0 | g0 | x1 | g1 | a/dO | P | dS | S1 | S2], tiles double buffered;
+    // x is not y (found cell):  [x  | y  | g  | -- | a/dO | P | dS | S1 | S2], single buffered
+    float* slab = slab0 + (size_t)warp * slab_floats;
     float* os = slab + 4 * CLr;
     float* Ps = os + CLr;
     float* dSs = Ps + LLr;
@@ -835,7 +839,7 @@ __global__ void __launch_bounds__(WPCB * 32, 1) k_node_bwd_warp(const bmnas_node
         }
     };
 
-    auto stage = [&](int b, float* dst) {    // x and gout of one sample: global -> shared, asynchronously
+    auto stage = [&](int b, float* dst) {    // x (, y) and gout of one sample: global -> shared, asynchronously
         const long long sb = (long long)b * CL;
 #pragma unroll
         for (int t = 0; t < T; ++t) {
@@ -844,23 +848,33 @@ __global__ void __launch_bounds__(WPCB * 32, 1) k_node_bwd_warp(const bmnas_node
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
                     cp_async16(dst + c * L + 4 * q, p.x + sb + c * L + 4 * q);
-                    cp_async16(dst + CLr + c * L + 4 * q, p.gout + sb + c * L + 4 * q);
+                    if (alias) {
+                        cp_async16(dst + CLr + c * L + 4 * q, p.gout + sb + c * L + 4 * q);
+                    } else {
+                        cp_async16(dst + CLr + c * L + 4 * q, p.y + sb + c * L + 4 * q);
+                        cp_async16(dst + 2 * CLr + c * L + 4 * q, p.gout + sb + c * L + 4 * q);
+                    }
                 }
             }
         }
     };
     int buf = 0;
-    if (gwarp < p.B) stage(gwarp, slab);
+    if (alias && gwarp < p.B) stage(gwarp, slab);
     for (int b = gwarp; b < p.B; b += gstride, buf ^= 1) {
         const long long base = (long long)b * CL;
         const unsigned long long gbase = (unsigned long long)(p.sample_offset + b) * CL;
         const float* Zb = p.Z ? p.Z + (long long)b * M * L : nullptr;
         float* GVb = p.GV ? p.GV + (long long)b * M * L : nullptr;
-        const float* xs = slab + buf * 2 * CLr;
-        const float* gs = xs + CLr;
+        const float* xs = alias ? slab + buf * 2 * CLr : slab;
+        const float* ys = alias ? xs : slab + CLr;
+        const float* gs = alias ? xs + CLr : slab + 2 * CLr;
+        if (!alias) {
+            __syncwarp();                    // the previous sample's readers of the single-buffered tiles are done
+            stage(b, slab);
+        }
         cp_async_wait_all();
         __syncwarp();                        // this sample's tiles are visible; the other buffer and os / P / dS are free
-        if (b + gstride < p.B) stage(b + gstride, slab + (buf ^ 1) * 2 * CLr);
+        if (alias && b + gstride < p.B) stage(b + gstride, slab + (buf ^ 1) * 2 * CLr);
 
         // ---- (B) attention primitive, recomputed as in the forward
         float a_mean = 0.f, a_rstd = 0.f;
@@ -875,7 +889,7 @@ __global__ void __launch_bounds__(WPCB * 32, 1) k_node_bwd_warp(const bmnas_node
                 const float a = xs[c * L + i];
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
-                    const float4 v = lds4(xs + c * L + 4 * q);
+                    const float4 v = lds4(ys + c * L + 4 * q);
                     sc[4 * q] = fmaf(a, v.x, sc[4 * q]);
                     sc[4 * q + 1] = fmaf(a, v.y, sc[4 * q + 1]);
                     sc[4 * q + 2] = fmaf(a, v.z, sc[4 * q + 2]);
@@ -914,7 +928,7 @@ __global__ void __launch_bounds__(WPCB * 32, 1) k_node_bwd_warp(const bmnas_node
                     const int c = t * 32 + lane;
 #pragma unroll
                     for (int q = 0; q < Q; ++q) {
-                        const float4 v = c < C ? lds4(xs + c * L + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 v = c < C ? lds4(ys + c * L + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
                         yr[t][4 * q] = v.x; yr[t][4 * q + 1] = v.y; yr[t][4 * q + 2] = v.z; yr[t][4 * q + 3] = v.w;
                     }
                 }
@@ -1018,8 +1032,8 @@ __global__ void __launch_bounds__(WPCB * 32, 1) k_node_bwd_warp(const bmnas_node
             for (int q = 0; q < Q; ++q) {
                 g4q[q] = lds4(gs + c * L + 4 * q);
                 if (has_sum) {
-                    const float4 xv = lds4(xs + c * L + 4 * q);
-                    dg_sum += 2.f * (g4q[q].x * xv.x + g4q[q].y * xv.y + g4q[q].z * xv.z + g4q[q].w * xv.w);
+                    const float4 xv = lds4(xs + c * L + 4 * q), yv = lds4(ys + c * L + 4 * q);
+                    dg_sum += g4q[q].x * (xv.x + yv.x) + g4q[q].y * (xv.y + yv.y) + g4q[q].z * (xv.z + yv.z) + g4q[q].w * (xv.w + yv.w);
                 }
             }
 #pragma unroll
@@ -1122,7 +1136,7 @@ __global__ void __launch_bounds__(WPCB * 32, 1) k_node_bwd_warp(const bmnas_node
                 const float a = os[c * L + i];
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
-                    const float4 v = lds4(xs + c * L + 4 * q);
+                    const float4 v = lds4(ys + c * L + 4 * q);
                     dp[4 * q] = fmaf(a, v.x, dp[4 * q]);
                     dp[4 * q + 1] = fmaf(a, v.y, dp[4 * q + 1]);
                     dp[4 * q + 2] = fmaf(a, v.z, dp[4 * q + 2]);
@@ -1152,25 +1166,28 @@ __global__ void __launch_bounds__(WPCB * 32, 1) k_node_bwd_warp(const bmnas_node
             __syncwarp();
         }
 
-        // ---- (E) gx = d/dx + d/dy for the lane's channel rows
-        if (p.gx) {
+        // ---- (E) d/dx and d/dy for the lane's channel rows (one tensor gx = dx + dy when x is y)
+        if (p.gx || p.gy) {
 #pragma unroll 1
             for (int t = 0; t < T; ++t) {
                 const int c = t * 32 + lane;
                 if (c >= C) break;
-                float out[L];
+                float dxo[L], dyo[L];
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
                     const float4 g4 = lds4(gs + c * L + 4 * q);
-                    const float w2 = has_sum ? 2.f * wsum : 0.f;
-                    out[4 * q] = w2 * g4.x; out[4 * q + 1] = w2 * g4.y; out[4 * q + 2] = w2 * g4.z; out[4 * q + 3] = w2 * g4.w;
+                    const float w1 = has_sum ? wsum : 0.f;
+                    dxo[4 * q] = w1 * g4.x; dxo[4 * q + 1] = w1 * g4.y; dxo[4 * q + 2] = w1 * g4.z; dxo[4 * q + 3] = w1 * g4.w;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) dyo[4 * q + e] = dxo[4 * q + e];
                 }
                 if (k_attn >= 0) {
-                    float xr[L], dor[L];
+                    float xr[L], yr2[L], dor[L];
 #pragma unroll
                     for (int q = 0; q < Q; ++q) {
-                        const float4 v = lds4(xs + c * L + 4 * q), d = lds4(os + c * L + 4 * q);
+                        const float4 v = lds4(xs + c * L + 4 * q), u = lds4(ys + c * L + 4 * q), d = lds4(os + c * L + 4 * q);
                         xr[4 * q] = v.x; xr[4 * q + 1] = v.y; xr[4 * q + 2] = v.z; xr[4 * q + 3] = v.w;
+                        yr2[4 * q] = u.x; yr2[4 * q + 1] = u.y; yr2[4 * q + 2] = u.z; yr2[4 * q + 3] = u.w;
                         dor[4 * q] = d.x; dor[4 * q + 1] = d.y; dor[4 * q + 2] = d.z; dor[4 * q + 3] = d.w;
                     }
 #pragma unroll
@@ -1185,22 +1202,37 @@ __global__ void __launch_bounds__(WPCB * 32, 1) k_node_bwd_warp(const bmnas_node
                         float dxr = 0.f;
 #pragma unroll
                         for (int j = 0; j < L; ++j) {
-                            dxr = fmaf(dsr[j], xr[j], dxr);                       // dx[c,r] = sum_j dS[r][j] y[c,j]
-                            out[j] = fmaf(dor[r], pr[j], out[j]);                 // dy[c,j] += dO[c,r] P[r][j]
-                            out[j] = fmaf(xr[r], dsr[j], out[j]);                 //          + x[c,r] dS[r][j]
+                            dxr = fmaf(dsr[j], yr2[j], dxr);                      // dx[c,r] = sum_j dS[r][j] y[c,j]
+                            dyo[j] = fmaf(dor[r], pr[j], dyo[j]);                 // dy[c,j] += dO[c,r] P[r][j]
+                            dyo[j] = fmaf(xr[r], dsr[j], dyo[j]);                 //          + x[c,r] dS[r][j]
                         }
-                        out[r] += dxr;
+                        dxo[r] += dxr;
                     }
+                }
+                if (alias) {
+#pragma unroll
+                    for (int j = 0; j < L; ++j) dxo[j] += dyo[j];
                 }
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
-                    float* dst = p.gx + base + c * L + 4 * q;
-                    float4 o4 = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
-                    if (p.gx_accum) {
-                        const float4 cur = *reinterpret_cast<const float4*>(dst);
-                        o4.x += cur.x; o4.y += cur.y; o4.z += cur.z; o4.w += cur.w;
+                    if (p.gx) {
+                        float* dst = p.gx + base + c * L + 4 * q;
+                        float4 o4 = make_float4(dxo[4 * q], dxo[4 * q + 1], dxo[4 * q + 2], dxo[4 * q + 3]);
+                        if (p.gx_accum) {
+                            const float4 cur = *reinterpret_cast<const float4*>(dst);
+                            o4.x += cur.x; o4.y += cur.y; o4.z += cur.z; o4.w += cur.w;
+                        }
+                        *reinterpret_cast<float4*>(dst) = o4;
                     }
-                    *reinterpret_cast<float4*>(dst) = o4;
+                    if (!alias && p.gy) {
+                        float* dst = p.gy + base + c * L + 4 * q;
+                        float4 o4 = make_float4(dyo[4 * q], dyo[4 * q + 1], dyo[4 * q + 2], dyo[4 * q + 3]);
+                        if (p.gy_accum) {
+                            const float4 cur = *reinterpret_cast<const float4*>(dst);
+                            o4.x += cur.x; o4.y += cur.y; o4.z += cur.z; o4.w += cur.w;
+                        }
+                        *reinterpret_cast<float4*>(dst) = o4;
+                    }
                 }
             }
         }
@@ -1690,7 +1722,8 @@ static bool node_vec_ok(const bmnas_node_params* p, bool bwd) {
 
 template <class Kern>
 static int node_smem_attr(Kern kern, size_t smem, size_t* configured) {
-    if (smem > 48 * 1024 && smem > *configured) {
+    // the 48 KB default limit counts static + dynamic shared memory: opt in with a margin for the static part
+    if (smem > 40 * 1024 && smem > *configured) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return BMNAS_ELAUNCH;
         *configured = smem;
@@ -1765,7 +1798,7 @@ static int launch_node_bwd_warp(const bmnas_node_params* p, size_t smem, cudaStr
 }
 
 static bool node_bwd_warp_ok(const bmnas_node_params* p) {
-    if (!p->alias_xy || !node_warp_ok(p, true)) return false;    // searchable cell only (x is y)
+    if (!node_warp_ok(p, true)) return false;
     return node_bwarp_smem_floats(p->C, p->L, p->M) * sizeof(float) <= 220 * 1024;
 }
 

@@ -440,8 +440,8 @@ int bmnas_set_pdl(int on);
  * launch is latency bound -- B < 768 forward, B < 640 backward -- one warp per sample beyond, where it is
  * throughput bound), 1 = always CTA per sample, 2 = warp per sample whenever the shape is eligible (L in
  * {4,8,16}, ceil(C/32)*L <= 32, 16-byte aligned tensors, at most 3 conv-backed primitives of which at most one
- * LinearGLU; the backward additionally needs x is y, i.e. the searchable cell).  All variants draw identical
- * dropout masks and agree to fp32 rounding. */
+ * LinearGLU; x is y -- the searchable cell -- double-buffers its tiles, x != y -- the found cell -- stages them
+ * per sample).  All variants draw identical dropout masks and agree to fp32 rounding. */
 int bmnas_set_node_variant(int v);
 int bmnas_get_node_variant(void);
 
