@@ -30,6 +30,10 @@ CONFIGS = {
                    B=32, classes=23, loss='bce', eta_max=1e-3, weight_decay=1e-4),
     'ego': dict(C=128, L=8, num_input_nodes=8, steps=2, multiplier=2, node_steps=3, node_multiplier=3, drpt=0.05,
                 B=96, classes=83, loss='ce', eta_max=3e-3, weight_decay=1e-4),
+    # BASELINE configs[3]: "larger C/L and more Step nodes" (the authors' C=256, steps=4, multiplier=4 exploration,
+    # structure_vis.ipynb cell 3)
+    'ego_large': dict(C=256, L=16, num_input_nodes=8, steps=4, multiplier=4, node_steps=3, node_multiplier=3, drpt=0.05,
+                      B=96, classes=83, loss='ce', eta_max=3e-3, weight_decay=1e-4),
 }
 L2_BYTES = 126 * 1024 * 1024
 
@@ -43,13 +47,19 @@ def peaks():
 
 
 # ----------------------------------------------------------------------------- CPU reference arm (oracle port)
-def cpu_reference(cfgname, steps, warmup, max_seconds=25.0):
+def cpu_reference(cfgname, steps, warmup, max_seconds=25.0, device='cpu'):
     """times oracle/bmnas_oracle.py (the CPU restatement of the reference's path, pinned against the
-    reference by tests/golden) on all host cores.  Returns (samples_per_s, ms_per_step, cores, steps_done)."""
+    reference by tests/golden) on all host cores.  Returns (samples_per_s, ms_per_step, cores, steps_done).
+    device='cuda': the same functional PyTorch code run eagerly on the GPU (cuDNN/cuBLAS kernels, TF32 off) --
+    the "reference-style eager PyTorch on B200" baseline SURVEY 8d asks for next to the CPU number."""
     from oracle import bmnas_oracle as O
     c = CONFIGS[cfgname]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    gpu = device != 'cpu'
+    if gpu:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
     cfg = O.Cfg(c['C'], c['L'], c['num_input_nodes'], c['steps'], c['multiplier'], c['node_steps'],
                 c['node_multiplier'], c['drpt'])
     P = O.init_params(cfg, c['classes'], seed=2, prefix='cell')
@@ -58,23 +68,38 @@ def cpu_reference(cfgname, steps, warmup, max_seconds=25.0):
     dev = O.synthetic_batch(cfg, c['B'], c['classes'], seed=2, loss=c['loss'])
     trn = O.synthetic_batch(cfg, c['B'], c['classes'], seed=3, loss=c['loss'])
     g = torch.Generator().manual_seed(7)
+    if gpu:
+        for k in list(P):
+            P[k] = P[k].to(device)
+        st.arch = [a.to(device) for a in st.arch]
+        dev = ([f.to(device) for f in dev[0]], dev[1].to(device))
+        trn = ([f.to(device) for f in trn[0]], trn[1].to(device))
+        g = torch.Generator(device=device).manual_seed(7)
 
     def masks():
         # the reference draws fresh dropout masks every forward; do the same work here
         m = {}
         for name in _dropout_sites(cfg):
             p = 0.1 if name.endswith('_ops.1.dropout') else cfg.drpt
-            m['fusion_net.' + name] = (torch.rand(c['B'], cfg.C, cfg.L, generator=g) >= p).to(torch.uint8)
+            m['fusion_net.' + name] = (torch.rand(c['B'], cfg.C, cfg.L, generator=g, device=device) >= p).to(torch.uint8)
         return m
+
+    def sync():
+        if gpu:
+            torch.cuda.synchronize()
     for _ in range(warmup):
         st.search_step(dev, trn, masks(), masks())
+    sync()
     t0 = time.perf_counter()
     done = 0
     for _ in range(steps):
         st.search_step(dev, trn, masks(), masks())
         done += 1
+        if gpu and done % 8 == 0:
+            sync()
         if time.perf_counter() - t0 > max_seconds:
             break
+    sync()
     dt = time.perf_counter() - t0
     return c['B'] * done / dt, 1e3 * dt / done, cores, done
 
@@ -428,6 +453,12 @@ def run_ours(args):
             cpu = {'value': round(v, 1), 'unit': 'samples/s', 'cores': cores, 'kind': 'port', 'ms_per_step': round(ms, 2),
                    'sample': f'{done} search steps of the same workload (B={c["B"]}) on the oracle port, '
                              f'torch CPU fp32, {cores} threads'}
+            try:    # the same functional PyTorch code, eager on this GPU (reported next to the CPU number)
+                gv, gms, _, gdone = cpu_reference(args.config, 60, 3, max_seconds=10.0, device=str(device))
+                cpu['torch_eager_gpu'] = {'value': round(gv, 1), 'unit': 'samples/s', 'ms_per_step': round(gms, 3),
+                                          'sample': f'{gdone} search steps, eager PyTorch fp32 (TF32 off) on the same B200'}
+            except Exception as e:
+                cpu['torch_eager_gpu'] = {'unavailable': repr(e)[:200]}
         out = {
             'metric': 'search-step samples/sec (fwd+bwd+arch step, fwd+bwd+weight step)', 'value': round(value, 1),
             'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
