@@ -209,8 +209,9 @@ def algorithmic_bytes(call, c, B):
     n = call.name
     if n == 'bmnas_mix_fwd':
         return (st.n + 1) * T
-    if n == 'bmnas_mix_bwd':
-        return (2 * st.n + 1) * T
+    if n == 'bmnas_mix_bwd':   # gout in; the x_j in when d(alpha) is wanted; the gx_j out (the two halves are separate launches)
+        n_gx = sum(1 for j in range(st.n) if st.gx[j])
+        return (1 + (st.n if st.gw else 0) + n_gx) * T
     if n == 'bmnas_node_fwd':
         return (1 if st.alias_xy else 2) * T + st.M * c['L'] * 4 * B + T
     if n == 'bmnas_node_bwd':

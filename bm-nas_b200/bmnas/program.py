@@ -41,6 +41,7 @@ class Slot:
 
 
 SIDE_WGRAD = os.environ.get('BMNAS_SIDE_WGRAD', '1') != '0'   # weight-gradient GEMMs on a side stream (parallel graph branch); see conv_backward
+SPLIT_MIX_BWD = os.environ.get('BMNAS_SPLIT_MIX_BWD', '1') != '0'   # edge-mix backward: input grads on the main chain, d(alpha) on the side branch
 _side_streams = {}
 
 
@@ -155,8 +156,8 @@ class Program:
             else:
                 getattr(st, field)[idx] = base + off
 
-    def emit(self, name, st):
-        self._cur.append(N.Call(name, st))
+    def emit(self, name, st, side=False):
+        self._cur.append(N.Call(name, st, side=side))
 
     def on_backward(self, fn):
         self._stack.append(fn)
@@ -219,7 +220,7 @@ class Program:
         sp = ctypes.c_void_p(side.cuda_stream)
         forked = False
         for c in self.bwd:
-            if c.name == 'bmnas_conv_wgrad':
+            if c.side:
                 ev = c.keep
                 if not ev:
                     ev = c.keep = torch.cuda.Event()
@@ -268,25 +269,40 @@ class Program:
         def bwd():
             if not self.has_grad(out):
                 return
-            sb = N.bmnas_mix_params()
-            sb.n, sb.w_is_logits, sb.numel = n, int(logits), numel
-            any_out = gw is not None
+            gout = self.grad_of(out)
+
+            def base():
+                sb = N.bmnas_mix_params()
+                sb.n, sb.w_is_logits, sb.numel = n, int(logits), numel
+                for j, x in enumerate(xs):
+                    self.setp(sb, 'x', x, j)
+                self.setp(sb, 'w', w, offset=w_off * 8)
+                self.setp(sb, 'gout', gout)
+                return sb
+            # the input gradients are what the rest of the backward waits for: a pure streaming launch on the main
+            # chain.  d(alpha) (dot products + cross-CTA reduction) only feeds the optimiser, so it goes on the side
+            # branch next to the weight-gradient GEMMs.
+            sb = base()
+            any_gx = False
             for j, x in enumerate(xs):
-                self.setp(sb, 'x', x, j)
                 if need[j]:
                     g = self.grad_of(x)
                     sb.gx_accum[j] = self.acc(g)
                     self.setp(sb, 'gx', g, j)
-                    any_out = True
-            if not any_out:
-                return
-            self.setp(sb, 'w', w, offset=w_off * 8)
-            self.setp(sb, 'gout', self.grad_of(out))
-            if gw is not None:
+                    any_gx = True
+            split = SPLIT_MIX_BWD and gw is not None and any_gx
+            if gw is not None and not split:
                 self.setp(sb, 'gw', gw, offset=w_off * 8)
                 self.setp(sb, 'partials', self.buf(int(N.lib().bmnas_mix_partials_size(ctypes.byref(sb))), zero=True))
                 self.setp(sb, 'counter', self.counter())
-            self.emit('bmnas_mix_bwd', sb)
+            if any_gx or (gw is not None and not split):
+                self.emit('bmnas_mix_bwd', sb)
+            if split:
+                sd = base()
+                self.setp(sd, 'gw', gw, offset=w_off * 8)
+                self.setp(sd, 'partials', self.buf(int(N.lib().bmnas_mix_partials_size(ctypes.byref(sd))), zero=True))
+                self.setp(sd, 'counter', self.counter())
+                self.emit('bmnas_mix_bwd', sd, side=True)
         self.on_backward(bwd)
 
     # ------------------------------------------------------------------ kernels: conv (+BN stats) and its backward
@@ -366,7 +382,7 @@ class Program:
             for i, sg in enumerate(segs):
                 self.setp(st, 'gW', sg.get('gW'), i)
                 self.setp(st, 'gbias', sg.get('gbias'), i)
-            self.emit('bmnas_conv_wgrad', st)
+            self.emit('bmnas_conv_wgrad', st, side=True)
         if any(need_src):
             st = base()
             for i, s in enumerate(srcs):
