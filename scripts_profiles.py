@@ -34,7 +34,8 @@ for f in sorted(os.listdir('gpurun_out')):
         m = re.match(r'(.*)_B(\d+)$', name)
         if m:
             key = {'node_fwd': 'bmnas_node_fwd', 'node_bwd': 'bmnas_node_bwd', 'sg_fwd': 'bmnas_conv_fwd', 'sg_dgrad': 'bmnas_conv_dgrad',
-                   'wgrad': 'bmnas_conv_wgrad', 'mix_bwd': 'bmnas_mix_bwd', 'ln_bwd': 'bmnas_ln_bwd', 'panel_fwd': 'bmnas_conv_fwd'}.get(m.group(1), m.group(1))
+                   'wgrad': 'bmnas_conv_wgrad', 'mix_bwd': 'bmnas_mix_bwd', 'ln_bwd': 'bmnas_ln_bwd', 'panel_fwd': 'bmnas_conv_fwd',
+                   'node_fwd_warp': 'bmnas_node_fwd', 'node_bwd_warp': 'bmnas_node_bwd'}.get(m.group(1), m.group(1))
             traffic[f'{key}@B{m.group(2)}'] = int(rd + wr)
     src = subprocess.run([sys.executable, 'scripts_ncu_src.py', rep, '14'], capture_output=True, text=True).stdout
     lines.append('# hottest SASS lines (sampled stalls)')
