@@ -17,6 +17,7 @@ import torch.nn as nn
 
 from . import native as N
 from . import runtime as _rt
+from . import program as _prog
 
 
 def _conv_struct(B, L, K, M, w_fold=1):
@@ -69,14 +70,36 @@ class _LinearFn(torch.autograd.Function):
         s = N.current_stream()
         gx = None
         if _lin_ok(x, weight) and (gw_view is None or gw_view.data_ptr() % 16 == 0):
-            st = N.bmnas_linear_params()
-            st.B, st.K, st.N = B, Kc, Nc
-            st.x, st.W, st.gout = x.data_ptr(), weight.data_ptr(), g.data_ptr()
+            def block():
+                st = N.bmnas_linear_params()
+                st.B, st.K, st.N = B, Kc, Nc
+                st.x, st.W, st.gout = x.data_ptr(), weight.data_ptr(), g.data_ptr()
+                return st
+            want_w = gw_view is not None or gb_view is not None
             if ctx.needs_input_grad[0]:
+                # the input gradient is what the rest of the backward waits for: main chain
                 gx = torch.empty_like(x)
+                st = block()
                 st.gx = gx.data_ptr()
-            st.gW, st.gbias = _p(gw_view), _p(gb_view)
-            N.launch('bmnas_linear_bwd', ctypes.byref(st), s)
+                if want_w and not _prog.SIDE_WGRAD:
+                    st.gW, st.gbias = _p(gw_view), _p(gb_view)
+                    want_w = False
+                N.launch('bmnas_linear_bwd', ctypes.byref(st), s)
+            if want_w:
+                # dW / db only feed the optimiser: side branch (joined by the launch plan's backward, the
+                # all-reduce and FusedAdam.step through program.join_side)
+                st = block()
+                st.gW, st.gbias = _p(gw_view), _p(gb_view)
+                if _prog.SIDE_WGRAD and not N.VALIDATE_ONLY and ctx.needs_input_grad[0]:
+                    main = torch.cuda.current_stream()
+                    side = _prog.side_stream(x.device)
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    side.wait_event(ev)
+                    g.record_stream(side)
+                    N.launch('bmnas_linear_bwd', ctypes.byref(st), ctypes.c_void_p(side.cuda_stream))
+                else:
+                    N.launch('bmnas_linear_bwd', ctypes.byref(st), s)
             return gx, None, None, None, None
         if ctx.needs_input_grad[0]:
             gx = torch.empty_like(x)

@@ -84,6 +84,12 @@ class FusedAdam(torch.optim.Optimizer):
     def step(self, closure=None):
         loss = closure() if closure is not None else None
         s = None
+        if torch.cuda.is_available() and not N.VALIDATE_ONLY:
+            from .program import join_side          # weight gradients may still be in flight on the side branch
+            for group in self.param_groups:
+                if group['params'] and group['params'][0].is_cuda:
+                    join_side(group['params'][0].device)
+                    break
         for gi, group in enumerate(self.param_groups):
             st = self._group_state(gi, group)
             if st is None:

@@ -52,6 +52,20 @@ def side_stream(device):
     return st
 
 
+def join_side(device):
+    """the current stream waits for everything forked onto the side branch (no-op if it was never used)"""
+    st = _side_streams.get(device)
+    if st is None:
+        return
+    cur = torch.cuda.current_stream(device)
+    if torch.cuda.is_current_stream_capturing():
+        with torch.cuda.stream(st):
+            forked = torch.cuda.is_current_stream_capturing()
+        if not forked:        # nothing of this capture runs on the side branch: an edge to it would be illegal
+            return
+    cur.wait_stream(st)
+
+
 def uid_of(name):
     return zlib.crc32(name.encode()) & 0xffffffff
 

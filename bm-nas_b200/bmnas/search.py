@@ -67,6 +67,8 @@ class SearchStep:
         """ONE collective per half step: sum the flat gradient arena [fusion weights | arch | classifier] over the
         ranks (the 1/world factor is applied inside the fused Adam as grad_scale)"""
         if self.world > 1:
+            from .program import join_side
+            join_side(self.device)
             torch.distributed.all_reduce(self.head._joint_arena(self.device).flat, group=self.group)
 
     def _run_half(self, which):
