@@ -1,7 +1,7 @@
 """GPU probe: per-engine error and warm launch time of the conv GEMM family at a given shape.
-   python scripts_gemm_probe.py [B]"""
+   python tools/gemm_probe.py [B]"""
 import ctypes, sys, os
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, 'bm-nas_b200')); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import torch
 from bmnas import native as N

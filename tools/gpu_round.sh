@@ -16,7 +16,7 @@ for cfg in mmimdb ego ego_large; do
   python -c "
 import json;d=json.loads(open('gpurun_out/bench_$cfg.log').read());print('$cfg',d['value'],'samples/s',d['ms_per_step'],'ms/step e2e',d['e2e']['value'])" 2>&1 | tail -1
 done
-timeout 600 bash scripts_ncu_list.sh > gpurun_out/launch_list.txt 2>&1
+timeout 600 bash tools/ncu_launch_list.sh > gpurun_out/launch_list.txt 2>&1
 head -16 gpurun_out/launch_list.txt
 cap() {  # name, mangled-name regex, extra bench args
   timeout 300 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k "regex:$2" -s 12 -c 1 \
@@ -24,7 +24,7 @@ cap() {  # name, mangled-name regex, extra bench args
 }
 capL() {  # name, mangled-name regex, plan-driver filter: the B=8192 plan, every call launched stand-alone
   timeout 300 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k "regex:$2" -s 2 -c 1 \
-    -o gpurun_out/prof_$1 -f python scripts_dbg_large.py 8192 $3 eager > gpurun_out/ncu_$1.log 2>&1
+    -o gpurun_out/prof_$1 -f python tools/plan_kernels.py 8192 $3 eager > gpurun_out/ncu_$1.log 2>&1
 }
 cap node_fwd_B96 "k_node_fwdILi4" ""
 cap node_bwd_B96 "k_node_bwdILi4" ""

@@ -1,5 +1,5 @@
 """turn the .ncu-rep files of gpurun_out/ into the text summaries committed under profiles/ (+ ncu_traffic.json)
-    python scripts_profiles.py r01_v5"""
+    python tools/make_profiles.py r01_v7"""
 import csv, json, os, re, subprocess, sys
 tag = sys.argv[1]
 os.makedirs('profiles', exist_ok=True)
@@ -37,7 +37,7 @@ for f in sorted(os.listdir('gpurun_out')):
                    'wgrad': 'bmnas_conv_wgrad', 'mix_bwd': 'bmnas_mix_bwd', 'ln_bwd': 'bmnas_ln_bwd', 'panel_fwd': 'bmnas_conv_fwd',
                    'node_fwd_warp': 'bmnas_node_fwd', 'node_bwd_warp': 'bmnas_node_bwd'}.get(m.group(1), m.group(1))
             traffic[f'{key}@B{m.group(2)}'] = int(rd + wr)
-    src = subprocess.run([sys.executable, 'scripts_ncu_src.py', rep, '14'], capture_output=True, text=True).stdout
+    src = subprocess.run([sys.executable, 'tools/ncu_src.py', rep, '14'], capture_output=True, text=True).stdout
     lines.append('# hottest SASS lines (sampled stalls)')
     lines += src.splitlines()
     open(f'profiles/{tag}_ncu_{name}.txt', 'w').write('\n'.join(lines) + '\n')

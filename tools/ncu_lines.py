@@ -1,6 +1,6 @@
 """executed warp-instructions of an .ncu-rep kernel bucketed by CUDA source line: joins the SASS source page of
 the report (per-instruction 'Instructions Executed', samples) with `nvdisasm --print-line-info` of the cubin by
-instruction order.   python scripts_ncu_lines.py report.ncu-rep build/obj.o mangled_kernel_substring [top]"""
+instruction order.   python tools/ncu_lines.py report.ncu-rep build/obj.o mangled_kernel_substring [top]"""
 import csv, os, re, subprocess, sys, tempfile
 rep, obj, kern = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40

@@ -1,4 +1,4 @@
-"""print selected metrics of an .ncu-rep (raw page csv): python scripts_ncu_read.py file.ncu-rep [regex]"""
+"""print selected metrics of an .ncu-rep (raw page csv): python tools/ncu_read.py file.ncu-rep [regex]"""
 import csv, re, subprocess, sys
 rep = sys.argv[1]
 pat = re.compile(sys.argv[2] if len(sys.argv) > 2 else

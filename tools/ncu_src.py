@@ -1,4 +1,4 @@
-"""top stall lines of an .ncu-rep source page: python scripts_ncu_src.py file.ncu-rep [topN]"""
+"""top stall lines of an .ncu-rep source page: python tools/ncu_src.py file.ncu-rep [topN]"""
 import csv, subprocess, sys
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 25

@@ -1,13 +1,13 @@
-"""debug helper: run every prepared call of the training plan standalone at a large batch, one at a time with a
+"""plan driver: run every prepared call of the training plan standalone at a large batch, one at a time with a
 synchronize, printing its name first (an illegal access is sticky: the first failure is the culprit).
-    python scripts_dbg_large.py [B] [name-filter]
-    compute-sanitizer --print-limit 8 python scripts_dbg_large.py 8192 conv_dgrad"""
+    python tools/plan_kernels.py [B] [name-filter] [eager|graph]
+    compute-sanitizer --print-limit 8 python tools/plan_kernels.py 8192 conv_dgrad"""
 import ctypes
 import os
 import sys
 import types
 
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, 'bm-nas_b200'))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402

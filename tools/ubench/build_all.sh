@@ -11,5 +11,5 @@ for f in bm-nas_b200/csrc/*.cu; do
   fi
 done
 wait
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o scratch/libbmnas_tl.so bm-nas_b200/build_tl/*.o
-ls -la bm-nas_b200/libbmnas_b200.so scratch/libbmnas_tl.so
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o tools/ubench/libbmnas_tl.so bm-nas_b200/build_tl/*.o
+ls -la bm-nas_b200/libbmnas_b200.so tools/ubench/libbmnas_tl.so

@@ -1,6 +1,6 @@
 """determinism stress of the tiny FusionNode used by test_gradcheck_dropout_mask_reuse"""
 import os, sys, types
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, 'bm-nas_b200')); sys.path.insert(0, ROOT)
 import torch
 from models.search.darts.model_search import FusionNetwork  # noqa (import order)

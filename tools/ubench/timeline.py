@@ -1,7 +1,7 @@
 """phase timeline (globaltimer, ns) of the tcgen05 GEMM kernels at the NTU B=96 shapes; needs the -DBMNAS_TIMELINE build"""
 import os, sys, types, ctypes
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-os.environ['BMNAS_LIB'] = os.path.join(ROOT, 'scratch', 'libbmnas_tl.so')
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ['BMNAS_LIB'] = os.path.join(ROOT, 'tools', 'ubench', 'libbmnas_tl.so')
 sys.path.insert(0, os.path.join(ROOT, 'bm-nas_b200')); sys.path.insert(0, ROOT)
 import torch
 import bench
