@@ -149,8 +149,11 @@ __device__ __forceinline__ void lxl_contract(const float* A, const float* Bm, fl
     __syncthreads();
 }
 
+// G == 4 kernels are only launched on 16-byte aligned tensors with L % 4 == 0 (node_vec_ok): no scalar path in them
+template <int G>
 __device__ __forceinline__ void load_tile(float* dst, const float* src, int CL) {
-    if ((CL & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0)) {
+    if (G == 4) {
+#pragma unroll 2
         for (int i = threadIdx.x; i < CL / 4; i += NTH)
             reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
     } else {
@@ -161,20 +164,27 @@ __device__ __forceinline__ void load_tile(float* dst, const float* src, int CL) 
 // softmax(gamma) (or given weights / ones): architecture parameters are never written inside a forward/backward
 // pass, so this is legal before pdl_wait()
 __device__ __forceinline__ void node_setup_gamma(const bmnas_node_params& p, const NodeSmem& sm) {
+    // rolled loops on purpose: this runs once, in one thread, and every instruction of an execute-once kernel is
+    // an instruction-cache miss on the launch's critical path (the unrolled form was 450 SASS instructions)
     if (threadIdx.x == 0) {
         float* gw = sm.gw;
         if (!p.gamma) {
+#pragma unroll 1
             for (int k = 0; k < p.n_ops; ++k) gw[k] = 1.f;
         } else if (p.gamma_is_logits) {
             float mx = -INFINITY;
+#pragma unroll 1
             for (int k = 0; k < p.n_ops; ++k) mx = fmaxf(mx, p.gamma[k]);
             float s = 0.f;
+#pragma unroll 1
             for (int k = 0; k < p.n_ops; ++k) {
                 gw[k] = expf(p.gamma[k] - mx);
                 s += gw[k];
             }
+#pragma unroll 1
             for (int k = 0; k < p.n_ops; ++k) gw[k] /= s;
         } else {
+#pragma unroll 1
             for (int k = 0; k < p.n_ops; ++k) gw[k] = p.gamma[k];
         }
     }
@@ -271,13 +281,14 @@ __global__ void __launch_bounds__(NTH) k_node_fwd(const bmnas_node_params p) {
     node_setup_gamma(p, sm);
     if (waited) node_setup_bn(p, sm);
     int k_attn = -1;
+#pragma unroll 1
     for (int k = 0; k < p.n_ops; ++k)
         if (p.op_type[k] == BMNAS_OP_ATTN) k_attn = k;
 
     for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
         __syncthreads();
-        load_tile(sm.xs, p.x + (long long)b * CL, CL);
-        if (!p.alias_xy) load_tile(sm.ys, p.y + (long long)b * CL, CL);
+        load_tile<G>(sm.xs, p.x + (long long)b * CL, CL);
+        if (!p.alias_xy) load_tile<G>(sm.ys, p.y + (long long)b * CL, CL);
         __syncthreads();
         float a_mean = 0.f, a_rstd = 0.f;
         if (k_attn >= 0) attn_forward<G>(p, sm, k_attn, b, &a_mean, &a_rstd);
@@ -1336,7 +1347,9 @@ __global__ void __launch_bounds__(WPCB * 32, 1) k_node_bwd_warp(const bmnas_node
     }
     if (p.g_gamma && threadIdx.x == 0) {
         float dot = 0.f;
+#pragma unroll 1
         for (int k = 0; k < p.n_ops; ++k) dot += s_gw[k] * s_dg[k];
+#pragma unroll 1
         for (int k = 0; k < p.n_ops; ++k)
             p.g_gamma[k] = p.gamma_is_logits ? s_gw[k] * (s_dg[k] - dot) : s_dg[k];
     }
@@ -1371,6 +1384,7 @@ __global__ void __launch_bounds__(NTH) k_node_bwd(const bmnas_node_params p) {
     node_setup_gamma(p, sm);
     node_setup_bn(p, sm);
     int k_attn = -1;
+#pragma unroll 1
     for (int k = 0; k < p.n_ops; ++k)
         if (p.op_type[k] == BMNAS_OP_ATTN) k_attn = k;
     for (int i = threadIdx.x; i < M; i += NTH) {
@@ -1391,8 +1405,8 @@ __global__ void __launch_bounds__(NTH) k_node_bwd(const bmnas_node_params p) {
 
     for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
         __syncthreads();
-        load_tile(sm.xs, p.x + (long long)b * CL, CL);
-        if (!p.alias_xy) load_tile(sm.ys, p.y + (long long)b * CL, CL);
+        load_tile<G>(sm.xs, p.x + (long long)b * CL, CL);
+        if (!p.alias_xy) load_tile<G>(sm.ys, p.y + (long long)b * CL, CL);
         __syncthreads();
         float a_mean = 0.f, a_rstd = 0.f;
         if (k_attn >= 0) attn_forward<G>(p, sm, k_attn, b, &a_mean, &a_rstd);
@@ -1400,7 +1414,7 @@ __global__ void __launch_bounds__(NTH) k_node_bwd(const bmnas_node_params p) {
             pdl_prologue();
             waited = true;
         }
-        load_tile(sm.gs, p.gout + (long long)b * CL, CL);
+        load_tile<G>(sm.gs, p.gout + (long long)b * CL, CL);
         __syncthreads();
         const float* Zb = p.Z ? p.Z + (long long)b * M * L : nullptr;
         float* GVb = p.GV ? p.GV + (long long)b * M * L : nullptr;
@@ -1671,7 +1685,9 @@ __global__ void __launch_bounds__(NTH) k_node_bwd(const bmnas_node_params p) {
     }
     if (p.g_gamma && threadIdx.x == 0) {
         float dot = 0.f;
+#pragma unroll 1
         for (int k = 0; k < p.n_ops; ++k) dot += sm.gw[k] * sm.tot[2 * M + k];
+#pragma unroll 1
         for (int k = 0; k < p.n_ops; ++k)
             p.g_gamma[k] = p.gamma_is_logits ? sm.gw[k] * (sm.tot[2 * M + k] - dot) : sm.tot[2 * M + k];
     }
