@@ -41,6 +41,7 @@ class Slot:
 
 
 SIDE_WGRAD = os.environ.get('BMNAS_SIDE_WGRAD', '1') != '0'   # weight-gradient GEMMs on a side stream (parallel graph branch); see conv_backward
+CHAIN_MIX = os.environ.get('BMNAS_CHAIN_MIX', '1') != '0'   # cell-level edge mix + the node cell's first inner mix in one launch
 SPLIT_MIX_BWD = os.environ.get('BMNAS_SPLIT_MIX_BWD', '1') != '0'   # edge-mix backward: input grads on the main chain, d(alpha) on the side branch
 _side_streams = {}
 
@@ -265,25 +266,39 @@ class Program:
         return None
 
     # ------------------------------------------------------------------ kernels: edge mix
-    def mix(self, xs, w, w_off, logits, out, gw=None, need=None):
-        """out = sum_j w[w_off+j, skip] * xs[j]; registers the backward."""
+    def mix(self, xs, w, w_off, logits, out, gw=None, need=None, chain=None, dots_only=False):
+        """out = sum_j w[w_off+j, skip] * xs[j]; registers the backward.
+        chain = dict(w=, w_off=, n=, out=): a second output chain['out'] = (sum of the n skip weights of
+        chain['w'] from row w_off) * out, written by the same launch -- the first inner edge mix of a searchable
+        NodeCell, which reads this mix's output twice; the backward then takes gout + s2 * g(chain out).
+        dots_only: that inner mix itself -- no forward launch, no input-gradient launch (both folded into the
+        producer's), only its d(beta) dot products on the side branch."""
         xs = list(xs)
         n = len(xs)
         assert 1 <= n <= N.BMNAS_MAX_MIX
         numel = self.B * self.C * self.L
-        st = N.bmnas_mix_params()
-        st.n, st.w_is_logits, st.numel = n, int(logits), numel
-        for j, x in enumerate(xs):
-            self.setp(st, 'x', x, j)
-        self.setp(st, 'w', w, offset=w_off * 8)
-        self.setp(st, 'out', out)
-        self.emit('bmnas_mix_fwd', st)
+
+        def set_chain(st, field, t):
+            st.n2 = chain['n']
+            self.setp(st, 'w2', chain['w'], offset=chain['w_off'] * 8)
+            self.setp(st, field, t)
+        if not dots_only:
+            st = N.bmnas_mix_params()
+            st.n, st.w_is_logits, st.numel = n, int(logits), numel
+            for j, x in enumerate(xs):
+                self.setp(st, 'x', x, j)
+            self.setp(st, 'w', w, offset=w_off * 8)
+            self.setp(st, 'out', out)
+            if chain is not None:
+                set_chain(st, 'out2', chain['out'])
+            self.emit('bmnas_mix_fwd', st)
         need = need if need is not None else [True] * n
 
         def bwd():
-            if not self.has_grad(out):
+            g2 = chain['out'] if (chain is not None and self.has_grad(chain['out'])) else None
+            if not self.has_grad(out) and g2 is None:
                 return
-            gout = self.grad_of(out)
+            gout = self.grad_of(out) if self.has_grad(out) else None
 
             def base():
                 sb = N.bmnas_mix_params()
@@ -292,19 +307,22 @@ class Program:
                     self.setp(sb, 'x', x, j)
                 self.setp(sb, 'w', w, offset=w_off * 8)
                 self.setp(sb, 'gout', gout)
+                if g2 is not None:
+                    set_chain(sb, 'gout2', self.grad_of(g2))
                 return sb
             # the input gradients are what the rest of the backward waits for: a pure streaming launch on the main
             # chain.  d(alpha) (dot products + cross-CTA reduction) only feeds the optimiser, so it goes on the side
             # branch next to the weight-gradient GEMMs.
             sb = base()
             any_gx = False
-            for j, x in enumerate(xs):
-                if need[j]:
-                    g = self.grad_of(x)
-                    sb.gx_accum[j] = self.acc(g)
-                    self.setp(sb, 'gx', g, j)
-                    any_gx = True
-            split = SPLIT_MIX_BWD and gw is not None and any_gx
+            if not dots_only:
+                for j, x in enumerate(xs):
+                    if need[j]:
+                        g = self.grad_of(x)
+                        sb.gx_accum[j] = self.acc(g)
+                        self.setp(sb, 'gx', g, j)
+                        any_gx = True
+            split = (SPLIT_MIX_BWD or dots_only) and gw is not None and (any_gx or dots_only)
             if gw is not None and not split:
                 self.setp(sb, 'gw', gw, offset=w_off * 8)
                 self.setp(sb, 'partials', self.buf(int(N.lib().bmnas_mix_partials_size(ctypes.byref(sb))), zero=True))
@@ -661,13 +679,15 @@ class Program:
 
     # ------------------------------------------------------------------ composite: searchable node cell
     def node_cell_search(self, x, y, need_x, need_y, edge_w, node_w, logits, g_edge_w, g_node_w, P, G, prefix,
-                         ops, ns, nm, out):
-        """NodeCell.forward node_search.py:48-70 (prefix ends with '.node_cell')."""
+                         ops, ns, nm, out, t0=None):
+        """NodeCell.forward node_search.py:48-70 (prefix ends with '.node_cell').
+        t0: the first inner edge mix, already written by the producer of x (chained mix, x is y)"""
         states, need = [x, y], [need_x, need_y]
         off = 0
         for i in range(ns):
-            t = self.buf(self.B, self.C, self.L)
-            self.mix(states, edge_w, off, logits, t, gw=g_edge_w, need=list(need))
+            t = t0 if (i == 0 and t0 is not None) else self.buf(self.B, self.C, self.L)
+            self.mix(states, edge_w, off, logits, t, gw=g_edge_w, need=list(need),
+                     dots_only=(i == 0 and t0 is not None))
             s = self.buf(self.B, self.C, self.L)
             pre = f'{prefix}.node_ops.{i}'
             self.node_op(t, t, ops, P, G, (lambda k, pre=pre: f'{pre}._ops.{k}'), node_w, i * len(ops), logits, s,
@@ -716,11 +736,14 @@ class Program:
         off = 0
         for i in range(steps):
             s_in = self.buf(self.B, self.C, self.L)
-            self.mix(states, alphas, off, logits, s_in, gw=g_alphas, need=list(need))
+            # the node cell's first inner mix reads s_in twice (x is y): one launch writes both tensors
+            t0 = self.buf(self.B, self.C, self.L) if (CHAIN_MIX and ns >= 1) else None
+            chain = dict(w=node_arch[i][0], w_off=0, n=2, out=t0) if t0 is not None else None
+            self.mix(states, alphas, off, logits, s_in, gw=g_alphas, need=list(need), chain=chain)
             s = self.buf(self.B, self.C, self.L)
             gb, gg = g_node_arch[i] if g_node_arch is not None else (None, None)
             self.node_cell_search(s_in, s_in, True, True, node_arch[i][0], node_arch[i][1], logits, gb, gg, P, G,
-                                  f'{prefix}._step_nodes.{i}.node_cell', ops, ns, nm, s)
+                                  f'{prefix}._step_nodes.{i}.node_cell', ops, ns, nm, s, t0=t0)
             off += len(states)
             states.append(s)
             need.append(True)

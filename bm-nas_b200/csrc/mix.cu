@@ -24,11 +24,25 @@ __device__ __forceinline__ void mix_weights(const bmnas_mix_params& p, float* ws
     __syncthreads();
 }
 
+// s2 = sum of the skip weights of the chained mix (0 when there is none); uniform, a handful of scalar loads
+__device__ __forceinline__ float mix_chain_scale(const bmnas_mix_params& p) {
+    float s2 = 0.f;
+    if (p.w2) {
+#pragma unroll 1
+        for (int j = 0; j < p.n2; ++j) {
+            const float a = __ldg(p.w2 + 2 * j), b = __ldg(p.w2 + 2 * j + 1);
+            s2 += p.w_is_logits ? 1.f / (1.f + expf(a - b)) : b;
+        }
+    }
+    return s2;
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(kMixThreads) k_mix_fwd(const bmnas_mix_params p) {
     pdl_prologue();
     __shared__ float ws[BMNAS_MAX_MIX], wn[BMNAS_MAX_MIX];
     mix_weights(p, ws, wn);
+    const float s2 = mix_chain_scale(p);
     const long long nvec = p.numel / VEC;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
@@ -43,10 +57,12 @@ __global__ void __launch_bounds__(kMixThreads) k_mix_fwd(const bmnas_mix_params 
                 acc.w = fmaf(w, v.w, acc.w);
             }
             reinterpret_cast<float4*>(p.out)[i] = acc;
+            if (p.out2) reinterpret_cast<float4*>(p.out2)[i] = make_float4(s2 * acc.x, s2 * acc.y, s2 * acc.z, s2 * acc.w);
         } else {
             float acc = 0.f;
             for (int j = 0; j < p.n; ++j) acc = fmaf(ws[j], __ldg(p.x[j] + i), acc);
             p.out[i] = acc;
+            if (p.out2) p.out2[i] = s2 * acc;
         }
     }
 }
@@ -57,6 +73,7 @@ __global__ void __launch_bounds__(kMixThreads) k_mix_bwd(const bmnas_mix_params 
     __shared__ float ws[BMNAS_MAX_MIX], wn[BMNAS_MAX_MIX];
     __shared__ float red[BMNAS_MAX_MIX * 32];
     mix_weights(p, ws, wn);
+    const float s2 = mix_chain_scale(p);
     float dot[BMNAS_MAX_MIX];
 #pragma unroll
     for (int j = 0; j < BMNAS_MAX_MIX; ++j) dot[j] = 0.f;
@@ -64,7 +81,11 @@ __global__ void __launch_bounds__(kMixThreads) k_mix_bwd(const bmnas_mix_params 
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
         if (VEC == 4) {
-            const float4 g = __ldg(reinterpret_cast<const float4*>(p.gout) + i);
+            float4 g = p.gout ? __ldg(reinterpret_cast<const float4*>(p.gout) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.gout2) {
+                const float4 h = __ldg(reinterpret_cast<const float4*>(p.gout2) + i);
+                g.x = fmaf(s2, h.x, g.x); g.y = fmaf(s2, h.y, g.y); g.z = fmaf(s2, h.z, g.z); g.w = fmaf(s2, h.w, g.w);
+            }
 #pragma unroll
             for (int j = 0; j < BMNAS_MAX_MIX; ++j) {
                 if (j < p.n) {
@@ -85,7 +106,8 @@ __global__ void __launch_bounds__(kMixThreads) k_mix_bwd(const bmnas_mix_params 
                 }
             }
         } else {
-            const float g = __ldg(p.gout + i);
+            float g = p.gout ? __ldg(p.gout + i) : 0.f;
+            if (p.gout2) g = fmaf(s2, __ldg(p.gout2 + i), g);
 #pragma unroll
             for (int j = 0; j < BMNAS_MAX_MIX; ++j) {
                 if (j < p.n) {
@@ -147,8 +169,8 @@ static int mix_vec(const bmnas_mix_params* p, bool bwd) {
         if (!aligned16(p->x[j])) return 1;
         if (bwd && p->gx[j] && !aligned16(p->gx[j])) return 1;
     }
-    if (!bwd && !aligned16(p->out)) return 1;
-    if (bwd && !aligned16(p->gout)) return 1;
+    if (!bwd && (!aligned16(p->out) || !aligned16(p->out2))) return 1;
+    if (bwd && (!aligned16(p->gout) || !aligned16(p->gout2))) return 1;
     return 4;
 }
 
@@ -163,6 +185,7 @@ extern "C" long long bmnas_mix_partials_size(const bmnas_mix_params* p) {
 
 extern "C" int bmnas_mix_fwd(const bmnas_mix_params* p, void* stream) {
     if (!p || p->n < 1 || p->n > BMNAS_MAX_MIX || p->numel <= 0 || !p->w || !p->out) return BMNAS_EINVAL;
+    if (p->out2 && (!p->w2 || p->n2 < 1)) return BMNAS_EINVAL;
     for (int j = 0; j < p->n; ++j)
         if (!p->x[j]) return BMNAS_EINVAL;
     BMNAS_DRY_RETURN();
@@ -178,8 +201,9 @@ extern "C" int bmnas_mix_fwd(const bmnas_mix_params* p, void* stream) {
 }
 
 extern "C" int bmnas_mix_bwd(const bmnas_mix_params* p, void* stream) {
-    if (!p || p->n < 1 || p->n > BMNAS_MAX_MIX || p->numel <= 0 || !p->w || !p->gout) return BMNAS_EINVAL;
+    if (!p || p->n < 1 || p->n > BMNAS_MAX_MIX || p->numel <= 0 || !p->w || (!p->gout && !p->gout2)) return BMNAS_EINVAL;
     if (p->gw && (!p->partials || !p->counter)) return BMNAS_EINVAL;
+    if (p->gout2 && (!p->w2 || p->n2 < 1)) return BMNAS_EINVAL;
     for (int j = 0; j < p->n; ++j)
         if (!p->x[j]) return BMNAS_EINVAL;
     BMNAS_DRY_RETURN();

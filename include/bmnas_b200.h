@@ -59,6 +59,10 @@ int bmnas_abi_version(void);
  * w is (n,2).  w_is_logits=1: w holds raw alpha/beta rows and the per-edge
  * 2-way softmax (model_search.py:95, node_search.py:102) is taken in-kernel;
  * the backward then returns d/d(logits).
+ * Chained mix (optional, out2 / gout2 / w2 / n2): the first inner edge mix of a searchable NodeCell reads the
+ * cell-level mix twice (states = [x, y] with x is y, node_search.py:49-54), i.e. it is s2 * out with
+ * s2 = sum_{j<n2} w2_j[skip].  The forward writes out2 = s2 * out from the same registers; the backward takes
+ * the upstream gradient as gout + s2 * gout2 (either may be NULL).  d/d(w2) is a separate dot-only call.
  * ---------------------------------------------------------------------- */
 typedef struct bmnas_mix_params {
     int n;
@@ -73,6 +77,10 @@ typedef struct bmnas_mix_params {
     float* gw;
     float* partials;
     unsigned int* counter;
+    int n2;
+    const float* w2;
+    float* out2;
+    const float* gout2;
 } bmnas_mix_params;
 int bmnas_mix_fwd(const bmnas_mix_params* p, void* stream);
 int bmnas_mix_bwd(const bmnas_mix_params* p, void* stream);
