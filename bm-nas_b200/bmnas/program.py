@@ -94,6 +94,7 @@ class Program:
         self.generation = 0
         self._prep = []          # convs whose weight images bmnas_wprep refreshes at the start of every forward
         self._prep_calls = []
+        self._rng_in_prep = False
         self.n_fwd_launches = 0
         self.n_bwd_launches = 0
 
@@ -208,13 +209,17 @@ class Program:
                 q += int(N.lib().bmnas_wprep_items(c['M'], c['K'], c['fmt']))
             st.q_start[len(group)] = q
             self._prep_calls.append(N.Call('bmnas_wprep', st))
-        self.n_fwd_launches = len(self.fwd) + len(self._prep_calls) + (1 if self.rng_state is not None else 0)
+        # the first weight-image launch also advances the dropout step counter (one launch less per forward)
+        self._rng_in_prep = bool(self._prep_calls) and self.rng_state is not None
+        if self._rng_in_prep:
+            self.setp(self._prep_calls[0].st, 'rng_state', self.rng_state)
+        self.n_fwd_launches = len(self.fwd) + len(self._prep_calls) + (1 if (self.rng_state is not None and not self._rng_in_prep) else 0)
         self.n_bwd_launches = len(self.bwd) + len(self._zero_ranges)
 
     # ------------------------------------------------------------------ execution
     def run_forward(self):
         s = N.current_stream()
-        if self.rng_state is not None:
+        if self.rng_state is not None and not self._rng_in_prep:
             N.launch('bmnas_rng_advance', ctypes.c_void_p(self.rng_state.data_ptr()), s)
         for c in self._prep_calls:
             c(s)

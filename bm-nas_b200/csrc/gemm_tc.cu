@@ -1001,6 +1001,8 @@ static int panel_dispatch(const bmnas_conv_params* p, int x3, cudaStream_t strea
 __global__ void __launch_bounds__(256) k_wprep(const bmnas_wprep_params p) {
     pdl_prologue();
     const long long q = (long long)blockIdx.x * 256 + threadIdx.x;
+    // the dropout step counter of this forward: every reader is a later kernel of the same stream
+    if (q == 0 && p.rng_state) p.rng_state[1] += 1ull;
     if (q >= p.q_start[p.n]) return;
     int i = 0;
     while (i + 1 < p.n && q >= p.q_start[i + 1]) ++i;

@@ -180,6 +180,7 @@ typedef struct bmnas_wprep_params {
     float* img_dgrad[BMNAS_MAX_PREP];
     long long q_start[BMNAS_MAX_PREP_P1];
     int fmt[BMNAS_MAX_PREP];
+    unsigned long long* rng_state; /* optional: also advance the dropout step counter (saves the bmnas_rng_advance launch) */
 } bmnas_wprep_params;
 int bmnas_wprep(const bmnas_wprep_params* p, void* stream);
 long long bmnas_wimg_floats(int M, int K, int which);               /* fmt 0 */
