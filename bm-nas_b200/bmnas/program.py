@@ -41,6 +41,8 @@ class Slot:
 
 
 SIDE_WGRAD = os.environ.get('BMNAS_SIDE_WGRAD', '1') != '0'   # weight-gradient GEMMs on a side stream (parallel graph branch); see conv_backward
+CHAIN_NODE = os.environ.get('BMNAS_CHAIN_NODE', '1') != '0'  # node op i also writes inner edge mix i+1 (CTA-per-sample kernels)
+CHAIN_NODE_MAX_B = 640                                       # beyond: the warp-per-sample node kernels, which do not chain
 CHAIN_MIX = os.environ.get('BMNAS_CHAIN_MIX', '1') != '0'   # cell-level edge mix + the node cell's first inner mix in one launch
 SPLIT_MIX_BWD = os.environ.get('BMNAS_SPLIT_MIX_BWD', '1') != '0'   # edge-mix backward: input grads on the main chain, d(alpha) on the side branch
 _side_streams = {}
@@ -431,11 +433,13 @@ class Program:
 
     # ------------------------------------------------------------------ kernels: step-node mixed op
     def node_op(self, x, y, ops, P, G, prefix_of, gamma, gamma_off, logits, out, g_gamma=None,
-                need_x=True, need_y=True, conv_srcs=None, conv_src_C=None, conv_need=None):
+                need_x=True, need_y=True, conv_srcs=None, conv_src_C=None, conv_need=None, chain=None):
         """ops: list of primitive names; prefix_of(k) -> parameter prefix of op k.
         x, y: tensors/Slots (x is y => aliased).  Emits conv (if any conv-backed op) + node kernels.
         conv_srcs / conv_src_C / conv_need: the conv reads these sources (any channel counts) instead of cat(x, y)
-        -- the reshape layers, whose conv block is ConcatFC over one pooled source; x and y are then unused."""
+        -- the reshape layers, whose conv block is ConcatFC over one pooled source; x and y are then unused.
+        chain = dict(w=, w_off=, priors=[...], need=[...], out=): the NEXT inner edge mix, written by this op's
+        forward launch (out2) and folded into its backward (see bmnas_node_params in the header)."""
         C, L = self.C, self.L
         alias = x is y
         ext = conv_srcs is not None
@@ -493,19 +497,39 @@ class Program:
             if self.rng_state is not None:
                 self.setp(st, 'rng_state', self.rng_state)
 
+        def fill_chain(st):
+            st.n_chain = len(chain['priors'])
+            st.chain_is_logits = int(logits)
+            self.setp(st, 'chain_w', chain['w'], offset=chain['w_off'] * 8)
+            for j, t in enumerate(chain['priors']):
+                self.setp(st, 'chain_x', t, j)
+
         st = N.bmnas_node_params()
         fill(st)
         self.setp(st, 'out', out)
+        if chain is not None:
+            assert len(chain['priors']) <= N.BMNAS_MAX_SRC
+            fill_chain(st)
+            self.setp(st, 'out2', chain['out'])
         st.early_ok = 1 if cv else 0      # the conv GEMM sits between the producers of x / y and this kernel
         self.emit('bmnas_node_fwd', st)
 
         def bwd():
-            if not self.has_grad(out):
+            g2 = chain['out'] if (chain is not None and self.has_grad(chain['out'])) else None
+            if not self.has_grad(out) and g2 is None:
                 return
             sb = N.bmnas_node_params()
             fill(sb)
             sb.early_ok = 1                   # backward: x, y, Z, mean, rstd are forward tensors
-            self.setp(sb, 'gout', self.grad_of(out))
+            self.setp(sb, 'gout', self.grad_of(out) if self.has_grad(out) else None)
+            if g2 is not None:
+                fill_chain(sb)
+                self.setp(sb, 'gout2', self.grad_of(g2))
+                for j, t in enumerate(chain['priors']):
+                    if chain['need'][j]:
+                        g = self.grad_of(t)
+                        sb.chain_gx_accum[j] = self.acc(g)
+                        self.setp(sb, 'chain_gx', g, j)
             if need_x:
                 gx = self.grad_of(x)
                 sb.gx_accum = self.acc(gx)
@@ -689,15 +713,24 @@ class Program:
         t0: the first inner edge mix, already written by the producer of x (chained mix, x is y)"""
         states, need = [x, y], [need_x, need_y]
         off = 0
+        # the one-CTA-per-sample node kernels (small batches) also write the NEXT inner edge mix and fold its
+        # input-gradient pass into their backward: one launch less per inner step in each direction
+        chain_ok = CHAIN_NODE and self.B < CHAIN_NODE_MAX_B
+        t_next = t0
         for i in range(ns):
-            t = t0 if (i == 0 and t0 is not None) else self.buf(self.B, self.C, self.L)
-            self.mix(states, edge_w, off, logits, t, gw=g_edge_w, need=list(need),
-                     dots_only=(i == 0 and t0 is not None))
+            chained_in = t_next is not None
+            t = t_next if chained_in else self.buf(self.B, self.C, self.L)
+            self.mix(states, edge_w, off, logits, t, gw=g_edge_w, need=list(need), dots_only=chained_in)
             s = self.buf(self.B, self.C, self.L)
             pre = f'{prefix}.node_ops.{i}'
-            self.node_op(t, t, ops, P, G, (lambda k, pre=pre: f'{pre}._ops.{k}'), node_w, i * len(ops), logits, s,
-                         g_gamma=g_node_w)
             off += len(states)
+            chain = None
+            t_next = None
+            if chain_ok and i + 1 < ns and len(states) <= N.BMNAS_MAX_SRC:
+                t_next = self.buf(self.B, self.C, self.L)
+                chain = dict(w=edge_w, w_off=off, priors=list(states), need=list(need), out=t_next)
+            self.node_op(t, t, ops, P, G, (lambda k, pre=pre: f'{pre}._ops.{k}'), node_w, i * len(ops), logits, s,
+                         g_gamma=g_node_w, chain=chain)
             states.append(s)
             need.append(True)
         self.node_tail(states, need, x, need_x, P, G, prefix, nm, out)

@@ -189,6 +189,16 @@ __device__ __forceinline__ void node_setup_gamma(const bmnas_node_params& p, con
         }
     }
 }
+// skip weights of the chained edge mix (n_chain priors + the op's own output); architecture parameters again
+__device__ __forceinline__ void node_setup_chain(const bmnas_node_params& p, float* cw) {
+    if (threadIdx.x == 0 && p.chain_w) {
+#pragma unroll 1
+        for (int j = 0; j <= p.n_chain; ++j) {
+            const float a = p.chain_w[2 * j], b = p.chain_w[2 * j + 1];
+            cw[j] = p.chain_is_logits ? 1.f / (1.f + expf(a - b)) : b;
+        }
+    }
+}
 // the folded per-channel BatchNorm constants (mean / rstd come from the conv kernel right before this one:
 // only after pdl_wait())
 __device__ __forceinline__ void node_setup_bn(const bmnas_node_params& p, const NodeSmem& sm) {
@@ -278,7 +288,9 @@ __global__ void __launch_bounds__(NTH) k_node_fwd(const bmnas_node_params p) {
     const int C = p.C, L = p.L, CL = C * L, M = p.M;
     NodeSmem sm = node_carve(smem, C, L, M, false);
     if (p.alias_xy) sm.ys = sm.xs;
+    __shared__ float s_cw[BMNAS_MAX_SRC + 1];
     node_setup_gamma(p, sm);
+    node_setup_chain(p, s_cw);
     if (waited) node_setup_bn(p, sm);
     int k_attn = -1;
 #pragma unroll 1
@@ -350,6 +362,21 @@ __global__ void __launch_bounds__(NTH) k_node_fwd(const bmnas_node_params p) {
                 for (int q = 0; q < G; ++q) acc[q] = fmaf(wk, o[q], acc[q]);
             }
             st_v<G>(p.out + li, acc);
+            if (p.out2) {                    // the next inner edge mix, from the same registers
+                float o2[G];
+                const float cl = s_cw[p.n_chain];
+#pragma unroll
+                for (int q = 0; q < G; ++q) o2[q] = cl * acc[q];
+#pragma unroll 1
+                for (int j = 0; j < p.n_chain; ++j) {
+                    float v[G];
+                    ldg_v<G>(p.chain_x[j] + li, v);
+                    const float cj = s_cw[j];
+#pragma unroll
+                    for (int q = 0; q < G; ++q) o2[q] = fmaf(cj, v[q], o2[q]);
+                }
+                st_v<G>(p.out2 + li, o2);
+            }
         }
     }
     if (!waited) pdl_prologue();
@@ -1381,7 +1408,9 @@ __global__ void __launch_bounds__(NTH) k_node_bwd(const bmnas_node_params p) {
     const int C = p.C, L = p.L, CL = C * L, M = p.M;
     NodeSmem sm = node_carve(smem, C, L, M, true);
     if (p.alias_xy) sm.ys = sm.xs;
+    __shared__ float s_cw[BMNAS_MAX_SRC + 1];
     node_setup_gamma(p, sm);
+    node_setup_chain(p, s_cw);
     node_setup_bn(p, sm);
     int k_attn = -1;
 #pragma unroll 1
@@ -1414,7 +1443,25 @@ __global__ void __launch_bounds__(NTH) k_node_bwd(const bmnas_node_params p) {
             pdl_prologue();
             waited = true;
         }
-        load_tile<G>(sm.gs, p.gout + (long long)b * CL, CL);
+        if (!p.gout2) {
+            load_tile<G>(sm.gs, p.gout + (long long)b * CL, CL);
+        } else {                             // upstream gradient = gout (if any) + cw_last * gout2 (chained edge mix)
+            const float cl = s_cw[p.n_chain];
+#pragma unroll 1
+            for (int g = threadIdx.x; g < CL / G; g += NTH) {
+                float a[G], h[G];
+                ldg_v<G>(p.gout2 + (long long)b * CL + g * G, h);
+                if (p.gout) {
+                    ldg_v<G>(p.gout + (long long)b * CL + g * G, a);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < G; ++q) a[q] = 0.f;
+                }
+#pragma unroll
+                for (int q = 0; q < G; ++q) a[q] = fmaf(cl, h[q], a[q]);
+                st_v<G>(sm.gs + g * G, a);
+            }
+        }
         __syncthreads();
         const float* Zb = p.Z ? p.Z + (long long)b * M * L : nullptr;
         float* GVb = p.GV ? p.GV + (long long)b * M * L : nullptr;
@@ -1587,6 +1634,25 @@ __global__ void __launch_bounds__(NTH) k_node_bwd(const bmnas_node_params p) {
         for (int g = threadIdx.x; g < NG; g += NTH) {
             const int e0 = g * G;
             const long long li = (long long)b * CL + e0;
+            if (p.gout2) {                   // gradients of the chained mix's earlier states: cw_j * gout2
+                float h[G];
+                ldg_v<G>(p.gout2 + li, h);
+#pragma unroll 1
+                for (int j = 0; j < p.n_chain; ++j) {
+                    if (!p.chain_gx[j]) continue;
+                    float o[G];
+                    const float cj = s_cw[j];
+#pragma unroll
+                    for (int q = 0; q < G; ++q) o[q] = cj * h[q];
+                    if (p.chain_gx_accum[j]) {
+                        float c_[G];
+                        lds_v<G>(p.chain_gx[j] + li, c_);
+#pragma unroll
+                        for (int q = 0; q < G; ++q) o[q] += c_[q];
+                    }
+                    st_v<G>(p.chain_gx[j] + li, o);
+                }
+            }
             float dx[G], dy[G];
             lds_v<G>(sm.dxs + e0, dx);
             lds_v<G>(sm.dys + e0, dy);
@@ -1715,8 +1781,13 @@ static int node_check(const bmnas_node_params* p, bool bwd) {
         if (p->p_drop[k] < 0.f || p->p_drop[k] >= 1.f) return BMNAS_EINVAL;
     }
     if (n_attn > 1) return BMNAS_EINVAL;
-    if (bwd && (!p->gout || !p->partials || !p->counter)) return BMNAS_EINVAL;
+    if (bwd && ((!p->gout && !p->gout2) || !p->partials || !p->counter)) return BMNAS_EINVAL;
     if (!bwd && !p->out) return BMNAS_EINVAL;
+    if (p->n_chain < 0 || p->n_chain > BMNAS_MAX_SRC) return BMNAS_EINVAL;
+    if ((p->out2 || p->gout2) && !p->chain_w) return BMNAS_EINVAL;
+    if (!bwd && p->out2)
+        for (int j = 0; j < p->n_chain; ++j)
+            if (!p->chain_x[j]) return BMNAS_EINVAL;
     return BMNAS_OK;
 }
 
@@ -1732,6 +1803,9 @@ static bool node_vec_ok(const bmnas_node_params* p, bool bwd) {
         if (!al16(p->ln_w[k]) || !al16(p->ln_b[k]) || !al16(p->g_ln_w[k]) || !al16(p->g_ln_b[k])) return false;
         if (p->mask[k] && (reinterpret_cast<uintptr_t>(p->mask[k]) & 3u)) return false;
     }
+    if (!al16(p->out2) || !al16(p->gout2)) return false;
+    for (int j = 0; j < BMNAS_MAX_SRC; ++j)
+        if (!al16(p->chain_x[j]) || !al16(p->chain_gx[j])) return false;
     (void)bwd;
     return true;
 }
@@ -1758,6 +1832,7 @@ extern "C" long long bmnas_node_partials_size(const bmnas_node_params* p) {
 // warp-per-sample kernels: shapes they take (see k_node_fwd_warp)
 static bool node_warp_ok(const bmnas_node_params* p, bool bwd) {
     const int L = p->L, T = (p->C + 31) / 32;
+    if (p->out2 || p->gout2) return false;          // the chained edge mix lives in the CTA-per-sample kernels
     if (!(L == 4 || L == 8 || L == 16) || T * L > 32 || !node_vec_ok(p, bwd)) return false;
     int nz = 0, nglu = 0;
     for (int k = 0; k < p->n_ops; ++k) {

@@ -279,6 +279,21 @@ typedef struct bmnas_node_params {
     float* partials;
     unsigned int* counter;
     int early_ok;
+    /* Chained edge mix (optional; one-CTA-per-sample kernels only): the NEXT inner edge mix of a searchable NodeCell
+     * (node_search.py:52-55) is sum_j w_j * states[j] over the earlier states and this op's own output, so the
+     * forward also writes   out2 = sum_{j<n_chain} cw_j * chain_x[j] + cw_{n_chain} * out
+     * (cw = skip weights of chain_w rows, 2-way softmax in-kernel when chain_is_logits), and the backward takes
+     * gout + cw_{n_chain} * gout2 as its upstream gradient (gout may then be NULL) and adds cw_j * gout2 into
+     * chain_gx[j] (overwrite when chain_gx_accum[j] == 0; NULL = not wanted).  d/d(chain_w) is a separate
+     * dot-only bmnas_mix_bwd call. */
+    int n_chain;
+    int chain_is_logits;
+    const float* chain_w;
+    const float* chain_x[BMNAS_MAX_SRC];
+    float* out2;
+    const float* gout2;
+    float* chain_gx[BMNAS_MAX_SRC];
+    int chain_gx_accum[BMNAS_MAX_SRC];
 } bmnas_node_params;
 int bmnas_node_fwd(const bmnas_node_params* p, void* stream);
 int bmnas_node_bwd(const bmnas_node_params* p, void* stream);

@@ -17,9 +17,14 @@ def node_variant(request):
     """every parity test runs twice: with the default kernel choice (CTA per sample at these batch sizes) and with
     the warp-per-sample node kernels forced wherever the shape is eligible (bmnas_set_node_variant)"""
     from bmnas import native as N
+    from bmnas import program
     lib = N.lib()
     lib.bmnas_set_node_variant(request.param)
+    chain = program.CHAIN_NODE
+    if request.param == 2:
+        program.CHAIN_NODE = False      # chained inner mixes live in the CTA kernels: keep every op on the warp kernels here
     yield request.param
+    program.CHAIN_NODE = chain
     lib.bmnas_set_node_variant(0)
 
 
