@@ -231,3 +231,31 @@ def test_reshape_layer_plan_and_state_dict(tag, validate_only):
     assert [c.name for c in runner.prog.bwd] == ['bmnas_node_bwd', 'bmnas_conv_wgrad', 'bmnas_conv_dgrad', 'bmnas_pool_bwd']
     assert x.grad is not None and x.grad.shape == x.shape
     assert all(p.grad is not None for p in mod.parameters())
+
+
+def test_chained_edge_mixes_remove_launches(validate_only, monkeypatch):
+    """launch-plan structure: with chaining the only stand-alone forward edge mixes are the cell-level ones (the
+    inner mixes are written by their producers), every inner mix keeps exactly one dot-only backward call for
+    d(beta), and the main-chain input-gradient calls of the inner mixes are gone; without chaining the plan is the
+    one-kernel-per-reference-op sequence"""
+    from bmnas import program
+    from bmnas.nn import CrossEntropyLoss
+    d = load('search_ego_small')             # steps=2, node_steps=3
+    cfg = cfg_of(d)
+    counts = {}
+    for chain in (True, False):
+        monkeypatch.setattr(program, 'CHAIN_MIX', chain)
+        monkeypatch.setattr(program, 'CHAIN_NODE', chain)
+        head = U.build_head(cfg, int(d['num_classes']), sub(d, 'sd0/'), arch_of(d, 'arch0/'), device=torch.device('cpu'))
+        head.train()
+        feats = [t.requires_grad_(True) for t in arch_of(d, 'fb/feat/')]
+        CrossEntropyLoss()(head(feats), torch.from_numpy(d['fb/labels'])).backward()
+        prog = list(head.fusion_net._bm_cache.values())[0].prog
+        f = [c.name for c in prog.fwd]
+        main_b = [c.name for c in prog.bwd if not c.side]
+        side_b = [c.name for c in prog.bwd if c.side]
+        counts[chain] = (f.count('bmnas_mix_fwd'), main_b.count('bmnas_mix_bwd'), side_b.count('bmnas_mix_bwd'),
+                         f.count('bmnas_node_fwd'))
+    n_cells, ns = cfg.steps, cfg.node_steps
+    assert counts[False] == (n_cells * (1 + ns), n_cells * (1 + ns), n_cells * (1 + ns), n_cells * ns)
+    assert counts[True] == (n_cells, n_cells, n_cells * (1 + ns), n_cells * ns)
