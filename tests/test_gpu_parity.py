@@ -215,6 +215,10 @@ CONFIGS = {
     'mmimdb': dict(cfg=O.Cfg(192, 16, 6, 2, 2, 1, 1, 0.1), B=32, classes=23, kind='bce'),
     'ego': dict(cfg=O.Cfg(128, 8, 8, 2, 2, 3, 3, 0.05), B=96, classes=83, kind='ce'),
     'ragged': dict(cfg=O.Cfg(40, 8, 5, 2, 2, 2, 2, 0.2), B=37, classes=11, kind='ce'),
+    # node_steps=2 > node_multiplier=1: the first inner state feeds nothing but the next edge mix, so its only
+    # upstream gradient arrives through the chained mix (gout NULL, gout2 set in bmnas_node_bwd)
+    'inner_only': dict(cfg=O.Cfg(32, 8, 4, 2, 2, 2, 1, 0.2), B=12, classes=5, kind='ce'),
+    'deep_node': dict(cfg=O.Cfg(32, 8, 4, 2, 2, 3, 2, 0.2), B=12, classes=5, kind='ce'),
 }
 
 
