@@ -136,10 +136,11 @@ class Linear(nn.Linear):
         if not x.is_cuda and not N.VALIDATE_ONLY:
             raise N.NativeError('bmnas.nn.Linear has no CPU implementation')
         x = x if x.is_contiguous() else x.contiguous()
-        leaves = [p for p in (self.weight, self.bias) if p is not None and p.requires_grad]
+        all_leaves = [p for p in (self.weight, self.bias) if p is not None and p.requires_grad]
+        leaves = _rt.filter_leaves(all_leaves)       # runtime.GRAD_MODE 'arch': the classifier's dW / db are not produced
         gw = gb = None
         if leaves and torch.is_grad_enabled():
-            ar = _rt.arena_for(self, leaves, x.device)
+            ar = _rt.arena_for(self, all_leaves, x.device)
             gw = ar.view(self.weight) if self.weight.requires_grad else None
             gb = ar.view(self.bias) if (self.bias is not None and self.bias.requires_grad) else None
         out = _LinearFn.apply(x, self.weight, self.bias, gw, gb)
@@ -241,7 +242,9 @@ class SearchHead(nn.Module):
 
     def _joint_arena(self, device):
         ar = self.__dict__.get('_bm_joint')
-        leaves = ([p for p in self.fusion_net.parameters() if p.requires_grad] + self.arch_parameters() +
+        # layout [alpha, beta, gamma | fusion weights | classifier]: the architecture gradients and the weight
+        # gradients are each one contiguous span (one small and one large NCCL bucket, see search.py)
+        leaves = (self.arch_parameters() + [p for p in self.fusion_net.parameters() if p.requires_grad] +
                   [p for p in self.central_classifier.parameters() if p.requires_grad])
         if ar is None or ar.flat.device != device or not ar.covers(leaves):
             ar = _rt.GradArena(leaves, device)

@@ -68,6 +68,8 @@ class FusedAdam(torch.optim.Optimizer):
                   counter=torch.zeros(1, dtype=torch.int32, device=dev), lr_host=float(group['lr']),
                   params=ps)
         self._g[gi] = st
+        if getattr(self, '_pending_fused', None):
+            self._apply_pending()            # a checkpoint loaded before the device state existed
         return st
 
     def set_lr(self, lr):
@@ -110,6 +112,50 @@ class FusedAdam(torch.optim.Optimizer):
             s = s or N.current_stream()
             N.launch('bmnas_adam_step', ctypes.byref(p), s)
         return loss
+
+    # -------------------------------------------------------------- state (checkpoint / warm-up restore)
+    def state_snapshot(self):
+        """clones of the device-side moments, step counters and learning rates per parameter group"""
+        return {gi: {k: st[k].clone() for k in ('m', 'v', 'step', 'lr')} | {'lr_host': st['lr_host']}
+                for gi, st in self._g.items()}
+
+    def state_restore(self, snap):
+        """put back a state_snapshot(); groups that did not exist at snapshot time restart from zero"""
+        with torch.no_grad():
+            for gi, st in self._g.items():
+                old = snap.get(gi)
+                if old is not None and old['m'].numel() == st['m'].numel():
+                    for k in ('m', 'v', 'step', 'lr'):
+                        st[k].copy_(old[k])
+                    st['lr_host'] = old['lr_host']
+                else:
+                    st['m'].zero_(); st['v'].zero_(); st['step'].zero_()
+
+    def state_dict(self):
+        """torch.optim state_dict plus the fused moments ('bmnas_fused': per group m, v, step) -- the moments live in
+        flat device buffers outside optimizer.state"""
+        sd = super().state_dict()
+        sd['bmnas_fused'] = {gi: {k: st[k].detach().cpu().clone() for k in ('m', 'v', 'step')} for gi, st in self._g.items()}
+        return sd
+
+    def load_state_dict(self, sd):
+        sd = dict(sd)
+        fused = sd.pop('bmnas_fused', None)
+        super().load_state_dict(sd)
+        self._pending_fused = fused
+        self._apply_pending()
+
+    def _apply_pending(self):
+        fused = getattr(self, '_pending_fused', None)
+        if not fused:
+            return
+        with torch.no_grad():
+            for gi in list(fused):
+                st = self._g.get(gi)
+                if st is not None and st['m'].numel() == fused[gi]['m'].numel():
+                    for k in ('m', 'v', 'step'):
+                        st[k].copy_(fused[gi][k].to(st[k].device))
+                    del fused[gi]
 
     def zero_grad(self, set_to_none=True):
         """Gradients live in a static arena that every backward overwrites: nothing to clear."""

@@ -19,6 +19,39 @@ from .program import Program, Slot
 
 SAMPLE_OFFSET = [0]      # global index of this rank's first sample (world-size-invariant dropout streams)
 
+# Which leaf gradients the next launch plans produce.  'all' (default, plain autograd use of the modules): every
+# parameter and architecture tensor.  'arch': alpha/beta/gamma only -- the Architect's step (architect.py:21-29)
+# back-propagates through everything but steps only the architecture tensors and the loop zeroes the weight
+# gradients unread (train_searchable/ntu.py:77), so the plan omits every weight-gradient GEMM, the classifier dW
+# and the BN/LN affine gradients.  'weights': parameters only -- the weight step's architecture gradients are
+# likewise cleared unread by the next arch_optimizer.zero_grad() (architect.py:22).  The reference distinguishes the
+# two sets the same way: architecture tensors are plain tensors, not nn.Parameters.
+GRAD_MODE = ['all']
+
+
+class grad_mode:
+    """context manager: with grad_mode('arch'): loss = crit(head(x), y); loss.backward()"""
+
+    def __init__(self, mode):
+        assert mode in ('all', 'arch', 'weights')
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = GRAD_MODE[0]
+        GRAD_MODE[0] = self.mode
+
+    def __exit__(self, *a):
+        GRAD_MODE[0] = self.prev
+
+
+def filter_leaves(leaves):
+    m = GRAD_MODE[0]
+    if m == 'arch':
+        return [t for t in leaves if not isinstance(t, torch.nn.Parameter)]
+    if m == 'weights':
+        return [t for t in leaves if isinstance(t, torch.nn.Parameter)]
+    return list(leaves)
+
 
 class GradArena:
     def __init__(self, tensors, device):
@@ -143,9 +176,11 @@ def run(root, kind, inputs, build, leaves, C, L, drpt, key_extra=(), masks=None,
     B = inputs[0].shape[0]
     use_masks = masks is not None
     drop_key = tuple(sorted(drop_p.items())) if drop_p else ()
-    key = (kind, B, C, L, device.index, bool(root.training), use_masks, need, SAMPLE_OFFSET[0], drop_key) + tuple(key_extra)
+    key = (kind, B, C, L, device.index, bool(root.training), use_masks, need, SAMPLE_OFFSET[0], drop_key,
+           GRAD_MODE[0]) + tuple(key_extra)
     cache = root.__dict__.setdefault('_bm_cache', {})
-    leaves = [t for t in leaves if t.requires_grad]
+    all_leaves = [t for t in leaves if t.requires_grad]
+    leaves = filter_leaves(all_leaves)
     ptr_sig = tuple(t.data_ptr() for t in leaves)
     runner = cache.get(key)
     if runner is not None and runner.ptr_sig != ptr_sig:
@@ -154,13 +189,13 @@ def run(root, kind, inputs, build, leaves, C, L, drpt, key_extra=(), masks=None,
         for t in leaves:
             if t.device != device:
                 raise ValueError('bmnas: parameter / architecture tensor on the wrong device; call module.to(device)')
-        arena = arena_for(root, leaves, device)
+        arena = arena_for(root, all_leaves, device)
         prog = Program(device, B, C, L, root.training, drpt)
         prog.use_masks = use_masks
         prog.drop_p = dict(drop_p or {})
         prog.sample_offset = SAMPLE_OFFSET[0]
         in_slots = [f'in{i}' for i in range(len(inputs))]
-        G = _GradViews(arena)
+        G = _GradViews(arena, GRAD_MODE[0])
         out = build(prog, [Slot(n) for n in in_slots], need, G)
         prog.seed_grad(out, Slot('gout'))
         prog.finalize()
@@ -178,9 +213,19 @@ def run(root, kind, inputs, build, leaves, C, L, drpt, key_extra=(), masks=None,
 class _GradViews:
     """name -> gradient view lookup used by the emitters: G.get(name) with the P dict alongside"""
 
-    def __init__(self, arena):
+    def __init__(self, arena, mode='all'):
         self.arena = arena
         self.P = None
+        self.mode = mode
+
+    def _wanted(self, t):
+        if t is None or not getattr(t, 'requires_grad', False):
+            return False
+        if self.mode == 'arch':
+            return not isinstance(t, torch.nn.Parameter)
+        if self.mode == 'weights':
+            return isinstance(t, torch.nn.Parameter)
+        return True
 
     def attach(self, P):
         self.P = P
@@ -188,14 +233,10 @@ class _GradViews:
 
     def get(self, name):
         t = self.P.get(name)
-        if t is None or not getattr(t, 'requires_grad', False):
-            return None
-        return self.arena.view(t)
+        return self.arena.view(t) if self._wanted(t) else None
 
     def of(self, t):
-        if t is None or not t.requires_grad:
-            return None
-        return self.arena.view(t)
+        return self.arena.view(t) if self._wanted(t) else None
 
 
 def named_tensors(module, prefix=''):

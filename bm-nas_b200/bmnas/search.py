@@ -7,9 +7,22 @@ Both halves are captured once (after a warm-up that builds the launch plans) and
 the learning rate is a device scalar written before each replay, inputs are copied into
 static buffers.  Data parallelism replaces nn.DataParallel (ntu_darts_searchable.py:50-51):
 one process per GPU, every rank holds a replica, the batch is sharded by sample, and ONE
-NCCL all-reduce over the flat gradient arena [weights | alpha,beta,gamma | classifier]
-sits between backward and the fused Adam (1/world folded into Adam's grad_scale).
+NCCL all-reduce per half step sits between backward and the fused Adam (1/world folded into
+Adam's grad_scale): the arch half reduces only the alpha/beta/gamma span of the flat gradient
+arena (70 floats at NTU), the weight half only the weight span.
 BatchNorm uses per-replica batch statistics, as nn.DataParallel does.
+
+Discarded work is not done (prune_grads=True): the Architect's backward computes weight
+gradients that train_searchable/ntu.py:77 zeroes unread, and the weight step computes
+architecture gradients that architect.py:22 zeroes unread; the two launch plans are built
+with runtime.grad_mode('arch') / ('weights') so neither set is produced.  The updates are
+bit-identical to the reference's (tests/test_gpu_parity.py::test_search_loop_golden).
+
+Schedule note: the reference loop runs a whole 'train' epoch of weight steps and then a whole
+'dev' epoch of Architect steps (train_searchable/ntu.py:31-38); SearchStep.step() is ONE arch
+half followed by ONE weight half (the unit SURVEY 8d defines as a step).  Callers that want the
+reference's epoch schedule call half('train') / half('dev') themselves
+(models/search/train_searchable/*.py do).
 """
 import torch
 
@@ -20,7 +33,7 @@ from .optim import FusedAdam
 class SearchStep:
     def __init__(self, head, criterion, B, num_classes, loss_kind='ce', eta_max=1e-3, eta_min=1e-6, Ti=1, Tm=2,
                  nbpe=100.0, weight_decay=3e-4, arch_lr=3e-4, arch_wd=1e-3, use_graphs=True, group=None,
-                 full_fidelity=True):
+                 prune_grads=True, sync_replicas=True):
         from models.auxiliary.scheduler import LRCosineAnnealingScheduler
         self.head, self.criterion = head, criterion
         self.device = next(head.parameters()).device
@@ -30,6 +43,14 @@ class SearchStep:
         self.group = group
         self.world = torch.distributed.get_world_size(group) if group is not None else 1
         self.use_graphs = use_graphs
+        self.prune_grads = prune_grads
+        self.rank = torch.distributed.get_rank(group) if group is not None else 0
+        if self.world > 1:
+            from . import runtime as _rt
+            # world-size-invariant dropout streams: Philox is keyed by the GLOBAL sample index
+            _rt.SAMPLE_OFFSET[0] = self.rank * B
+            if sync_replicas:
+                self.sync_replicas()
         self.w_opt = FusedAdam(head.central_params(), lr=eta_max, weight_decay=weight_decay)
         self.a_opt = FusedAdam(head.arch_parameters(), lr=arch_lr, betas=(0.5, 0.999), weight_decay=arch_wd)
         self.w_opt.grad_scale = self.a_opt.grad_scale = 1.0 / self.world
@@ -54,22 +75,48 @@ class SearchStep:
 
     # ------------------------------------------------------------------ one half step, eager
     def _half(self, which):
+        from . import runtime as _rt
         head = self.head
-        loss = self.criterion(head(self.feats[which]), self.labels[which])
-        loss.backward()
-        self.allreduce_grads()
+        mode = ('arch' if which == 'dev' else 'weights') if self.prune_grads else 'all'
+        with _rt.grad_mode(mode):
+            loss = self.criterion(head(self.feats[which]), self.labels[which])
+            loss.backward()
+        self.allreduce_grads(which)
         (self.a_opt if which == 'dev' else self.w_opt).step()
         # detach: holding the autograd graph would keep the AccumulateGrad nodes (and the stream they were
         # created on) alive across steps, which breaks CUDA-graph capture on another stream
         return loss.detach()
 
-    def allreduce_grads(self):
-        """ONE collective per half step: sum the flat gradient arena [fusion weights | arch | classifier] over the
-        ranks (the 1/world factor is applied inside the fused Adam as grad_scale)"""
+    def grad_span(self, which):
+        """the contiguous slice of the flat gradient arena [alpha,beta,gamma | fusion weights | classifier] that the
+        optimiser of this half step reads"""
+        ar = self.head._joint_arena(self.device)
+        if which == 'dev':
+            return ar.span(self.head.arch_parameters())
+        return ar.span([p for p in self.head.parameters() if p.requires_grad])
+
+    def allreduce_grads(self, which=None):
+        """ONE collective per half step: sum this half's span of the gradient arena over the ranks (the 1/world
+        factor is applied inside the fused Adam as grad_scale).  which=None: the whole arena."""
         if self.world > 1:
             from .program import join_side
             join_side(self.device)
-            torch.distributed.all_reduce(self.head._joint_arena(self.device).flat, group=self.group)
+            buf = self.head._joint_arena(self.device).flat if which is None else self.grad_span(which)
+            torch.distributed.all_reduce(buf, group=self.group)
+
+    def sync_replicas(self):
+        """rank 0's weights, BatchNorm buffers, architecture tensors and Philox seed become every rank's (differently
+        seeded replicas would otherwise train apart silently: every rank applies the same reduced gradient)"""
+        if self.world <= 1:
+            return
+        from . import rng
+        with torch.no_grad():
+            ts = list(self.head.parameters()) + list(self.head.buffers()) + list(self.head.arch_parameters())
+            for t in ts:
+                torch.distributed.broadcast(t.data, 0, group=self.group)
+            sd = torch.tensor([rng._state['seed'], rng._state['n']], dtype=torch.int64, device=self.device)
+            torch.distributed.broadcast(sd, 0, group=self.group)
+            rng._state['seed'], rng._state['n'] = int(sd[0]), int(sd[1])
 
     def _run_half(self, which):
         ev = self._ready[which]
@@ -117,8 +164,13 @@ class SearchStep:
         import copy
         snap = {'sd': {k: v.detach().clone() for k, v in self.head.state_dict().items()},
                 'arch': [a.detach().clone() for a in self.head.arch_parameters()],
-                'sched': copy.deepcopy(self.sched.__dict__), 'steps': self.steps_done}
+                'sched': copy.deepcopy(self.sched.__dict__), 'steps': self.steps_done,
+                'opt': [opt.state_snapshot() for opt in (self.w_opt, self.a_opt)],
+                'rng': [(p.rng_state.clone() if p.rng_state is not None else None) for p in self._programs()]}
         return snap
+
+    def _programs(self):
+        return [r.prog for r in self.head.fusion_net.__dict__.get('_bm_cache', {}).values()]
 
     def _restore(self, snap):
         with torch.no_grad():
@@ -127,11 +179,15 @@ class SearchStep:
                 sd[k].copy_(v)
             for a, b in zip(self.head.arch_parameters(), snap['arch']):
                 a.copy_(b)
-            for opt in (self.w_opt, self.a_opt):
-                for st in opt._g.values():
-                    st['m'].zero_()
-                    st['v'].zero_()
-                    st['step'].zero_()
+            for opt, osnap in zip((self.w_opt, self.a_opt), snap['opt']):
+                opt.state_restore(osnap)          # moments / step counters as they were (zero if they did not exist)
+            progs = self._programs()
+            for p, r in zip(progs, snap['rng']):   # plans that existed at snapshot time get their step counter back;
+                if r is not None and p.rng_state is not None:
+                    p.rng_state.copy_(r)
+            for p in progs[len(snap['rng']):]:     # plans built during the warm-up restart at step 0
+                if p.rng_state is not None:
+                    p.rng_state[1] = 0
         self.sched.__dict__.update(snap['sched'])
         self.steps_done = snap['steps']
 
@@ -165,18 +221,78 @@ class SearchStep:
             self._restore(snap)
         torch.cuda.synchronize()
 
+    def half(self, which):
+        """one half step ('dev' = Architect.step, 'train' = weight step incl. the LR schedule tick) on the batch in
+        the static buffers; returns the loss as a device scalar"""
+        if which == 'train':
+            self.sched.step()
+            self.w_opt.set_lr(float(self.sched.eta))
+        self._run_half(which)
+        return self.loss[which]
+
     def step(self):
         """one search step on whatever currently sits in the static buffers; returns (arch loss, weight loss)
         as device scalars (no host sync)."""
-        self._run_half('dev')
-        lr = self.sched.step()
-        self.w_opt.set_lr(float(self.sched.eta))
-        self._run_half('train')
+        self.half('dev')
+        self.half('train')
         self.steps_done += 1
         return self.loss['dev'], self.loss['train']
 
+    def metrics_forward(self, which='dev'):
+        """the reference's dev-phase metrics pass (train_searchable/ntu.py:81-85): a no-grad forward in train mode
+        (batch statistics, fresh dropout masks, BN running statistics updated -- C-13) on the same batch the
+        Architect just used.  Returns (loss, logits) as device tensors."""
+        g = self.graphs.get('metrics:' + which)
+        if g is not None:
+            g.replay()
+            return self._metrics[which]
+        with torch.no_grad():
+            logits = self.head(self.feats[which])
+            loss = self.criterion(logits, self.labels[which])
+        return loss, logits
+
+    def capture_metrics_forward(self, which='dev'):
+        """capture metrics_forward as a CUDA graph (after prepare())"""
+        if not self.use_graphs:
+            return
+        self.metrics_forward(which)
+        torch.cuda.synchronize()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self.metrics_forward(which)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        if not hasattr(self, '_metrics'):
+            self._metrics = {}
+        with torch.cuda.graph(g, stream=s):
+            self._metrics[which] = self.metrics_forward(which)
+        self.graphs['metrics:' + which] = g
+
     def genotype(self):
+        """alpha/beta/gamma are bit-identical on every rank (same reduced gradient, same Adam), so any rank may
+        derive the genotype without a collective"""
         return self.head.genotype()
+
+    def checkpoint(self):
+        """what the reference saves (best_model.pt = state_dict, train_searchable/ntu.py:141-144) plus what it loses
+        (SURVEY C-3): architecture tensors, both optimisers incl. the fused moments, the schedule.  BatchNorm running
+        statistics are rank 0's, as under nn.DataParallel -- call on rank 0 (or sync_buffers() on all ranks first)."""
+        return {'state_dict': {k: v.detach().cpu().clone() for k, v in self.head.state_dict().items()},
+                'arch': [a.detach().cpu().clone() for a in self.head.arch_parameters()],
+                'w_opt': self.w_opt.state_dict(), 'a_opt': self.a_opt.state_dict(),
+                'sched': dict(self.sched.__dict__), 'steps': self.steps_done}
+
+    def load_checkpoint(self, ck):
+        with torch.no_grad():
+            self.head.load_state_dict(ck['state_dict'])
+            for a, b in zip(self.head.arch_parameters(), ck['arch']):
+                a.copy_(b.to(a.device))
+        self.w_opt.load_state_dict(ck['w_opt'])
+        self.a_opt.load_state_dict(ck['a_opt'])
+        self.sched.__dict__.update(ck['sched'])
+        self.steps_done = ck['steps']
 
     def sync_buffers(self):
         """BatchNorm running statistics follow rank 0, as under nn.DataParallel"""

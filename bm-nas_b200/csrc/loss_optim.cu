@@ -123,6 +123,14 @@ __global__ void k_rng_advance(unsigned long long* st) {
     st[1] += 1ull;
 }
 
+// the keep decision the fused kernels draw for dropout site `uid` in this (seed, step): one byte per element
+__global__ void k_philox_keep_mask(const unsigned long long* rng, uint32_t uid, float p, long long sample_offset,
+                                   long long per_sample, long long total, unsigned char* out) {
+    pdl_prologue();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+        out[i] = philox_keep(rng, uid, (unsigned long long)(sample_offset * per_sample + i), p) ? 1 : 0;
+}
+
 }  // namespace bmnas
 
 using namespace bmnas;
@@ -192,6 +200,17 @@ extern "C" int bmnas_rng_advance(unsigned long long* rng_state, void* stream) {
     if (!rng_state) return BMNAS_EINVAL;
     BMNAS_DRY_RETURN();
     launch_k(k_rng_advance, 1, 1, 0, (cudaStream_t)stream, rng_state);
+    BMNAS_LAUNCH_CHECK();
+    return BMNAS_OK;
+}
+
+extern "C" int bmnas_philox_keep_mask(const unsigned long long* rng_state, unsigned int uid, float p, long long sample_offset,
+                                      long long per_sample, long long B, unsigned char* out, void* stream) {
+    if (!rng_state || !out || per_sample <= 0 || B <= 0 || !(p >= 0.f && p < 1.f)) return BMNAS_EINVAL;
+    BMNAS_DRY_RETURN();
+    const long long total = per_sample * B;
+    launch_k(k_philox_keep_mask, grid_for(total), OTH, 0, (cudaStream_t)stream, rng_state, (uint32_t)uid, p, sample_offset,
+             per_sample, total, out);
     BMNAS_LAUNCH_CHECK();
     return BMNAS_OK;
 }

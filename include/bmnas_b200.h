@@ -472,6 +472,14 @@ int bmnas_get_node_variant(void);
 /* rng_state = {seed, step}: advance the step counter on-device (one launch per search step) */
 int bmnas_rng_advance(unsigned long long* rng_state, void* stream);
 
+/* Test hook for the in-kernel dropout streams: writes the keep decision (1 = kept) that every fused kernel draws for
+ * dropout site `uid` (bmnas_node_params.op_uid / bmnas_ln_params.op_uid) with probability p under rng_state =
+ * {seed, step}, for B samples of per_sample (= C*L) elements starting at global sample sample_offset.  A parity test
+ * runs a Philox-mode forward/backward, reads the masks of that very step through this entry and hands them to the
+ * oracle (nn.Dropout draws, node_operations.py:29,48,89, node_search.py:46 -- bit-matching torch's stream is not a
+ * goal; matching the SAME mask in forward, backward and every kernel variant is). */
+int bmnas_philox_keep_mask(const unsigned long long* rng_state, unsigned int uid, float p, long long sample_offset, long long per_sample, long long B, unsigned char* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,3 +61,36 @@ def random_masks(root, B, C, L, seed, drpt):
 
 def grads_by_name(head):
     return {n: (p.grad.detach().cpu().clone() if p.grad is not None else None) for n, p in head.named_parameters()}
+
+
+def training_program(head, mode=None):
+    """the launch plan the last training-mode forward of head.fusion_net ran (mode: runtime.GRAD_MODE of that plan)"""
+    progs = [(k, r.prog) for k, r in head.fusion_net._bm_cache.items() if r.prog.training and not r.prog.use_masks]
+    if mode is not None:
+        progs = [(k, p) for k, p in progs if mode in k]
+    assert len(progs) == 1, [k for k, _ in progs]
+    return progs[0][1]
+
+
+def philox_masks(head, B, prog):
+    """keep-masks the kernels drew in the LAST forward/backward of `prog` (Philox mode), read back through the C-ABI
+    test hook bmnas_philox_keep_mask with the plan's own (seed, step); keyed like named_modules() so the oracle can
+    consume them (prefix 'fusion_net.')."""
+    import ctypes
+    from bmnas import native as N
+    from bmnas.program import uid_of
+    assert prog.rng_state is not None, 'plan has no Philox dropout site'
+    C, L = prog.C, prog.L
+    masks = {}
+    for name, m in head.named_modules():
+        if not isinstance(m, nn.Dropout) or name.endswith('node_cell.dropout') or m.p <= 0:
+            continue
+        site = name[len('fusion_net.'):] if name.startswith('fusion_net.') else name
+        key = site if site.endswith('out_dropout') else site[:-len('.dropout')]
+        out = torch.empty(B, C, L, dtype=torch.uint8, device=prog.device)
+        N.launch('bmnas_philox_keep_mask', ctypes.c_void_p(prog.rng_state.data_ptr()), ctypes.c_uint(uid_of(key)),
+                 ctypes.c_float(m.p), ctypes.c_longlong(prog.sample_offset), ctypes.c_longlong(C * L),
+                 ctypes.c_longlong(B), ctypes.c_void_p(out.data_ptr()), N.current_stream())
+        masks[name] = out.cpu()
+    torch.cuda.synchronize()
+    return masks

@@ -75,3 +75,13 @@ def assert_close(a, b, tol, what='', atol=0.0):
     err = (a - b).abs().max().item() if a.numel() else 0.0
     lim = tol * (b.abs().max().item() if b.numel() else 0.0) + atol
     assert err <= lim, f'{what}: max abs err {err:.3e} > {lim:.3e} (rel {rel_err(a, b):.3e})'
+
+
+def close_vs_referee(ours, ref32, ref64, tol, what, atol=0.0):
+    """ours must be as close to the fp64 referee as tol, or as the fp32 CPU reference itself (x3):
+    a gradient that is the difference of large terms is not computable to 1e-5 in fp32 by anyone."""
+    ours = torch.as_tensor(ours).double().cpu()
+    r32, r64 = ref32.double(), ref64.double()
+    err = (ours - r64).abs().max().item()
+    lim = max(tol * r64.abs().max().item(), 3.0 * (r32 - r64).abs().max().item()) + atol
+    assert err <= lim, f'{what}: max abs err {err:.3e} > {lim:.3e}'

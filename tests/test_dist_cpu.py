@@ -42,16 +42,36 @@ def _worker(rank, world, port, q):
         P = O.init_params(cfg, ncls, seed=1, prefix='cell')
         arch = O.init_arch(cfg, seed=1, scale=0.3)
         head = U.build_head(cfg, ncls, P, arch, device=torch.device('cpu'))
+        if rank != 0:                     # a differently initialised replica: SearchStep must pull rank 0's state
+            with torch.no_grad():
+                for t in list(head.parameters()) + head.arch_parameters():
+                    t.add_(0.5)
+        from bmnas import runtime as rt
         ss = SearchStep(head, CrossEntropyLoss(), Bl, ncls, group=dist.group.WORLD, use_graphs=False)
         assert ss.world == world and abs(ss.w_opt.grad_scale - 1.0 / world) < 1e-12
+        assert rt.SAMPLE_OFFSET[0] == rank * Bl          # world-size-invariant dropout streams
+        for k, v in head.state_dict().items():
+            assert torch.equal(v, P[k]), k               # sync_replicas(): rank 0's weights everywhere
+        for a_, b_ in zip(head.arch_parameters(), arch):
+            assert torch.equal(a_.detach(), b_)
         feats, labels = O.synthetic_batch(cfg, Bg, ncls, seed=2)
 
         # host path end to end in validate-only mode: plan build, backward wiring, all-reduce, fused Adam call
         ss.load('dev', torch.stack([f[rank * Bl:(rank + 1) * Bl] for f in feats]), labels[rank * Bl:(rank + 1) * Bl])
+        ss.load('train', torch.stack([f[rank * Bl:(rank + 1) * Bl] for f in feats]), labels[rank * Bl:(rank + 1) * Bl])
         ss._half('dev')
         arena = head._joint_arena(torch.device('cpu'))
-        leaves = list(head.fusion_net.parameters()) + head.arch_parameters() + list(head.central_classifier.parameters())
-        assert all(t.grad is not None and t.grad.data_ptr() == arena.view(t).data_ptr() for t in leaves)
+        weights = list(head.fusion_net.parameters()) + list(head.central_classifier.parameters())
+        archs = head.arch_parameters()
+        # the arch half produces alpha/beta/gamma gradients only (the reference zeroes the weight gradients unread)
+        assert all(t.grad is not None and t.grad.data_ptr() == arena.view(t).data_ptr() for t in archs)
+        assert all(t.grad is None for t in weights)
+        ss._half('train')
+        assert all(t.grad is not None and t.grad.data_ptr() == arena.view(t).data_ptr() for t in weights)
+        # the two NCCL buckets: [alpha, beta, gamma] and [weights] are disjoint contiguous spans of one arena
+        sa, sw = ss.grad_span('dev'), ss.grad_span('train')
+        assert sa.data_ptr() == arena.flat.data_ptr() and sa.numel() == sum((a_.numel() + 3) // 4 * 4 for a_ in archs)
+        assert sw.data_ptr() == sa.data_ptr() + 4 * sa.numel() and sa.numel() + sw.numel() == arena.flat.numel()
 
         # per-shard oracle gradients (per-replica BN statistics), written into the arena views
         def shard_grads(r):
@@ -67,11 +87,17 @@ def _worker(rank, world, port, q):
                 arena.view(p_).copy_(gw[k])
             for a_, g_ in zip(head.arch_parameters(), ga):
                 arena.view(a_).copy_(g_)
-        ss.allreduce_grads()                                   # ONE collective over the flat bucket
+        ss.allreduce_grads('train')                            # ONE collective over the weight span ...
         # expected: sum over shards (the 1/world factor is Adam's grad_scale)
         exp_w = {k: sum(shard_grads(r)[0][k] for r in range(world)) for k in names}
         for k, p_ in names.items():
             assert torch.allclose(arena.view(p_), exp_w[k], rtol=1e-6, atol=1e-8), k
+        for a_, g_ in zip(head.arch_parameters(), ga):         # ... which leaves the arch span alone
+            assert torch.equal(arena.view(a_), g_)
+        ss.allreduce_grads('dev')                              # ... and one over the 70-float arch span
+        exp_a = [sum(shard_grads(r)[1][i] for r in range(world)) for i in range(len(ga))]
+        for a_, g_ in zip(head.arch_parameters(), exp_a):
+            assert torch.allclose(arena.view(a_), g_, rtol=1e-6, atol=1e-8)
         # every rank applies the identical update -> replicas stay bit-identical without a broadcast
         st = {}
         params = [p_.detach() for p_ in names.values()]

@@ -7,6 +7,7 @@ import pytest
 import torch
 
 from helpers import O, load, sub, cfg_of, arch_of, unpickle_genotype, geno_plain, assert_close
+from helpers import close_vs_referee as _close_vs_referee
 import gpu_util as U
 
 pytestmark = pytest.mark.gpu
@@ -220,16 +221,6 @@ CONFIGS = {
     'inner_only': dict(cfg=O.Cfg(32, 8, 4, 2, 2, 2, 1, 0.2), B=12, classes=5, kind='ce'),
     'deep_node': dict(cfg=O.Cfg(32, 8, 4, 2, 2, 3, 2, 0.2), B=12, classes=5, kind='ce'),
 }
-
-
-def _close_vs_referee(ours, ref32, ref64, tol, what, atol=0.0):
-    """ours must be as close to the fp64 referee as tol, or as the fp32 CPU reference itself (x3):
-    a gradient that is the difference of large terms is not computable to 1e-5 in fp32 by anyone."""
-    ours = torch.as_tensor(ours).double().cpu()
-    r32, r64 = ref32.double(), ref64.double()
-    err = (ours - r64).abs().max().item()
-    lim = max(tol * r64.abs().max().item(), 3.0 * (r32 - r64).abs().max().item()) + atol
-    assert err <= lim, f'{what}: max abs err {err:.3e} > {lim:.3e}'
 
 
 @pytest.mark.parametrize('name', list(CONFIGS))
