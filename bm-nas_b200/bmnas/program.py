@@ -45,6 +45,12 @@ CHAIN_NODE = os.environ.get('BMNAS_CHAIN_NODE', '1') != '0'  # node op i also wr
 CHAIN_NODE_MAX_B = 640                                       # beyond: the warp-per-sample node kernels, which do not chain
 CHAIN_MIX = os.environ.get('BMNAS_CHAIN_MIX', '1') != '0'   # cell-level edge mix + the node cell's first inner mix in one launch
 SPLIT_MIX_BWD = os.environ.get('BMNAS_SPLIT_MIX_BWD', '1') != '0'   # edge-mix backward: input grads on the main chain, d(alpha) on the side branch
+# NodeMixedOp forward as ONE fused tcgen05 kernel (bmnas_mixed_fwd: conv GEMM + BatchNorm statistics + grid barrier + every
+# primitive + gamma-weighted sum, Z written only when a backward will follow) instead of bmnas_conv_fwd + bmnas_node_fwd.
+# 0 = off, 1 = whenever the shape is supported, default: batches of FUSED_MIXED_MIN_B samples or more
+FUSED_MIXED = os.environ.get('BMNAS_FUSED_MIXED', 'auto')
+FUSED_MIXED_MIN_B = int(os.environ.get('BMNAS_FUSED_MIXED_MIN_B', '0'))
+FUSED_OPS_RANK = {'Sum': 0, 'ScaleDotAttn': 1, 'LinearGLU': 2, 'ConcatFC': 3, 'CatConvMish': 3}
 _side_streams = {}
 
 
@@ -99,6 +105,20 @@ class Program:
         self._rng_in_prep = False
         self.n_fwd_launches = 0
         self.n_bwd_launches = 0
+        self.want_backward = True    # False: a no-grad forward (metrics pass, inference): nothing is kept for a backward
+        self._cur_tag = None
+
+    def fused_mixed_ok(self, ops, alias=True):
+        """shape-level test for the fused NodeMixedOp forward kernel (the library re-checks pointers / alignment)"""
+        if FUSED_MIXED == '0' or not alias or self.C != 128 or self.L not in (4, 8, 16):
+            return False
+        if FUSED_MIXED == 'auto' and self.B < FUSED_MIXED_MIN_B:
+            return False
+        if N.lib().bmnas_get_gemm_mode() == 0:
+            return False
+        ranks = [FUSED_OPS_RANK.get(o, -1) for o in ops]
+        return (all(r >= 0 for r in ranks) and ranks == sorted(set(ranks)) and 'LinearGLU' in ops
+                and ops[-1] in ('ConcatFC', 'CatConvMish') and ops.index('LinearGLU') == len(ops) - 2)
 
     # ------------------------------------------------------------------ storage
     def buf(self, *shape, dtype=torch.float32, zero=False):
@@ -174,8 +194,8 @@ class Program:
             else:
                 getattr(st, field)[idx] = base + off
 
-    def emit(self, name, st, side=False):
-        self._cur.append(N.Call(name, st, side=side))
+    def emit(self, name, st, side=False, args=None):
+        self._cur.append(N.Call(name, st, side=side, args=args, tag=self._cur_tag))
 
     def on_backward(self, fn):
         self._stack.append(fn)
@@ -345,8 +365,10 @@ class Program:
         self.on_backward(bwd)
 
     # ------------------------------------------------------------------ kernels: conv (+BN stats) and its backward
-    def conv(self, srcs, src_C, segs, w_fold, bn):
-        """segs: list of dict(W=, bias=, M=, rm=, rv=, nbt=, gW=, gbias=).  Returns dict(Z, mean, rstd, M, st)."""
+    def conv(self, srcs, src_C, segs, w_fold, bn, emit=True, fwd_fmt=None, want_Z=True):
+        """segs: list of dict(W=, bias=, M=, rm=, rv=, nbt=, gW=, gbias=).  Returns dict(Z, mean, rstd, M, st).
+        emit=False: the caller launches the forward itself (fused mixed op); fwd_fmt: image format of the forward weight
+        image (the dgrad image keeps the library's choice); want_Z=False: no Z buffer (no backward will follow)."""
         st = N.bmnas_conv_params()
         K = sum(src_C)
         M = sum(s['M'] for s in segs)
@@ -364,19 +386,26 @@ class Program:
                 self.setp(st, 'running_mean', sg['rm'], i)
                 self.setp(st, 'running_var', sg['rv'], i)
                 self.setp(st, 'num_batches_tracked', sg['nbt'], i)
-        Z = self.buf(self.B, M, self.L)
+        Z = self.buf(self.B, M, self.L) if want_Z else None
         self.setp(st, 'Z', Z)
         # weight images (refreshed by ONE bmnas_wprep launch at the start of every forward): the library picks the
         # format = GEMM engine for this problem size (plain fp32 for the small-N cp.async kernels, tcgen05 slabs beyond)
         img_f = img_d = None
         fmt = int(N.lib().bmnas_conv_image_fmt(self.B, self.L, K, M))
-        if fmt >= 0 and all(c % 4 == 0 for c in src_C) and all(sg['W'].data_ptr() % 16 == 0 for sg in segs):
-            img_f = self.buf(int(N.lib().bmnas_wimg_floats_fmt(M, K, 0, fmt)))
-            img_d = self.buf(int(N.lib().bmnas_wimg_floats_fmt(M, K, 1, fmt)))
+        fmt_f = fmt if fwd_fmt is None else fwd_fmt
+        if fmt_f >= 0 and all(c % 4 == 0 for c in src_C) and all(sg['W'].data_ptr() % 16 == 0 for sg in segs):
+            seg_list = [(sg['W'], sg['M']) for sg in segs]
+            img_f = self.buf(int(N.lib().bmnas_wimg_floats_fmt(M, K, 0, fmt_f)))
             self.setp(st, 'wimg_fwd', img_f)
-            st.wimg_fmt = fmt
-            self._prep.append(dict(M=M, K=K, fold=w_fold, segs=[(sg['W'], sg['M']) for sg in segs], img_f=img_f, img_d=img_d,
-                                   fmt=fmt))
+            st.wimg_fmt = fmt_f
+            if fmt >= 0 and want_Z:
+                img_d = self.buf(int(N.lib().bmnas_wimg_floats_fmt(M, K, 1, fmt)))
+            if fmt == fmt_f:
+                self._prep.append(dict(M=M, K=K, fold=w_fold, segs=seg_list, img_f=img_f, img_d=img_d, fmt=fmt))
+            else:       # two formats: the conv is listed twice, each entry writes one image (NULL = skipped)
+                self._prep.append(dict(M=M, K=K, fold=w_fold, segs=seg_list, img_f=img_f, img_d=None, fmt=fmt_f))
+                if img_d is not None:
+                    self._prep.append(dict(M=M, K=K, fold=w_fold, segs=seg_list, img_f=None, img_d=img_d, fmt=fmt))
         mean = rstd = None
         if bn:
             mean, rstd = self.buf(M), self.buf(M)
@@ -385,9 +414,10 @@ class Program:
             if self.training:
                 self.setp(st, 'stat_part', self.buf(int(N.lib().bmnas_conv_stat_part_size(ctypes.byref(st)))))
                 self.setp(st, 'counter', self.counter(N.lib().bmnas_conv_num_counters(ctypes.byref(st))))
-        self.emit('bmnas_conv_fwd', st)
+        if emit:
+            self.emit('bmnas_conv_fwd', st)
         return dict(Z=Z, mean=mean, rstd=rstd, M=M, K=K, srcs=srcs, src_C=src_C, segs=segs, w_fold=w_fold, img_d=img_d,
-                    fmt=max(fmt, 0))
+                    fmt=max(fmt, 0), st=st)
 
     def conv_backward(self, cv, GV, coef, need_src):
         """dgrad into the source grads + wgrad into the parameter grad views."""
@@ -459,12 +489,16 @@ class Program:
                 off += rows
         assert len(segs) <= N.BMNAS_MAX_SEG
         cv = None
+        self._mixed_id = getattr(self, '_mixed_id', 0) + 1
+        prev_tag, self._cur_tag = self._cur_tag, f'mixed{self._mixed_id}'
+        fused = bool(segs) and not ext and chain is None and self.fused_mixed_ok(ops, alias)
         if segs and ext:
             cv = self.conv(list(conv_srcs), list(conv_src_C), segs, 1, bn=True)
             x = y = cv['Z']               # placeholders: no primitive of an external-source op reads x / y
             alias = True
         elif segs:
-            cv = self.conv([x] if alias else [x, y], [C] if alias else [C, C], segs, 2 if alias else 1, bn=True)
+            cv = self.conv([x] if alias else [x, y], [C] if alias else [C, C], segs, 2 if alias else 1, bn=True,
+                           emit=not fused, fwd_fmt=0 if fused else None, want_Z=(self.want_backward or not fused))
         M = cv['M'] if cv else 0
 
         def fill(st):
@@ -512,12 +546,24 @@ class Program:
             fill_chain(st)
             self.setp(st, 'out2', chain['out'])
         st.early_ok = 1 if cv else 0      # the conv GEMM sits between the producers of x / y and this kernel
-        self.emit('bmnas_node_fwd', st)
+        if fused and N.lib().bmnas_mixed_supported(ctypes.byref(cv['st']), ctypes.byref(st)):
+            ws = self.buf((int(N.lib().bmnas_mixed_workspace_bytes()) + 3) // 4, zero=True)
+            self.emit('bmnas_mixed_fwd', st, args=(ctypes.byref(cv['st']), ctypes.byref(st), ctypes.c_void_p(ws.data_ptr())))
+            self._keep.append(cv['st'])
+        else:
+            if fused:                     # the library declined (alignment / pointers): the two-kernel path
+                assert cv['Z'] is not None, 'fused mixed op declined by the library in a no-grad plan'
+                self.emit('bmnas_conv_fwd', cv['st'])
+            self.emit('bmnas_node_fwd', st)
+        self._cur_tag = prev_tag
+
+        tag = f'mixed{self._mixed_id}'
 
         def bwd():
             g2 = chain['out'] if (chain is not None and self.has_grad(chain['out'])) else None
             if not self.has_grad(out) and g2 is None:
                 return
+            self._cur_tag = tag
             sb = N.bmnas_node_params()
             fill(sb)
             sb.early_ok = 1                   # backward: x, y, Z, mean, rstd are forward tensors
@@ -561,6 +607,7 @@ class Program:
             self.emit('bmnas_node_bwd', sb)
             if cv:
                 self.conv_backward(cv, GV, coef, list(conv_need) if ext else ([need_x] if alias else [need_x, need_y]))
+            self._cur_tag = None
         self.on_backward(bwd)
 
     # ------------------------------------------------------------------ kernels: adaptive max pool (reshape layers)
@@ -715,7 +762,7 @@ class Program:
         off = 0
         # the one-CTA-per-sample node kernels (small batches) also write the NEXT inner edge mix and fold its
         # input-gradient pass into their backward: one launch less per inner step in each direction
-        chain_ok = CHAIN_NODE and self.B < CHAIN_NODE_MAX_B
+        chain_ok = CHAIN_NODE and self.B < CHAIN_NODE_MAX_B and not self.fused_mixed_ok(ops)
         t_next = t0
         for i in range(ns):
             chained_in = t_next is not None

@@ -176,11 +176,12 @@ def run(root, kind, inputs, build, leaves, C, L, drpt, key_extra=(), masks=None,
     B = inputs[0].shape[0]
     use_masks = masks is not None
     drop_key = tuple(sorted(drop_p.items())) if drop_p else ()
-    key = (kind, B, C, L, device.index, bool(root.training), use_masks, need, SAMPLE_OFFSET[0], drop_key,
-           GRAD_MODE[0]) + tuple(key_extra)
-    cache = root.__dict__.setdefault('_bm_cache', {})
     all_leaves = [t for t in leaves if t.requires_grad]
     leaves = filter_leaves(all_leaves)
+    want_backward = bool(grad_on and (any(need) or leaves))
+    key = (kind, B, C, L, device.index, bool(root.training), use_masks, need, SAMPLE_OFFSET[0], drop_key,
+           GRAD_MODE[0], want_backward) + tuple(key_extra)
+    cache = root.__dict__.setdefault('_bm_cache', {})
     ptr_sig = tuple(t.data_ptr() for t in leaves)
     runner = cache.get(key)
     if runner is not None and runner.ptr_sig != ptr_sig:
@@ -194,10 +195,13 @@ def run(root, kind, inputs, build, leaves, C, L, drpt, key_extra=(), masks=None,
         prog.use_masks = use_masks
         prog.drop_p = dict(drop_p or {})
         prog.sample_offset = SAMPLE_OFFSET[0]
+        prog.want_backward = want_backward
         in_slots = [f'in{i}' for i in range(len(inputs))]
         G = _GradViews(arena, GRAD_MODE[0])
         out = build(prog, [Slot(n) for n in in_slots], need, G)
         prog.seed_grad(out, Slot('gout'))
+        if not want_backward:
+            prog._stack.clear()            # a no-grad plan keeps nothing for (and emits no) backward
         prog.finalize()
         span = arena.span(leaves)
         if span is not None:

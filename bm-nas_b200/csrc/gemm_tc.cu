@@ -27,6 +27,7 @@
 // of the MMAs.  A 4-stage ring lets the next slab's loads fly while the current slab's MMAs run.
 #include "common.cuh"
 #include "gemm_shared.cuh"
+#include "tc_ptx.cuh"
 
 #ifdef BMNAS_TIMELINE
 __device__ unsigned long long g_tl[64];
@@ -49,128 +50,8 @@ namespace bmnas {
 namespace tc {
 
 constexpr int TCT = 256;  // threads per CTA (8 warps: all stage; all read TMEM in the epilogue)
-constexpr int TCM = 128;  // accumulator rows per CTA = UMMA M
-constexpr int KC = 32;    // reduction elements per ring stage (4 UMMA k-steps of 8 tf32)
 constexpr int NST_MAX = 4;  // ring stages (3 when four would not fit in 227 KB)
 constexpr int FWD = 0, DGRAD = 1, WGRAD = 2;
-
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred P1;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, 0x989680;\n\t"
-            "selp.b32 %0, 1, 0, P1;\n\t"
-            "}"
-            : "=r"(done)
-            : "r"(s32(bar)), "r"(phase)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(s32(bar)) : "memory");
-}
-// TMA bulk copy global -> shared; completion is signalled on `bar` as transaction bytes
-__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst_smem)),
-                 "l"(src), "r"(bytes), "r"(s32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(dst_smem)), "r"(ncols));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols));
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T, tf32 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d),
-        "l"(da), "l"(db), "r"(idesc), "r"(accum)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
-}
-// 32 lanes x 16 consecutive fp32 columns: thread t of the warp receives lane (base lane + t)
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-// sum of the same 16 columns of the first `used` of NA accumulators (accumulator a starts BNC columns after a-1)
-template <int NA, int BNC>
-__device__ __forceinline__ void tmem_ld16_sum(uint32_t taddr, float (&v)[16], int used) {
-    tmem_ld16(taddr, v);
-#pragma unroll
-    for (int a = 1; a < NA; ++a) {
-        if (a < used) {
-            float w[16];
-            tmem_ld16(taddr + (uint32_t)(a * BNC), w);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += w[i];
-        }
-    }
-}
-__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                 : "memory");
-}
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-// [0,14) start>>4, [16,30) leading byte offset>>4 (unused for swizzled K-major, 1), [32,46) stride byte offset>>4
-// (8 rows x 128 B = 1024), [46,48) version=1, [61,64) layout type (2 = SWIZZLE_128B).  One operand row holds the
-// KC = 32 reduction elements of a slab in 128 contiguous bytes; inside each 8-row x 128 B atom the 16-byte chunk c
-// of row r sits at chunk position c ^ (r & 7) (sw_off below).  A k-step of 8 tf32 advances the start address by
-// 32 bytes inside the atom (the hardware applies the XOR to the address bits), atoms are 1024-byte aligned.
-// (The SWIZZLE_NONE "interleave" layout this replaced fed the tensor core at ~40 B/clk: 130 cycles per
-// 128x32x8 MMA, measured; see profiles/.)
-__device__ __forceinline__ uint64_t kdesc(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3fffu) | (1ull << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-__host__ __device__ __forceinline__ uint32_t sw_off(int row, int kc) {
-    return (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((kc ^ (row & 7)) << 4);
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6)=1, a=tf32 [7,10)=2, b=tf32 [10,13)=2,
-// a/b K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ float tf32_hi(float v) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-    return __uint_as_float(r);
-}
-
-// write one 16-byte K-chunk (4 reduction elements of one operand row) as hi (and lo) tf32 values
-template <bool X3>
-__device__ __forceinline__ void put_chunk(uint8_t* hi_base, uint8_t* lo_base, uint32_t off, float4 v) {
-    float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-    *reinterpret_cast<float4*>(hi_base + off) = h;
-    if (X3) *reinterpret_cast<float4*>(lo_base + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-}
 
 template <int BN, bool X3>
 struct Smem {
@@ -433,27 +314,30 @@ __global__ void __launch_bounds__(TCT, 1) k_gemm_tc(const bmnas_conv_params p, c
         fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor-core (async) proxy
         __syncthreads();
         if (c == 0) TL(4);
-        if (tid == 0) {
+        if (warp == 0) {             // warp-uniform issue loop, one elected lane issues (see elect_one())
             if (use_img) mbar_wait(&bar_full[stage], (uint32_t)(c / NST) & 1u);      // weight slab has landed
             if (c == 0) TL(5);
             tc_fence_after();
             const uint32_t base = s32(smem + (size_t)stage * S::STAGE);
             const uint32_t a_hi = base, a_lo = base + S::A_BYTES;
             const uint32_t b_hi = base + (X3 ? 2u : 1u) * S::A_BYTES, b_lo = b_hi + S::B_BYTES;
+            if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < KC / 8; ++ks) {
-                const uint32_t ko = (uint32_t)ks * 32u;              // 8 tf32 = 32 bytes inside the 128-byte swizzled row
-                const uint32_t first = (c == 0 && ks == 0) ? 0u : 1u;
-                if (X3) {
-                    umma_tf32(tmem_d, kdesc(a_lo + ko), kdesc(b_hi + ko), IDESC, first);
-                    umma_tf32(tmem_d, kdesc(a_hi + ko), kdesc(b_lo + ko), IDESC, 1u);
-                    umma_tf32(tmem_d, kdesc(a_hi + ko), kdesc(b_hi + ko), IDESC, 1u);
-                } else {
-                    umma_tf32(tmem_d, kdesc(a_hi + ko), kdesc(b_hi + ko), IDESC, first);
+                for (int ks = 0; ks < KC / 8; ++ks) {
+                    const uint32_t ko = (uint32_t)ks * 32u;              // 8 tf32 = 32 bytes inside the 128-byte swizzled row
+                    const uint32_t first = (c == 0 && ks == 0) ? 0u : 1u;
+                    if (X3) {
+                        umma_tf32(tmem_d, kdesc(a_lo + ko), kdesc(b_hi + ko), IDESC, first);
+                        umma_tf32(tmem_d, kdesc(a_hi + ko), kdesc(b_lo + ko), IDESC, 1u);
+                        umma_tf32(tmem_d, kdesc(a_hi + ko), kdesc(b_hi + ko), IDESC, 1u);
+                    } else {
+                        umma_tf32(tmem_d, kdesc(a_hi + ko), kdesc(b_hi + ko), IDESC, first);
+                    }
                 }
+                umma_commit(&bar_free[stage]);                   // slot reusable once these MMAs have read it
+                if (c + 1 == n_chunks) umma_commit(bar_done);    // accumulator complete
             }
-            umma_commit(&bar_free[stage]);                   // slot reusable once these MMAs have read it
-            if (c + 1 == n_chunks) umma_commit(bar_done);    // accumulator complete
+            __syncwarp();
         }
     }
 
@@ -671,17 +555,22 @@ __global__ void __launch_bounds__(TCT, 1) k_gemm_panel(const bmnas_conv_params p
     constexpr uint32_t IMG_SLAB = 2u * TCM * KC * 4;           // image slab: [hi 16 KB | lo 16 KB]
     const uint8_t* img_rt = reinterpret_cast<const uint8_t*>(MODE == FWD ? p.wimg_fwd : p.wimg_dgrad) +
                             (size_t)blockIdx.y * (size_t)n_chunks * IMG_SLAB;
-    long long a_issued = 0, a_used = 0;                        // thread 0 only
-    auto produce = [&]() {                                      // thread 0: keep up to nsta weight slabs in flight
+    // warp 0 runs the TMA / MMA issue code warp-uniformly; `leader` (one elected lane) executes the instructions
+    // themselves -- in a thread-divergent branch every tcgen05.mma costs ~157 cycles of issue (see elect_one())
+    long long a_issued = 0, a_used = 0;                        // warp 0 (uniform)
+    const bool leader = warp == 0 && elect_one();
+    auto produce = [&]() {                                      // warp 0: keep up to nsta weight slabs in flight
         while (a_issued < total_slabs && a_issued < a_used + nsta) {
             const int st = (int)(a_issued % nsta);
             if (a_issued >= nsta) mbar_wait(&bar_free[st], (uint32_t)((a_issued / nsta) - 1) & 1u);
-            mbar_expect_tx(&bar_full[st], S::A_ST);
-            tma_bulk_g2s(smA + (size_t)st * S::A_ST, img_rt + (size_t)(a_issued % n_chunks) * IMG_SLAB, S::A_ST, &bar_full[st]);
+            if (leader) {
+                mbar_expect_tx(&bar_full[st], S::A_ST);
+                tma_bulk_g2s(smA + (size_t)st * S::A_ST, img_rt + (size_t)(a_issued % n_chunks) * IMG_SLAB, S::A_ST, &bar_full[st]);
+            }
             ++a_issued;
         }
     };
-    if (tid == 0 && my_tiles > 0) produce();
+    if (warp == 0 && my_tiles > 0) produce();
 
     const bool has_coef = MODE == DGRAD && p.coef_a != nullptr;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -709,7 +598,7 @@ __global__ void __launch_bounds__(TCT, 1) k_gemm_panel(const bmnas_conv_params p
 
     for (int ti = 0; ti < my_tiles; ++ti) {
         const int col0 = ((int)blockIdx.x + ti * (int)gridDim.x) * BN;
-        uint32_t n_mma = 0;                                    // thread 0: MMAs issued for this tile
+        uint32_t n_mma = 0;                                    // warp 0: MMAs issued for this tile
         for (int pc0 = 0; pc0 < n_chunks; pc0 += pcap) {
             const int npc = min(pcap, n_chunks - pc0);
             if (pc0 > 0) {                                       // the MMAs that read the previous panel must be done
@@ -796,7 +685,7 @@ __global__ void __launch_bounds__(TCT, 1) k_gemm_panel(const bmnas_conv_params p
             tc_fence_before();         // this thread's TMEM reads of the previous tile are ordered before the sync
             __syncthreads();
             if (ti == 0 && pc0 == 0) TL(4);
-            if (tid == 0) {
+            if (warp == 0) {
                 tc_fence_after();
                 for (int c = 0; c < npc; ++c) {
                     produce();
@@ -808,28 +697,29 @@ __global__ void __launch_bounds__(TCT, 1) k_gemm_panel(const bmnas_conv_params p
                     tc_fence_after();
                     const uint32_t a_hi = s32(smA + (size_t)st * S::A_ST), a_lo = a_hi + TCM * KC * 4;
                     const uint32_t b_hi = s32(smB + (size_t)c * S::B_CH), b_lo = b_hi + S::B_HALF;
+                    if (leader) {
 #pragma unroll
-                    for (int ks = 0; ks < KC / 8; ++ks) {
-                        const uint32_t ko = (uint32_t)ks * 32u;              // 8 tf32 = 32 bytes inside the swizzled row
-                        if (X3) {
-                            umma_tf32(tmem_d + (n_mma % NACC) * BN, kdesc(a_lo + ko), kdesc(b_hi + ko), IDESC, n_mma >= NACC);
-                            ++n_mma;
-                            umma_tf32(tmem_d + (n_mma % NACC) * BN, kdesc(a_hi + ko), kdesc(b_lo + ko), IDESC, n_mma >= NACC);
-                            ++n_mma;
-                            umma_tf32(tmem_d + (n_mma % NACC) * BN, kdesc(a_hi + ko), kdesc(b_hi + ko), IDESC, n_mma >= NACC);
-                            ++n_mma;
-                        } else {
-                            umma_tf32(tmem_d + (n_mma % NACC) * BN, kdesc(a_hi + ko), kdesc(b_hi + ko), IDESC, n_mma >= NACC);
-                            ++n_mma;
+                        for (int ks = 0; ks < KC / 8; ++ks) {
+                            const uint32_t ko = (uint32_t)ks * 32u;          // 8 tf32 = 32 bytes inside the swizzled row
+                            const uint32_t m0 = n_mma + (uint32_t)ks * (X3 ? 3u : 1u);
+                            if (X3) {
+                                umma_tf32(tmem_d + ((m0 + 0) % NACC) * BN, kdesc(a_lo + ko), kdesc(b_hi + ko), IDESC, m0 + 0 >= NACC);
+                                umma_tf32(tmem_d + ((m0 + 1) % NACC) * BN, kdesc(a_hi + ko), kdesc(b_lo + ko), IDESC, m0 + 1 >= NACC);
+                                umma_tf32(tmem_d + ((m0 + 2) % NACC) * BN, kdesc(a_hi + ko), kdesc(b_hi + ko), IDESC, m0 + 2 >= NACC);
+                            } else {
+                                umma_tf32(tmem_d + (m0 % NACC) * BN, kdesc(a_hi + ko), kdesc(b_hi + ko), IDESC, m0 >= NACC);
+                            }
                         }
+                        if (!resident) umma_commit(&bar_free[st]);           // slot reusable once these MMAs have read it
                     }
-                    if (!resident) {
-                        umma_commit(&bar_free[st]);                  // slot reusable once these MMAs have read it
-                        ++a_used;
-                    }
+                    n_mma += (KC / 8) * (X3 ? 3u : 1u);
+                    if (!resident) ++a_used;
                 }
-                if (pc0 + npc >= n_chunks) umma_commit(bar_done);    // accumulator complete
-                else umma_commit(bar_panel);                         // panel buffer reusable
+                if (leader) {
+                    if (pc0 + npc >= n_chunks) umma_commit(bar_done);    // accumulator complete
+                    else umma_commit(bar_panel);                         // panel buffer reusable
+                }
+                __syncwarp();
                 if (!resident) produce();                            // next tile's first slabs fly during the epilogue
             }
         }
@@ -1022,6 +912,7 @@ __global__ void __launch_bounds__(256) k_wprep(const bmnas_wprep_params p) {
         const int MT32 = (M + 31) / 32, KT32 = (K + 31) / 32;
         const long long nf = (long long)MT32 * K * 8;
         if (ql < nf) {
+            if (!p.img_fwd[i]) return;
             const int c4 = (int)(ql & 7), k = (int)((ql >> 3) % K), t = (int)((ql >> 3) / K);
             float e[4];
 #pragma unroll
@@ -1037,6 +928,7 @@ __global__ void __launch_bounds__(256) k_wprep(const bmnas_wprep_params p) {
             *reinterpret_cast<float4*>(p.img_fwd[i] + ql * 4) = make_float4(e[0], e[1], e[2], e[3]);
         } else {
             ql -= nf;
+            if (!p.img_dgrad[i]) return;
             const int c4 = (int)(ql & 7), m = (int)((ql >> 3) % M), t = (int)((ql >> 3) / M);
             const int k4 = t * 32 + c4 * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1058,6 +950,7 @@ __global__ void __launch_bounds__(256) k_wprep(const bmnas_wprep_params p) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     float* dst;
     if (ql < nf) {
+        if (!p.img_fwd[i]) return;
         const long long slab = ql >> 10;
         const int w = (int)(ql & 1023), rt = (int)(slab / KSf), ks = (int)(slab % KSf);
         const int r8 = w & 7, kc = (w >> 3) & 7, rg = w >> 6;
@@ -1073,6 +966,7 @@ __global__ void __launch_bounds__(256) k_wprep(const bmnas_wprep_params p) {
         dst = p.img_fwd[i] + slab * (2 * TCM * KC) + sw_off(rg * 8 + r8, kc) / 4;
     } else {
         ql -= nf;
+        if (!p.img_dgrad[i]) return;
         const int MSd = (M + KC - 1) / KC;
         const long long slab = ql >> 10;
         const int w = (int)(ql & 1023), rt = (int)(slab / MSd), ms = (int)(slab % MSd);
@@ -1209,7 +1103,7 @@ extern "C" int bmnas_wprep(const bmnas_wprep_params* p, void* stream) {
     for (int i = 0; i < p->n; ++i) {
         if (p->M[i] < 1 || p->K[i] < 4 || (p->K[i] & 3) || p->n_seg[i] < 1 || p->n_seg[i] > BMNAS_MAX_SEG) return BMNAS_EINVAL;
         if (p->w_fold[i] != 1 && p->w_fold[i] != 2) return BMNAS_EINVAL;
-        if (!p->img_fwd[i] || !p->img_dgrad[i]) return BMNAS_EINVAL;
+        if (!p->img_fwd[i] && !p->img_dgrad[i]) return BMNAS_EINVAL;      // either image may be skipped (NULL)
         int m = 0;
         for (int s = 0; s < p->n_seg[i]; ++s) {
             if (!p->W[i * BMNAS_MAX_SEG + s] || (reinterpret_cast<uintptr_t>(p->W[i * BMNAS_MAX_SEG + s]) & 15u)) return BMNAS_EINVAL;

@@ -165,6 +165,8 @@ int bmnas_conv_num_counters(const bmnas_conv_params* p);         /* uints   */
  * slabs and stored slab by slab as the K-major core-matrix shared-memory picture the MMA descriptors read.
  * q_start is the exclusive prefix sum of bmnas_wprep_items(M, K, fmt) over the convs (n + 1 entries);
  * fmt[i] selects the image format of conv i (see bmnas_conv_params.wimg_fmt).
+ * Either image pointer of a conv may be NULL (that image is then not written): a conv can so be listed twice with two
+ * formats, e.g. tcgen05 slabs for the fused forward kernel and the plain fp32 image for the small-N dgrad GEMM.
  * One launch per forward replaces the per-CTA fold / transpose / split of the weights
  * (torch.cat([x, x]) + nn.Conv1d weight use in node_operations.py:30-34, 49-53, node_search.py:59-62).
  * ---------------------------------------------------------------------- */
@@ -298,6 +300,33 @@ typedef struct bmnas_node_params {
 int bmnas_node_fwd(const bmnas_node_params* p, void* stream);
 int bmnas_node_bwd(const bmnas_node_params* p, void* stream);
 long long bmnas_node_partials_size(const bmnas_node_params* p); /* floats */
+
+/* ------------------------------------------------------------------------
+ * Fused step-node mixed op (the north-star kernel): bmnas_conv_fwd + bmnas_node_fwd of a searchable NodeMixedOp in
+ * ONE persistent cooperative launch on the tcgen05 tensor cores, without the pre-BatchNorm activations Z ever
+ * leaving the SM unless the caller asks for them:
+ *   out = sum_k softmax(gamma)_k * op_k(t, t),   ops a canonical-order subset of
+ *         {Sum, ScaleDotAttn, LinearGLU, ConcatFC | CatConvMish} containing LinearGLU and one FC-type op
+ * replaces NodeMixedOp.forward with everything below it: node_operations.py:118-120 (weighted sum), :19-20 (Sum),
+ * :92-108 (ScaledDotAttn: QK^T, softmax, PV, dropout, LayerNorm), :30-39 (LinearGLU: cat, Conv1d, BatchNorm1d with
+ * batch statistics, GLU, dropout), :49-56 (ConcatFC), :75-82 (CatConvMish), called with x is y (node_search.py:55).
+ * Per 64-column tile (64/L samples): producer warps stage the activation tile once (fp32 -> hi/lo tf32 or bf16,
+ * K-major SWIZZLE_128B), a TMA warp streams the prepared weight slabs (bmnas_wprep image), one thread issues the
+ * UMMAs for the three 128-row output tiles (GLU value | GLU gate | FC) AND the Gram matrix t^T t whose diagonal
+ * L x L blocks are the attention scores; accumulators are double buffered in tensor memory; eight epilogue warps
+ * reduce the BatchNorm batch statistics per output row (Welford per CTA -> fp64 atomics -> ONE grid barrier),
+ * then apply BN / GLU / ReLU / Mish / softmax / PV / dropout / LayerNorm / the gamma-weighted sum straight from
+ * tensor memory.  Batches larger than one resident wave (2 tiles per SM) recompute the GEMM in a second pass.
+ * cv: the conv block (B, L, K = C = 128, w_fold, W / bias / running statistics, mean / rstd outputs, bn_mode,
+ *     wimg_fwd in format 0 (3xTF32) or 2 (bf16); cv->Z NULL = do not write Z (no-grad forward), else Z (B, 3C, L) is
+ *     written for the backward kernels).   nd: the node block (ops, gamma, dropout sites, LayerNorm affine, out).
+ * workspace: bmnas_mixed_workspace_bytes() bytes, zeroed once by the caller, owned by this (cv, nd) pair.
+ * Returns BMNAS_EINVAL for shapes it does not take (bmnas_mixed_supported() == 0): the caller then uses
+ * bmnas_conv_fwd + bmnas_node_fwd.
+ * ---------------------------------------------------------------------- */
+int bmnas_mixed_fwd(const bmnas_conv_params* cv, const bmnas_node_params* nd, void* workspace, void* stream);
+int bmnas_mixed_supported(const bmnas_conv_params* cv, const bmnas_node_params* nd);
+long long bmnas_mixed_workspace_bytes(void);
 
 /* ------------------------------------------------------------------------
  * LayerNorm block over a virtual channel concat.

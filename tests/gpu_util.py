@@ -65,7 +65,8 @@ def grads_by_name(head):
 
 def training_program(head, mode=None):
     """the launch plan the last training-mode forward of head.fusion_net ran (mode: runtime.GRAD_MODE of that plan)"""
-    progs = [(k, r.prog) for k, r in head.fusion_net._bm_cache.items() if r.prog.training and not r.prog.use_masks]
+    progs = [(k, r.prog) for k, r in head.fusion_net._bm_cache.items()
+             if r.prog.training and not r.prog.use_masks and r.prog.want_backward]
     if mode is not None:
         progs = [(k, p) for k, p in progs if mode in k]
     assert len(progs) == 1, [k for k, _ in progs]
