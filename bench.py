@@ -46,7 +46,41 @@ def peaks():
     return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src='fallback')
 
 
-# ----------------------------------------------------------------------------- CPU reference arm (oracle port)
+# ----------------------------------------------------------------------------- reference arm
+def reference_arm(cfgname, steps, warmup, max_seconds, device='cpu', full_fidelity=False, batch=None):
+    """The reference's own modules (FusionNetwork, Architect, LRCosineAnnealingScheduler, torch.optim.Adam, unmodified,
+    vendored by tools/vendor_ref.sh into the git-ignored oracle/_ref/) driven through the reference's loop body by
+    oracle/ref_harness.py.  Runs in THIS process: only call it from a process that never imported the product package
+    (`bench.py --impl reference`; run_ours() reaches it through a subprocess).  Falls back to the oracle port (kind
+    "port") when oracle/_ref is absent.  Returns (kind, samples/s, ms/step, threads, steps done)."""
+    from oracle import ref_harness as H
+    c = dict(CONFIGS[cfgname])
+    if batch:
+        c['B'] = batch
+    if H.available():
+        v, ms, thr, done = H.time_search(c, steps, warmup, max_seconds, device=device, full_fidelity=full_fidelity)
+        return 'reference', v, ms, thr, done
+    v, ms, thr, done = cpu_reference(cfgname, steps, warmup, max_seconds=max_seconds, device=device)
+    return 'port', v, ms, thr, done
+
+
+def reference_subprocess(cfgname, steps, warmup, max_seconds, device='cpu', full_fidelity=False, batch=None):
+    """run `bench.py --impl reference` in a child process and return its JSON line (dict) or {'unavailable': why}"""
+    cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--config', cfgname, '--steps', str(steps),
+           '--warmup', str(warmup), '--max-seconds', str(max_seconds), '--ref-device', device]
+    if full_fidelity:
+        cmd.append('--full-fidelity')
+    if batch:
+        cmd += ['--batch', str(batch)]
+    env = {k: v for k, v in os.environ.items() if k not in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE', 'MASTER_ADDR', 'MASTER_PORT')}
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=max_seconds * 3 + 180, env=env)
+        lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
+        return json.loads(lines[-1]) if lines else {'unavailable': (out.stderr or 'no output')[-300:]}
+    except Exception as e:
+        return {'unavailable': repr(e)[:300]}
+
+
 def cpu_reference(cfgname, steps, warmup, max_seconds=25.0, device='cpu'):
     """times oracle/bmnas_oracle.py (the CPU restatement of the reference's path, pinned against the
     reference by tests/golden) on all host cores.  Returns (samples_per_s, ms_per_step, cores, steps_done).
@@ -212,6 +246,8 @@ def algorithmic_bytes(call, c, B):
     if n == 'bmnas_mix_bwd':   # gout in; the x_j in when d(alpha) is wanted; the gx_j out (the two halves are separate launches)
         n_gx = sum(1 for j in range(st.n) if st.gx[j])
         return (1 + (st.n if st.gw else 0) + n_gx) * T
+    if n == 'bmnas_mixed_fwd':     # SURVEY 8(d) node_mixed fwd, aliased inputs: t in, out out, weights once per launch
+        return 2 * T + 6 * c['C'] * c['C'] * 4
     if n == 'bmnas_node_fwd':
         return (1 if st.alias_xy else 2) * T + st.M * c['L'] * 4 * B + T
     if n == 'bmnas_node_bwd':
@@ -227,6 +263,12 @@ def algorithmic_bytes(call, c, B):
     if n == 'bmnas_ln_bwd':
         return 4 * st.Ctot * c['L'] * 4 * B
     return 0
+
+
+def mode_name():
+    from bmnas import native as N
+    return {0: 'fp32 FFMA', 1: '3xTF32 tcgen05 (fp32-class)', 2: '1xTF32 tcgen05', 3: 'bf16 operands in the fused MixedOp forward, 3xTF32 elsewhere'}[
+        int(N.lib().bmnas_get_gemm_mode())]
 
 
 def large_batch_roofline(args, c, pk, device, B):
@@ -246,15 +288,22 @@ def large_batch_roofline(args, c, pk, device, B):
     for _ in range(2):
         ss.step()
     torch.cuda.synchronize()
-    runner = [r for r in head.fusion_net._bm_cache.values() if r.prog.training][0]
+    runner = training_runner(head)
     keep_gout = torch.zeros_like(runner.out)
     runner.prog.bind('gout', keep_gout)        # the upstream-gradient slot pointed at a freed autograd temporary
+    mo = mixedop_roofline(runner.prog, c, B, pk, R=10, reps=3)
     best = {}
     for call in runner.prog.fwd + runner.prog.bwd:
         by = algorithmic_bytes(call, c, B)
         if by and (call.name not in best or by > best[call.name][1]):
             best[call.name] = (call, by)
-    out = {'B': B, 'peak_GBs': pk['hbm'], 'peak_source': pk['src'], 'kernels': {}}
+    tr = ncu_traffic()
+    for ph, d in mo.items():
+        t = sum(tr.get(f'{k}@B{B}', 0) for k in d['launches'])
+        d['traffic'] = t or None
+        d['traffic_over_algorithmic'] = round(t / d['algorithmic_bytes'], 2) if t else None
+    out = {'B': B, 'peak_GBs': pk['hbm'], 'peak_TFLOPs_bf16': pk['bf16'], 'peak_source': pk['src'], 'gemm_mode': mode_name(),
+           'mixedop': mo, 'kernels': {}}
     for name, (call, by) in sorted(best.items()):
         us = graph_time_us(call, R=10, reps=3)
         gbs = by / (us * 1e-6) / 1e9
@@ -265,42 +314,94 @@ def large_batch_roofline(args, c, pk, device, B):
     return out
 
 
-def ncu_traffic(kernel, B):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (profiles/)"""
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the ncu --set full captures committed under profiles/
+    (tools/make_profiles.py rewrites the file from the .ncu-rep files of a build and stamps that build's git SHA)"""
     try:
-        d = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
-        return d.get(f'{kernel}@B{B}')
+        return json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
     except Exception:
-        return None
+        return {}
 
 
-def kernel_roofline(head, ss, c, pk):
-    """average duration of the dominant fused MixedOp kernels (bmnas_node_fwd / bmnas_node_bwd), timed live with
-    CUDA events around graph-replayed back-to-back launches of the prepared parameter blocks."""
-    from bmnas import native as N
-    runner = [r for r in head.fusion_net._bm_cache.values() if r.prog.training][0]
+def training_runner(head):
+    rs = [r for r in head.fusion_net._bm_cache.values() if r.prog.training and r.prog.want_backward]
+    # the weight-step plan carries every kernel of a training step (the arch-step plan omits the weight-gradient GEMMs)
+    rs.sort(key=lambda r: -len(r.prog.bwd))
+    return rs[0]
+
+
+def mixedop_roofline(prog, c, B, pk, R=50, reps=4):
+    """Roofline of the NodeMixedOp as SURVEY 8(d) defines it -- ALL launches that implement one mixed op, summed:
+         forward  = bmnas_mixed_fwd, or bmnas_conv_fwd + bmnas_node_fwd on the two-kernel path
+         backward = bmnas_node_bwd + bmnas_conv_dgrad + bmnas_conv_wgrad
+       algorithmic bytes (fp32, inputs aliased as in the searchable cell): fwd 2*T1*B + 6C^2*4 (t in, out out, weights once),
+       bwd 3*T1*B + 2*6C^2*4 (g and t in, gt out; weights in, weight gradients out);  T1 = C*L*4
+       algorithmic FLOPs: fwd (12*L*C^2 + 4*L^2*C)*B, bwd twice that.
+       Time = sum of the launches' device times, each measured live (CUDA events around graph-replayed launches)."""
+    C, L = c['C'], c['L']
+    T1 = C * L * 4
+    groups = {}
+    for phase, calls in (('fwd', prog.fwd), ('bwd', prog.bwd)):
+        for call in calls:
+            if getattr(call, 'tag', None):
+                groups.setdefault((call.tag, phase), []).append(call)
+    out = {}
+    for phase in ('fwd', 'bwd'):
+        cand = [(k, v) for k, v in groups.items() if k[1] == phase]
+        if not cand:
+            continue
+        # the first mixed op of the plan that carries no chained edge mix (its bytes are the plain SURVEY 8(d) ones)
+        plain = [(k, v) for k, v in cand if not any(getattr(x.st, 'out2', None) or getattr(x.st, 'gout2', None) for x in v
+                                                    if x.name.startswith('bmnas_node'))]
+        key, calls = (plain or cand)[0]
+        times = {x.name: graph_time_us(x, R=R, reps=reps) for x in calls}
+        us = sum(times.values())
+        mult = 1 if phase == 'fwd' else 2
+        by = (2 if phase == 'fwd' else 3) * T1 * B + mult * 6 * C * C * 4
+        fl = mult * (12 * L * C * C + 4 * L * L * C) * B
+        gbs, tfs = by / (us * 1e-6) / 1e9, fl / (us * 1e-6) / 1e12
+        t_roof = max(by / (pk['hbm'] * 1e9), fl / (pk['bf16'] * 1e12)) * 1e6
+        out[phase] = {'launches': {k: round(v, 2) for k, v in times.items()}, 'us': round(us, 2),
+                      'algorithmic_bytes': by, 'algorithmic_flops': fl, 'GBs': round(gbs, 1), 'TFLOPs': round(tfs, 2),
+                      'hbm_frac': round(gbs / pk['hbm'], 4), 'tensor_frac': round(tfs / pk['bf16'], 4),
+                      'roofline_us': round(t_roof, 2), 'roofline_frac': round(t_roof / us, 4)}
+    return out
+
+
+def step_shares(prog, R=20):
+    """device time of every launch of a training plan grouped by kernel: {name: (us per fwd+bwd, launches)}"""
+    tot = {}
+    for call in prog.fwd + prog.bwd:
+        us = graph_time_us(call, R=R, reps=2)
+        t, n = tot.get(call.name, (0.0, 0))
+        tot[call.name] = (t + us, n + 1)
+    return tot
+
+
+def kernel_roofline(head, c, pk, B):
+    """the `roofline` object of the bench line, for the batch the line is quoted on: the MixedOp kernel group that takes
+    the largest share of the step (measured), against the HBM roofline, SURVEY 8(d) bytes."""
+    runner = training_runner(head)
     prog = runner.prog
     keep_gout = torch.zeros_like(runner.out)
-    prog.bind('gout', keep_gout)
-    res = {}
-    for name, calls in (('bmnas_node_fwd', prog.fwd), ('bmnas_node_bwd', prog.bwd)):
-        cand = [x for x in calls if x.name == name]
-        plain = [x for x in cand if not (x.st.out2 or x.st.gout2)]   # an instance without a chained edge mix: the bytes below
-        call = (plain or cand)[0]
-        res[name] = graph_time_us(call)                # us per launch
-    T1 = c['C'] * c['L'] * 4
-    M = 3 * c['C']
-    # algorithmic bytes per sample of the fused node kernel (DESIGN.md): x (aliased with y) + Z (3C rows) in, out
-    fwd_bytes = c['B'] * (T1 + M * c['L'] * 4 + T1)
-    t = res['bmnas_node_fwd'] * 1e-6
-    ach = fwd_bytes / t / 1e9
-    return {'bound': 'hbm', 'kernel': 'bmnas_node_fwd (fused NodeMixedOp forward)', 'achieved': round(ach, 2),
-            'peak': pk['hbm'], 'peak_source': pk['src'], 'unit': 'GB/s', 'frac': round(ach / pk['hbm'], 5),
-            'traffic': ncu_traffic('bmnas_node_fwd', c['B']), 'avg_launch_us': {k: round(v, 3) for k, v in res.items()},
-            'algorithmic_bytes_per_launch': fwd_bytes,
-            'note': 'B=%d working set is L2-resident and the kernel is latency-bound at this size (graph-replayed launches, '
-                    'programmatic dependent launch overlaps the early section of launch i+1 with launch i); '
-                    'roofline_large_batch times the same kernels where they are bandwidth bound' % c['B']}
+    prog.bind('gout', keep_gout)               # the upstream-gradient slot pointed at a freed autograd temporary
+    mo = mixedop_roofline(prog, c, B, pk)
+    shares = step_shares(prog)
+    total = sum(t for t, _ in shares.values())
+    n_mixed = len({x.tag for x in prog.fwd if getattr(x, 'tag', None)})
+    dom = max(('fwd', 'bwd'), key=lambda ph: mo.get(ph, {}).get('us', 0.0))
+    d = mo[dom]
+    tr = ncu_traffic()
+    traffic = sum(tr.get(f'{k}@B{B}', 0) for k in d['launches']) or None
+    return {'bound': 'hbm', 'kernel': f'NodeMixedOp {dom} = ' + ' + '.join(d['launches']), 'achieved': d['GBs'], 'peak': pk['hbm'],
+            'peak_source': pk['src'] + ' (burst: kernels timed alone)', 'unit': 'GB/s', 'frac': d['hbm_frac'],
+            'traffic': traffic, 'traffic_git': tr.get('_git'), 'traffic_over_algorithmic': round(traffic / d['algorithmic_bytes'], 2) if traffic else None,
+            'tensor_frac_vs_bf16_peak': d['tensor_frac'], 'roofline_frac': d['roofline_frac'],
+            'share_of_fwd_bwd': round(n_mixed * d['us'] / total, 3), 'mixedop': mo,
+            'time_share_by_kernel': {k: {'us': round(t, 1), 'launches': n, 'share': round(t / total, 3)}
+                                     for k, (t, n) in sorted(shares.items(), key=lambda kv: -kv[1][0])},
+            'note': f'B={B}: the whole working set is L2-resident and every launch is latency bound; roofline_large_batch '
+                    'times the same plan where the kernels are throughput bound'}
 
 
 def profile_kernels(head, R=50):
@@ -309,7 +410,7 @@ def profile_kernels(head, R=50):
     host-bound at ~3 us and hide anything shorter)"""
     from bmnas import native as N
     import ctypes
-    runner = [r for r in head.fusion_net._bm_cache.values() if r.prog.training][0]
+    runner = training_runner(head)
     prog = runner.prog
     keep_gout = torch.zeros_like(runner.out)
     prog.bind('gout', keep_gout)               # the upstream-gradient slot pointed at a freed autograd temporary
@@ -323,12 +424,109 @@ def profile_kernels(head, R=50):
     return rows
 
 
+METRIC = 'search-step samples/sec (fwd+bwd+arch step, fwd+bwd+weight step)'
+
+
+def workload_string(cfgname, c, gB):
+    """identical in both arms (the driver compares the strings)"""
+    return (f'{cfgname.upper()} fusion search step on synthetic frozen-backbone features, global batch {gB}, C={c["C"]}, '
+            f'L={c["L"]}, n_in={c["num_input_nodes"]}, steps={c["steps"]}, node_steps={c["node_steps"]}, classes={c["classes"]}')
+
+
+def build_search(c, device, group=None, use_graphs=True, nbpe=400.0):
+    import types
+    from bmnas.nn import SearchHead, CrossEntropyLoss, BCEWithLogitsLoss
+    from bmnas.search import SearchStep
+    a = types.SimpleNamespace(**{k: c[k] for k in ('C', 'L', 'num_input_nodes', 'steps', 'multiplier', 'node_steps',
+                                                    'node_multiplier', 'drpt')}, weight_decay=c['weight_decay'])
+    crit = CrossEntropyLoss() if c['loss'] == 'ce' else BCEWithLogitsLoss()
+    head = SearchHead(a, c['classes'], criterion=crit).to(device)
+    ss = SearchStep(head, crit, c['B'], c['classes'], loss_kind=c['loss'], eta_max=c['eta_max'],
+                    weight_decay=c['weight_decay'], nbpe=nbpe, use_graphs=use_graphs, group=group)
+    return head, ss
+
+
+def quick_value(cfgname, device, steps=60, warmup=5, batch=None):
+    """value / ms_per_step of another BASELINE config (single GPU, graphs, inputs resident and rotated through a pool
+    larger than L2), for the `configs` block of the bench line"""
+    c = dict(CONFIGS[cfgname])
+    if batch:
+        c['B'] = batch
+    torch.manual_seed(2)
+    head, ss = build_search(c, device)
+    per_batch = c['num_input_nodes'] * c['B'] * c['C'] * c['L'] * 4
+    n_pool = max(4, int(1.3 * L2_BYTES / per_batch) + 1)
+    n_pool += n_pool % 2
+    pool = make_pool(c, n_pool, 300, device)
+    ss.load('dev', *pool[0]); ss.load('train', *pool[1])
+    ss.prepare(warmup=3, restore=False)
+    for i in range(warmup):
+        ss.load('dev', *pool[(2 * i) % n_pool]); ss.load('train', *pool[(2 * i + 1) % n_pool]); ss.step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(steps):
+        ss.load('dev', *pool[(2 * i) % n_pool]); ss.load('train', *pool[(2 * i + 1) % n_pool]); ss.step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    out = {'workload': workload_string(cfgname, c, c['B']), 'value': round(c['B'] / ms * 1e3, 1), 'unit': 'samples/s',
+           'ms_per_step': round(ms, 4), 'steps': steps, 'launches_per_step': ss.launches_per_step,
+           'weights': sum(p.numel() for p in head.parameters())}
+    del ss, head, pool
+    torch.cuda.empty_cache()
+    return out
+
+
+def found_sweep(device, batches=(96, 1024, 8192), steps=30):
+    """BASELINE configs[4]: found (fixed-genotype) NTU network, train and inference throughput (bench_found.py)"""
+    import bench_found as BF
+    return BF.sweep(device, batches, steps)
+
+
+def dp_check(ss, head, group, world, rank, device):
+    """N > 1 only, before timing: (1) the reduced weight / architecture gradients every rank holds after the collective
+    equal the sum of the per-rank gradients (all-gathered and summed here), (2) replicas hold bit-identical parameters and
+    architecture tensors.  Raises on mismatch."""
+    import torch.distributed as dist
+    from bmnas import runtime as rt
+    res = {}
+    for which, mode in (('dev', 'arch'), ('train', 'weights')):
+        with rt.grad_mode(mode):
+            loss = ss.criterion(head(ss.feats[which]), ss.labels[which])
+            loss.backward()
+        from bmnas.program import join_side
+        join_side(device)
+        span = ss.grad_span(which)
+        local = span.clone()
+        gathered = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local, group=group)
+        expect = torch.stack(gathered).double().sum(0)
+        ss.allreduce_grads(which)
+        torch.cuda.synchronize()
+        err = (span.double() - expect).abs().max().item()
+        scale = expect.abs().max().item()
+        if not err <= 1e-5 * scale + 1e-12:
+            raise SystemExit(f'dp_check: reduced {which} gradients differ from the sum of the per-rank gradients: {err} vs scale {scale}')
+        res[which + '_grad_err'] = err
+    return res
+
+
+def replica_checksum(head, group, world, device):
+    import torch.distributed as dist
+    flat = torch.cat([p.detach().reshape(-1) for p in head.parameters()] + [a.detach().reshape(-1) for a in head.arch_parameters()])
+    bits = flat.view(torch.int32).to(torch.int64)
+    sig = torch.stack([bits.sum(), (bits * torch.arange(1, bits.numel() + 1, device=device) % 1000003).sum()])
+    sigs = [torch.empty_like(sig) for _ in range(world)]
+    dist.all_gather(sigs, sig, group=group)
+    if not all(torch.equal(sigs[0], x) for x in sigs):
+        raise SystemExit('dp_check: replicas diverged (parameter checksums differ across ranks)')
+    return 'ok'
+
+
 def run_ours(args):
     import torch.distributed as dist
     from bmnas import native as N
-    from bmnas.nn import SearchHead, CrossEntropyLoss, BCEWithLogitsLoss
-    from bmnas.search import SearchStep
-    import types
     rank = int(os.environ.get('RANK', 0))
     local = int(os.environ.get('LOCAL_RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -340,24 +538,29 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=device)
         group = dist.group.WORLD
+    if args.gemm_mode is not None:
+        N.lib().bmnas_set_gemm_mode(args.gemm_mode)
     c = dict(CONFIGS[args.config])
     if args.batch:
         c['B'] = args.batch
+    gB = c['B'] * world if args.scaling == 'weak' else c['B']
+    if args.scaling == 'strong':
+        # SURVEY 8(d) config 3 / nn.DataParallel semantics (ntu_darts_searchable.py:50-51): the GLOBAL batch stays at
+        # the script's value and is chunked over the GPUs
+        if c['B'] % world:
+            raise SystemExit(f'--scaling strong: global batch {c["B"]} is not divisible by {world} GPUs')
+        c['B'] = c['B'] // world
     torch.manual_seed(2)                              # main_darts_searchable_ntu.py:17 (all ranks: identical replicas)
-    a = types.SimpleNamespace(**{k: c[k] for k in ('C', 'L', 'num_input_nodes', 'steps', 'multiplier', 'node_steps',
-                                                    'node_multiplier', 'drpt')}, weight_decay=c['weight_decay'])
-    crit = CrossEntropyLoss() if c['loss'] == 'ce' else BCEWithLogitsLoss()
-    head = SearchHead(a, c['classes'], criterion=crit).to(device)
-    from bmnas import runtime as rt
-    rt.SAMPLE_OFFSET[0] = rank * c['B']               # world-size-invariant dropout streams
-    ss = SearchStep(head, crit, c['B'], c['classes'], loss_kind=c['loss'], eta_max=c['eta_max'],
-                    weight_decay=c['weight_decay'], nbpe=400.0, use_graphs=not args.no_graphs, group=group)
+    head, ss = build_search(c, device, group=group, use_graphs=not args.no_graphs)
     # input pool larger than L2 so every step's inputs come from HBM
     per_batch = c['num_input_nodes'] * c['B'] * c['C'] * c['L'] * 4
     n_pool = max(4, int(1.3 * L2_BYTES / per_batch) + 1)
     n_pool += n_pool % 2
     pool = make_pool(c, n_pool, 100 + rank, device)
     ss.load('dev', *pool[0]); ss.load('train', *pool[1])
+    dp = None
+    if world > 1:
+        dp = dp_check(ss, head, group, world, rank, device)
     ss.prepare(warmup=3, restore=False)
     n_weights = sum(p.numel() for p in head.parameters())
     n_arch = sum(p.numel() for p in head.arch_parameters())
@@ -367,14 +570,20 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(K, loader, read_loss):
+    def timed(K, loader, read_loss, metrics_fwd=False):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         t0 = time.perf_counter()
         e0.record()
         for i in range(K):
             loader(i)
-            la, lw = ss.step()
+            if metrics_fwd:                       # the reference's dev phase: Architect.step, then a no-grad metrics forward
+                ss.half('dev')
+                ss.metrics_forward('dev')
+                lw = ss.half('train')
+                ss.steps_done += 1
+            else:
+                la, lw = ss.step()
             if read_loss:
                 lw_host = lw.item()               # device->host read of the step's result
         e1.record()
@@ -389,7 +598,15 @@ def run_ours(args):
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
-    dev_ms, wall = timed(args.steps, load_dev, read_loss=False)
+    # EXACTLY --steps steps per timed region; the region is repeated so that at least ~200 steps are inside timed regions
+    # in total and the spread is visible (a 20-step region is 13 ms)
+    reps = max(1, min(10, -(-200 // max(args.steps, 1))))
+    regions = [timed(args.steps, load_dev, read_loss=False)[0] for _ in range(reps)]
+    dev_ms = sorted(regions)[len(regions) // 2]
+    # full fidelity: + the dev-phase no-grad metrics forward of the reference loop (train_searchable/ntu.py:81-85)
+    ss.capture_metrics_forward('dev')
+    timed(max(3, args.warmup), load_dev, read_loss=False, metrics_fwd=True)
+    ff_ms, _ = timed(args.steps, load_dev, read_loss=False, metrics_fwd=True)
     # ---- end to end: pinned host inputs, H2D every step, D2H loss read every step
     hpool = make_pool(c, 8, 500 + rank, device, pinned=True)
 
@@ -414,13 +631,14 @@ def run_ours(args):
         barrier()
         return time.perf_counter() - t0
     timed_pipelined(max(3, args.warmup))
-    e2e_wall = timed_pipelined(args.steps)
+    e2e_wall = sorted(timed_pipelined(args.steps) for _ in range(min(reps, 5)))[min(reps, 5) // 2]
     clk = clocks.stop() if rank == 0 else None
-    t = torch.tensor([dev_ms, e2e_wall * 1e3, serial_wall * 1e3], device=device, dtype=torch.float64)
+    t = torch.tensor([dev_ms, e2e_wall * 1e3, serial_wall * 1e3, ff_ms], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms_wall, serial_ms_wall = t.tolist()
-    gB = c['B'] * world
+    dev_ms, e2e_ms_wall, serial_ms_wall, ff_ms = t.tolist()
+    if world > 1:
+        dp['replicas_after_timed_steps'] = replica_checksum(head, group, world, device)
     ms_per_step = dev_ms / args.steps
     value = gB / (ms_per_step * 1e-3)
     e2e_value = gB * args.steps / (e2e_ms_wall * 1e-3)
@@ -446,35 +664,56 @@ def run_ours(args):
             print('%s %3d %-18s %8.2f us  %s' % r)
     if rank == 0:
         pk = peaks()
-        roof = kernel_roofline(head, ss, c, pk)
-        big = None
+        roof = kernel_roofline(head, c, pk, c['B'])
+        big = big16 = None
+        extra = None
         if world == 1 and args.roofline_batch > 0:
             big = large_batch_roofline(args, c, pk, device, args.roofline_batch)
+            if args.gemm_mode is None:             # the same plan with bf16 operands in the fused MixedOp forward
+                N.lib().bmnas_set_gemm_mode(3)
+                try:
+                    big16 = large_batch_roofline(args, c, pk, device, args.roofline_batch)
+                finally:
+                    N.lib().bmnas_set_gemm_mode(1)
+        if world == 1 and not args.no_configs and args.config == 'ntu' and not args.batch:
+            extra = {}
+            for name in ('mmimdb', 'ego', 'ego_large'):
+                try:
+                    extra[name] = quick_value(name, device)
+                except Exception as e:
+                    extra[name] = {'error': repr(e)[:200]}
+            try:
+                extra['found_ntu'] = found_sweep(device)
+            except Exception as e:
+                extra['found_ntu'] = {'error': repr(e)[:200]}
         cpu = None
         if world == 1 and not args.no_cpu:
-            v, ms, cores, done = cpu_reference(args.config, 40, 3, max_seconds=20.0)
-            cpu = {'value': round(v, 1), 'unit': 'samples/s', 'cores': cores, 'kind': 'port', 'ms_per_step': round(ms, 2),
-                   'sample': f'{done} search steps of the same workload (B={c["B"]}) on the oracle port, '
-                             f'torch CPU fp32, {cores} threads'}
-            try:    # the same functional PyTorch code, eager on this GPU (reported next to the CPU number)
-                gv, gms, _, gdone = cpu_reference(args.config, 60, 3, max_seconds=10.0, device=str(device))
-                cpu['torch_eager_gpu'] = {'value': round(gv, 1), 'unit': 'samples/s', 'ms_per_step': round(gms, 3),
-                                          'sample': f'{gdone} search steps, eager PyTorch fp32 (TF32 off) on the same B200'}
-            except Exception as e:
-                cpu['torch_eager_gpu'] = {'unavailable': repr(e)[:200]}
+            r = reference_subprocess(args.config, 40, 3, 20.0, batch=c['B'])
+            if 'unavailable' in r:
+                cpu = r
+            else:
+                cpu = dict(r['cpu_baseline'], ms_per_step=r['ms_per_step'])
+                g = reference_subprocess(args.config, 60, 3, 10.0, device='cuda', batch=c['B'])
+                cpu['torch_eager_gpu'] = ({'value': g['value'], 'unit': 'samples/s', 'ms_per_step': g['ms_per_step'],
+                                           'sample': g['cpu_baseline']['sample']} if 'value' in g else g)
         out = {
-            'metric': 'search-step samples/sec (fwd+bwd+arch step, fwd+bwd+weight step)', 'value': round(value, 1),
+            'metric': METRIC, 'value': round(value, 1),
             'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': round(ms_per_step, 4), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'{args.config.upper()} fusion search step on synthetic frozen-backbone features, '
-                                   f'B={c["B"]} per GPU, C={c["C"]}, L={c["L"]}, n_in={c["num_input_nodes"]}, '
-                                   f'steps={c["steps"]}, node_steps={c["node_steps"]}, classes={c["classes"]}',
-                       'global_batch': gB, 'weights': n_weights, 'arch_scalars': n_arch,
-                       'parallelism': f'dp{world} (batch-sharded, one NCCL all-reduce of the flat grad arena per half step)',
-                       'cuda_graphs': not args.no_graphs,
+            'ms_per_step': round(ms_per_step, 4), 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
+            'dtype': 'f32' if N.lib().bmnas_get_gemm_mode() != 3 else 'f32 (bf16 operands in the fused MixedOp forward)',
+            'data': 'synthetic',
+            'config': {'workload': workload_string(args.config, c, gB),
+                       'global_batch': gB, 'per_gpu_batch': c['B'], 'weights': n_weights, 'arch_scalars': n_arch,
+                       'parallelism': f'dp{world} (batch-sharded; arch half: one NCCL all-reduce of the {n_arch}-float alpha/beta/gamma '
+                                      f'span, weight half: one of the weight-gradient span)',
+                       'cuda_graphs': not args.no_graphs, 'gemm_mode': mode_name(),
                        'l2_policy': f'inputs larger than L2: pool of {n_pool} distinct resident batches '
                                     f'({n_pool * per_batch / 2**20:.0f} MiB) rotated every step'},
+            'timed_regions': {'repeats': reps, 'steps_each': args.steps, 'ms_per_step_min': round(min(regions) / args.steps, 4),
+                              'ms_per_step_max': round(max(regions) / args.steps, 4), 'reported': 'median region'},
+            'value_full_fidelity': round(gB / (ff_ms / args.steps * 1e-3), 1),
+            'full_fidelity_how': 'arch half + no-grad train-mode metrics forward on the dev batch (train_searchable/ntu.py:81-85) + '
+                                 'weight half; device time',
             'e2e': {'value': round(e2e_value, 1), 'unit': 'samples/s',
                     'h2d_bytes_per_step': 2 * (per_batch + lab_bytes), 'd2h_bytes_per_step': 4,
                     'ms_per_step': round(e2e_ms_wall / args.steps, 4),
@@ -484,7 +723,8 @@ def run_ours(args):
                     'serial_how': 'SearchStep.load() + step() + loss.item(): copy, compute and read strictly in sequence'},
             'gpu_launches': (ss.launches_per_step or 0) * args.steps,
             'launches_per_step': ss.launches_per_step,
-            'roofline': roof, 'roofline_large_batch': big, 'cpu_baseline': cpu, 'clocks': clk,
+            'roofline': roof, 'roofline_large_batch': big, 'roofline_large_batch_bf16': big16, 'configs': extra,
+            'cpu_baseline': cpu, 'dp_check': dp, 'clocks': clk,
         }
         print(json.dumps(out), flush=True)
     if world > 1:
@@ -500,20 +740,30 @@ def run_ours(args):
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path (oracle/_ref driven by
+    oracle/ref_harness.py; the oracle port if that is absent) on all host cores, same config / metric / unit;
+    at N > 1 rank 0 alone runs it, on the GLOBAL batch of our arm."""
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
-    c = CONFIGS[args.config]
-    v, ms, cores, done = cpu_reference(args.config, max(args.steps, 1), max(args.warmup, 1), max_seconds=120.0)
+    c = dict(CONFIGS[args.config])
+    if args.batch:
+        c['B'] = args.batch
+    gB = c['B'] * max(args.gpus, 1) if args.scaling == 'weak' else c['B']
+    dev = args.ref_device
+    kind, v, ms, cores, done = reference_arm(args.config, max(args.steps, 1), max(args.warmup, 1), args.max_seconds,
+                                             device=dev, full_fidelity=args.full_fidelity, batch=gB)
+    what = ('reference modules (oracle/_ref: FusionNetwork + Architect + torch.optim.Adam + LRCosineAnnealingScheduler, unmodified)'
+            if kind == 'reference' else 'oracle port (oracle/_ref absent)')
+    where = f'torch CPU fp32, {cores} threads' if dev == 'cpu' else 'eager PyTorch fp32 (TF32 off) on the B200, alpha/beta/gamma left on the CPU as shipped'
+    sample = f'{done} search steps of the same workload (global batch {gB}) through the {what}; {where}'
     print(json.dumps({
-        'impl': 'reference', 'metric': 'search-step samples/sec (fwd+bwd+arch step, fwd+bwd+weight step)',
+        'impl': 'reference', 'metric': METRIC,
         'value': round(v, 1), 'unit': 'samples/s', 'n_gpus': args.gpus, 'steps': done, 'warmup': args.warmup,
-        'ms_per_step': round(ms, 3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'ms_per_step': round(ms, 3), 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'{args.config.upper()} fusion search step on synthetic frozen-backbone features, '
-                               f'B={c["B"]}, C={c["C"]}, L={c["L"]}', 'global_batch': c['B']},
-        'cpu_baseline': {'value': round(v, 1), 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
-                         'sample': f'{done} search steps on the oracle port (torch CPU fp32, {cores} threads)'},
+        'config': {'workload': workload_string(args.config, c, gB), 'global_batch': gB},
+        'cpu_baseline': {'value': round(v, 1), 'unit': 'samples/s', 'cores': cores, 'kind': kind, 'sample': sample},
         'e2e': {'value': round(v, 1), 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }), flush=True)
 
@@ -526,11 +776,18 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', default='ntu', choices=list(CONFIGS))
     ap.add_argument('--batch', type=int, default=0, help='per-GPU batch override')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak: the config batch per GPU; strong: the config batch is the GLOBAL batch (nn.DataParallel chunking)')
+    ap.add_argument('--gemm-mode', type=int, default=None, help='bmnas_set_gemm_mode: 1 = 3xTF32 (default), 3 = bf16 fused MixedOp forward')
     ap.add_argument('--no-graphs', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-configs', action='store_true', help='skip the other BASELINE configs (mmimdb, ego, ego_large, found sweep)')
     ap.add_argument('--profile-kernels', action='store_true')
     ap.add_argument('--roofline-batch', type=int, default=8192,
                     help='also time the kernels at this per-GPU batch (bandwidth-bound regime); 0 = skip')
+    ap.add_argument('--max-seconds', type=float, default=120.0, help='--impl reference: wall-clock bound of the timed loop')
+    ap.add_argument('--ref-device', default='cpu', help='--impl reference: cpu (the arm) or cuda (eager-GPU baseline)')
+    ap.add_argument('--full-fidelity', action='store_true', help='--impl reference: include the dev-phase metrics forward')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

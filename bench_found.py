@@ -51,17 +51,13 @@ def graph_ms(fn, steps, warm=3):
     return e0.elapsed_time(e1) / steps
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--batches', default='96,1024,8192,32768')
-    ap.add_argument('--steps', type=int, default=30)
-    args = ap.parse_args()
+def sweep(dev, batches, steps, emit=None):
     from bmnas.nn import SearchHead, CrossEntropyLoss
     from bmnas.optim import FusedAdam
-    dev = torch.device('cuda:0')
+    rows = {}
     a = types.SimpleNamespace(C=128, L=8, num_input_nodes=8, steps=2, multiplier=2, node_steps=2, node_multiplier=2,
                               drpt=0.2, weight_decay=1e-4)
-    for B in [int(b) for b in args.batches.split(',')]:
+    for B in batches:
         torch.manual_seed(2)
         crit = CrossEntropyLoss()
         head = SearchHead(a, 60, criterion=crit, genotype=golden_genotype()).to(dev)
@@ -76,20 +72,33 @@ def main():
             opt.step()
             return loss.detach()
         head.train()
-        t_train = graph_ms(train_step, args.steps)
+        t_train = graph_ms(train_step, steps)
         head.eval()
 
         def infer():
             with torch.no_grad():
                 return head(feats)
-        t_inf = graph_ms(infer, args.steps)
+        t_inf = graph_ms(infer, steps)
         n_w = sum(p.numel() for p in head.parameters())
-        print(json.dumps({'workload': 'found NTU fusion network (golden genotype), synthetic features', 'B': B,
-                          'weights': n_w, 'train_ms': round(t_train, 4), 'train_samples_per_s': round(B / t_train * 1e3, 1),
-                          'infer_ms': round(t_inf, 4), 'infer_samples_per_s': round(B / t_inf * 1e3, 1),
-                          'dtype': 'f32', 'cuda_graphs': True}), flush=True)
+        row = {'workload': 'found NTU fusion network (golden genotype), synthetic features', 'B': B,
+               'weights': n_w, 'train_ms': round(t_train, 4), 'train_samples_per_s': round(B / t_train * 1e3, 1),
+               'infer_ms': round(t_inf, 4), 'infer_samples_per_s': round(B / t_inf * 1e3, 1),
+               'dtype': 'f32', 'cuda_graphs': True}
+        rows[f'B{B}'] = row
+        if emit:
+            emit(row)
         del head, opt, feats
         torch.cuda.empty_cache()
+    return rows
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--batches', default='96,1024,8192,32768')
+    ap.add_argument('--steps', type=int, default=30)
+    args = ap.parse_args()
+    sweep(torch.device('cuda:0'), [int(b) for b in args.batches.split(',')], args.steps,
+          emit=lambda row: print(json.dumps(row), flush=True))
 
 
 if __name__ == '__main__':

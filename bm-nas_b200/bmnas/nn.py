@@ -38,7 +38,7 @@ def _lin_ok(x, weight):
 
 class _LinearFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, gw_view, gb_view):
+    def forward(ctx, x, weight, bias, gw_view, gb_view, arena=None):
         B, Kc = x.shape
         Nc = weight.shape[0]
         s = N.current_stream()
@@ -58,6 +58,15 @@ class _LinearFn(torch.autograd.Function):
         ctx.save_for_backward(x, weight)
         ctx.views = (gw_view, gb_view)
         ctx.has_bias = bias is not None
+        # autograd accumulate semantics outside runtime.STATIC_IO: parameters whose arena view already holds an unconsumed
+        # gradient get it added back after this backward overwrote the view
+        ctx.pending = []
+        if arena is not None and not _rt.STATIC_IO[0]:
+            for t, v in ((weight, gw_view), (bias, gb_view)):
+                if t is not None and v is not None:
+                    if id(t) in arena.dirty and t.grad is not None and t.grad.data_ptr() == v.data_ptr():
+                        ctx.pending.append(v)
+                    arena.dirty.add(id(t))
         return out
 
     @staticmethod
@@ -65,6 +74,17 @@ class _LinearFn(torch.autograd.Function):
         x, weight = ctx.saved_tensors
         gw_view, gb_view = ctx.views
         g = g.contiguous()
+        if ctx.pending:
+            saved = [v.clone() for v in ctx.pending]
+            res = _LinearFn._backward(ctx, g, x, weight, gw_view, gb_view)
+            _prog.join_side(x.device)
+            for v, old in zip(ctx.pending, saved):
+                v.add_(old)
+            return res
+        return _LinearFn._backward(ctx, g, x, weight, gw_view, gb_view)
+
+    @staticmethod
+    def _backward(ctx, g, x, weight, gw_view, gb_view):
         B, Kc = x.shape
         Nc = weight.shape[0]
         s = N.current_stream()
@@ -100,7 +120,7 @@ class _LinearFn(torch.autograd.Function):
                     N.launch('bmnas_linear_bwd', ctypes.byref(st), ctypes.c_void_p(side.cuda_stream))
                 else:
                     N.launch('bmnas_linear_bwd', ctypes.byref(st), s)
-            return gx, None, None, None, None
+            return gx, None, None, None, None, None
         if ctx.needs_input_grad[0]:
             gx = torch.empty_like(x)
             st = _conv_struct(1, Kc, Nc, B)   # gx[b][l] = sum_class g[b][class] * W[class][l]
@@ -116,7 +136,7 @@ class _LinearFn(torch.autograd.Function):
             N.launch('bmnas_conv_dgrad', ctypes.byref(st), s)
         if gb_view is not None:
             N.launch('bmnas_colsum', ctypes.c_void_p(gb_view.data_ptr()), ctypes.c_void_p(g.data_ptr()), B, Nc, s)
-        return gx, None, None, None, None
+        return gx, None, None, None, None, None
 
 
 def _assign_grad(t, view):
@@ -138,12 +158,12 @@ class Linear(nn.Linear):
         x = x if x.is_contiguous() else x.contiguous()
         all_leaves = [p for p in (self.weight, self.bias) if p is not None and p.requires_grad]
         leaves = _rt.filter_leaves(all_leaves)       # runtime.GRAD_MODE 'arch': the classifier's dW / db are not produced
-        gw = gb = None
+        gw = gb = ar = None
         if leaves and torch.is_grad_enabled():
             ar = _rt.arena_for(self, all_leaves, x.device)
             gw = ar.view(self.weight) if self.weight.requires_grad else None
             gb = ar.view(self.bias) if (self.bias is not None and self.bias.requires_grad) else None
-        out = _LinearFn.apply(x, self.weight, self.bias, gw, gb)
+        out = _LinearFn.apply(x, self.weight, self.bias, gw, gb, ar)
         if gw is not None or gb is not None:
             w, b = self.weight, self.bias
 

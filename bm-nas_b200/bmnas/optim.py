@@ -111,7 +111,12 @@ class FusedAdam(torch.optim.Optimizer):
             p.counter = st['counter'].data_ptr()
             s = s or N.current_stream()
             N.launch('bmnas_adam_step', ctypes.byref(p), s)
+        self._clear_dirty()
         return loss
+
+    def _clear_dirty(self):
+        from . import runtime as _rt
+        _rt.clear_dirty([p for g in self.param_groups for p in g['params']])
 
     # -------------------------------------------------------------- state (checkpoint / warm-up restore)
     def state_snapshot(self):
@@ -158,5 +163,7 @@ class FusedAdam(torch.optim.Optimizer):
                     del fused[gi]
 
     def zero_grad(self, set_to_none=True):
-        """Gradients live in a static arena that every backward overwrites: nothing to clear."""
+        """Gradients live in a static arena; the next backward into these parameters starts from zero again (the
+        arena's dirty marks are dropped -- no memset needed, every plan zeroes its span before it accumulates)."""
+        self._clear_dirty()
         return None

@@ -498,7 +498,7 @@ class Program:
             alias = True
         elif segs:
             cv = self.conv([x] if alias else [x, y], [C] if alias else [C, C], segs, 2 if alias else 1, bn=True,
-                           emit=not fused, fwd_fmt=0 if fused else None, want_Z=(self.want_backward or not fused))
+                           emit=not fused, fwd_fmt=(2 if N.lib().bmnas_get_gemm_mode() == 3 else 0) if fused else None, want_Z=(self.want_backward or not fused))
         M = cv['M'] if cv else 0
 
         def fill(st):

@@ -17,6 +17,33 @@ from . import native as N
 from .program import Program, Slot
 
 
+import weakref
+
+# Plain module use (model(x); loss.backward(); several losses / micro-batches before one optimizer.step()) gets autograd's
+# semantics: gradients ACCUMULATE across backward passes until zero_grad()/step(), and outputs / input gradients are fresh
+# tensors.  SearchStep (and anything else that owns the whole step) switches to STATIC_IO: outputs and input gradients
+# are views of the plan's static buffers and every backward overwrites the arena -- what the captured graphs need and what
+# the reference loop's zero_grad-before-every-backward amounts to (train_searchable/ntu.py:77, architect.py:22).
+STATIC_IO = [False]
+_ARENAS = weakref.WeakSet()
+
+
+class static_io:
+    def __enter__(self):
+        self.prev = STATIC_IO[0]
+        STATIC_IO[0] = True
+
+    def __exit__(self, *a):
+        STATIC_IO[0] = self.prev
+
+
+def clear_dirty(tensors):
+    """optimizer.step() / zero_grad(): the next backward into these leaves starts from zero again"""
+    ids = {id(t) for t in tensors}
+    for ar in list(_ARENAS):
+        ar.dirty -= ids
+
+
 SAMPLE_OFFSET = [0]      # global index of this rank's first sample (world-size-invariant dropout streams)
 
 # Which leaf gradients the next launch plans produce.  'all' (default, plain autograd use of the modules): every
@@ -64,6 +91,8 @@ class GradArena:
         self.flat = torch.zeros(max(off, 4), dtype=torch.float32, device=device)
         self.views = {id(t): self.flat[o:o + n].view(t.shape) for t, (o, n) in
                       ((t, self.offsets[id(t)]) for t in self.tensors)}
+        self.dirty = set()       # ids of leaves whose arena view holds a gradient not yet consumed by step()/zero_grad()
+        _ARENAS.add(self)
 
     def view(self, t):
         return self.views.get(id(t))
@@ -121,18 +150,27 @@ class Runner:
             raise RuntimeError('bmnas: stale activation workspace -- another forward of the same module/shape ran '
                                'before this backward (activations live in a static per-shape workspace)')
         p.bind('gout', gout)
+        static = STATIC_IO[0]
+        # autograd semantics outside STATIC_IO: a leaf that already holds an unconsumed gradient in the arena accumulates
+        pending = [] if static else [t for t in self.leaves if t.grad is not None and id(t) in self.arena.dirty
+                                     and t.grad.data_ptr() == self.arena.view(t).data_ptr()]
+        saved = [t.grad.clone() for t in pending]
         p.run_backward()
+        for t, old in zip(pending, saved):
+            t.grad.add_(old)
         for t in self.leaves:
             v = self.arena.view(t)
             if t.grad is None:
                 t.grad = v
             elif t.grad.data_ptr() != v.data_ptr():
                 t.grad.add_(v)
+            self.arena.dirty.add(id(t))
         outs = []
         for name, need in zip(self.in_slots, self.in_need):
             g = p._grads.get(name) if need else None
             # inputs the (found) genotype never reads get no gradient
-            outs.append(g.detach() if (g is not None and g.data_ptr() in p._written) else None)
+            ok = g is not None and g.data_ptr() in p._written
+            outs.append((g.detach() if static else g.detach().clone()) if ok else None)
         return outs
 
 
@@ -146,7 +184,8 @@ class _ProgFn(torch.autograd.Function):
         ctx.n_in = n_in
         ctx.n_rest = len(tensors) - n_in
         ctx.save_for_backward(*inputs)      # keep the bound input pointers alive until backward
-        return out.detach()                 # fresh tensor object over the static output buffer
+        # STATIC_IO: a fresh tensor object over the static output buffer; otherwise a copy the caller may keep
+        return out.detach() if STATIC_IO[0] else out.detach().clone()
 
     @staticmethod
     def backward(ctx, gout):
@@ -211,7 +250,8 @@ def run(root, kind, inputs, build, leaves, C, L, drpt, key_extra=(), masks=None,
     if any(t.requires_grad for t in inputs) or leaves:
         if grad_on:
             return _ProgFn.apply(runner, masks, len(inputs), *inputs, *leaves)
-    return runner.forward(inputs, masks).detach()
+    out = runner.forward(inputs, masks).detach()
+    return out if STATIC_IO[0] else out.clone()
 
 
 class _GradViews:

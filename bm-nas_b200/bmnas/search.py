@@ -78,7 +78,7 @@ class SearchStep:
         from . import runtime as _rt
         head = self.head
         mode = ('arch' if which == 'dev' else 'weights') if self.prune_grads else 'all'
-        with _rt.grad_mode(mode):
+        with _rt.grad_mode(mode), _rt.static_io():
             loss = self.criterion(head(self.feats[which]), self.labels[which])
             loss.backward()
         self.allreduce_grads(which)
@@ -246,7 +246,8 @@ class SearchStep:
         if g is not None:
             g.replay()
             return self._metrics[which]
-        with torch.no_grad():
+        from . import runtime as _rt
+        with torch.no_grad(), _rt.static_io():
             logits = self.head(self.feats[which])
             loss = self.criterion(logits, self.labels[which])
         return loss, logits

@@ -13,6 +13,7 @@
 // extent of both operands staged in shared memory with one burst of independent
 // 128-bit loads (one DRAM/L2 round trip, up to 384 reduction rows per pass), then a
 // dependency-free FFMA loop (4x2 register micro-tile, 128 threads).
+#include <cstdlib>
 #include "common.cuh"
 #include "gemm_shared.cuh"
 
@@ -450,10 +451,12 @@ bool sgw_eligible(const bmnas_conv_params* p);
 int sg_conv_wgrad(const bmnas_conv_params* p, cudaStream_t stream);
 }  // namespace bmnas
 
-// GEMM engine: 0 = fp32 FFMA tiles, 1 = tcgen05 3xTF32 (fp32-class accuracy), 2 = tcgen05 1xTF32 (reduced precision)
+// GEMM engine: 0 = fp32 FFMA tiles, 1 = tcgen05 3xTF32 (fp32-class accuracy), 2 = tcgen05 1xTF32 (reduced precision),
+// 3 = as 1, but the fused NodeMixedOp forward (mixed_tc.cu) stages bf16 operands (kind::f16, fp32 accumulation)
 int bmnas_gemm_mode_flag = 1;
+static inline bool gemm_x3() { return bmnas_gemm_mode_flag == 1 || bmnas_gemm_mode_flag == 3; }
 extern "C" int bmnas_set_gemm_mode(int mode) {
-    if (mode < 0 || mode > 2) return BMNAS_EINVAL;
+    if (mode < 0 || mode > 3) return BMNAS_EINVAL;
     bmnas_gemm_mode_flag = mode;
     return BMNAS_OK;
 }
@@ -467,7 +470,16 @@ extern "C" int bmnas_conv_image_fmt(int B, int L, int K, int M) {
     const long long N = (long long)B * L;
     const bool sg_ok = (L & (L - 1)) == 0 && L <= 32;      // gemm_sg.cu: a 32-column tile is 32 / L whole samples
     if (bmnas_gemm_mode_flag == 0) return sg_ok ? 1 : -1;
-    return (sg_ok && N <= 4096) ? 1 : 0;
+    // by the GEMM's work, not by its column count alone: the small-N cp.async FFMA engine wins while the problem is
+    // latency bound (NTU B=96: 768 x 384 x 128 = 38 M MACs), the tensor cores once there is arithmetic to amortise
+    // their pipeline -- Ego-large (C=256, L=16, B=96: 1536 columns but 768 x 256 weights, 302 M MACs) belongs there.
+    // BMNAS_TC_MIN_MACS overrides the crossover (measured: profiles/r02_*_engine_crossover.txt).
+    static long long min_macs = -1;
+    if (min_macs < 0) {
+        const char* e = getenv("BMNAS_TC_MIN_MACS");
+        min_macs = e ? atoll(e) : 200000000LL;
+    }
+    return (sg_ok && N * (long long)M * K <= min_macs) ? 1 : 0;
 }
 
 extern "C" long long bmnas_conv_stat_part_size(const bmnas_conv_params* p) {
@@ -511,7 +523,7 @@ extern "C" int bmnas_conv_fwd(const bmnas_conv_params* p, void* stream) {
         q_.wimg_fwd = q_.wimg_dgrad = nullptr;
         p = &q_;
     }
-    if (bmnas_gemm_mode_flag && tc_eligible(p, 0)) return tc_conv_fwd(p, bmnas_gemm_mode_flag == 1, (cudaStream_t)stream);
+    if (bmnas_gemm_mode_flag && tc_eligible(p, 0)) return tc_conv_fwd(p, gemm_x3(), (cudaStream_t)stream);
     const int N = p->B * p->L;
     const int KC = min(KC_MAX, round_up(p->K, 4));
     const bool vec = conv_vec_ok(p, false);
@@ -543,7 +555,7 @@ extern "C" int bmnas_conv_dgrad(const bmnas_conv_params* p, void* stream) {
         q_.wimg_fwd = q_.wimg_dgrad = nullptr;
         p = &q_;
     }
-    if (bmnas_gemm_mode_flag && tc_eligible(p, 1)) return tc_conv_dgrad(p, bmnas_gemm_mode_flag == 1, (cudaStream_t)stream);
+    if (bmnas_gemm_mode_flag && tc_eligible(p, 1)) return tc_conv_dgrad(p, gemm_x3(), (cudaStream_t)stream);
     const int N = p->B * p->L;
     const int KC = min(KC_MAX, round_up(p->M, 4));
     bool vec = (p->L & 3) == 0 && (p->K & 3) == 0 && gal16(p->GV) && (!p->coef_a || gal16(p->Z));
@@ -576,7 +588,7 @@ extern "C" int bmnas_conv_wgrad(const bmnas_conv_params* p, void* stream) {
     const long long Ncols = (long long)p->B * p->L;
     const bool tc_ok = bmnas_gemm_mode_flag && tc_eligible(p, 2);
     if (bmnas_gemm_mode_flag != 2 && sgw_eligible(p) && (Ncols <= 2560 || !tc_ok)) return sg_conv_wgrad(p, (cudaStream_t)stream);
-    if (bmnas_gemm_mode_flag && tc_eligible(p, 2)) return tc_conv_wgrad(p, bmnas_gemm_mode_flag == 1, (cudaStream_t)stream);
+    if (bmnas_gemm_mode_flag && tc_eligible(p, 2)) return tc_conv_wgrad(p, gemm_x3(), (cudaStream_t)stream);
     const int N = p->B * p->L, L = p->L;
     const int tiles = ((p->K + TN - 1) / TN) * ((p->M + TM - 1) / TM);
     bool vec = (L & 3) == 0 && L <= KC_MAX && gal16(p->GV) && (!p->coef_a || gal16(p->Z));

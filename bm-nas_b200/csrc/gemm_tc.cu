@@ -945,6 +945,32 @@ __global__ void __launch_bounds__(256) k_wprep(const bmnas_wprep_params p) {
         (void)KT32;
         return;
     }
+    if (p.fmt[i] == 2) {
+        // bf16 forward image for the fused mixed-op kernel: slab (row tile, 64-element k slab) = 128 rows x 128 bytes,
+        // SWIZZLE_128B K-major; one work item = one 16-byte chunk (8 bf16 along k).  No dgrad image in this format.
+        const int KS64 = (K + 63) / 64, RT = (M + TCM - 1) / TCM;
+        if (ql >= (long long)RT * KS64 * 1024 || !p.img_fwd[i]) return;
+        const long long slab = ql >> 10;
+        const int w = (int)(ql & 1023), rt = (int)(slab / KS64), ks = (int)(slab % KS64);
+        const int r8 = w & 7, kc = (w >> 3) & 7, rg = w >> 6;
+        const int m = rt * TCM + rg * 8 + r8, k = ks * 64 + kc * 8;
+        float e[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            e[j] = 0.f;
+            if (m < M && k + j < K) {
+                const float* r = wrow(m) + k + j;
+                e[j] = __ldg(r);
+                if (fold == 2) e[j] += __ldg(r + K);
+            }
+        }
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk[j]) : "f"(e[2 * j + 1]), "f"(e[2 * j]));
+        uint8_t* dst8 = reinterpret_cast<uint8_t*>(p.img_fwd[i]) + slab * (TCM * 128) + sw_off(rg * 8 + r8, kc);
+        *reinterpret_cast<uint4*>(dst8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        return;
+    }
     const int KSf = (K + KC - 1) / KC, RTf = (M + TCM - 1) / TCM;
     const long long nf = (long long)RTf * KSf * 1024;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1082,13 +1108,14 @@ using namespace bmnas;
 
 extern "C" long long bmnas_wimg_floats(int M, int K, int which);
 extern "C" long long bmnas_wimg_floats_fmt(int M, int K, int which, int fmt) {
+    if (fmt == 2) return which == 0 ? (long long)((M + tc::TCM - 1) / tc::TCM) * ((K + 63) / 64) * (tc::TCM * 128 / 4) : 0;
     if (fmt == 1) return which == 0 ? (long long)((M + 31) / 32) * K * 32 : (long long)((K + 31) / 32) * M * 32;
     return bmnas_wimg_floats(M, K, which);
 }
 
 extern "C" long long bmnas_wprep_items(int M, int K, int fmt) {
     const long long f = bmnas_wimg_floats_fmt(M, K, 0, fmt) + bmnas_wimg_floats_fmt(M, K, 1, fmt);
-    return fmt == 1 ? f / 4 : f / 8;      // one work item = one 16-byte chunk of output (fmt 0: hi and lo)
+    return fmt == 0 ? f / 8 : f / 4;      // one work item = one 16-byte chunk of output (fmt 0: hi and lo)
 }
 
 extern "C" long long bmnas_wimg_floats(int M, int K, int which) {
@@ -1111,7 +1138,7 @@ extern "C" int bmnas_wprep(const bmnas_wprep_params* p, void* stream) {
         }
         if (m != p->M[i]) return BMNAS_EINVAL;
         if (p->q_start[i] != q) return BMNAS_EINVAL;
-        if (p->fmt[i] != 0 && p->fmt[i] != 1) return BMNAS_EINVAL;
+        if (p->fmt[i] < 0 || p->fmt[i] > 2 || (p->fmt[i] == 2 && !p->img_fwd[i])) return BMNAS_EINVAL;
         q += bmnas_wprep_items(p->M[i], p->K[i], p->fmt[i]);
     }
     if (p->q_start[p->n] != q) return BMNAS_EINVAL;

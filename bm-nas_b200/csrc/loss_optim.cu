@@ -24,12 +24,17 @@ __global__ void __launch_bounds__(OTH) k_loss_fwd(const bmnas_loss_params p) {
             float s = 0.f;
             for (int j = lane; j < n; j += 32) s += expf(x[j] - mx);
             s = warp_sum(s);
-            const int lab = (int)p.labels[b];
+            const long long lab64 = p.labels[b];
+            // a label outside [0, n_classes) (ignore_index = -100, corrupt data) must not become an out-of-bounds read and a
+            // silently wrong loss: the loss turns NaN (torch asserts on the device; a captured graph cannot) and the row's
+            // gradient is NaN too, so the first optimiser step makes the failure visible
+            const bool bad = lab64 < 0 || lab64 >= (long long)n;
+            const int lab = bad ? 0 : (int)lab64;
             const float lse = mx + logf(s);
-            if (lane == 0) lsum[0] += lse - x[lab];
+            if (lane == 0) lsum[0] += bad ? __int_as_float(0x7fc00000) : lse - x[lab];
             const float inv = 1.f / s;
             for (int j = lane; j < n; j += 32)
-                p.glogits[(long long)b * n + j] = (expf(x[j] - mx) * inv - (j == lab ? 1.f : 0.f)) * invB;
+                p.glogits[(long long)b * n + j] = bad ? __int_as_float(0x7fc00000) : (expf(x[j] - mx) * inv - (j == lab ? 1.f : 0.f)) * invB;
         }
     } else {
         const long long tot = (long long)p.B * n;

@@ -42,9 +42,13 @@ constexpr int CT = 128;             // channels: K of the folded conv and rows o
 constexpr int NT = 64;              // columns per tile
 constexpr int MT = 3;               // Z row tiles
 constexpr int NPROD = 128;          // producer threads
-constexpr int NEPI = 256;           // epilogue threads
-constexpr int W_MMA = 12, W_TMA = 13;
-constexpr int THREADS = 14 * 32;
+// column groups of a tile, one per epilogue warp quartet.  Measured (B=8192, 3xTF32): NQ = 2 (8 epilogue warps, 128
+// registers) 176 us; NQ = 4 (16 warps, capped at 80 registers, 328 B of spills in the epilogue) 219 us -- kept at 2
+constexpr int NQ = 2;
+constexpr int CW = NT / NQ;         // columns per epilogue thread
+constexpr int NEPI = 128 * NQ;      // epilogue threads
+constexpr int W_MMA = 4 + 4 * NQ, W_TMA = W_MMA + 1;
+constexpr int THREADS = (W_TMA + 1) * 32;
 constexpr uint32_t TBUF = 256;      // TMEM columns per accumulator set: Z0 | Z1 | Z2 | Gram
 constexpr int MAXL = 16;
 
@@ -66,9 +70,18 @@ struct Ws {                          // per-(conv, node) workspace, zeroed once 
     unsigned int bar_count;
     unsigned int bar_gen;
     unsigned int epoch;
-    unsigned int pad;
+    unsigned int timeline;           // test hook: != 0 -> CTA 0 records %globaltimer stamps into tl[]
     double acc[2][MT * CT][2];       // [epoch parity][row][sum, sum of squares]
+    unsigned long long tl[16];
 };
+#define MX_TL(i)                                                        \
+    do {                                                                \
+        if (tl_on) {                                                    \
+            unsigned long long t__;                                     \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));     \
+            ws->tl[i] = t__;                                            \
+        }                                                               \
+    } while (0)
 
 struct Ops {                         // host-resolved op list (canonical order Sum < Attn < GLU < FC)
     int k_sum, k_attn, k_glu, k_fc, fc_mish;
@@ -80,10 +93,14 @@ struct Shared {
     uint32_t epoch;
     float gw[BMNAS_MAX_OPS];
     float rs[MT * CT], mr[MT * CT], bw[MT * CT], bb[MT * CT], bias[MT * CT];
-    float P[NT * MAXL];              // softmax(QK^T / sqrt C) rows of the tile's samples
-    float G[NT * 33];                // Gram window staging (row n, 32 columns of its warp's window)
-    float red[8][16];                // LayerNorm partial sums: [epilogue warp][sample slot]
-    float4 hst[MT][CT];              // column-half exchange of the Welford triples
+    float red[4 * NQ][16];           // LayerNorm partial sums: [epilogue warp][sample slot | 8 + sample slot]
+    union {                          // pass 2 | end of pass 1 (separated by epilogue-wide barriers)
+        struct {
+            alignas(16) float P[NT * MAXL];      // softmax(QK^T / sqrt C) rows of the tile's samples
+            float G[NT * (CW + 1)];              // Gram window staging (row n, the CW columns of its own group)
+        } a;
+        float4 hst[NQ - 1][MT][CT];  // column-group exchange of the Welford triples
+    } u;
 };
 
 // ---- work list shared by all roles: item i of this CTA (T tiles, two_pass = train-mode BatchNorm)
@@ -107,7 +124,82 @@ __device__ __forceinline__ Item item_at(int i, int T, bool two_pass, bool has_at
     return w;
 }
 
-__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory"); }
+// the four epilogue warps that share a column group (128 threads): named barriers 2 .. 2 + NQ - 1
+__device__ __forceinline__ void half_sync(int h) { asm volatile("bar.sync %0, 128;" ::"r"(2 + h) : "memory"); }
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+// tcgen05.ld without the wait: issue several, then one tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// NW consecutive fp32 columns of this thread's TMEM lane, NW in {4, 8, 16}
+template <int NW>
+__device__ __forceinline__ void tmem_ld_nowait(uint32_t taddr, float (&v)[NW]) {
+    uint32_t r[NW];
+    if (NW == 4) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+    } else if (NW == 8) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4 % NW]), "=r"(r[5 % NW]), "=r"(r[6 % NW]), "=r"(r[7 % NW])
+                     : "r"(taddr));
+    } else {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4 % NW]), "=r"(r[5 % NW]), "=r"(r[6 % NW]), "=r"(r[7 % NW]),
+              "=r"(r[8 % NW]), "=r"(r[9 % NW]), "=r"(r[10 % NW]), "=r"(r[11 % NW]), "=r"(r[12 % NW]), "=r"(r[13 % NW]), "=r"(r[14 % NW]),
+              "=r"(r[15 % NW])
+            : "r"(taddr));
+    }
+#pragma unroll
+    for (int i = 0; i < NW; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <int NW>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[NW]) {
+    if constexpr (NW == 32) {
+        float a[16], b[16];
+        tmem_ld_nowait<16>(taddr, a);
+        tmem_ld_nowait<16>(taddr + 16, b);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            v[i] = a[i];
+            v[16 + i] = b[i];
+        }
+    } else {
+        tmem_ld_nowait<NW>(taddr, v);
+        tmem_ld_wait();
+    }
+}
+template <int NW>
+__device__ __forceinline__ void tmem_st(uint32_t taddr, const float (&v)[NW]) {
+    uint32_t r[NW];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) r[i] = __float_as_uint(v[i]);
+    if (NW == 4) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3])
+                     : "memory");
+    } else if (NW == 8) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                     "r"(r[2]), "r"(r[3]), "r"(r[4 % NW]), "r"(r[5 % NW]), "r"(r[6 % NW]), "r"(r[7 % NW])
+                     : "memory");
+    } else {
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+            "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4 % NW]), "r"(r[5 % NW]), "r"(r[6 % NW]), "r"(r[7 % NW]), "r"(r[8 % NW]),
+            "r"(r[9 % NW]), "r"(r[10 % NW]), "r"(r[11 % NW]), "r"(r[12 % NW]), "r"(r[13 % NW]), "r"(r[14 % NW]), "r"(r[15 % NW])
+            : "memory");
+    }
+}
 
 // 32 lanes x 32 consecutive fp32 columns
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
@@ -119,6 +211,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
         v[i] = a[i];
         v[16 + i] = b[i];
     }
+}
+
+// t[b, c, 0..L) of one sample for this thread's channel (zeros past the batch end)
+template <int L>
+__device__ __forceinline__ void load_xrow(const float* x, long long b, int B, int c, float4 (&r)[L / 4]) {
+    const float4* xp = reinterpret_cast<const float4*>(x + (b * CT + c) * L);
+#pragma unroll
+    for (int j4 = 0; j4 < L / 4; ++j4) r[j4] = b < B ? __ldg(xp + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 struct Drop {                        // one dropout site (same decision as drop_v / philox_keep in the node kernels)
@@ -196,6 +296,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_mixed_fwd(const bmnas_conv_param
     __shared__ Shared sh;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool tl_on = ws->timeline != 0 && blockIdx.x == 0 && lane == 0;
+    if (tid == 0) MX_TL(0);
     const int B = cv.B;
     const int G_ = (int)gridDim.x;
     const int T = (n_tiles - (int)blockIdx.x + G_ - 1) / G_;           // tiles of this CTA (>= 1: grid <= n_tiles)
@@ -260,6 +362,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_mixed_fwd(const bmnas_conv_param
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = sh.tmem_base;
+    if (tid == 0) MX_TL(1);
 
     // number of MMA items and the local tile of MMA item m (pass 1: tiles 0..T-1, pass 2: tiles T-3 .. 0)
     const int n_mma = two_pass ? T + max(T - 2, 0) : T;
@@ -310,6 +413,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_mixed_fwd(const bmnas_conv_param
             }
             fence_proxy_async();                                  // generic-proxy writes -> visible to the tensor core
             mbar_arrive(&sh.b_full[stage]);
+            if (tid == 0 && it == 0) MX_TL(2);
+            if (tid == 0 && it == total - 1) MX_TL(3);
 #pragma unroll
             for (int j = 0; j < RK; ++j) cur[j] = nxt[j];
         }
@@ -359,6 +464,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_mixed_fwd(const bmnas_conv_param
                 const uint32_t stage = itb % CF::NB;
                 mbar_wait(&sh.b_full[stage], (itb / CF::NB) & 1u);
                 tc_fence_after();
+                if (itb == 0) MX_TL(4);
                 const uint32_t b_hi = s32(smB + (size_t)stage * CF::B_ST), b_lo = b_hi + CF::B_HALF;
                 if (gram && leader) {                            // G += t^T t: the activation stage is both operands
 #pragma unroll
@@ -403,16 +509,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_mixed_fwd(const bmnas_conv_param
             }
             if (leader) umma_commit(&sh.t_full[buf]);
             __syncwarp();
+            if (m == 0) MX_TL(5);
         }
     } else {
         // =============================================================== epilogue warps
-        const int e = tid - NPROD;                  // 0..255
-        const int we = e >> 5;                      // epilogue warp 0..7
+        const int e = tid - NPROD;                  // 0..NEPI-1
+        const int we = e >> 5;                      // epilogue warp 0..4*NQ-1
         const int lq = warp & 3;                    // TMEM lane quarter this warp may read
-        const int h = we >> 2;                      // which 32 of the tile's 64 columns
+        const int h = we >> 2;                      // column group: columns [h * CW, (h + 1) * CW) of the tile
         const int c = lq * 32 + lane;               // output channel = TMEM lane
         const uint32_t lane_addr = (uint32_t)(lq * 32) << 16;
-        constexpr int SH = 32 / L;                  // samples per column half
+        constexpr int SH = CW / L;                  // samples per column group
         constexpr int CL = CT * L;
         uint32_t fc0 = 0, fc1 = 0;                  // t_full completions consumed per accumulator set
         Wf run[MT] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
@@ -422,30 +529,32 @@ __global__ void __launch_bounds__(THREADS, 1) k_mixed_fwd(const bmnas_conv_param
         const float inv_sqrt_c = 1.f / sqrtf((float)CT);
         const float bias0 = sh.bias[c], bias1 = sh.bias[CT + c], bias2 = sh.bias[2 * CT + c];
 
+
         for (int i = 0; i < n_items; ++i) {
             const Item w = item_at(i, T, two_pass, has_attn);
             const int buf = w.t & 1;
             const int tile = (int)blockIdx.x + w.t * G_;
-            const int col0 = tile * NT + h * 32;                   // first global column of this thread's half
+            const int col0 = tile * NT + h * CW;                   // first global column of this thread's group
             if (w.mma) {
                 const uint32_t f = buf ? fc1 : fc0;
                 mbar_wait(&sh.t_full[buf], f & 1u);
                 if (buf) ++fc1; else ++fc0;
                 tc_fence_after();
+                if (e == 0 && i == 0) MX_TL(6);
             }
             const uint32_t tz = tmem_base + (uint32_t)buf * TBUF + lane_addr;
 
             if (w.pass1) {
                 // ---- BatchNorm statistics of rows c, C + c, 2C + c over this thread's 32 columns
-                const int nv = max(0, min(32, N - col0));           // valid columns (N % 4 == 0)
+                const int nv = max(0, min(CW, N - col0));           // valid columns (N % 4 == 0)
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
-                    float v[32];
-                    tmem_ld32(tz + (uint32_t)(mt * NT + h * 32), v);
+                    float v[CW];
+                    tmem_ld<CW>(tz + (uint32_t)(mt * NT + h * CW), v);
                     const float bs = mt == 0 ? bias0 : mt == 1 ? bias1 : bias2;
                     float s = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
+                    for (int j = 0; j < CW; ++j) {
                         v[j] += bs;
                         if (j < nv) s += v[j];
                     }
@@ -453,7 +562,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_mixed_fwd(const bmnas_conv_param
                         const float mean = s / (float)nv;
                         float m2 = 0.f;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
+                        for (int j = 0; j < CW; ++j) {
                             const float d = v[j] - mean;
                             if (j < nv) m2 = fmaf(d, d, m2);
                         }
@@ -467,18 +576,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_mixed_fwd(const bmnas_conv_param
                 }
                 if (i == T - 1) {
                     // ---- end of pass 1: CTA totals -> fp64 atomics -> grid barrier -> mean / rstd
-                    if (h == 1) {
+                    if (h > 0) {
 #pragma unroll
-                        for (int mt = 0; mt < MT; ++mt) sh.hst[mt][c] = make_float4(run[mt].n, run[mt].mean, run[mt].m2, 0.f);
+                        for (int mt = 0; mt < MT; ++mt) sh.u.hst[h - 1][mt][c] = make_float4(run[mt].n, run[mt].mean, run[mt].m2, 0.f);
                     }
                     epi_sync();
                     double* acc = &ws->acc[sh.epoch & 1u][0][0];
                     if (h == 0) {
 #pragma unroll
                         for (int mt = 0; mt < MT; ++mt) {
-                            const float4 o = sh.hst[mt][c];
-                            const Wf b = {o.x, o.y, o.z};
-                            const Wf t = wf_merge(run[mt], b);
+                            Wf t = run[mt];
+#pragma unroll
+                            for (int q = 0; q < NQ - 1; ++q) {      // fixed merge order: deterministic
+                                const float4 o = sh.u.hst[q][mt][c];
+                                const Wf b = {o.x, o.y, o.z};
+                                t = wf_merge(t, b);
+                            }
                             const double mu = (double)t.mean, n = (double)t.n;
                             atomicAdd(acc + 2 * (mt * CT + c), n * mu);
                             atomicAdd(acc + 2 * (mt * CT + c) + 1, (double)t.m2 + n * mu * mu);
@@ -486,7 +599,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_mixed_fwd(const bmnas_conv_param
                         __threadfence();
                     }
                     epi_sync();
+                    if (e == 0) MX_TL(7);
                     if (e == 0) grid_barrier(ws);
+                    if (e == 0) MX_TL(8);
                     epi_sync();
                     if (h == 0) {
 #pragma unroll
@@ -524,138 +639,164 @@ __global__ void __launch_bounds__(THREADS, 1) k_mixed_fwd(const bmnas_conv_param
                 continue;
             }
 
-            // ---- pass 2: the mixed op for this thread's channel over its 32 columns (SH samples x L positions)
+            // ---- pass 2: the mixed op for this thread's channel over its 32 columns (SH samples x L positions).
+            // Every loop over samples is ROLLED and per-sample state lives in tensor memory / shared memory, not in
+            // registers: the unrolled form of this block was 12 k instructions with 555 spill accesses, and at one tile
+            // per CTA every instruction is an instruction-cache miss (profiles/: 16 us for 32 columns).
             const long long b0 = (long long)(col0 / L);            // first sample of this half
-            float ov[32];                                           // dropped attention output O[c, (s, i)]
-            float a_mean[SH], a_rstd[SH];
+            const uint32_t t_ov = tz + (uint32_t)(3 * NT + h * CW); // the Gram accumulator, reused as scratch for O
+            float4 xn[L / 4];                                       // software-prefetched activations of the next sample
+            load_xrow<L>(nd.x, b0, B, c, xn);
             if (has_attn) {
-                // softmax rows: Gram rows n < 64 live in lanes 0..63; the 4 warps of column half 0 with lane quarter 0 / 1
-                // stage their 32-column window, every thread then picks the L columns of its own sample
-                if (h == 0 && lq < 2) {
-                    float g[32];
-                    tmem_ld32(tz + (uint32_t)(3 * NT + lq * 32), g);
+                // softmax rows of this half's samples: Gram rows h*32 .. h*32+31 live in the TMEM lanes of quarter lq == h,
+                // so warp (lq == h) of each half computes them; barriers below are local to the half (128 threads)
+                if (lq == (h * CW) / 32) {                       // the warp whose TMEM lanes hold the Gram rows of this group
+                    float g[CW];
+                    tmem_ld<CW>(t_ov, g);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) sh.G[c * 33 + j] = g[j];
+                    for (int j = 0; j < CW; ++j) sh.u.a.G[c * (CW + 1) + j] = g[j];
                     __syncwarp();
-                    const int j0 = (lane / L) * L;
-                    float sc[L], mxv = -INFINITY, sum = 0.f;
+                    if (c >= h * CW && c < (h + 1) * CW) {       // row c = column (sample, position) c of the tile
+                        const int j0 = ((c - h * CW) / L) * L;
+                        float sc[L], mxv = -INFINITY, sum = 0.f;
 #pragma unroll
-                    for (int j = 0; j < L; ++j) {
-                        sc[j] = sh.G[c * 33 + j0 + j] * inv_sqrt_c;
-                        mxv = fmaxf(mxv, sc[j]);
+                        for (int j = 0; j < L; ++j) {
+                            sc[j] = sh.u.a.G[c * (CW + 1) + j0 + j] * inv_sqrt_c;
+                            mxv = fmaxf(mxv, sc[j]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < L; ++j) {
+                            sc[j] = __expf(sc[j] - mxv);
+                            sum += sc[j];
+                        }
+                        const float inv = 1.f / sum;
+#pragma unroll
+                        for (int j = 0; j < L; ++j) sh.u.a.P[c * L + j] = sc[j] * inv;
                     }
-#pragma unroll
-                    for (int j = 0; j < L; ++j) {
-                        sc[j] = expf(sc[j] - mxv);
-                        sum += sc[j];
-                    }
-#pragma unroll
-                    for (int j = 0; j < L; ++j) sh.P[c * L + j] = sc[j] / sum;
+                    tc_fence_before();       // this warp's Gram reads are done before any thread overwrites the region
                 }
-                epi_sync();
-                // O[c, i] = sum_j P[i][j] t[c, j] per sample, dropout, LayerNorm statistics over (C, L)
-                float s1[SH];
-#pragma unroll
+                half_sync(h);
+                tc_fence_after();
+                // O[c, i] = sum_j P[i][j] t[c, j] per sample, dropout; parked in the Gram region; LayerNorm sums
+#pragma unroll 1
                 for (int s = 0; s < SH; ++s) {
-                    s1[s] = 0.f;
                     const long long b = b0 + s;
                     const bool ok = b < B;
-                    float xv[L];
-                    const float* xp = nd.x + (b * CT + c) * L;
+                    float xs[L], o[L];
 #pragma unroll
                     for (int j4 = 0; j4 < L / 4; ++j4) {
-                        const float4 q = ok ? __ldg(reinterpret_cast<const float4*>(xp) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        xv[j4 * 4] = q.x; xv[j4 * 4 + 1] = q.y; xv[j4 * 4 + 2] = q.z; xv[j4 * 4 + 3] = q.w;
+                        xs[j4 * 4] = xn[j4].x; xs[j4 * 4 + 1] = xn[j4].y; xs[j4 * 4 + 2] = xn[j4].z; xs[j4 * 4 + 3] = xn[j4].w;
                     }
-                    const float* Pb = sh.P + (h * SH + s) * L * L;
+                    load_xrow<L>(nd.x, s + 1 < SH ? b + 1 : b0, B, c, xn);   // next sample; after the last one: sample 0 for the loop below
+                    const float* Pb = sh.u.a.P + (h * SH + s) * L * L;
+                    float s1 = 0.f;
 #pragma unroll
                     for (int i4 = 0; i4 < L / 4; ++i4) {
-                        float o[4], ds[4] = {1.f, 1.f, 1.f, 1.f};
+                        float ds[4] = {1.f, 1.f, 1.f, 1.f};
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            o[q] = 0.f;
+                            float acc = 0.f;
 #pragma unroll
-                            for (int j = 0; j < L; ++j) o[q] = fmaf(Pb[(i4 * 4 + q) * L + j], xv[j], o[q]);
+                            for (int j4 = 0; j4 < L / 4; ++j4) {
+                                const float4 pq = *reinterpret_cast<const float4*>(Pb + (i4 * 4 + q) * L + j4 * 4);
+                                acc = fmaf(pq.x, xs[j4 * 4], acc);
+                                acc = fmaf(pq.y, xs[j4 * 4 + 1], acc);
+                                acc = fmaf(pq.z, xs[j4 * 4 + 2], acc);
+                                acc = fmaf(pq.w, xs[j4 * 4 + 3], acc);
+                            }
+                            o[i4 * 4 + q] = acc;
                         }
                         const long long e0 = (long long)c * L + i4 * 4;
                         if (ok) drop4(d_attn, b * CL + e0, (unsigned long long)(nd.sample_offset + b) * CL + e0, ds);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            o[q] *= ds[q];
-                            s1[s] += o[q];
-                            ov[s * L + i4 * 4 + q] = o[q];
+                            o[i4 * 4 + q] *= ds[q];
+                            s1 += o[i4 * 4 + q];
                         }
                     }
+                    tmem_st<L>(t_ov + (uint32_t)(s * L), o);
+                    s1 = warp_sum(s1);
+                    if (lane == 0) sh.red[we][s] = s1;
                 }
-                // two-pass LayerNorm statistics: sum over the 128 channels (4 warps of this half) x L positions
-#pragma unroll
-                for (int s = 0; s < SH; ++s) s1[s] = warp_sum(s1[s]);
-                if (lane == 0) {
-#pragma unroll
-                    for (int s = 0; s < SH; ++s) sh.red[we][s] = s1[s];
-                }
-                epi_sync();
-#pragma unroll
+                tmem_st_wait();
+                half_sync(h);
+                // second LayerNorm pass: sum of squared deviations (two-pass, as the node kernels do)
+#pragma unroll 1
                 for (int s = 0; s < SH; ++s) {
                     const float tot = (sh.red[h * 4][s] + sh.red[h * 4 + 1][s]) + (sh.red[h * 4 + 2][s] + sh.red[h * 4 + 3][s]);
-                    a_mean[s] = tot / (float)CL;
-                }
-                float s2[SH];
-#pragma unroll
-                for (int s = 0; s < SH; ++s) {
-                    s2[s] = 0.f;
+                    const float mean = tot / (float)CL;
+                    float o[L];
+                    tmem_ld<L>(t_ov + (uint32_t)(s * L), o);
+                    float s2 = 0.f;
 #pragma unroll
                     for (int i = 0; i < L; ++i) {
-                        const float d = ov[s * L + i] - a_mean[s];
-                        s2[s] = fmaf(d, d, s2[s]);
+                        const float d = o[i] - mean;
+                        s2 = fmaf(d, d, s2);
                     }
-                    s2[s] = warp_sum(s2[s]);
+                    s2 = warp_sum(s2);
+                    if (lane == 0) sh.red[we][8 + s] = s2;
                 }
-                if (lane == 0) {
-#pragma unroll
-                    for (int s = 0; s < SH; ++s) sh.red[we][8 + s] = s2[s];
-                }
-                epi_sync();
-#pragma unroll
-                for (int s = 0; s < SH; ++s) {
-                    const float tot = (sh.red[h * 4][8 + s] + sh.red[h * 4 + 1][8 + s]) + (sh.red[h * 4 + 2][8 + s] + sh.red[h * 4 + 3][8 + s]);
-                    a_rstd[s] = 1.f / sqrtf(tot / (float)CL + kLnEps);
-                }
+                half_sync(h);
             }
+            if (e == 0 && i == n_items - 1) MX_TL(10);
 
-            // ---- BatchNorm + GLU / FC, LayerNorm affine, gamma-weighted sum; 16 columns at a time
-            const float r0 = sh.rs[c], m0 = sh.mr[c], g0 = sh.bw[c], h0 = sh.bb[c];
-            const float r1 = sh.rs[CT + c], m1 = sh.mr[CT + c], g1 = sh.bw[CT + c], h1 = sh.bb[CT + c];
-            const float r2 = sh.rs[2 * CT + c], m2 = sh.mr[2 * CT + c], g2 = sh.bw[2 * CT + c], h2 = sh.bb[2 * CT + c];
+            // ---- BatchNorm + GLU / FC, LayerNorm affine, gamma-weighted sum: one sample (L columns) per iteration
+#pragma unroll 1
+            for (int s = 0; s < SH; ++s) {
+                const long long b = b0 + s;
+                float za[L], zb[L], zf[L], ovs[L];
+                const uint32_t tcol = (uint32_t)(h * CW + s * L);
+                tmem_ld_nowait<L>(tz + tcol, za);
+                tmem_ld_nowait<L>(tz + (uint32_t)NT + tcol, zb);
+                tmem_ld_nowait<L>(tz + (uint32_t)(2 * NT) + tcol, zf);
+                if (has_attn) tmem_ld_nowait<L>(t_ov + (uint32_t)(s * L), ovs);
+                float a_mean = 0.f, a_rstd = 0.f;
+                if (has_attn) {
+                    const float t1 = (sh.red[h * 4][s] + sh.red[h * 4 + 1][s]) + (sh.red[h * 4 + 2][s] + sh.red[h * 4 + 3][s]);
+                    const float t2 = (sh.red[h * 4][8 + s] + sh.red[h * 4 + 1][8 + s]) + (sh.red[h * 4 + 2][8 + s] + sh.red[h * 4 + 3][8 + s]);
+                    a_mean = t1 / (float)CL;
+                    a_rstd = 1.f / sqrtf(t2 / (float)CL + kLnEps);
+                }
+                const bool ok = b < B;
+                float xs[L];
 #pragma unroll
-            for (int half16 = 0; half16 < 2; ++half16) {
-                float za[16], zb[16], zf[16];
-                tmem_ld16(tz + (uint32_t)(0 * NT + h * 32 + half16 * 16), za);
-                tmem_ld16(tz + (uint32_t)(1 * NT + h * 32 + half16 * 16), zb);
-                tmem_ld16(tz + (uint32_t)(2 * NT + h * 32 + half16 * 16), zf);
-                if (half16 == 1) {                               // last TMEM read of this item: release the accumulator set
+                for (int j4 = 0; j4 < L / 4; ++j4) {
+                    xs[j4 * 4] = xn[j4].x; xs[j4 * 4 + 1] = xn[j4].y; xs[j4 * 4 + 2] = xn[j4].z; xs[j4 * 4 + 3] = xn[j4].w;
+                }
+                if (s + 1 < SH) load_xrow<L>(nd.x, b + 1, B, c, xn);
+                // folded BatchNorm constants of rows c, C + c, 2C + c and the attention LayerNorm affine of channel c: re-read
+                // per sample (shared memory / L1) instead of living in 28 registers across the whole item loop
+                const float r0 = sh.rs[c], m0 = sh.mr[c], g0 = sh.bw[c], h0 = sh.bb[c];
+                const float r1 = sh.rs[CT + c], m1 = sh.mr[CT + c], g1 = sh.bw[CT + c], h1 = sh.bb[CT + c];
+                const float r2 = sh.rs[2 * CT + c], m2 = sh.mr[2 * CT + c], g2 = sh.bw[2 * CT + c], h2 = sh.bb[2 * CT + c];
+                float lnw[L], lnb[L];
+#pragma unroll
+                for (int j4 = 0; j4 < L / 4; ++j4) {
+                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), bq = a;
+                    if (has_attn) {
+                        a = __ldg(reinterpret_cast<const float4*>(nd.ln_w[ops.k_attn] + (long long)c * L) + j4);
+                        bq = __ldg(reinterpret_cast<const float4*>(nd.ln_b[ops.k_attn] + (long long)c * L) + j4);
+                    }
+                    lnw[j4 * 4] = a.x; lnw[j4 * 4 + 1] = a.y; lnw[j4 * 4 + 2] = a.z; lnw[j4 * 4 + 3] = a.w;
+                    lnb[j4 * 4] = bq.x; lnb[j4 * 4 + 1] = bq.y; lnb[j4 * 4 + 2] = bq.z; lnb[j4 * 4 + 3] = bq.w;
+                }
+                tmem_ld_wait();
+                if (s == SH - 1) {                               // last TMEM read of this item: release the accumulator set
                     tc_fence_before();
                     mbar_arrive(&sh.t_empty[buf]);
                 }
+                if (ok) {
 #pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    const int jc = half16 * 16 + q4 * 4;          // column of this thread's half
-                    const int n = col0 + jc;
-                    if (n < N) {
-                        const long long b = n / L;
-                        const int l0 = n - (int)b * L;
-                        constexpr int dummy_ = 0; (void)dummy_;
-                        const int s = jc / L;                      // sample slot in this half (compile time after unrolling)
+                    for (int q4 = 0; q4 < L / 4; ++q4) {
+                        const int l0 = q4 * 4;
                         const long long e0 = (long long)c * L + l0, li = b * CL + e0;
                         const unsigned long long gi = (unsigned long long)(nd.sample_offset + b) * CL + e0;
-                        const float4 xq = __ldg(reinterpret_cast<const float4*>(nd.x + li));
-                        const float xv[4] = {xq.x, xq.y, xq.z, xq.w};
                         float va[4], vb[4], vf[4], dg[4], df[4], out[4];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            va[q] = za[q4 * 4 + q] + bias0;
-                            vb[q] = zb[q4 * 4 + q] + bias1;
-                            vf[q] = zf[q4 * 4 + q] + bias2;
+                            va[q] = za[l0 + q] + bias0;
+                            vb[q] = zb[l0 + q] + bias1;
+                            vf[q] = zf[l0 + q] + bias2;
                         }
                         if (cv.Z) {                                // keep the pre-BatchNorm activations for the backward pass
                             float* zp = cv.Z + (b * (MT * CT) + c) * L + l0;
@@ -665,24 +806,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_mixed_fwd(const bmnas_conv_param
                         }
                         drop4(d_glu, li, gi, dg);
                         drop4(d_fc, li, gi, df);
-                        float lw[4] = {0.f, 0.f, 0.f, 0.f}, lb[4] = {0.f, 0.f, 0.f, 0.f};
-                        if (has_attn) {
-                            const float4 a = __ldg(reinterpret_cast<const float4*>(nd.ln_w[ops.k_attn] + e0));
-                            const float4 bq = __ldg(reinterpret_cast<const float4*>(nd.ln_b[ops.k_attn] + e0));
-                            lw[0] = a.x; lw[1] = a.y; lw[2] = a.z; lw[3] = a.w;
-                            lb[0] = bq.x; lb[1] = bq.y; lb[2] = bq.z; lb[3] = bq.w;
-                        }
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             float acc = 0.f;
-                            if (ops.k_sum >= 0) acc = fmaf(w_sum, xv[q] + xv[q], acc);
+                            if (ops.k_sum >= 0) acc = fmaf(w_sum, xs[l0 + q] + xs[l0 + q], acc);
                             if (has_attn) {
-                                const float o = (ov[jc + q] - a_mean[s]) * a_rstd[s] * lw[q] + lb[q];
+                                const float o = (ovs[l0 + q] - a_mean) * a_rstd * lnw[l0 + q] + lnb[l0 + q];
                                 acc = fmaf(w_attn, o, acc);
                             }
                             const float ya = fmaf(fmaf(va[q], r0, -m0), g0, h0);
                             const float yg = fmaf(fmaf(vb[q], r1, -m1), g1, h1);
-                            acc = fmaf(w_glu, ya * sigmoidf_(yg) * dg[q], acc);
+                            acc = fmaf(w_glu, ya * sigmoid_fast(yg) * dg[q], acc);
                             const float yf = fmaf(fmaf(vf[q], r2, -m2), g2, h2);
                             acc = fmaf(w_fc, (ops.fc_mish ? mishf_(yf) : fmaxf(yf, 0.f)) * df[q], acc);
                             out[q] = acc;
@@ -695,8 +829,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_mixed_fwd(const bmnas_conv_param
     }
 
     // ---- teardown
+    if (tid == NPROD) MX_TL(11);
     tc_fence_before();
     __syncthreads();
+    if (tid == 0) MX_TL(12);
     if (warp == W_TMA) tmem_dealloc(tmem_base, 512);
 }
 

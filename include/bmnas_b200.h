@@ -147,7 +147,8 @@ typedef struct bmnas_conv_params {
     int early_ok;
 } bmnas_conv_params;
 /* wimg_fwd / wimg_dgrad (optional): images of the stacked, folded weight produced by bmnas_wprep (below), in
- * format wimg_fmt: 0 = tcgen05 slabs (the tensor-core GEMMs fetch them with TMA bulk copies), 1 = plain fp32
+ * format wimg_fmt: 0 = tcgen05 tf32 hi/lo slabs (the tensor-core GEMMs fetch them with TMA bulk copies), 2 = bf16
+ * slabs (128 rows x 64 k, forward image only; bmnas_mixed_fwd in gemm mode 3), 1 = plain fp32
  * (tile major [row tile of 32][reduction][32], fold applied; the small-N cp.async FFMA GEMMs of gemm_sg.cu).  They must be
  * refreshed (bmnas_wprep) whenever W changes.  bmnas_conv_image_fmt() picks the format for a problem size. */
 int bmnas_conv_fwd(const bmnas_conv_params* p, void* stream);
@@ -475,7 +476,9 @@ int bmnas_sizeof_params(int which); /* 0 mix, 1 conv, 2 node, 3 ln, 4 loss, 5 ad
 int bmnas_set_validate_only(int on);
 
 /* GEMM engine behind bmnas_conv_*: 0 = fp32 FFMA tiles, 1 = tcgen05 tensor cores with 3xTF32 operand
- * splitting (fp32-class accuracy; default), 2 = tcgen05 single-pass TF32 (reduced precision).  Shapes the
+ * splitting (fp32-class accuracy; default), 2 = tcgen05 single-pass TF32 (reduced precision), 3 = as 1 with bf16
+ * operands (kind::f16, fp32 accumulation in tensor memory) in the fused mixed-op forward bmnas_mixed_fwd -- the
+ * north_star's reduced-precision mode, parity gate 2e-2 (weight image format 2, forward only).  Shapes the
  * tensor-core path cannot take (L, K or a concat width not a multiple of 4, unaligned tensors) use mode 0. */
 int bmnas_set_gemm_mode(int mode);
 int bmnas_get_gemm_mode(void);

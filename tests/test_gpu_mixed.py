@@ -164,3 +164,39 @@ def test_fused_equals_two_kernel_path_philox(B, L):
             assert_close(a[3][k], b[3][k], 2e-5, k, atol=1e-7)
     for k in a[4]:
         assert_close(a[4][k], b[4][k], 1e-5, k)
+
+
+@pytest.mark.parametrize('B,L', [(96, 8), (2500, 8), (300, 16)])
+def test_fused_bf16_operand_mode(B, L):
+    """gemm mode 3: the fused kernel stages bf16 operands (kind::f16, fp32 accumulation in TMEM, fp32 epilogue and
+    fp32 Z / statistics); north_star's reduced-precision gate: 2e-2 relative against the fp32 oracle."""
+    from bmnas import native as N
+    lib = N.lib()
+    lib.bmnas_set_gemm_mode(3)
+    try:
+        ops = OPS_MISH
+        mod = _mixed(L, ops=ops).to(U.DEV).train()
+        sd0 = {k: v.clone() for k, v in mod.state_dict().items()}
+        g = torch.Generator().manual_seed(1)
+        x = torch.randn(B, C, L, generator=g).to(U.DEV).requires_grad_(True)
+        w = torch.softmax(torch.randn(4, generator=g), -1).to(U.DEV).requires_grad_(True)
+        go = torch.randn(B, C, L, generator=g).to(U.DEV)
+        masks = _masks(mod, B, L, 2)
+        U.inject_masks(mod, masks)
+        out = mod(x, x, w)
+        out.backward(go)
+        torch.cuda.synchronize()
+        names = _fused_launches(mod)
+        assert 'bmnas_mixed_fwd' in names
+        call = [c for r in mod._bm_cache.values() for c in r.prog.fwd if c.name == 'bmnas_mixed_fwd'][0]
+        assert call.args[0]._obj.wimg_fmt == 2, 'bf16 weight image expected in gemm mode 3'
+        ref = _oracle(_restore(_mixed(L, ops=ops), sd0), x, w, go, masks, True, L, 0.2, ops=ops)
+        assert_close(out, ref[0], 2e-2, 'out (bf16 operands)')
+        assert (out.detach().cpu() - ref[0]).abs().max().item() > 1e-6, 'suspiciously exact: is the bf16 path really running?'
+        assert_close(x.grad, ref[1], 2e-2, 'gx')
+        assert_close(w.grad, ref[2], 2e-2, 'gw')
+        for k, p in mod.named_parameters():
+            if not k.endswith('conv.bias'):
+                assert_close(p.grad, ref[3]['mix.' + k], 2e-2, k)
+    finally:
+        lib.bmnas_set_gemm_mode(1)

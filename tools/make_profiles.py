@@ -35,7 +35,8 @@ for f in sorted(os.listdir('gpurun_out')):
         if m:
             key = {'node_fwd': 'bmnas_node_fwd', 'node_bwd': 'bmnas_node_bwd', 'sg_fwd': 'bmnas_conv_fwd', 'sg_dgrad': 'bmnas_conv_dgrad',
                    'wgrad': 'bmnas_conv_wgrad', 'mix_bwd': 'bmnas_mix_bwd', 'ln_bwd': 'bmnas_ln_bwd', 'panel_fwd': 'bmnas_conv_fwd',
-                   'node_fwd_warp': 'bmnas_node_fwd', 'node_bwd_warp': 'bmnas_node_bwd'}.get(m.group(1), m.group(1))
+                   'node_fwd_warp': 'bmnas_node_fwd', 'node_bwd_warp': 'bmnas_node_bwd', 'mixed_fwd': 'bmnas_mixed_fwd', 'mixed_fwd_tf32': 'bmnas_mixed_fwd',
+                   'mixed_fwd_bf16': 'bmnas_mixed_fwd_bf16', 'panel_dgrad': 'bmnas_conv_dgrad', 'tc_wgrad': 'bmnas_conv_wgrad'}.get(m.group(1), m.group(1))
             traffic[f'{key}@B{m.group(2)}'] = int(rd + wr)
     src = subprocess.run([sys.executable, 'tools/ncu_src.py', rep, '14'], capture_output=True, text=True).stdout
     lines.append('# hottest SASS lines (sampled stalls)')
@@ -46,6 +47,10 @@ if traffic:
     p = 'profiles/ncu_traffic.json'
     old = json.load(open(p)) if os.path.exists(p) else {}
     old.update(traffic)
+    # which build the captures belong to (bench.py prints it next to roofline.traffic)
+    old['_git'] = subprocess.run(['git', 'rev-parse', '--short', 'HEAD'], capture_output=True, text=True).stdout.strip() + \
+        ('+dirty' if subprocess.run(['git', 'status', '--porcelain', '--', 'bm-nas_b200/csrc', 'include'], capture_output=True, text=True).stdout.strip() else '')
+    old['_tag'] = tag
     json.dump(old, open(p, 'w'), indent=1, sort_keys=True)
     print(traffic)
 for src, dst in (('bench.log', f'{tag}_bench.json'), ('bench_reference.log', f'{tag}_bench_reference.json'), ('launch_list.txt', f'{tag}_launch_list.txt')):
