@@ -433,7 +433,7 @@ def workload_string(cfgname, c, gB):
             f'L={c["L"]}, n_in={c["num_input_nodes"]}, steps={c["steps"]}, node_steps={c["node_steps"]}, classes={c["classes"]}')
 
 
-def build_search(c, device, group=None, use_graphs=True, nbpe=400.0):
+def build_search(c, device, group=None, use_graphs=True, nbpe=400.0, peer_step=None):
     import types
     from bmnas.nn import SearchHead, CrossEntropyLoss, BCEWithLogitsLoss
     from bmnas.search import SearchStep
@@ -442,7 +442,7 @@ def build_search(c, device, group=None, use_graphs=True, nbpe=400.0):
     crit = CrossEntropyLoss() if c['loss'] == 'ce' else BCEWithLogitsLoss()
     head = SearchHead(a, c['classes'], criterion=crit).to(device)
     ss = SearchStep(head, crit, c['B'], c['classes'], loss_kind=c['loss'], eta_max=c['eta_max'],
-                    weight_decay=c['weight_decay'], nbpe=nbpe, use_graphs=use_graphs, group=group)
+                    weight_decay=c['weight_decay'], nbpe=nbpe, use_graphs=use_graphs, group=group, peer_step=peer_step)
     return head, ss
 
 
@@ -485,30 +485,52 @@ def found_sweep(device, batches=(96, 1024, 8192), steps=30):
 
 
 def dp_check(ss, head, group, world, rank, device):
-    """N > 1 only, before timing: (1) the reduced weight / architecture gradients every rank holds after the collective
-    equal the sum of the per-rank gradients (all-gathered and summed here), (2) replicas hold bit-identical parameters and
-    architecture tensors.  Raises on mismatch."""
+    """N > 1 only, before timing, on the REAL optimiser path (peer-memory reduce-scatter + Adam + all-gather kernel, or NCCL
+    all-reduce + FusedAdam): for each half step, the parameters every rank holds after the data-parallel step must equal
+    one torch Adam step (zero moments, step 1) on the gradient summed over the ranks and divided by the world size --
+    the per-rank gradients are all-gathered and summed here independently of the path under test.  State is restored
+    afterwards.  Raises on mismatch."""
     import torch.distributed as dist
     from bmnas import runtime as rt
-    res = {}
+    from bmnas.program import join_side
+    snap = ss._snapshot()
+    res = {'path': 'peer-memory fused reduce-scatter + Adam + all-gather (bmnas_dp_adam_step)' if ss.peer is not None
+           else 'ncclAllReduce + bmnas_adam_step'}
+    hyp = {'dev': (ss.a_opt.defaults['lr'], ss.a_opt.defaults['betas'], ss.a_opt.defaults['weight_decay']),
+           'train': (ss.w_opt.param_groups[0]['lr'], ss.w_opt.defaults['betas'], ss.w_opt.defaults['weight_decay'])}
     for which, mode in (('dev', 'arch'), ('train', 'weights')):
-        with rt.grad_mode(mode):
+        tensors = head.arch_parameters() if which == 'dev' else [p for p in head.parameters() if p.requires_grad]
+        before = [t.detach().clone() for t in tensors]
+        with rt.grad_mode(mode), rt.static_io():
             loss = ss.criterion(head(ss.feats[which]), ss.labels[which])
             loss.backward()
-        from bmnas.program import join_side
         join_side(device)
-        span = ss.grad_span(which)
-        local = span.clone()
+        torch.cuda.synchronize()
+        local = torch.cat([t.grad.detach().reshape(-1) for t in tensors])
         gathered = [torch.empty_like(local) for _ in range(world)]
         dist.all_gather(gathered, local, group=group)
-        expect = torch.stack(gathered).double().sum(0)
-        ss.allreduce_grads(which)
+        g = (torch.stack(gathered).double().sum(0) / world).float()
+        if ss.peer is not None:
+            ss.peer.step(which)
+        else:
+            ss.allreduce_grads(which)
+            (ss.a_opt if which == 'dev' else ss.w_opt).step()
         torch.cuda.synchronize()
-        err = (span.double() - expect).abs().max().item()
-        scale = expect.abs().max().item()
-        if not err <= 1e-5 * scale + 1e-12:
-            raise SystemExit(f'dp_check: reduced {which} gradients differ from the sum of the per-rank gradients: {err} vs scale {scale}')
-        res[which + '_grad_err'] = err
+        lr, (b1, b2), wd = hyp[which]
+        p0 = torch.cat([t.reshape(-1) for t in before])
+        g = g + wd * p0
+        m, v = (1 - b1) * g, (1 - b2) * g * g
+        expect = p0 - (lr / (1 - b1)) * (m / (v.sqrt() / (1 - b2) ** 0.5 + 1e-8))
+        got = torch.cat([t.detach().reshape(-1) for t in tensors])
+        err = (got - expect).abs().max().item()
+        moved = (expect - p0).abs().max().item()
+        if not err <= 1e-3 * moved + 1e-9:
+            raise SystemExit(f'dp_check: {which} parameters after the data-parallel step differ from Adam(sum of per-rank gradients / world): '
+                             f'err {err:.3e}, step size {moved:.3e}')
+        res[which] = {'max_err': err, 'max_update': moved}
+    ss._restore(snap)
+    torch.cuda.synchronize()
+    dist.barrier(group)
     return res
 
 
@@ -551,7 +573,7 @@ def run_ours(args):
             raise SystemExit(f'--scaling strong: global batch {c["B"]} is not divisible by {world} GPUs')
         c['B'] = c['B'] // world
     torch.manual_seed(2)                              # main_darts_searchable_ntu.py:17 (all ranks: identical replicas)
-    head, ss = build_search(c, device, group=group, use_graphs=not args.no_graphs)
+    head, ss = build_search(c, device, group=group, use_graphs=not args.no_graphs, peer_step=(False if args.nccl else None))
     # input pool larger than L2 so every step's inputs come from HBM
     per_batch = c['num_input_nodes'] * c['B'] * c['C'] * c['L'] * 4
     n_pool = max(4, int(1.3 * L2_BYTES / per_batch) + 1)
@@ -704,8 +726,10 @@ def run_ours(args):
             'data': 'synthetic',
             'config': {'workload': workload_string(args.config, c, gB),
                        'global_batch': gB, 'per_gpu_batch': c['B'], 'weights': n_weights, 'arch_scalars': n_arch,
-                       'parallelism': f'dp{world} (batch-sharded; arch half: one NCCL all-reduce of the {n_arch}-float alpha/beta/gamma '
-                                      f'span, weight half: one of the weight-gradient span)',
+                       'parallelism': f'dp{world} (batch-sharded; per half step ONE ' +
+                                      ('peer-memory kernel: reduce-scatter + Adam on the shard + all-gather of parameters over NVLink'
+                                       if ss.peer is not None else 'NCCL all-reduce of the half\'s gradient span, then fused Adam') +
+                                      f'; arch bucket {n_arch} floats, weight bucket {n_weights} floats)',
                        'cuda_graphs': not args.no_graphs, 'gemm_mode': mode_name(),
                        'l2_policy': f'inputs larger than L2: pool of {n_pool} distinct resident batches '
                                     f'({n_pool * per_batch / 2**20:.0f} MiB) rotated every step'},
@@ -780,6 +804,7 @@ def main():
                     help='weak: the config batch per GPU; strong: the config batch is the GLOBAL batch (nn.DataParallel chunking)')
     ap.add_argument('--gemm-mode', type=int, default=None, help='bmnas_set_gemm_mode: 1 = 3xTF32 (default), 3 = bf16 fused MixedOp forward')
     ap.add_argument('--no-graphs', action='store_true')
+    ap.add_argument('--nccl', action='store_true', help='N > 1: NCCL all-reduce + FusedAdam instead of the peer-memory fused optimiser step')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-configs', action='store_true', help='skip the other BASELINE configs (mmimdb, ego, ego_large, found sweep)')
     ap.add_argument('--profile-kernels', action='store_true')

@@ -49,7 +49,7 @@ SPLIT_MIX_BWD = os.environ.get('BMNAS_SPLIT_MIX_BWD', '1') != '0'   # edge-mix b
 # primitive + gamma-weighted sum, Z written only when a backward will follow) instead of bmnas_conv_fwd + bmnas_node_fwd.
 # 0 = off, 1 = whenever the shape is supported, default: batches of FUSED_MIXED_MIN_B samples or more
 FUSED_MIXED = os.environ.get('BMNAS_FUSED_MIXED', 'auto')
-FUSED_MIXED_MIN_B = int(os.environ.get('BMNAS_FUSED_MIXED_MIN_B', '0'))
+FUSED_MIXED_MIN_B = int(os.environ.get('BMNAS_FUSED_MIXED_MIN_B', '768'))   # measured crossover (profiles/r02_fused_crossover.txt): 3xTF32 ties at 512, wins from 1024
 FUSED_OPS_RANK = {'Sum': 0, 'ScaleDotAttn': 1, 'LinearGLU': 2, 'ConcatFC': 3, 'CatConvMish': 3}
 _side_streams = {}
 

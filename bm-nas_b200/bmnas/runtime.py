@@ -81,14 +81,16 @@ def filter_leaves(leaves):
 
 
 class GradArena:
-    def __init__(self, tensors, device):
+    def __init__(self, tensors, device, flat=None):
         self.tensors = [t for t in tensors]
         self.offsets = {}
         off = 0
         for t in self.tensors:
             self.offsets[id(t)] = (off, t.numel())
             off += (t.numel() + 3) // 4 * 4          # keep every view 16-byte aligned
-        self.flat = torch.zeros(max(off, 4), dtype=torch.float32, device=device)
+        # flat: a caller-provided buffer of the right size (bmnas.dp puts the arena into peer-mapped symmetric memory)
+        assert flat is None or flat.numel() >= max(off, 4)
+        self.flat = torch.zeros(max(off, 4), dtype=torch.float32, device=device) if flat is None else flat
         self.views = {id(t): self.flat[o:o + n].view(t.shape) for t, (o, n) in
                       ((t, self.offsets[id(t)]) for t in self.tensors)}
         self.dirty = set()       # ids of leaves whose arena view holds a gradient not yet consumed by step()/zero_grad()

@@ -33,7 +33,7 @@ from .optim import FusedAdam
 class SearchStep:
     def __init__(self, head, criterion, B, num_classes, loss_kind='ce', eta_max=1e-3, eta_min=1e-6, Ti=1, Tm=2,
                  nbpe=100.0, weight_decay=3e-4, arch_lr=3e-4, arch_wd=1e-3, use_graphs=True, group=None,
-                 prune_grads=True, sync_replicas=True):
+                 prune_grads=True, sync_replicas=True, peer_step=None):
         from models.auxiliary.scheduler import LRCosineAnnealingScheduler
         self.head, self.criterion = head, criterion
         self.device = next(head.parameters()).device
@@ -51,6 +51,14 @@ class SearchStep:
             _rt.SAMPLE_OFFSET[0] = self.rank * B
             if sync_replicas:
                 self.sync_replicas()
+        # world > 1: the optimiser step fused with its collective over NVLink peer memory (bmnas.dp); peer_step=False
+        # forces the NCCL all-reduce + FusedAdam path, None tries the fused one and falls back
+        self.peer = None
+        if self.world > 1 and peer_step is not False and str(self.device).startswith('cuda') and not N.VALIDATE_ONLY:
+            from .dp import PeerStep
+            self.peer = PeerStep.create(head, group, self.device,
+                                        dict(lr=eta_max, betas=(0.9, 0.999), weight_decay=weight_decay),
+                                        dict(lr=arch_lr, betas=(0.5, 0.999), weight_decay=arch_wd))
         self.w_opt = FusedAdam(head.central_params(), lr=eta_max, weight_decay=weight_decay)
         self.a_opt = FusedAdam(head.arch_parameters(), lr=arch_lr, betas=(0.5, 0.999), weight_decay=arch_wd)
         self.w_opt.grad_scale = self.a_opt.grad_scale = 1.0 / self.world
@@ -81,11 +89,19 @@ class SearchStep:
         with _rt.grad_mode(mode), _rt.static_io():
             loss = self.criterion(head(self.feats[which]), self.labels[which])
             loss.backward()
-        self.allreduce_grads(which)
-        (self.a_opt if which == 'dev' else self.w_opt).step()
+        if self.peer is not None:
+            self.peer.step(which)            # reduce-scatter + Adam on the shard + all-gather of parameters: one launch
+        else:
+            self.allreduce_grads(which)
+            (self.a_opt if which == 'dev' else self.w_opt).step()
         # detach: holding the autograd graph would keep the AccumulateGrad nodes (and the stream they were
         # created on) alive across steps, which breaks CUDA-graph capture on another stream
         return loss.detach()
+
+    def set_lr(self, lr):
+        self.w_opt.set_lr(lr)
+        if self.peer is not None:
+            self.peer.set_lr(lr)
 
     def grad_span(self, which):
         """the contiguous slice of the flat gradient arena [alpha,beta,gamma | fusion weights | classifier] that the
@@ -166,6 +182,7 @@ class SearchStep:
                 'arch': [a.detach().clone() for a in self.head.arch_parameters()],
                 'sched': copy.deepcopy(self.sched.__dict__), 'steps': self.steps_done,
                 'opt': [opt.state_snapshot() for opt in (self.w_opt, self.a_opt)],
+                'peer': self.peer.state_snapshot() if self.peer is not None else None,
                 'rng': [(p.rng_state.clone() if p.rng_state is not None else None) for p in self._programs()]}
         return snap
 
@@ -181,6 +198,8 @@ class SearchStep:
                 a.copy_(b)
             for opt, osnap in zip((self.w_opt, self.a_opt), snap['opt']):
                 opt.state_restore(osnap)          # moments / step counters as they were (zero if they did not exist)
+            if self.peer is not None:
+                self.peer.state_restore(snap['peer'])
             progs = self._programs()
             for p, r in zip(progs, snap['rng']):   # plans that existed at snapshot time get their step counter back;
                 if r is not None and p.rng_state is not None:
@@ -226,7 +245,7 @@ class SearchStep:
         the static buffers; returns the loss as a device scalar"""
         if which == 'train':
             self.sched.step()
-            self.w_opt.set_lr(float(self.sched.eta))
+            self.set_lr(float(self.sched.eta))
         self._run_half(which)
         return self.loss[which]
 

@@ -34,9 +34,17 @@
 #include "gemm_shared.cuh"
 #include "tc_ptx.cuh"
 
+#ifndef MX_UNROLL_A
+#define MX_UNROLL_A 1
+#endif
+#ifndef MX_UNROLL_B
+#define MX_UNROLL_B 1
+#endif
+
 namespace bmnas {
 namespace mx {
 using namespace tc;
+constexpr int UNROLL_A = MX_UNROLL_A, UNROLL_B = MX_UNROLL_B;   // samples per iteration of the rolled epilogue loops (ILP vs registers)
 
 constexpr int CT = 128;             // channels: K of the folded conv and rows of one output tile
 constexpr int NT = 64;              // columns per tile
@@ -678,7 +686,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_mixed_fwd(const bmnas_conv_param
                 half_sync(h);
                 tc_fence_after();
                 // O[c, i] = sum_j P[i][j] t[c, j] per sample, dropout; parked in the Gram region; LayerNorm sums
-#pragma unroll 1
+#pragma unroll UNROLL_A
                 for (int s = 0; s < SH; ++s) {
                     const long long b = b0 + s;
                     const bool ok = b < B;
@@ -741,7 +749,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_mixed_fwd(const bmnas_conv_param
             if (e == 0 && i == n_items - 1) MX_TL(10);
 
             // ---- BatchNorm + GLU / FC, LayerNorm affine, gamma-weighted sum: one sample (L columns) per iteration
-#pragma unroll 1
+#pragma unroll UNROLL_B
             for (int s = 0; s < SH; ++s) {
                 const long long b = b0 + s;
                 float za[L], zb[L], zf[L], ovs[L];

@@ -467,6 +467,39 @@ typedef struct bmnas_adam_params {
 } bmnas_adam_params;
 int bmnas_adam_step(const bmnas_adam_params* p, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Data-parallel optimiser step fused with its collective, over NVLink peer memory (one launch per rank and bucket):
+ *   reduce-scatter of the gradient bucket (P2P loads, rank-ordered sum) -> Adam on this rank's 1/world shard ->
+ *   all-gather of the UPDATED parameters (P2P stores into every replica)
+ * replaces nn.DataParallel's gradient reduce-add (ntu_darts_searchable.py:50-51) + torch.optim.Adam.step on every
+ * replica (:42 weights, :46-47 architecture; architect.py:24) -- i.e. ncclAllReduce + bmnas_adam_step.
+ * grad_ptrs / param_ptrs / signal_ptrs are DEVICE arrays of `world` pointers: rank r's gradient bucket, parameter bucket
+ * (same element layout as the gradients) and signal pad, all in peer-mapped ("symmetric") memory.  The launch uses
+ * 2 * world uint32 slots of every signal pad from signal_base; they must start at 0.  m / v hold this rank's shard only
+ * (ceil(n / 4 / world) * 4 floats).  n % 4 == 0.  Every rank must issue the same launch; the kernels wait for one another.
+ * ---------------------------------------------------------------------- */
+typedef struct bmnas_dp_adam_params {
+    int world;
+    int rank;
+    long long n;
+    const float* const* grad_ptrs;
+    float* const* param_ptrs;
+    unsigned int* const* signal_ptrs;
+    int signal_base;
+    float* m;
+    float* v;
+    const float* lr;
+    float beta1;
+    float beta2;
+    float eps;
+    float weight_decay;
+    float grad_scale;
+    long long* step;
+    unsigned int* epoch;
+    unsigned int* done_counter;
+} bmnas_dp_adam_params;
+int bmnas_dp_adam_step(const bmnas_dp_adam_params* p, void* stream);
+
 /* stream-ordered zero fill (cudaMemsetAsync) and ABI self-description for binding tests */
 int bmnas_zero(void* ptr, long long nbytes, void* stream);
 int bmnas_sizeof_params(int which); /* 0 mix, 1 conv, 2 node, 3 ln, 4 loss, 5 adam_tensor, 6 adam */

@@ -77,7 +77,7 @@ def assert_close(a, b, tol, what='', atol=0.0):
     assert err <= lim, f'{what}: max abs err {err:.3e} > {lim:.3e} (rel {rel_err(a, b):.3e})'
 
 
-def close_vs_referee(ours, ref32, ref64, tol, what, atol=0.0, knife=0):
+def close_vs_referee(ours, ref32, ref64, tol, what, atol=0.0, knife=0, cpu_mult=3.0):
     """ours must be as close to the fp64 referee as tol, or as the fp32 CPU reference itself (x3):
     a gradient that is the difference of large terms is not computable to 1e-5 in fp32 by anyone.
     knife > 0 (large-batch gradient checks only): up to `knife` dim-0 slices (samples of an input gradient, output
@@ -85,10 +85,13 @@ def close_vs_referee(ours, ref32, ref64, tol, what, atol=0.0, knife=0):
     its gradient: where a BatchNorm output lies within fp32 rounding of 0, two correct forwards disagree on the mask
     and that ONE element moves its whole sample of gx and its whole row of dW (measured: B=2500, sample 2210, FC row
     16 -- tools/diag_mixed2.py); with millions of activations per tensor such an element exists with probability
-    O(0.2) per test.  Every other slice still has to meet `tol`."""
+    O(0.2) per test.  Every other slice still has to meet `tol`.
+    cpu_mult: how many times the CPU-fp32 reference's own distance to the referee is accepted (3 by default; 10 for
+    plans whose reductions run over >= 8192 columns or through >= 12 stacked mixed ops, where the fp32 accumulation ORDER
+    -- tensor-core K-chunk order and split-K atomics here, MKL's blocked summation there -- sets the error)."""
     ours = torch.as_tensor(ours).double().cpu()
     r32, r64 = ref32.double(), ref64.double()
-    lim = max(tol * r64.abs().max().item(), 3.0 * (r32 - r64).abs().max().item()) + atol
+    lim = max(tol * r64.abs().max().item(), cpu_mult * (r32 - r64).abs().max().item()) + atol
     d = (ours - r64).abs()
     err = d.max().item() if d.numel() else 0.0
     if err <= lim:

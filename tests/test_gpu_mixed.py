@@ -17,6 +17,16 @@ TOL, GTOL = 1e-5, 3e-5
 C = 128
 
 
+@pytest.fixture(autouse=True)
+def _fused_everywhere():
+    """the fused kernel is the default only from program.FUSED_MIXED_MIN_B samples on; these tests want it at every size"""
+    from bmnas import program
+    old = program.FUSED_MIXED_MIN_B
+    program.FUSED_MIXED_MIN_B = 0
+    yield
+    program.FUSED_MIXED_MIN_B = old
+
+
 OPS_RELU = ['Sum', 'ScaleDotAttn', 'LinearGLU', 'ConcatFC']
 # ReLU has a knife edge: where the BatchNorm output is within rounding distance of 0, two correct fp32 forwards
 # disagree on the gradient mask and ONE flipped element moves a whole sample of gx and a whole row of dW (seen at

@@ -75,8 +75,8 @@ def test_philox_plan_vs_oracle(name, variant):
     # pass are read back right after it and the oracle takes the same two passes (BN buffers advance twice)
     Pc = {k: v.clone() for k, v in P.items()}
     for it in range(2):
-        for p in head.parameters():
-            p.grad = None
+        for p in list(head.parameters()) + head.arch_parameters():
+            p.grad = None                      # plain module use accumulates like autograd: start each pass from zero
         out = head([f.to(U.DEV) for f in feats])
         loss = _loss_mod(kind)(out, labels.to(U.DEV))
         loss.backward()
@@ -104,7 +104,7 @@ def test_philox_plan_vs_oracle(name, variant):
         if gw.get(k) is None:
             continue
         close_vs_referee(p.grad, gw[k], gw64[k], GTOL, 'grad ' + k, atol=_bias_atol(k),
-                         knife=max(2, p.shape[0] // 64) if (big and p.dim() >= 2) else 0)
+                         knife=max(2, p.shape[0] // 64) if (big and p.dim() >= 2) else 0, cpu_mult=10.0 if big else 3.0)
     if arch is not None:
         for i, a in enumerate(head.arch_parameters()):
             close_vs_referee(a.grad, ga[i], ga64[i], GTOL, f'garch{i}')
