@@ -551,6 +551,28 @@ def loss_and_grads(feats, labels, arch, P, masks, cfg, loss='ce', genotype=None,
     return lv.detach(), logits.detach(), gw, ga
 
 
+def unrolled_arch_grad(train, valid, arch, P, cfg, eta, weight_decay, masks=None, loss='ce'):
+    """Second-order DARTS architecture gradient (Liu et al. 2019, eq. 7-8, finite-difference Hessian-vector product) --
+    the update the reference's unused ``--unrolled`` flag (main_darts_found_ntu.py:48) names; restated here so that the
+    product's Architect.step_unrolled has an independent CPU check.  train / valid = (feats, labels)."""
+    names = trainable_names(P)
+    Pw = {k: v.clone() for k, v in P.items()}
+    _, _, gw, _ = loss_and_grads(train[0], train[1], arch, Pw, masks, cfg, loss)
+    P1 = {k: v.clone() for k, v in P.items()}
+    for k in names:
+        P1[k] = P[k] - eta * (gw[k] + weight_decay * P[k])
+    _, _, dw, da = loss_and_grads(valid[0], valid[1], arch, P1, masks, cfg, loss)
+    norm = math.sqrt(sum(float((dw[k].double() ** 2).sum()) for k in names))
+    eps = 0.01 / max(norm, 1e-30)
+    outs = []
+    for sign in (1.0, -1.0):
+        Pp = {k: v.clone() for k, v in P.items()}
+        for k in names:
+            Pp[k] = P[k] + sign * eps * dw[k]
+        outs.append(loss_and_grads(train[0], train[1], arch, Pp, masks, cfg, loss)[3])
+    return [d - eta * (p - n) / (2.0 * eps) for d, p, n in zip(da, outs[0], outs[1])]
+
+
 class SearchState:
     """Everything one search run carries: weights, arch tensors, both Adam states,
     LR schedule.  ``search_step`` restates train_searchable/ntu.py:70-93 +

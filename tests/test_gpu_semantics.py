@@ -85,3 +85,40 @@ def test_out_of_range_label_poisons_the_loss():
     loss = CrossEntropyLoss()(logits, y)
     loss.backward()
     assert torch.isnan(loss).item() and torch.isnan(logits.grad[5]).all() and torch.isfinite(logits.grad[0]).all()
+
+
+def test_second_order_architect_vs_oracle():
+    """the unrolled DARTS update (the reference names it with --unrolled, main_darts_found_ntu.py:48, but
+    ships only the first-order Architect) against the oracle's restatement of the same finite-difference formula"""
+    import types
+    from bmnas.nn import CrossEntropyLoss
+    from models.search.darts.architect import Architect
+    cfg, head = _head()
+    P0 = {k: v.detach().cpu().clone() for k, v in head.state_dict().items()}
+    arch0 = [a.detach().cpu().clone() for a in head.arch_parameters()]
+    tr = O.synthetic_batch(cfg, 6, 5, seed=2)
+    va = O.synthetic_batch(cfg, 6, 5, seed=3)
+    eta, wd = 0.05, 3e-4
+
+    class Capture(torch.optim.Optimizer):            # records the gradient Architect hands to the optimiser
+        def __init__(self, params):
+            super().__init__(params, {})
+            self.seen = None
+
+        def step(self):
+            self.seen = [p.grad.detach().cpu().clone() for g in self.param_groups for p in g['params']]
+
+    opt = Capture(head.arch_parameters())
+    arc = Architect(head, types.SimpleNamespace(weight_decay=wd), CrossEntropyLoss(), opt)
+    buf0 = [b.detach().clone() for b in head.buffers()]
+    w0 = [p.detach().clone() for p in head.parameters()]
+    arc.step_unrolled([f.to(U.DEV) for f in tr[0]], tr[1].to(U.DEV), [f.to(U.DEV) for f in va[0]], va[1].to(U.DEV), eta)
+    torch.cuda.synchronize()
+    want = O.unrolled_arch_grad(tr, va, arch0, P0, cfg, eta, wd)
+    for got, ref in zip(opt.seen, want):
+        # a finite difference of two fp32 gradients divided by 2 eps: the quotient amplifies rounding by eta / (2 eps)
+        assert_close(got, ref, 2e-3, 'unrolled architecture gradient', atol=1e-6)
+    for a, b in zip(head.parameters(), w0):
+        assert torch.equal(a.detach(), b), 'weights must be restored after the virtual steps'
+    for a, b in zip(head.buffers(), buf0):
+        assert torch.equal(a, b), 'BatchNorm buffers must be restored'

@@ -165,3 +165,135 @@ def test_loop_matches_the_reference_loop(status, tmp_path):
     assert ours['plots'] == ref['plots'] and ours['files'] == ref['files'] and ours['arch_calls'] == ref['arch_calls']
     for k in ours['sd']:
         assert torch.equal(ours['sd'][k], ref['sd'][k]), k
+
+
+# ------------------------------------------------------------------ EgoGesture and MM-IMDB loops
+class ToyEgoNet(ToyNet):
+    """inputs arrive as (rgb (B,3,T,H,W), depth (B,1,T,H,W)) slices of one tensor"""
+
+    def forward(self, feats):
+        rgb, depth = feats
+        return super().forward((rgb.flatten(1)[:, :6], depth.flatten(1)[:, :4]))
+
+
+def make_ego_data(seed, n_batches, B):
+    g = torch.Generator().manual_seed(seed)
+    return [(torch.randn(B, 4, 2, 2, 2, generator=g), torch.randint(0, 3, (B,), generator=g)) for _ in range(n_batches)]
+
+
+class ToyMMNet(ToyNet):
+    def forward(self, feats):
+        text, image = feats
+        return super().forward((image, text))
+
+
+def make_mm_data(seed, n_batches, B):
+    g = torch.Generator().manual_seed(seed)
+    return [{'image': torch.randn(B, 6, generator=g), 'text': torch.randn(B, 4, generator=g),
+             'label': (torch.rand(B, 3, generator=g) < 0.4).float()} for _ in range(n_batches)]
+
+
+class TaskPlotter(ListPlotter):
+    def plot(self, genotype, file_name, task=None):
+        self.calls.append((str(genotype), os.path.basename(file_name), task))
+
+
+class LRArchitect(ToyArchitect):
+    def log_learning_rate(self, logger):
+        logger.info("Architecture Learning Rate: {}".format(3e-4))
+
+
+def run_task_loop(task, loop_mod, sched_mod, Genotype, save_dir, status, num_epochs=2):
+    os.makedirs(os.path.join(save_dir, 'best'), exist_ok=True)
+    os.makedirs(os.path.join(save_dir, 'architectures'), exist_ok=True)
+    model = (ToyEgoNet if task == 'ego' else ToyMMNet)(Genotype)
+    arch = LRArchitect(model)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    sched = sched_mod.LRCosineAnnealingScheduler(1e-2, 1e-5, 1, 2, 3)
+    mk = make_ego_data if task == 'ego' else make_mm_data
+    loaders = {'train': mk(1, 3, 8), 'dev': mk(2, 2, 8), 'test': mk(3, 2, 8)}
+    sizes = {'train': 24, 'dev': 16, 'test': 16}
+    logger, plotter = ListLogger(), TaskPlotter()
+    args = types.SimpleNamespace(save=save_dir)
+    if task == 'ego':
+        res, geno = loop_mod.train_ego_track_acc(model, arch, nn.CrossEntropyLoss(), opt, sched, loaders, sizes,
+                                                 device=torch.device('cpu'), num_epochs=num_epochs, parallel=False, logger=logger,
+                                                 plotter=plotter, args=args, status=status)
+    else:
+        res, geno = loop_mod.train_mmimdb_track_f1(model, arch, nn.BCEWithLogitsLoss(), opt, sched, loaders, sizes, torch.device('cpu'),
+                                                   num_epochs, False, logger, plotter, args, status=status)
+    return dict(res=float(res), geno=str(geno), lines=logger.lines, plots=plotter.calls, arch_calls=arch.calls,
+                sd={k: v.clone() for k, v in model.state_dict().items()}, files=sorted(os.listdir(os.path.join(save_dir, 'best'))))
+
+
+def _our_loop(task):
+    _ours()
+    import importlib
+    return importlib.import_module(f'models.search.train_searchable.{task}')
+
+
+@pytest.mark.parametrize('task', ['ego', 'mmimdb'])
+@pytest.mark.parametrize('status', ['search', 'eval'])
+def test_ego_mmimdb_loop_bookkeeping(task, status, tmp_path):
+    _, sched, Genotype = _ours()
+    r = run_task_loop(task, _our_loop(task), sched, Genotype, str(tmp_path), status)
+    assert r['arch_calls'] == (2 * 2 if status == 'search' else 0)
+    assert [p[1:] for p in r['plots']] == [('epoch_0', task), ('epoch_1', task)]
+    assert sum(l.startswith('Architecture Learning Rate') for l in r['lines']) == (2 if (task == 'mmimdb' or status == 'search') else 0)
+    if task == 'mmimdb':
+        assert sum('weighted F1' in l and l.startswith('dev Loss') for l in r['lines']) == 2
+        assert 0.0 <= r['res'] <= 1.0
+    else:
+        assert sum(l.startswith('Learning Rate:') for l in r['lines']) == 4       # every phase (ego.py:53-55)
+    tag = 'best' if status == 'search' else 'best_test'
+    assert f'{tag}_genotype.pkl' in r['files']
+
+
+def test_mmimdb_nan_failsafes(tmp_path):
+    """a NaN training loss returns best_f1 right away with the model in eval mode (mmimdb.py:150-153)"""
+    _, sched, Genotype = _ours()
+    loop = _our_loop('mmimdb')
+    os.makedirs(os.path.join(str(tmp_path), 'best'), exist_ok=True)
+    model = ToyMMNet(Genotype)
+    with torch.no_grad():
+        model.fusion_net.weight.fill_(float('nan'))
+    logger = ListLogger()
+    out = loop.train_mmimdb_track_f1(model, LRArchitect(model), nn.BCEWithLogitsLoss(), torch.optim.Adam(model.parameters(), lr=1e-2),
+                                     sched.LRCosineAnnealingScheduler(1e-2, 1e-5, 1, 2, 3),
+                                     {'train': make_mm_data(1, 2, 8), 'dev': make_mm_data(2, 1, 8)}, {'train': 16, 'dev': 8},
+                                     torch.device('cpu'), 1, False, logger, TaskPlotter(), types.SimpleNamespace(save=str(tmp_path)))
+    assert out == 0.0 and not model.training and any('Nan loss during training' in l for l in logger.lines)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason='reference checkout not present (GPU box)')
+@pytest.mark.parametrize('task', ['ego', 'mmimdb'])
+@pytest.mark.parametrize('status', ['search', 'eval'])
+def test_ego_mmimdb_loops_match_the_reference(task, status, tmp_path):
+    """the reference's own loops on the same toy model, data and seeds: identical result, genotype, log lines, plots, files
+    and final weights"""
+    _, sched, Genotype = _ours()
+    ours = run_task_loop(task, _our_loop(task), sched, Genotype, str(tmp_path / 'ours'), status)
+    ip = types.ModuleType('IPython'); ip.embed = lambda *a, **k: None
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k == 'models' or k.startswith('models.')}
+    saved_path = list(sys.path)
+    try:
+        for k in saved:
+            del sys.modules[k]
+        sys.modules.setdefault('IPython', ip)
+        sys.path.insert(0, REF)
+        import importlib
+        ref_loop = importlib.import_module(f'models.search.train_searchable.{task}')
+        import models.auxiliary.scheduler as ref_sched
+        from models.search.darts.genotypes import Genotype as RefGenotype
+        ref = run_task_loop(task, ref_loop, ref_sched, RefGenotype, str(tmp_path / 'ref'), status)
+    finally:
+        for k in [k for k in sys.modules if k == 'models' or k.startswith('models.')]:
+            del sys.modules[k]
+        sys.modules.update({k: v for k, v in saved.items() if v is not None})
+        sys.path[:] = saved_path
+    assert abs(ours['res'] - ref['res']) < 1e-12 and ours['geno'] == ref['geno']
+    strip = lambda ls: [l for l in ls if not l.startswith('EXP:')]
+    assert strip(ours['lines']) == strip(ref['lines'])
+    assert ours['plots'] == ref['plots'] and ours['files'] == ref['files'] and ours['arch_calls'] == ref['arch_calls']
+    for k in ours['sd']:
+        assert torch.equal(ours['sd'][k], ref['sd'][k]), k
