@@ -324,10 +324,14 @@ def ncu_traffic():
 
 
 def training_runner(head):
-    rs = [r for r in head.fusion_net._bm_cache.values() if r.prog.training and r.prog.want_backward]
-    # the weight-step plan carries every kernel of a training step (the arch-step plan omits the weight-gradient GEMMs)
-    rs.sort(key=lambda r: -len(r.prog.bwd))
-    return rs[0]
+    """the weight-step plan (runtime.GRAD_MODE 'weights', else 'all'): it carries every GEMM of a training step -- the
+    arch-step plan omits the weight-gradient GEMMs"""
+    rs = {k: r for k, r in head.fusion_net._bm_cache.items() if r.prog.training and r.prog.want_backward}
+    for mode in ('weights', 'all', 'arch'):
+        for k, r in rs.items():
+            if mode in k:
+                return r
+    raise RuntimeError('no training plan built yet')
 
 
 def mixedop_roofline(prog, c, B, pk, R=50, reps=4):

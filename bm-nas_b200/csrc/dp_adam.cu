@@ -32,6 +32,8 @@ __device__ __forceinline__ float4 ld_peer4(const float* p) {          // peer da
     return v;
 }
 
+// WT: the world size as a compile-time constant (2 / 4 / 8; 0 = generic), U: float4 groups in flight per thread
+template <int WT, int U>
 __global__ void __launch_bounds__(TH) k_dp_adam(const bmnas_dp_adam_params p) {
     pdl_prologue();
     __shared__ float s_c[2];
@@ -62,30 +64,60 @@ __global__ void __launch_bounds__(TH) k_dp_adam(const bmnas_dp_adam_params p) {
     const long long n4 = p.n / 4;
     const long long per = (n4 + W - 1) / W;
     const long long lo = (long long)R * per, hi = min(n4, lo + per);
-    for (long long q = lo + (long long)blockIdx.x * TH + threadIdx.x; q < hi; q += (long long)gridDim.x * TH) {
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int r = 0; r < W; ++r) {                        // rank order: the same sum on whichever rank owns the element
-            const float4 a = ld_peer4(p.grad_ptrs[r] + 4 * q);
-            g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w;
-        }
-        float* pw = p.param_ptrs[R] + 4 * q;
-        float4 w = *reinterpret_cast<const float4*>(pw);
-        float4 m = *reinterpret_cast<const float4*>(p.m + 4 * (q - lo));
-        float4 v = *reinterpret_cast<const float4*>(p.v + 4 * (q - lo));
-        float ww[4] = {w.x, w.y, w.z, w.w}, gg[4] = {g.x, g.y, g.z, g.w}, mm[4] = {m.x, m.y, m.z, m.w}, vv[4] = {v.x, v.y, v.z, v.w};
+    // every remote load is a ~2 us NVLink round trip: a thread keeps U float4 groups x W ranks in flight at once
+    const long long stride = (long long)gridDim.x * TH;
+    for (long long q0 = lo + (long long)blockIdx.x * TH + threadIdx.x; q0 < hi; q0 += stride * U) {
+        float4 g[U];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {                        // identical arithmetic to k_adam (loss_optim.cu)
-            float gj = gg[j] * p.grad_scale;
-            if (p.weight_decay != 0.f) gj = fmaf(p.weight_decay, ww[j], gj);
-            mm[j] = mm[j] + (gj - mm[j]) * (1.f - b1);
-            vv[j] = vv[j] * b2 + (1.f - b2) * gj * gj;
-            const float denom = sqrtf(vv[j]) / bc2s + p.eps;
-            ww[j] = ww[j] - step_size * (mm[j] / denom);
+        for (int u = 0; u < U; ++u) g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (WT > 0) {
+            float4 a[U][WT > 0 ? WT : 1];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long long q = q0 + u * stride;
+#pragma unroll
+                for (int r = 0; r < WT; ++r) a[u][r] = q < hi ? ld_peer4(p.grad_ptrs[r] + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+#pragma unroll
+                for (int r = 0; r < WT; ++r) {               // rank order: the same sum on whichever rank owns the element
+                    g[u].x += a[u][r].x; g[u].y += a[u][r].y; g[u].z += a[u][r].z; g[u].w += a[u][r].w;
+                }
+            }
+        } else {
+            for (int u = 0; u < U; ++u) {
+                const long long q = q0 + u * stride;
+                if (q >= hi) break;
+                for (int r = 0; r < W; ++r) {
+                    const float4 a = ld_peer4(p.grad_ptrs[r] + 4 * q);
+                    g[u].x += a.x; g[u].y += a.y; g[u].z += a.z; g[u].w += a.w;
+                }
+            }
         }
-        *reinterpret_cast<float4*>(p.m + 4 * (q - lo)) = make_float4(mm[0], mm[1], mm[2], mm[3]);
-        *reinterpret_cast<float4*>(p.v + 4 * (q - lo)) = make_float4(vv[0], vv[1], vv[2], vv[3]);
-        const float4 nw = make_float4(ww[0], ww[1], ww[2], ww[3]);
-        for (int r = 0; r < W; ++r) *reinterpret_cast<float4*>(p.param_ptrs[r] + 4 * q) = nw;    // all-gather by push
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long q = q0 + u * stride;
+            if (q >= hi) break;
+            float* pw = p.param_ptrs[R] + 4 * q;
+            const float4 w = *reinterpret_cast<const float4*>(pw);
+            const float4 m = *reinterpret_cast<const float4*>(p.m + 4 * (q - lo));
+            const float4 v = *reinterpret_cast<const float4*>(p.v + 4 * (q - lo));
+            float ww[4] = {w.x, w.y, w.z, w.w}, gg[4] = {g[u].x, g[u].y, g[u].z, g[u].w}, mm[4] = {m.x, m.y, m.z, m.w}, vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {                    // identical arithmetic to k_adam (loss_optim.cu)
+                float gj = gg[j] * p.grad_scale;
+                if (p.weight_decay != 0.f) gj = fmaf(p.weight_decay, ww[j], gj);
+                mm[j] = mm[j] + (gj - mm[j]) * (1.f - b1);
+                vv[j] = vv[j] * b2 + (1.f - b2) * gj * gj;
+                const float denom = sqrtf(vv[j]) / bc2s + p.eps;
+                ww[j] = ww[j] - step_size * (mm[j] / denom);
+            }
+            *reinterpret_cast<float4*>(p.m + 4 * (q - lo)) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+            *reinterpret_cast<float4*>(p.v + 4 * (q - lo)) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+            const float4 nw = make_float4(ww[0], ww[1], ww[2], ww[3]);
+            for (int r = 0; r < W; ++r) *reinterpret_cast<float4*>(p.param_ptrs[r] + 4 * q) = nw;    // all-gather by push
+        }
     }
     // ---- barrier B: the last CTA of this rank announces that all its pushes are out; everyone waits for all ranks
     __threadfence_system();
@@ -121,10 +153,18 @@ extern "C" int bmnas_dp_adam_step(const bmnas_dp_adam_params* p, void* stream) {
         return BMNAS_EINVAL;
     BMNAS_DRY_RETURN();
     const long long n4 = p->n / 4, per = (n4 + p->world - 1) / p->world;
-    long long blocks = (per + dp::TH - 1) / dp::TH;
+    // the shard is a few hundred KB and every pass over it costs an NVLink round trip: spread it over the whole machine
+    // (nothing else runs at this point of the step) so that one pass of U groups per thread covers it
+    const int U = p->world <= 2 ? 4 : (p->world <= 4 ? 2 : 1);
+    long long blocks = (per + (long long)dp::TH * U - 1) / ((long long)dp::TH * U);
     if (blocks < 1) blocks = 1;
-    if (blocks > 32) blocks = 32;                 // a shard is a few hundred KB: 32 CTAs keep NVLink busy without hogging the SMs
-    launch_k(dp::k_dp_adam, (unsigned)blocks, dp::TH, 0, (cudaStream_t)stream, *p);
+    if (blocks > kNumSMs) blocks = kNumSMs;
+    const dim3 grid((unsigned)blocks);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p->world == 2) launch_k(dp::k_dp_adam<2, 4>, grid, dp::TH, 0, st, *p);
+    else if (p->world == 4) launch_k(dp::k_dp_adam<4, 2>, grid, dp::TH, 0, st, *p);
+    else if (p->world == 8) launch_k(dp::k_dp_adam<8, 1>, grid, dp::TH, 0, st, *p);
+    else launch_k(dp::k_dp_adam<0, 1>, grid, dp::TH, 0, st, *p);
     BMNAS_LAUNCH_CHECK();
     return BMNAS_OK;
 }
