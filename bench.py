@@ -584,6 +584,11 @@ def run_ours(args):
     n_pool += n_pool % 2
     pool = make_pool(c, n_pool, 100 + rank, device)
     ss.load('dev', *pool[0]); ss.load('train', *pool[1])
+    # one resident byte tensor per step (SearchStep.pack_step: [dev feats | train feats | dev labels | train labels]):
+    # a step's inputs reach the static buffers with ONE device-to-device copy
+    ppool = [ss.pack_step(pool[2 * j][0], pool[2 * j][1], pool[2 * j + 1][0], pool[2 * j + 1][1], device=device)
+             for j in range(n_pool // 2)]
+    del pool[2:]
     dp = None
     if world > 1:
         dp = dp_check(ss, head, group, world, rank, device)
@@ -618,7 +623,7 @@ def run_ours(args):
         return e0.elapsed_time(e1), wall          # device time span of the K steps (idle gaps included)
 
     def load_dev(i):
-        ss.load('dev', *pool[(2 * i) % n_pool]); ss.load('train', *pool[(2 * i + 1) % n_pool])
+        ss.load_step(ppool[i % len(ppool)])
     for i in range(args.warmup):
         load_dev(i); ss.step()
     clocks = Clocks(local)
@@ -636,8 +641,10 @@ def run_ours(args):
     # ---- end to end: pinned host inputs, H2D every step, D2H loss read every step
     hpool = make_pool(c, 8, 500 + rank, device, pinned=True)
 
+    hppool = [ss.pack_step(hpool[2 * j][0], hpool[2 * j][1], hpool[2 * j + 1][0], hpool[2 * j + 1][1], pinned=True) for j in range(4)]
+
     def load_host(i):
-        ss.load('dev', *hpool[(2 * i) % 8]); ss.load('train', *hpool[(2 * i + 1) % 8])
+        ss.load_step(hppool[i % 4])
     for i in range(max(3, args.warmup)):
         load_host(i); ss.step()
     serial_ms, serial_wall = timed(args.steps, load_host, read_loss=True)   # copy, then compute, then read: no overlap

@@ -25,15 +25,15 @@ class _Bucket:
 
 class PeerStep:
     @staticmethod
-    def create(head, group, device, w_hyper, a_hyper):
+    def create(head, group, device, w_hyper, a_hyper, lr_ring=0):
         try:
-            return PeerStep(head, group, device, w_hyper, a_hyper)
+            return PeerStep(head, group, device, w_hyper, a_hyper, lr_ring)
         except Exception as e:  # no symmetric memory on this platform / build: NCCL path
             import warnings
             warnings.warn(f'bmnas.dp: peer-memory optimiser step unavailable ({e!r}); using NCCL all-reduce + FusedAdam')
             return None
 
-    def __init__(self, head, group, device, w_hyper, a_hyper):
+    def __init__(self, head, group, device, w_hyper, a_hyper, lr_ring=0):
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
         self.group, self.device = group, device
@@ -77,7 +77,8 @@ class PeerStep:
             per = ((n // 4 + self.world - 1) // self.world) * 4
             b.m, b.v = torch.zeros(per, device=device), torch.zeros(per, device=device)
             b.step = torch.zeros(1, dtype=torch.int64, device=device)
-            b.lr = torch.full((1,), float(hyp['lr']), device=device)
+            b.lr_ring = lr_ring if which == 'train' else 0       # the weight step follows the schedule, the arch lr is constant
+            b.lr = torch.full((max(1, b.lr_ring),), float(hyp['lr']), device=device)
             b.epoch = torch.zeros(1, dtype=torch.int32, device=device)
             b.done = torch.zeros(1, dtype=torch.int32, device=device)
             st = N.bmnas_dp_adam_params()
@@ -88,11 +89,18 @@ class PeerStep:
             st.beta1, st.beta2 = hyp['betas']
             st.eps, st.weight_decay, st.grad_scale = hyp.get('eps', 1e-8), hyp['weight_decay'], 1.0 / self.world
             st.epoch, st.done_counter = b.epoch.data_ptr(), b.done.data_ptr()
+            st.lr_ring = b.lr_ring
             b.st = st
             self.buckets[which] = b
 
     def set_lr(self, lr):
         self.buckets['train'].lr.fill_(float(lr))
+
+    def write_lr_ring(self, start, values):
+        """FusedAdam.write_lr_ring for the weight bucket"""
+        b = self.buckets['train']
+        idx = torch.tensor([(start + i) % b.lr_ring for i in range(len(values))], dtype=torch.int64, device=self.device)
+        b.lr.index_copy_(0, idx, torch.tensor(values, dtype=torch.float32).to(self.device))
 
     def step(self, which):
         """reduce-scatter + Adam + all-gather for this half's bucket: one launch, stream ordered, graph capturable"""

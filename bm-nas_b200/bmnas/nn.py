@@ -11,6 +11,7 @@
                        with the reference's attribute names, one joint gradient arena.
 """
 import ctypes
+import os
 
 import torch
 import torch.nn as nn
@@ -18,6 +19,13 @@ import torch.nn as nn
 from . import native as N
 from . import runtime as _rt
 from . import program as _prog
+
+
+# classifier + criterion + their backward as ONE kernel (bmnas_head_fused, csrc/head_fused.cu) wherever SearchHead.loss_fused
+# is used (SearchStep does); 0 = the five-launch chain Linear -> criterion -> backward of both
+FUSED_HEAD = os.environ.get('BMNAS_FUSED_HEAD', '1') != '0'
+# SearchStep calls loss.backward() itself: the incoming gradient of the loss is the constant 1 and is not multiplied in
+UNIT_LOSS_GRAD = [False]
 
 
 def _conv_struct(B, L, K, M, w_fold=1):
@@ -239,6 +247,64 @@ class BCEWithLogitsLoss(_Loss):
     _kind = 1
 
 
+class _HeadLossFn(torch.autograd.Function):
+    """loss, logits = criterion(x W^T + b, target) with d loss / d x computed by the same launch (bmnas_head_fused);
+    backward only forks the classifier's dW / db onto the side branch and hands the stored input gradient on."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, target, kind, ws, gw_view, gb_view):
+        B, Kc = x.shape
+        Nc = weight.shape[0]
+        want_gx = bool(ctx.needs_input_grad[0])      # Function.forward runs with grad mode off: ask autograd
+        logits = torch.empty(B, Nc, device=x.device, dtype=torch.float32)
+        loss = torch.empty((), device=x.device, dtype=torch.float32)
+        gl = torch.empty(B, Nc, device=x.device, dtype=torch.float32) if want_gx else None
+        gx = torch.empty_like(x) if want_gx else None
+        st = N.bmnas_head_params()
+        st.B, st.K, st.N, st.kind = B, Kc, Nc, kind
+        st.x, st.W, st.bias = x.data_ptr(), weight.data_ptr(), _p(bias)
+        if kind == 0:
+            st.labels = target.data_ptr()
+        else:
+            st.targets = target.data_ptr()
+        st.logits, st.loss, st.glogits, st.gx = logits.data_ptr(), loss.data_ptr(), _p(gl), _p(gx)
+        st.partials, st.counter = ws[0].data_ptr(), ws[1].data_ptr()
+        N.launch('bmnas_head_fused', ctypes.byref(st), N.current_stream())
+        ctx.x, ctx.gl, ctx.gx = x, gl, gx
+        ctx.views = (gw_view, gb_view)
+        ctx.dims = (B, Kc, Nc, weight.data_ptr())
+        ctx.mark_non_differentiable(logits)
+        ctx.set_materialize_grads(False)     # no zero tensor for the logits' (non-existent) gradient
+        return loss, logits
+
+    @staticmethod
+    def backward(ctx, g, _unused):
+        x, gl, gx = ctx.x, ctx.gl, ctx.gx
+        gw_view, gb_view = ctx.views
+        B, Kc, Nc, wptr = ctx.dims
+        if not UNIT_LOSS_GRAD[0]:             # a caller that scales the loss: d/dx and d/dlogits are linear in it
+            gl = gl * g
+            gx = gx * g
+        if gw_view is not None or gb_view is not None:
+            st = N.bmnas_linear_params()
+            st.B, st.K, st.N = B, Kc, Nc
+            st.x, st.W, st.gout = x.data_ptr(), wptr, gl.data_ptr()
+            st.gW, st.gbias = _p(gw_view), _p(gb_view)
+            if _prog.SIDE_WGRAD and not N.VALIDATE_ONLY:
+                # dW / db only feed the optimiser: side branch (joined by the launch plan's backward, the all-reduce and
+                # FusedAdam.step through program.join_side)
+                main = torch.cuda.current_stream()
+                side = _prog.side_stream(x.device)
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                gl.record_stream(side)
+                N.launch('bmnas_linear_bwd', ctypes.byref(st), ctypes.c_void_p(side.cuda_stream))
+            else:
+                N.launch('bmnas_linear_bwd', ctypes.byref(st), N.current_stream())
+        return gx, None, None, None, None, None, None, None
+
+
 class SearchHead(nn.Module):
     """fusion network + classifier: what the search step optimises once backbone features are given.
     ``genotype=None`` builds the searchable hypernet, otherwise the found network."""
@@ -277,6 +343,56 @@ class SearchHead(nn.Module):
     def forward(self, feats):
         self._joint_arena(feats[0].device)
         return self.central_classifier(self.fusion_net(feats))
+
+    def loss_fused(self, feats, labels, criterion):
+        """criterion(self(feats), labels) with the classifier, the criterion and the gradient they send back into the fusion
+        network in ONE launch (bmnas_head_fused).  Returns (loss, logits), or None when the fused kernel does not take the
+        case (then call criterion(self(feats), labels)): it needs a bmnas criterion, the overwrite semantics of
+        runtime.static_io (or no gradient at all) and a shape bmnas_head_supported accepts."""
+        if not FUSED_HEAD or not isinstance(criterion, _Loss):
+            return None
+        if torch.is_grad_enabled() and not _rt.STATIC_IO[0]:
+            return None
+        lin = self.central_classifier
+        dev = feats[0].device
+        if not feats[0].is_cuda and not N.VALIDATE_ONLY:
+            raise N.NativeError('bmnas.nn.SearchHead has no CPU implementation')
+        kind = criterion._kind
+        st = N.bmnas_head_params()
+        st.B, st.K, st.N, st.kind = feats[0].shape[0], lin.in_features, lin.out_features, kind
+        # pointer fields only need to be non-NULL / aligned for the support check
+        st.x = st.W = st.logits = st.loss = st.partials = st.counter = 16
+        st.labels = st.targets = 16
+        if not N.lib().bmnas_head_supported(ctypes.byref(st)) or lin.weight.data_ptr() % 16:
+            return None
+        ws = self.__dict__.get('_bm_head_ws')
+        n = int(N.lib().bmnas_head_partials_size(ctypes.byref(st)))
+        if ws is None or ws[0].device != dev or ws[0].numel() < n:
+            ws = (torch.zeros(max(n, 1), device=dev), torch.zeros(1, dtype=torch.int32, device=dev))
+            self.__dict__['_bm_head_ws'] = ws
+        self._joint_arena(dev)
+        x = self.fusion_net(feats)
+        x = x if x.is_contiguous() else x.contiguous()
+        if x.data_ptr() % 16:
+            return None
+        target = labels.to(torch.int64).contiguous() if kind == 0 else labels.to(torch.float32).contiguous()
+        all_leaves = [p for p in (lin.weight, lin.bias) if p is not None and p.requires_grad]
+        leaves = _rt.filter_leaves(all_leaves)
+        gw = gb = None
+        if leaves and torch.is_grad_enabled():
+            ar = _rt.arena_for(lin, all_leaves, dev)
+            gw = ar.view(lin.weight) if lin.weight.requires_grad else None
+            gb = ar.view(lin.bias) if (lin.bias is not None and lin.bias.requires_grad) else None
+        loss, logits = _HeadLossFn.apply(x, lin.weight, lin.bias, target, kind, ws, gw, gb)
+        if (gw is not None or gb is not None) and loss.requires_grad:
+            w, b = lin.weight, lin.bias
+
+            def hook(_g, w=w, b=b, gw=gw, gb=gb):
+                _assign_grad(w, gw)
+                if b is not None:
+                    _assign_grad(b, gb)
+            loss.register_hook(hook)
+        return loss, logits
 
     def genotype(self):
         return self.fusion_net.genotype()

@@ -22,6 +22,7 @@ class FusedAdam(torch.optim.Optimizer):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
         self.grad_scale = 1.0
+        self.lr_ring = 0      # > 0 (set before the first step): the device lr is a ring of this many schedule values, see write_lr_ring
         self._g = {}          # group index -> device state
 
     # -------------------------------------------------------------- device state
@@ -47,7 +48,7 @@ class FusedAdam(torch.optim.Optimizer):
             m = torch.zeros(tot, device=dev)
             v = torch.zeros(tot, device=dev)
             step = torch.zeros(1, dtype=torch.int64, device=dev)
-            lr = torch.full((1,), float(group['lr']), device=dev)
+            lr = torch.full((max(1, self.lr_ring),), float(group['lr']), device=dev)
         table = (N.bmnas_adam_tensor * len(ps))()
         off, blk = 0, 0
         for i, p in enumerate(ps):
@@ -82,6 +83,33 @@ class FusedAdam(torch.optim.Optimizer):
                 st['lr'].fill_(float(lr))
                 st['lr_host'] = float(lr)
 
+    def note_lr(self, lr):
+        """host bookkeeping only (param_groups[i]['lr'] for loggers): the device already holds the value (write_lr_ring)"""
+        for gi, group in enumerate(self.param_groups):
+            group['lr'] = float(lr)
+            st = self._g.get(gi)
+            if st is not None:
+                st['lr_host'] = float(lr)
+
+    def write_lr_ring(self, start, values):
+        """schedule values of the optimiser steps start, start + 1, ... (step = how many steps this optimiser has taken
+        before the one that uses the value) go to ring[(start + i) % lr_ring]: ONE stream-ordered upload for hundreds of
+        captured steps instead of a scalar write before every replay"""
+        R = self.lr_ring
+        assert R > 0 and len(values) <= R
+        ok = True
+        for gi, group in enumerate(self.param_groups):
+            st = self._g.get(gi)
+            if st is None:                   # no device state yet: it will be created with every entry = group['lr']
+                group['lr'] = float(values[0])
+                ok = False
+                continue
+            idx = torch.tensor([(start + i) % R for i in range(len(values))], dtype=torch.int64)
+            host = torch.tensor(values, dtype=torch.float32)
+            st['lr'].index_copy_(0, idx.to(st['lr'].device), host.to(st['lr'].device))
+            group['lr'] = st['lr_host'] = float(values[0])
+        return ok
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
@@ -109,6 +137,7 @@ class FusedAdam(torch.optim.Optimizer):
             p.eps, p.weight_decay, p.grad_scale = group['eps'], group['weight_decay'], self.grad_scale
             p.step = st['step'].data_ptr()
             p.counter = st['counter'].data_ptr()
+            p.lr_ring = self.lr_ring
             s = s or N.current_stream()
             N.launch('bmnas_adam_step', ctypes.byref(p), s)
         self._clear_dirty()

@@ -52,6 +52,23 @@ FUSED_MIXED = os.environ.get('BMNAS_FUSED_MIXED', 'auto')
 FUSED_MIXED_MIN_B = int(os.environ.get('BMNAS_FUSED_MIXED_MIN_B', '768'))   # measured crossover (profiles/r02_fused_crossover.txt): 3xTF32 ties at 512, wins from 1024
 FUSED_OPS_RANK = {'Sum': 0, 'ScaleDotAttn': 1, 'LinearGLU': 2, 'ConcatFC': 3, 'CatConvMish': 3}
 _side_streams = {}
+# SearchStep's half steps: the gradient-arena span a plan accumulates into is cleared at the START of the forward, on the
+# side branch, instead of at the start of the backward on the main chain (where the memset node and its edges cost ~10 us
+# between the loss and the first backward kernel, tools/timeline.py).  Legal there because the optimiser consumed the span
+# at the end of the previous half step and forward + backward are always issued together; plain autograd use of the
+# modules keeps the zero fill in the backward (pending gradients may live in the span until then).
+EARLY_ZERO = [False]
+EARLY_ZERO_AT = int(os.environ.get('BMNAS_EARLY_ZERO_AT', '4'))   # forward launch after which the clear is forked
+
+
+class early_zero:
+    def __enter__(self):
+        self.prev = EARLY_ZERO[0]
+        EARLY_ZERO[0] = True
+
+    def __exit__(self, *a):
+        EARLY_ZERO[0] = self.prev
+
 
 
 def side_stream(device):
@@ -239,20 +256,41 @@ class Program:
         self.n_bwd_launches = len(self.bwd) + len(self._zero_ranges)
 
     # ------------------------------------------------------------------ execution
+    def _zero(self, stream_ptr):
+        for t in self._zero_ranges:
+            N.launch('bmnas_zero', ctypes.c_void_p(t.data_ptr()), ctypes.c_longlong(t.numel() * t.element_size()), stream_ptr)
+
     def run_forward(self):
         s = N.current_stream()
+        self._zero_ev = None
+        early = EARLY_ZERO[0] and self._zero_ranges and self.want_backward and SIDE_WGRAD and not N.VALIDATE_ONLY
+        fork_at = min(EARLY_ZERO_AT, len(self.fwd) - 1) if early else -1
         if self.rng_state is not None and not self._rng_in_prep:
             N.launch('bmnas_rng_advance', ctypes.c_void_p(self.rng_state.data_ptr()), s)
         for c in self._prep_calls:
             c(s)
-        for c in self.fwd:
+        for i, c in enumerate(self.fwd):
             c(s)
+            if i == fork_at:
+                # not at the very start: a fork right behind the root of a captured graph delayed the first kernels of
+                # the main chain by 5-11 us (tools/timeline.py)
+                main = torch.cuda.current_stream()
+                side = side_stream(self.device)
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                self._zero(ctypes.c_void_p(side.cuda_stream))
+                self._zero_ev = torch.cuda.Event()
+                self._zero_ev.record(side)
         self.generation += 1
 
     def run_backward(self):
         s = N.current_stream()
-        for t in self._zero_ranges:
-            N.launch('bmnas_zero', ctypes.c_void_p(t.data_ptr()), ctypes.c_longlong(t.numel() * t.element_size()), s)
+        if getattr(self, '_zero_ev', None) is not None:
+            torch.cuda.current_stream().wait_event(self._zero_ev)      # cleared during the forward, on the side branch
+            self._zero_ev = None
+        else:
+            self._zero(s)
         if not SIDE_WGRAD or N.VALIDATE_ONLY:
             for c in self.bwd:
                 c(s)

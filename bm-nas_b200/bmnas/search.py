@@ -29,6 +29,8 @@ import torch
 from . import native as N
 from .optim import FusedAdam
 
+LR_RING = 1024      # device ring of weight-step learning rates (bmnas_adam_params.lr_ring); refilled half a ring at a time
+
 
 class SearchStep:
     def __init__(self, head, criterion, B, num_classes, loss_kind='ce', eta_max=1e-3, eta_min=1e-6, Ti=1, Tm=2,
@@ -58,20 +60,36 @@ class SearchStep:
             from .dp import PeerStep
             self.peer = PeerStep.create(head, group, self.device,
                                         dict(lr=eta_max, betas=(0.9, 0.999), weight_decay=weight_decay),
-                                        dict(lr=arch_lr, betas=(0.5, 0.999), weight_decay=arch_wd))
-        self.w_opt = FusedAdam(head.central_params(), lr=eta_max, weight_decay=weight_decay)
+                                        dict(lr=arch_lr, betas=(0.5, 0.999), weight_decay=arch_wd), lr_ring=LR_RING)
+        # the reference hands Adam two parameter groups with identical hyper-parameters (central_params(),
+        # ntu_darts_searchable.py:38-42): one group here = one multi-tensor launch per weight step
+        self.w_opt = FusedAdam([p for g in head.central_params() for p in g['params']], lr=eta_max, weight_decay=weight_decay)
+        # the schedule is uploaded LR_RING / 2 steps ahead (FusedAdam.write_lr_ring): no host write between replays
+        self.w_opt.lr_ring = LR_RING
+        self.w_steps = 0            # host mirror of the weight optimiser's device step counter
+        self._ring_until = -1       # weight steps < this have their learning rate on the device
         self.a_opt = FusedAdam(head.arch_parameters(), lr=arch_lr, betas=(0.5, 0.999), weight_decay=arch_wd)
         self.w_opt.grad_scale = self.a_opt.grad_scale = 1.0 / self.world
         self.sched = LRCosineAnnealingScheduler(eta_max, eta_min, Ti, Tm, nbpe)
         dev = self.device
-        # static input buffers: feats as views of one flat tensor so a batch arrives with ONE copy
-        self.flat = {k: torch.zeros(self.n_in, B, self.C, self.L, device=dev) for k in ('dev', 'train')}
+        # static input buffers: ONE byte buffer per search step, [dev feats | train feats | dev labels | train labels]
+        # (pack_step() builds that layout), so a whole step's inputs arrive with one copy (load_step) and a half's
+        # features with one (load / prefetch); feats / labels are typed views into it
+        nf = self.n_in * B * self.C * self.L * 4
+        nl = B * 8 if loss_kind == 'ce' else B * num_classes * 4
+        nl16 = (nl + 15) // 16 * 16
+        self._layout = {'dev': (0, 2 * nf), 'train': (nf, 2 * nf + nl16), 'nf': nf, 'nl': nl, 'total': 2 * nf + 2 * nl16}
+        self.packed = torch.zeros(self._layout['total'], dtype=torch.uint8, device=dev)
+        self.flat, self.labels = {}, {}
+        for k in ('dev', 'train'):
+            fo, lo = self._layout[k]
+            self.flat[k] = self.packed[fo:fo + nf].view(torch.float32).view(self.n_in, B, self.C, self.L)
+            lab = self.packed[lo:lo + nl]
+            self.labels[k] = lab.view(torch.int64) if loss_kind == 'ce' else lab.view(torch.float32).view(B, num_classes)
         self.feats = {k: [v[i] for i in range(self.n_in)] for k, v in self.flat.items()}
-        if loss_kind == 'ce':
-            self.labels = {k: torch.zeros(B, dtype=torch.int64, device=dev) for k in ('dev', 'train')}
-        else:
-            self.labels = {k: torch.zeros(B, num_classes, device=dev) for k in ('dev', 'train')}
+        self._one = torch.ones((), device=dev)
         self.loss = {'dev': None, 'train': None}
+        self.logits = {'dev': None, 'train': None}     # logits of the last half step (fused head only; static buffers under graphs)
         self.graphs = {}
         self.launches_per_step = None
         self.steps_done = 0
@@ -84,11 +102,20 @@ class SearchStep:
     # ------------------------------------------------------------------ one half step, eager
     def _half(self, which):
         from . import runtime as _rt
+        from . import nn as _nn
+        from . import program as _prog
         head = self.head
         mode = ('arch' if which == 'dev' else 'weights') if self.prune_grads else 'all'
-        with _rt.grad_mode(mode), _rt.static_io():
-            loss = self.criterion(head(self.feats[which]), self.labels[which])
-            loss.backward()
+        with _rt.grad_mode(mode), _rt.static_io(), _prog.early_zero():
+            # classifier + criterion + the gradient they send back: one launch where the head takes the case
+            res = head.loss_fused(self.feats[which], self.labels[which], self.criterion) if hasattr(head, 'loss_fused') else None
+            loss = res[0] if res is not None else self.criterion(head(self.feats[which]), self.labels[which])
+            self.logits[which] = res[1] if res is not None else None
+            _nn.UNIT_LOSS_GRAD[0] = True       # the backward below is seeded with the constant 1 (a resident tensor: no fill launch)
+            try:
+                torch.autograd.backward(loss, grad_tensors=self._one)
+            finally:
+                _nn.UNIT_LOSS_GRAD[0] = False
         if self.peer is not None:
             self.peer.step(which)            # reduce-scatter + Adam on the shard + all-gather of parameters: one launch
         else:
@@ -99,9 +126,27 @@ class SearchStep:
         return loss.detach()
 
     def set_lr(self, lr):
+        """a constant learning rate for the weight step (until the next half('train'), which follows the schedule)"""
         self.w_opt.set_lr(lr)
         if self.peer is not None:
             self.peer.set_lr(lr)
+        self._ring_until = -1
+
+    def _refill_lr(self):
+        """upload the schedule values of the next LR_RING / 2 weight steps (scheduler.py:25-40, one tick per step)"""
+        import copy
+        c = copy.deepcopy(self.sched)
+        vals = []
+        for _ in range(LR_RING // 2):
+            c.step()
+            vals.append(float(c.eta))
+        if self.peer is not None:
+            self.peer.write_lr_ring(self.w_steps, vals)
+            ok = True
+        else:
+            ok = self.w_opt.write_lr_ring(self.w_steps, vals)
+        # before the optimiser's device state exists only the value of the very next step is in place (group['lr'])
+        self._ring_until = self.w_steps + (len(vals) if ok else 1)
 
     def grad_span(self, which):
         """the contiguous slice of the flat gradient arena [alpha,beta,gamma | fusion weights | classifier] that the
@@ -142,8 +187,11 @@ class SearchStep:
         g = self.graphs.get(which)
         if g is not None:
             g.replay()
+            self.loss[which], self.logits[which] = self._half_out[which]
         else:
             self.loss[which] = self._half(which)
+        if which == 'train':
+            self.w_steps += 1
         if self.copy_stream is not None:     # the next prefetch() into these buffers must wait for this reader
             d = self._done[which]
             if d is None:
@@ -154,6 +202,30 @@ class SearchStep:
         """copy a batch (any device, e.g. pinned host memory) into the static buffers; async"""
         self.flat[which].copy_(feats_flat, non_blocking=True)
         self.labels[which].copy_(labels, non_blocking=True)
+
+    def pack_step(self, dev_feats, dev_labels, train_feats, train_labels, pinned=False, device=None):
+        """one contiguous byte tensor holding a whole step's inputs in the layout of the static buffers (for load_step);
+        feats: (n_in, B, C, L) fp32, labels as the criterion takes them"""
+        out = torch.empty(self._layout['total'], dtype=torch.uint8, device=device or 'cpu')
+        if pinned:
+            out = out.pin_memory()
+        nf, nl = self._layout['nf'], self._layout['nl']
+        for k, f, y in (('dev', dev_feats, dev_labels), ('train', train_feats, train_labels)):
+            fo, lo = self._layout[k]
+            out[fo:fo + nf].view(torch.float32).view(self.flat[k].shape).copy_(f)
+            lab = out[lo:lo + nl]
+            (lab.view(torch.int64) if self.kind == 'ce' else lab.view(torch.float32).view(self.labels[k].shape)).copy_(y)
+        return out
+
+    def load_step(self, packed):
+        """both halves' inputs with ONE copy (packed: pack_step(); any device, e.g. pinned host memory); async"""
+        if (packed.is_cuda and packed.device == self.packed.device and packed.dtype == torch.uint8 and packed.is_contiguous()
+                and packed.numel() == self.packed.numel() and packed.data_ptr() % 16 == 0 and packed.numel() % 16 == 0):
+            import ctypes
+            N.launch('bmnas_copy', ctypes.c_void_p(self.packed.data_ptr()), ctypes.c_void_p(packed.data_ptr()),
+                     ctypes.c_longlong(packed.numel()), N.current_stream(self.device))
+        else:
+            self.packed.copy_(packed, non_blocking=True)
 
     def prefetch(self, which, feats_flat, labels):
         """load() for an input pipeline: the copy runs on a dedicated stream, ordered after the last half step that
@@ -180,7 +252,7 @@ class SearchStep:
         import copy
         snap = {'sd': {k: v.detach().clone() for k, v in self.head.state_dict().items()},
                 'arch': [a.detach().clone() for a in self.head.arch_parameters()],
-                'sched': copy.deepcopy(self.sched.__dict__), 'steps': self.steps_done,
+                'sched': copy.deepcopy(self.sched.__dict__), 'steps': self.steps_done, 'w_steps': self.w_steps,
                 'opt': [opt.state_snapshot() for opt in (self.w_opt, self.a_opt)],
                 'peer': self.peer.state_snapshot() if self.peer is not None else None,
                 'rng': [(p.rng_state.clone() if p.rng_state is not None else None) for p in self._programs()]}
@@ -209,6 +281,8 @@ class SearchStep:
                     p.rng_state[1] = 0
         self.sched.__dict__.update(snap['sched'])
         self.steps_done = snap['steps']
+        self.w_steps = snap['w_steps']
+        self._ring_until = -1
 
     def prepare(self, warmup=3, restore=True):
         """warm-up (builds launch plans, arenas, Adam tables) then capture the two graphs; with restore=True
@@ -230,12 +304,24 @@ class SearchStep:
         torch.cuda.synchronize()
         n0 = N.LAUNCHES[0]
         self.loss = {'dev': None, 'train': None}
+        self._half_out = {}
         for which in ('dev', 'train'):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=s):
                 self.loss[which] = self._half(which)
             self.graphs[which] = g
+            self._half_out[which] = (self.loss[which], self.logits[which])     # static outputs of this graph
         self.launches_per_step = N.LAUNCHES[0] - n0
+        # the whole step as ONE graph as well: with the schedule on the device (lr ring) nothing happens on the host
+        # between the two halves, so step() is a single launch and the arch half's Adam -> weight half's first kernel
+        # boundary is an ordinary graph edge
+        g = torch.cuda.CUDAGraph()
+        self._step_out = {}
+        with torch.cuda.graph(g, stream=s):
+            for which in ('dev', 'train'):
+                loss = self._half(which)
+                self._step_out[which] = (loss, self.logits[which])
+        self.graphs['step'] = g
         if restore:
             self._restore(snap)
         torch.cuda.synchronize()
@@ -244,14 +330,28 @@ class SearchStep:
         """one half step ('dev' = Architect.step, 'train' = weight step incl. the LR schedule tick) on the batch in
         the static buffers; returns the loss as a device scalar"""
         if which == 'train':
+            if self.w_steps >= self._ring_until:
+                self._refill_lr()
             self.sched.step()
-            self.set_lr(float(self.sched.eta))
+            self.w_opt.note_lr(float(self.sched.eta))
         self._run_half(which)
         return self.loss[which]
 
     def step(self):
         """one search step on whatever currently sits in the static buffers; returns (arch loss, weight loss)
         as device scalars (no host sync)."""
+        g = self.graphs.get('step')
+        if g is not None and self.copy_stream is None:          # (the prefetch pipeline hands over per half step)
+            if self.w_steps >= self._ring_until:
+                self._refill_lr()
+            self.sched.step()
+            self.w_opt.note_lr(float(self.sched.eta))
+            g.replay()
+            self.w_steps += 1
+            self.steps_done += 1
+            for which in ('dev', 'train'):
+                self.loss[which], self.logits[which] = self._step_out[which]
+            return self.loss['dev'], self.loss['train']
         self.half('dev')
         self.half('train')
         self.steps_done += 1
@@ -267,6 +367,9 @@ class SearchStep:
             return self._metrics[which]
         from . import runtime as _rt
         with torch.no_grad(), _rt.static_io():
+            res = self.head.loss_fused(self.feats[which], self.labels[which], self.criterion) if hasattr(self.head, 'loss_fused') else None
+            if res is not None:
+                return res
             logits = self.head(self.feats[which])
             loss = self.criterion(logits, self.labels[which])
         return loss, logits
@@ -302,7 +405,7 @@ class SearchStep:
         return {'state_dict': {k: v.detach().cpu().clone() for k, v in self.head.state_dict().items()},
                 'arch': [a.detach().cpu().clone() for a in self.head.arch_parameters()],
                 'w_opt': self.w_opt.state_dict(), 'a_opt': self.a_opt.state_dict(),
-                'sched': dict(self.sched.__dict__), 'steps': self.steps_done}
+                'sched': dict(self.sched.__dict__), 'steps': self.steps_done, 'w_steps': self.w_steps}
 
     def load_checkpoint(self, ck):
         with torch.no_grad():
@@ -313,6 +416,8 @@ class SearchStep:
         self.a_opt.load_state_dict(ck['a_opt'])
         self.sched.__dict__.update(ck['sched'])
         self.steps_done = ck['steps']
+        self.w_steps = ck.get('w_steps', ck['steps'])
+        self._ring_until = -1
 
     def sync_buffers(self):
         """BatchNorm running statistics follow rank 0, as under nn.DataParallel"""

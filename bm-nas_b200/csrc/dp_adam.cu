@@ -53,9 +53,11 @@ __global__ void __launch_bounds__(TH) k_dp_adam(const bmnas_dp_adam_params p) {
         while ((int)(ld_acquire_sys(flag) - epoch) < 0) {}
     }
     if (threadIdx.x == 0) {
-        const double t = (double)(p.step[0] + 1);
+        const long long t0 = p.step[0];
+        const double t = (double)(t0 + 1);
         const double bc1 = 1.0 - pow((double)p.beta1, t), bc2 = 1.0 - pow((double)p.beta2, t);
-        s_c[0] = (float)((double)p.lr[0] / bc1);
+        const float lr = p.lr[p.lr_ring > 0 ? (int)(t0 % p.lr_ring) : 0];
+        s_c[0] = (float)((double)lr / bc1);
         s_c[1] = (float)sqrt(bc2);
     }
     __syncthreads();

@@ -94,9 +94,11 @@ __global__ void __launch_bounds__(OTH) k_adam(const bmnas_adam_params p) {
     }
     const bmnas_adam_tensor T = p.tensors[lo];
     if (threadIdx.x == 0) {
-        const double t = (double)(p.step[0] + 1);
+        const long long t0 = p.step[0];
+        const double t = (double)(t0 + 1);
         const double bc1 = 1.0 - pow((double)p.beta1, t), bc2 = 1.0 - pow((double)p.beta2, t);
-        s_c[0] = (float)((double)p.lr[0] / bc1);  // step size
+        const float lr = p.lr[p.lr_ring > 0 ? (int)(t0 % p.lr_ring) : 0];
+        s_c[0] = (float)((double)lr / bc1);  // step size
         s_c[1] = (float)sqrt(bc2);
     }
     __syncthreads();
@@ -121,6 +123,27 @@ __global__ void __launch_bounds__(OTH) k_adam(const bmnas_adam_params p) {
     if (last_block(p.counter, gridDim.x)) {
         if (threadIdx.x == 0) p.step[0] += 1;
     }
+}
+
+// zero fill as a KERNEL node: inside a captured graph a memset node sits on another engine and every edge into or out of
+// it costs 5-7 us of dependency latency (tools/timeline.py: the first backward kernel waited 6.2 us behind a 1.1 us memset)
+__global__ void __launch_bounds__(OTH) k_zero(uint4* p16, long long n16, unsigned char* tail, int ntail) {
+    pdl_prologue();
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (long long i = (long long)blockIdx.x * OTH + threadIdx.x; i < n16; i += (long long)gridDim.x * OTH) p16[i] = z;
+    if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail[threadIdx.x] = 0;
+}
+
+// device-to-device copy on the SMs (a copy-engine cudaMemcpyAsync moved the 6.3 MB of a step's inputs in 7.4 us; this takes ~2.5)
+__global__ void __launch_bounds__(OTH) k_copy(uint4* dst, const uint4* src, long long n16) {
+    pdl_prologue();
+    const long long stride = (long long)gridDim.x * OTH;
+    long long i = (long long)blockIdx.x * OTH + threadIdx.x;
+    for (; i + 3 * stride < n16; i += 4 * stride) {          // four independent 16-byte loads in flight per thread
+        const uint4 a = __ldcs(src + i), b = __ldcs(src + i + stride), c = __ldcs(src + i + 2 * stride), d = __ldcs(src + i + 3 * stride);
+        dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = d;
+    }
+    for (; i < n16; i += stride) dst[i] = __ldcs(src + i);
 }
 
 __global__ void k_rng_advance(unsigned long long* st) {
@@ -192,7 +215,7 @@ extern "C" int bmnas_colsum(float* out, const float* in, int rows, int n, void* 
 
 extern "C" int bmnas_adam_step(const bmnas_adam_params* p, void* stream) {
     if (!p || p->n_tensors < 1 || p->total_blocks < 1 || p->block_elems < 1 || !p->tensors || !p->lr || !p->step ||
-        !p->counter)
+        !p->counter || p->lr_ring < 0)
         return BMNAS_EINVAL;
     if (p->total_blocks > 0x7fffffffLL) return BMNAS_EINVAL;
     BMNAS_DRY_RETURN();
@@ -244,7 +267,28 @@ extern "C" int bmnas_zero(void* ptr, long long nbytes, void* stream) {
     if (!ptr || nbytes < 0) return BMNAS_EINVAL;
     if (nbytes == 0) return BMNAS_OK;
     BMNAS_DRY_RETURN();
-    return cudaMemsetAsync(ptr, 0, (size_t)nbytes, (cudaStream_t)stream) == cudaSuccess ? BMNAS_OK : BMNAS_ELAUNCH;
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15u) || nbytes > (1ll << 28))       // unaligned or huge: the driver's memset
+        return cudaMemsetAsync(ptr, 0, (size_t)nbytes, (cudaStream_t)stream) == cudaSuccess ? BMNAS_OK : BMNAS_ELAUNCH;
+    const long long n16 = nbytes >> 4;
+    long long blocks = (n16 + OTH * 4 - 1) / (OTH * 4);
+    if (blocks < 1) blocks = 1;
+    if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+    launch_k(k_zero, (unsigned)blocks, OTH, 0, (cudaStream_t)stream, reinterpret_cast<uint4*>(ptr), n16,
+             reinterpret_cast<unsigned char*>(ptr) + (n16 << 4), (int)(nbytes & 15));
+    BMNAS_LAUNCH_CHECK();
+    return BMNAS_OK;
+}
+extern "C" int bmnas_copy(void* dst, const void* src, long long nbytes, void* stream) {
+    if (!dst || !src || nbytes < 0 || (nbytes & 15) || ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15u))
+        return BMNAS_EINVAL;
+    if (nbytes == 0) return BMNAS_OK;
+    BMNAS_DRY_RETURN();
+    const long long n16 = nbytes >> 4;
+    long long blocks = (n16 + OTH * 4 - 1) / (OTH * 4);
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    launch_k(k_copy, (unsigned)blocks, OTH, 0, (cudaStream_t)stream, reinterpret_cast<uint4*>(dst), reinterpret_cast<const uint4*>(src), n16);
+    BMNAS_LAUNCH_CHECK();
+    return BMNAS_OK;
 }
 extern "C" int bmnas_sizeof_params(int which) {
     switch (which) {

@@ -435,6 +435,40 @@ int bmnas_linear_fwd(const bmnas_linear_params* p, void* stream);
 int bmnas_linear_bwd(const bmnas_linear_params* p, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Classifier head + criterion + their backward in ONE launch (the tail of a forward and the head of a backward
+ * of the search step):
+ *   logits = x W^T + bias                       central_classifier (ntu_darts_searchable.py:100-101, 176-178)
+ *   loss   = mean CE(logits, labels)   kind 0   nn.CrossEntropyLoss   (ntu_darts_searchable.py:25)
+ *          | mean BCE-with-logits      kind 1   nn.BCEWithLogitsLoss  (mmimdb_darts_searchable.py:22)
+ *   glogits = d loss / d logits                 what loss.backward() (train_searchable/ntu.py:88, architect.py:27-28)
+ *   gx      = glogits W                         hands to the classifier and through it to the fusion network
+ * gx NULL: forward + loss only.  glogits NULL: not stored.  gW / gbias are bmnas_linear_bwd's from glogits.
+ * Labels outside [0, N) give a NaN loss and NaN gradients for that sample (as bmnas_loss_fwd).
+ * partials: bmnas_head_partials_size floats of workspace; counter: one zeroed unsigned int (the kernel re-zeroes it).
+ * K % 4 == 0, N <= 128, 16-byte aligned x / W / gx; bmnas_head_supported tells (0: use linear_fwd + loss_fwd + ...).
+ * ---------------------------------------------------------------------- */
+typedef struct bmnas_head_params {
+    int B;
+    int K;
+    int N;
+    int kind;
+    const float* x;
+    const float* W;
+    const float* bias;
+    const long long* labels;
+    const float* targets;
+    float* logits;
+    float* loss;
+    float* glogits;
+    float* gx;
+    float* partials;
+    unsigned int* counter;
+} bmnas_head_params;
+int bmnas_head_supported(const bmnas_head_params* p);
+long long bmnas_head_partials_size(const bmnas_head_params* p); /* floats */
+int bmnas_head_fused(const bmnas_head_params* p, void* stream);
+
+/* ------------------------------------------------------------------------
  * Multi-tensor Adam, identical arithmetic to torch.optim.Adam (coupled L2 weight
  * decay, bias correction, eps outside the sqrt):
  *   weights  ntu_darts_searchable.py:42    arch  :46-47   (architect.py:24 step)
@@ -442,6 +476,9 @@ int bmnas_linear_bwd(const bmnas_linear_params* p, void* stream);
  * device memory so a captured CUDA graph sees the per-iteration schedule value
  * (replaces scheduler.update_optimizer's state_dict round trip, scheduler.py:42-46).
  * grad_scale multiplies every gradient first (1/world_size after an all-reduce).
+ * lr_ring > 0: lr points at a ring of lr_ring schedule values and the step uses lr[step % lr_ring] -- the host
+ * uploads the cosine-restart schedule (scheduler.py:25-40) a few hundred steps ahead instead of writing a scalar before
+ * every replay; lr_ring == 0: lr[0].
  * ---------------------------------------------------------------------- */
 typedef struct bmnas_adam_tensor {
     float* p;
@@ -464,6 +501,7 @@ typedef struct bmnas_adam_params {
     float grad_scale;
     long long* step;
     unsigned int* counter;
+    int lr_ring;
 } bmnas_adam_params;
 int bmnas_adam_step(const bmnas_adam_params* p, void* stream);
 
@@ -497,11 +535,15 @@ typedef struct bmnas_dp_adam_params {
     long long* step;
     unsigned int* epoch;
     unsigned int* done_counter;
+    int lr_ring;
 } bmnas_dp_adam_params;
 int bmnas_dp_adam_step(const bmnas_dp_adam_params* p, void* stream);
 
 /* stream-ordered zero fill (cudaMemsetAsync) and ABI self-description for binding tests */
 int bmnas_zero(void* ptr, long long nbytes, void* stream);
+/* device-to-device copy as a kernel (16-byte aligned pointers, nbytes % 16 == 0): the step's packed input batch into the
+ * static buffers the captured graphs read (SearchStep.load_step) */
+int bmnas_copy(void* dst, const void* src, long long nbytes, void* stream);
 int bmnas_sizeof_params(int which); /* 0 mix, 1 conv, 2 node, 3 ln, 4 loss, 5 adam_tensor, 6 adam */
 
 /* validate-only mode: every entry point checks its parameter block and returns before launching

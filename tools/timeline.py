@@ -1,0 +1,67 @@
+"""Kernel timeline of graph-replayed search steps (CUPTI through torch.profiler): start, duration, stream and the idle gap
+before every kernel of ONE step, plus per-kernel totals.  python tools/timeline.py [config] [--batch B]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, 'bm-nas_b200')):
+    sys.path.insert(0, p)
+import torch  # noqa: E402
+import bench  # noqa: E402
+
+
+def main():
+    cfgname = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith('--') else 'ntu'
+    c = dict(bench.CONFIGS[cfgname])
+    if '--batch' in sys.argv:
+        c['B'] = int(sys.argv[sys.argv.index('--batch') + 1])
+    dev = torch.device('cuda', 0)
+    torch.cuda.set_device(0)
+    torch.manual_seed(2)
+    head, ss = bench.build_search(c, dev, group=None, use_graphs=True, peer_step=None)
+    pool = bench.make_pool(c, 4, 100, dev)
+    ss.load('dev', *pool[0]); ss.load('train', *pool[1])
+    ss.prepare(warmup=3, restore=False)
+    pp = [ss.pack_step(pool[2 * j][0], pool[2 * j][1], pool[2 * j + 1][0], pool[2 * j + 1][1], device=dev) for j in range(2)]
+    for i in range(10):
+        ss.load_step(pp[i % 2]); ss.step()
+    torch.cuda.synchronize()
+    from torch.profiler import profile, ProfilerActivity
+    NS = 6
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for i in range(NS):
+            ss.load_step(pp[i % 2]); ss.step()
+        torch.cuda.synchronize()
+    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    evs.sort(key=lambda e: e.time_range.start)
+    # one step = from one 'Memcpy DtoD' group to the next: split at the first copy of each step
+    t0 = evs[0].time_range.start
+    rows = [(e.time_range.start - t0, e.time_range.end - e.time_range.start, e.name) for e in evs]
+    # find step boundaries: the first memcpy after a kernel
+    starts = [i for i, r in enumerate(rows) if 'emcpy' in r[2] and (i == 0 or 'emcpy' not in rows[i - 1][2])]
+    # a step has two loads (dev + train) back to back -> boundaries every group; keep groups that start a step
+    print('# events', len(rows), 'memcpy groups', len(starts))
+    per = len(starts) // NS if NS else 1
+    b = starts[per * (NS - 2)] if len(starts) >= per * (NS - 1) else 0
+    e = starts[per * (NS - 1)] if len(starts) > per * (NS - 1) else len(rows)
+    step = rows[b:e]
+    base = step[0][0]
+    end_prev = base
+    print('# one step: %d events, span %.1f us' % (len(step), step[-1][0] + step[-1][1] - base))
+    tot = {}
+    busy_end = base
+    for s, d, n in step:
+        gap = s - busy_end
+        short = n.split('(')[0].replace('void ', '').replace('bmnas::', '')[:60]
+        print('%9.2f  dur %7.2f  gap %6.2f  %s' % (s - base, d, gap, short))
+        busy_end = max(busy_end, s + d)
+        a = tot.setdefault(short, [0, 0.0])
+        a[0] += 1; a[1] += d
+    print('# per kernel (one step)')
+    for k, (n, d) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
+        print('%8.1f us  n=%3d  avg %6.2f  %s' % (d, n, d / n, k))
+    print('# sum of durations %.1f us' % sum(v[1] for v in tot.values()))
+
+
+if __name__ == '__main__':
+    main()
