@@ -50,6 +50,9 @@ SPLIT_MIX_BWD = os.environ.get('BMNAS_SPLIT_MIX_BWD', '1') != '0'   # edge-mix b
 # 0 = off, 1 = whenever the shape is supported, default: batches of FUSED_MIXED_MIN_B samples or more
 FUSED_MIXED = os.environ.get('BMNAS_FUSED_MIXED', 'auto')
 FUSED_MIXED_MIN_B = int(os.environ.get('BMNAS_FUSED_MIXED_MIN_B', '768'))   # measured crossover (profiles/r02_fused_crossover.txt): 3xTF32 ties at 512, wins from 1024
+# ... and below FUSED_MIXED_MIN_B the small-batch variant (bmnas_mixed_small_fwd: fp32 FFMA tiles, one grid barrier, also writes the
+# chained inner edge mix): 0 = off (bmnas_conv_fwd + bmnas_node_fwd), 1 = whenever the library takes the shape
+FUSED_MIXED_SMALL = os.environ.get('BMNAS_FUSED_MIXED_SMALL', '1')
 FUSED_OPS_RANK = {'Sum': 0, 'ScaleDotAttn': 1, 'LinearGLU': 2, 'ConcatFC': 3, 'CatConvMish': 3}
 _side_streams = {}
 # SearchStep's half steps: the gradient-arena span a plan accumulates into is cleared at the START of the forward, on the
@@ -132,6 +135,19 @@ class Program:
         if FUSED_MIXED == 'auto' and self.B < FUSED_MIXED_MIN_B:
             return False
         if N.lib().bmnas_get_gemm_mode() == 0:
+            return False
+        ranks = [FUSED_OPS_RANK.get(o, -1) for o in ops]
+        return (all(r >= 0 for r in ranks) and ranks == sorted(set(ranks)) and 'LinearGLU' in ops
+                and ops[-1] in ('ConcatFC', 'CatConvMish') and ops.index('LinearGLU') == len(ops) - 2)
+
+    def fused_small_ok(self, ops):
+        """shape-level test for bmnas_mixed_small_fwd (csrc/mixed_small.cu)"""
+        C, L, B = self.C, self.L, self.B
+        if C % 32 or C > 256 or L not in (4, 8, 16):
+            return False
+        if ((B * L + 31) // 32) * (C // 32) > 148:          # one co-resident wave (grid barrier)
+            return False
+        if int(N.lib().bmnas_conv_image_fmt(B, L, C, 3 * C)) != 1:   # the library would put this GEMM on the tensor cores
             return False
         ranks = [FUSED_OPS_RANK.get(o, -1) for o in ops]
         return (all(r >= 0 for r in ranks) and ranks == sorted(set(ranks)) and 'LinearGLU' in ops
@@ -530,13 +546,17 @@ class Program:
         self._mixed_id = getattr(self, '_mixed_id', 0) + 1
         prev_tag, self._cur_tag = self._cur_tag, f'mixed{self._mixed_id}'
         fused = bool(segs) and not ext and chain is None and self.fused_mixed_ok(ops, alias)
+        # small batches: the FFMA variant (takes the chained mix too); decided on the shape, the library re-checks pointers
+        small = (not fused and bool(segs) and not ext and alias and FUSED_MIXED_SMALL != '0' and self.fused_small_ok(ops))
         if segs and ext:
             cv = self.conv(list(conv_srcs), list(conv_src_C), segs, 1, bn=True)
             x = y = cv['Z']               # placeholders: no primitive of an external-source op reads x / y
             alias = True
         elif segs:
             cv = self.conv([x] if alias else [x, y], [C] if alias else [C, C], segs, 2 if alias else 1, bn=True,
-                           emit=not fused, fwd_fmt=(2 if N.lib().bmnas_get_gemm_mode() == 3 else 0) if fused else None, want_Z=(self.want_backward or not fused))
+                           emit=not (fused or small),
+                           fwd_fmt=((2 if N.lib().bmnas_get_gemm_mode() == 3 else 0) if fused else (1 if small else None)),
+                           want_Z=(self.want_backward or not (fused or small)))
         M = cv['M'] if cv else 0
 
         def fill(st):
@@ -588,8 +608,15 @@ class Program:
             ws = self.buf((int(N.lib().bmnas_mixed_workspace_bytes()) + 3) // 4, zero=True)
             self.emit('bmnas_mixed_fwd', st, args=(ctypes.byref(cv['st']), ctypes.byref(st), ctypes.c_void_p(ws.data_ptr())))
             self._keep.append(cv['st'])
+        elif small and N.lib().bmnas_mixed_small_supported(ctypes.byref(cv['st']), ctypes.byref(st)):
+            nbytes = int(N.lib().bmnas_mixed_small_workspace_bytes(ctypes.byref(cv['st']), ctypes.byref(st)))
+            ws = self.buf((nbytes + 3) // 4, zero=True)
+            # the weight tile may be fetched before griddepcontrol.wait when a kernel sits between bmnas_wprep and this one
+            cv['st'].early_ok = 1 if len(self.fwd) >= 1 else 0
+            self.emit('bmnas_mixed_small_fwd', st, args=(ctypes.byref(cv['st']), ctypes.byref(st), ctypes.c_void_p(ws.data_ptr())))
+            self._keep.append(cv['st'])
         else:
-            if fused:                     # the library declined (alignment / pointers): the two-kernel path
+            if fused or small:            # the library declined (alignment / pointers): the two-kernel path
                 assert cv['Z'] is not None, 'fused mixed op declined by the library in a no-grad plan'
                 self.emit('bmnas_conv_fwd', cv['st'])
             self.emit('bmnas_node_fwd', st)

@@ -330,6 +330,20 @@ int bmnas_mixed_supported(const bmnas_conv_params* cv, const bmnas_node_params* 
 long long bmnas_mixed_workspace_bytes(void);
 
 /* ------------------------------------------------------------------------
+ * The same fused mixed op for batches SMALLER than the machine (the reference batch: NTU 96 x 8 = 768 columns), where the
+ * problem is latency, not throughput: fp32 FFMA from a TMA-staged 96-row x 32-column tile per CTA (32 channels: their
+ * GLU value / GLU gate / FC rows; 32 columns = 32/L whole samples), grid = (B*L/32) x (C/32) co-resident CTAs, the
+ * attention primitive computed from the same activation tile while the BatchNorm partials travel, ONE grid barrier,
+ * epilogue from registers.  Also writes the NEXT inner edge mix (nd->out2, n_chain, chain_x: node_search.py:52-55).
+ * Needs cv->wimg_fwd in format 1 (tile-major fp32), C % 32 == 0, C <= 256, L in {4, 8, 16} and a grid that fits the
+ * machine (bmnas_mixed_small_supported); same parameter blocks and call sites as bmnas_mixed_fwd; the workspace is
+ * bmnas_mixed_small_workspace_bytes(cv, nd) bytes, zeroed once.
+ * ---------------------------------------------------------------------- */
+int bmnas_mixed_small_fwd(const bmnas_conv_params* cv, const bmnas_node_params* nd, void* workspace, void* stream);
+int bmnas_mixed_small_supported(const bmnas_conv_params* cv, const bmnas_node_params* nd);
+long long bmnas_mixed_small_workspace_bytes(const bmnas_conv_params* cv, const bmnas_node_params* nd);
+
+/* ------------------------------------------------------------------------
  * LayerNorm block over a virtual channel concat.
  * mode 0 (CAT):  v = cat(src[0..n_src)) [+ residual];  out = LN_{[Ctot,L]}(v) [ReLU]
  *   replaces FusionCell tail  model_search.py:63-67  (cat -> LayerNorm -> ReLU -> view)

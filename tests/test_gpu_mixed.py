@@ -96,6 +96,20 @@ def _fused_launches(mod):
 def test_fused_mixed_vs_oracle(B, L):
     from bmnas import program
     assert program.FUSED_MIXED != '0'
+    _check_vs_oracle(B, L, 'bmnas_mixed_fwd')
+
+
+@pytest.mark.parametrize('B,L', [(96, 8), (37, 8), (8, 8), (148, 8), (1, 8), (64, 4), (50, 16), (3, 16), (74, 16)])
+def test_small_fused_mixed_vs_oracle(B, L, monkeypatch):
+    """bmnas_mixed_small_fwd (csrc/mixed_small.cu): the FFMA variant that serves batches smaller than the machine --
+    partial tiles, one sample, a grid that exactly fills the 148 SMs (B=148, L=8 and B=74, L=16), every L"""
+    from bmnas import program
+    monkeypatch.setattr(program, 'FUSED_MIXED', '0')
+    monkeypatch.setattr(program, 'FUSED_MIXED_SMALL', '1')
+    _check_vs_oracle(B, L, 'bmnas_mixed_small_fwd')
+
+
+def _check_vs_oracle(B, L, expect):
     ops = OPS_MISH if B * L > 4096 else OPS_RELU
     mod = _mixed(L, ops=ops).to(U.DEV).train()
     sd0 = {k: v.clone() for k, v in mod.state_dict().items()}
@@ -108,7 +122,7 @@ def test_fused_mixed_vs_oracle(B, L):
     out = mod(x, x, w)
     out.backward(go)
     torch.cuda.synchronize()
-    assert 'bmnas_mixed_fwd' in _fused_launches(mod), 'the fused kernel did not take this shape'
+    assert expect in _fused_launches(mod), 'the fused kernel did not take this shape'
     ref = _oracle(_restore(_mixed(L, ops=ops), sd0), x, w, go, masks, True, L, 0.2, ops=ops)
     ref64 = _oracle(_restore(_mixed(L, ops=ops), sd0), x, w, go, masks, True, L, 0.2, torch.float64, ops=ops)
     close_vs_referee(out, ref[0], ref64[0], TOL, 'out')
@@ -139,14 +153,17 @@ def _restore(mod, sd):
     return mod
 
 
-@pytest.mark.parametrize('B,L', [(96, 8), (700, 8), (2500, 8)])
-def test_fused_equals_two_kernel_path_philox(B, L):
-    """same Philox seed and step: the fused kernel and bmnas_conv_fwd + bmnas_node_fwd must draw the same masks and
+@pytest.mark.parametrize('B,L,kernel', [(96, 8, 'bmnas_mixed_fwd'), (700, 8, 'bmnas_mixed_fwd'), (2500, 8, 'bmnas_mixed_fwd'),
+                                        (96, 8, 'bmnas_mixed_small_fwd'), (50, 16, 'bmnas_mixed_small_fwd'), (41, 4, 'bmnas_mixed_small_fwd')])
+def test_fused_equals_two_kernel_path_philox(B, L, kernel, monkeypatch):
+    """same Philox seed and step: the fused kernels and bmnas_conv_fwd + bmnas_node_fwd must draw the same masks and
     agree to rounding (both write Z, mean, rstd; the backward kernels are shared)"""
     from bmnas import program, rng
     outs = []
+    big = kernel == 'bmnas_mixed_fwd'
     for fused in ('1', '0'):
-        program.FUSED_MIXED = fused
+        program.FUSED_MIXED = fused if big else '0'
+        monkeypatch.setattr(program, 'FUSED_MIXED_SMALL', '0' if big else fused)
         try:
             rng.manual_seed(1234)
             mod = _mixed(L, seed=3, ops=OPS_MISH if B * L > 4096 else OPS_RELU).to(U.DEV).train()
@@ -158,7 +175,8 @@ def test_fused_equals_two_kernel_path_philox(B, L):
             out.backward(go)
             torch.cuda.synchronize()
             names = _fused_launches(mod)
-            assert ('bmnas_mixed_fwd' in names) == (fused == '1'), names
+            assert (kernel in names) == (fused == '1'), names
+            assert ('bmnas_conv_fwd' in names) == (fused == '0'), names
             outs.append((out.detach().clone(), x.grad.clone(), w.grad.clone(),
                          {k: p.grad.clone() for k, p in mod.named_parameters()},
                          {k: v.clone() for k, v in mod.state_dict().items()}))

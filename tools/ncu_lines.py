@@ -39,7 +39,7 @@ for d, ln in zip(data[:n], lines[:n]):
 ts = sum(a[1] for a in agg.values())
 print('total executed warp instructions', tot, 'samples', ts)
 src = {}
-for (f, ln, inl), (e, s) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+for (f, ln, inl), (e, s) in sorted(agg.items(), key=lambda kv: -kv[1][1 if os.environ.get("BY_SAMPLES") else 0])[:top]:
     if f not in src:
         p = os.path.join('bm-nas_b200/csrc', f)
         src[f] = open(p).read().splitlines() if os.path.exists(p) else []

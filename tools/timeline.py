@@ -38,7 +38,7 @@ def main():
     t0 = evs[0].time_range.start
     rows = [(e.time_range.start - t0, e.time_range.end - e.time_range.start, e.name) for e in evs]
     # find step boundaries: the first memcpy after a kernel
-    starts = [i for i, r in enumerate(rows) if 'emcpy' in r[2] and (i == 0 or 'emcpy' not in rows[i - 1][2])]
+    starts = [i for i, r in enumerate(rows) if ('emcpy' in r[2] or 'k_copy' in r[2]) and (i == 0 or not ('emcpy' in rows[i - 1][2] or 'k_copy' in rows[i - 1][2]))]
     # a step has two loads (dev + train) back to back -> boundaries every group; keep groups that start a step
     print('# events', len(rows), 'memcpy groups', len(starts))
     per = len(starts) // NS if NS else 1
