@@ -28,9 +28,19 @@ def main():
     torch.cuda.synchronize()
     from torch.profiler import profile, ProfilerActivity
     NS = 6
+    mode = os.environ.get('TL_MODE', 'step')
+    if mode == 'upload':          # upload the graph for the next launch on another stream while this one runs
+        import ctypes
+        rt_ = ctypes.CDLL('libcudart.so.12')
+        up = torch.cuda.Stream()
+        ex = ctypes.c_void_p(ss.graphs['step'].raw_cuda_graph_exec())
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         for i in range(NS):
-            ss.load_step(pp[i % 2]); ss.step()
+            ss.load_step(pp[i % 2])
+            if mode == 'upload':
+                rc = rt_.cudaGraphUpload(ex, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+                assert rc == 0, rc
+            ss.step()
         torch.cuda.synchronize()
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     evs.sort(key=lambda e: e.time_range.start)
