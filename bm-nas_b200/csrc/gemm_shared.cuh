@@ -82,10 +82,11 @@ __device__ __forceinline__ void bn_eval_stats(const bmnas_conv_params& p, int m,
 // and the running statistics are fetched while the partials are still in flight.
 template <class CntFn>
 __device__ __forceinline__ void bn_finalize_rows(const bmnas_conv_params& p, int N, int n_parts, CntFn cnt_of, int m0,
-                                                 int rows, int ldw) {
+                                                 int rows, int ldw, int nthr = 0) {
     const int tid = threadIdx.x;
     const int M = p.M;
-    int tpr = (int)blockDim.x / rows;            // lanes per row: power of two, <= 32 (256 / 128 = 2, 256 / 32 = 8)
+    // nthr: threads that take part (whole warps; default the CTA) -- CTAs whose size / rows is not a power of two pass one
+    int tpr = (nthr > 0 ? nthr : (int)blockDim.x) / rows;   // lanes per row: power of two, <= 32 (256 / 128 = 2, 256 / 32 = 8)
     if (tpr > 32) tpr = 32;
     const int r = tid / tpr, q = tid - r * tpr;
     const int m = m0 + r;

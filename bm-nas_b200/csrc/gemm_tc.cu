@@ -1054,8 +1054,15 @@ bool tc_eligible(const bmnas_conv_params* p, int mode) {
     return true;
 }
 
+bool ws_eligible(const bmnas_conv_params* p, int mode);
+int ws_conv_fwd(const bmnas_conv_params* p, int x3, cudaStream_t stream);
+int ws_conv_dgrad(const bmnas_conv_params* p, int x3, cudaStream_t stream);
+bool wgrad_ws_eligible(const bmnas_conv_params* p);
+int ws_conv_wgrad(const bmnas_conv_params* p, int x3, cudaStream_t stream);
+
 int tc_conv_fwd(const bmnas_conv_params* p, int x3, cudaStream_t stream) {
     using namespace tc;
+    if (p->wimg_fwd && p->wimg_fmt == 0 && ws_eligible(p, 0)) return ws_conv_fwd(p, x3, stream);   // gemm_ws.cu
     if (p->wimg_fwd) return panel_dispatch<FWD>(p, x3, stream);
     const int N = p->B * p->L;
     const int row_tiles = (p->M + TCM - 1) / TCM;
@@ -1070,6 +1077,7 @@ int tc_conv_fwd(const bmnas_conv_params* p, int x3, cudaStream_t stream) {
 
 int tc_conv_dgrad(const bmnas_conv_params* p, int x3, cudaStream_t stream) {
     using namespace tc;
+    if (p->wimg_dgrad && p->wimg_fmt == 0 && ws_eligible(p, 1)) return ws_conv_dgrad(p, x3, stream);   // gemm_ws.cu
     if (p->wimg_dgrad) return panel_dispatch<DGRAD>(p, x3, stream);
     const int N = p->B * p->L;
     const int row_tiles = (p->K + TCM - 1) / TCM;
@@ -1082,6 +1090,7 @@ int tc_conv_dgrad(const bmnas_conv_params* p, int x3, cudaStream_t stream) {
 
 int tc_conv_wgrad(const bmnas_conv_params* p, int x3, cudaStream_t stream) {
     using namespace tc;
+    if (wgrad_ws_eligible(p)) return ws_conv_wgrad(p, x3, stream);     // wgrad_ws.cu
     const int N = p->B * p->L;
     const int row_tiles = (p->M + TCM - 1) / TCM;
     const int bn = p->K >= 128 ? 128 : (p->K > 32 ? 64 : 32);

@@ -1,0 +1,457 @@
+// Warp-specialised tcgen05 conv GEMM (FWD / DGRAD) -- the large-problem engine behind bmnas_conv_fwd /
+// bmnas_conv_dgrad when bmnas_wprep weight images exist (replaces the phase-serial panel kernel of gemm_tc.cu,
+// which staged a whole activation panel, then issued its MMAs, then ran its epilogue, one after the other).
+//
+//   FWD    Z[b,m,l]  = sum_k Weff[m,k] U[b,k,l] + bias[m]      (+ BatchNorm batch statistics per output row)
+//          -- Conv1d(k=1) over the virtual concat, node_operations.py:30-34,49-53 / node_search.py:59-62
+//   DGRAD  dU[b,k,l] = sum_m Weff[m,k] (a[m] GV[b,m,l] + b[m] Z[b,m,l] + c[m])     (BatchNorm backward folded in)
+//
+// Work split: CTA (x, y) owns accumulator row tile y (128 rows) and a CONTIGUOUS span of 32-column units
+// [x U / gx, (x+1) U / gx): perfectly balanced over the 148 SMs whatever the batch; the span is cut into tiles of at
+// most 256 columns whose width becomes the N of the UMMA instruction (runtime instruction descriptor), so there is no
+// ragged last wave.  Two 256-column accumulator sets in tensor memory let the epilogue of tile i overlap the MMAs of
+// tile i + 1.
+//
+// Warp roles (448 threads, one CTA per SM), every hand-over an mbarrier:
+//   warps 0-7   producers: global fp32 -> registers (P register blocks of 4 reduction rows x 4 columns in flight per
+//               thread: 32-64 KB of loads in flight per SM) -> BatchNorm-backward fold (DGRAD) -> hi/lo tf32 split ->
+//               K-major SWIZZLE_128B activation stages (256 columns x 32 reduction elements)
+//   warps 8-11  epilogue: tcgen05.ld (thread = accumulator row), bias + Z store + Welford row statistics (FWD) or
+//               store / red.add into the source gradients (DGRAD)
+//   warp 12     MMA issue (warp-uniform loop, one elected lane issues tcgen05.mma kind::tf32, 3 per k-step in 3xTF32)
+//   warp 13     weight slabs: TMA bulk copies of the bmnas_wprep image through a ring (resident when the whole
+//               reduction fits in it) + TMEM allocation
+#include "common.cuh"
+#include "gemm_shared.cuh"
+#include "tc_ptx.cuh"
+
+namespace bmnas {
+static int g_ws_on = -1, g_ws_max_ctas = 0;     // bmnas_set_ws_gemm
+namespace ws {
+using namespace tc;
+
+constexpr int FWD = 0, DGRAD = 1;
+constexpr int NPW = 8, NPROD = NPW * 32, NEPI = 128;
+constexpr int W_MMA = NPW + 4, W_TMA = W_MMA + 1;
+constexpr int THREADS = (W_TMA + 1) * 32;
+constexpr int BNMAX = 256;
+constexpr uint32_t TSET = 256;                   // TMEM columns per accumulator set
+
+template <bool X3>
+struct Cfg {
+    static constexpr uint32_t B_HALF = BNMAX * 128;                 // 32 KB: 256 columns x one 128-byte reduction row
+    static constexpr uint32_t B_ST = X3 ? 2 * B_HALF : B_HALF;     // [hi | lo]
+    static constexpr uint32_t A_HALF = TCM * 128;                   // 16 KB
+    static constexpr uint32_t A_ST = X3 ? 2 * A_HALF : A_HALF;
+    static constexpr int NB = X3 ? 2 : 4;
+    static constexpr int NA = X3 ? 3 : 4;
+    static constexpr uint32_t DYN = NB * B_ST + NA * A_ST + 1024;
+};
+
+struct Bars {
+    uint64_t b_full[4], b_empty[4], a_full[4], a_empty[4], t_full[2], t_empty[2];
+    uint32_t tmem_base;
+};
+
+// span / tile geometry shared by all roles
+struct Geo {
+    int u_lo, su, nt;
+    // t * su < 2^31 for any span a 148-CTA grid sees below 2^31 columns (su <= U / gx, t < su / 8)
+    __device__ __forceinline__ int tile_u0(int t) const { return u_lo + (int)((unsigned)(t * su) / (unsigned)nt); }
+    __device__ __forceinline__ int tile_wu(int t) const { return (int)((unsigned)((t + 1) * su) / (unsigned)nt) - (int)((unsigned)(t * su) / (unsigned)nt); }
+};
+__host__ __device__ __forceinline__ int span_lo(int x, int U, int gx) { return (int)((long long)x * U / gx); }
+
+template <int MODE, bool X3>
+__global__ void __launch_bounds__(THREADS, 1) k_gemm_ws(const bmnas_conv_params p, const int N) {
+    using CF = Cfg<X3>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smB = smem;
+    uint8_t* smA = smem + (size_t)CF::NB * CF::B_ST;
+    __shared__ Bars sh;
+    float4* s_stat = reinterpret_cast<float4*>(smB);          // the activation ring is free once the last tile's MMAs are done
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int K = p.K, M = p.M, L = p.L, ldw = p.w_fold * p.K;
+    const int row0 = blockIdx.y * TCM;
+    const int n_rows = MODE == DGRAD ? K : M;                  // valid accumulator rows overall
+    const int r_end = MODE == FWD ? K : M;                     // reduction extent
+    const int n_chunks = (r_end + KC - 1) / KC;
+    const int U = (N + 31) >> 5, gx = (int)gridDim.x;
+    Geo g;
+    g.u_lo = span_lo((int)blockIdx.x, U, gx);
+    g.su = span_lo((int)blockIdx.x + 1, U, gx) - g.u_lo;
+    g.nt = (g.su + 7) >> 3;
+    const int total_st = g.nt * n_chunks;                       // activation stages of this CTA
+    const bool resident = n_chunks <= CF::NA;                   // the row tile's whole weight fits in the ring
+
+    // ---- set-up that touches no global memory: overlaps the tail of the preceding kernel (PDL)
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&sh.b_full[i], NPROD);
+            mbar_init(&sh.b_empty[i], 1);
+            mbar_init(&sh.a_full[i], 1);
+            mbar_init(&sh.a_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&sh.t_full[i], 1);
+            mbar_init(&sh.t_empty[i], NEPI);
+        }
+        fence_barrier_init();
+    }
+    if (warp == W_TMA) tmem_alloc(&sh.tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sh.tmem_base;
+    pdl_wait();
+    pdl_trigger();
+
+    if (warp < NPW) {
+        // =============================================================== producers
+        // block = 4 reduction rows (one 16-byte chunk kb of the 128-byte operand row) x 4 columns (column group cg);
+        // the 8 lanes of a quarter warp write the 8 chunks of ONE operand row: conflict-free 128-bit shared stores
+        const int kb = tid & 7, cg0 = tid >> 3;                 // column groups cg0 and cg0 + 32 of every stage
+        constexpr int P = MODE == FWD ? 4 : 2;                  // register blocks in flight per thread (even)
+        const bool has_coef = MODE == DGRAD && p.coef_a != nullptr;
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 v[P][4], zz[MODE == DGRAD ? P : 1][4], ca[MODE == DGRAD ? P : 1], cb[MODE == DGRAD ? P : 1], cc[MODE == DGRAD ? P : 1];
+        const int total_st2 = total_st * 2;
+
+        // a cursor walks the units (tile t, reduction slab kc, half u) in order and keeps everything that only changes
+        // with the tile (column validity, sample / position of this thread's two column groups): no division per unit
+        struct Cur {
+            int t, kc, w4;                   // tile, slab, tile width in 4-column groups
+            bool ok[2];                      // column group u lies inside the tile and the batch
+            long long b[2];                  // its sample ...
+            int l0[2];                       // ... and first position
+        };
+        auto set_tile = [&](Cur& c_) {
+            const int col0 = g.tile_u0(c_.t) * 32;
+            c_.w4 = g.tile_wu(c_.t) * 8;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int cg = cg0 + u * 32, n = col0 + cg * 4;
+                c_.ok[u] = cg < c_.w4 && n < N;
+                const int b = n / L;
+                c_.b[u] = b;
+                c_.l0[u] = n - b * L;
+            }
+        };
+        auto advance = [&](Cur& c_) {        // called after the u = 1 unit of a slab
+            if (++c_.kc == n_chunks) {
+                c_.kc = 0;
+                if (++c_.t < g.nt) set_tile(c_);
+            }
+        };
+        Cur lc = {0, 0, 0, {false, false}, {0, 0}, {0, 0}}, cc_ = lc;
+        set_tile(lc);
+        set_tile(cc_);
+
+        auto load = [&](int q, const int u, float4 (&d)[4], float4 (&dz)[4], float4& a_, float4& b_, float4& c_) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) d[j] = z4;
+            if (MODE == DGRAD) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dz[j] = z4;
+                a_ = b_ = c_ = z4;
+            }
+            if (q >= total_st2) return;
+            const int r = lc.kc * KC + kb * 4;
+            if (lc.ok[u] && r < r_end) {
+                if (MODE == FWD) {
+                    int s, kl;
+                    src_of(p, r, &s, &kl);
+                    const float* u_ = p.src[s] + (lc.b[u] * p.src_C[s] + kl) * L + lc.l0[u];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) d[j] = __ldg(reinterpret_cast<const float4*>(u_ + (long long)j * L));
+                } else {
+                    const long long idx = (lc.b[u] * M + r) * L + lc.l0[u];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) d[j] = __ldg(reinterpret_cast<const float4*>(p.GV + idx + (long long)j * L));
+                    if (has_coef) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dz[j] = __ldg(reinterpret_cast<const float4*>(p.Z + idx + (long long)j * L));
+                        a_ = __ldg(reinterpret_cast<const float4*>(p.coef_a + r));
+                        b_ = __ldg(reinterpret_cast<const float4*>(p.coef_b + r));
+                        c_ = __ldg(reinterpret_cast<const float4*>(p.coef_c + r));
+                    }
+                }
+            }
+            if (u == 1) advance(lc);
+        };
+        auto consume = [&](int q, const int u, float4 (&d)[4], float4 (&dz)[4], const float4& a_, const float4& b_, const float4& c_) {
+            const int it = q >> 1;
+            const int stage = it % CF::NB, round = it / CF::NB;
+            if (u == 0 && round > 0) mbar_wait(&sh.b_empty[stage], (uint32_t)(round - 1) & 1u);
+            const int cg = cg0 + u * 32;
+            if (cg < cc_.w4) {
+                if (has_coef && cc_.ok[u] && cc_.kc * KC + kb * 4 < r_end) {   // padding columns / reduction rows stay exactly zero
+                    const float av[4] = {a_.x, a_.y, a_.z, a_.w}, bv[4] = {b_.x, b_.y, b_.z, b_.w}, cv[4] = {c_.x, c_.y, c_.z, c_.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        d[j].x = fmaf(av[j], d[j].x, fmaf(bv[j], dz[j].x, cv[j]));
+                        d[j].y = fmaf(av[j], d[j].y, fmaf(bv[j], dz[j].y, cv[j]));
+                        d[j].z = fmaf(av[j], d[j].z, fmaf(bv[j], dz[j].z, cv[j]));
+                        d[j].w = fmaf(av[j], d[j].w, fmaf(bv[j], dz[j].w, cv[j]));
+                    }
+                }
+                uint8_t* hi = smB + (size_t)stage * CF::B_ST;
+                uint8_t* lo = hi + CF::B_HALF;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {                   // column cg*4 + i of the block = (row0[i], row1[i], row2[i], row3[i])
+                    float4 e;
+                    e.x = i == 0 ? d[0].x : i == 1 ? d[0].y : i == 2 ? d[0].z : d[0].w;
+                    e.y = i == 0 ? d[1].x : i == 1 ? d[1].y : i == 2 ? d[1].z : d[1].w;
+                    e.z = i == 0 ? d[2].x : i == 1 ? d[2].y : i == 2 ? d[2].z : d[2].w;
+                    e.w = i == 0 ? d[3].x : i == 1 ? d[3].y : i == 2 ? d[3].z : d[3].w;
+                    put_chunk<X3>(hi, lo, sw_off(cg * 4 + i, kb), e);
+                }
+            }
+            if (u == 1) {
+                fence_proxy_async();                             // generic-proxy writes -> visible to the tensor core
+                mbar_arrive(&sh.b_full[stage]);
+                advance(cc_);
+            }
+        };
+#pragma unroll
+        for (int s = 0; s < P; ++s)
+            load(s, s & 1, v[s], zz[MODE == DGRAD ? s : 0], ca[MODE == DGRAD ? s : 0], cb[MODE == DGRAD ? s : 0], cc[MODE == DGRAD ? s : 0]);
+        for (int q0 = 0; q0 < total_st2; q0 += P) {             // total_st2 is even and P is even: slot s always holds half u = s & 1
+#pragma unroll
+            for (int s = 0; s < P; ++s) {
+                if (q0 + s < total_st2) {
+                    consume(q0 + s, s & 1, v[s], zz[MODE == DGRAD ? s : 0], ca[MODE == DGRAD ? s : 0], cb[MODE == DGRAD ? s : 0], cc[MODE == DGRAD ? s : 0]);
+                    load(q0 + s + P, s & 1, v[s], zz[MODE == DGRAD ? s : 0], ca[MODE == DGRAD ? s : 0], cb[MODE == DGRAD ? s : 0], cc[MODE == DGRAD ? s : 0]);
+                }
+            }
+        }
+    } else if (warp == W_TMA) {
+        // =============================================================== weight slabs (TMA bulk copies)
+        constexpr uint32_t IMG_SLAB = 2u * TCM * KC * 4;       // image slab: [hi 16 KB | lo 16 KB]
+        const uint8_t* img = reinterpret_cast<const uint8_t*>(MODE == FWD ? p.wimg_fwd : p.wimg_dgrad) +
+                             (size_t)blockIdx.y * (size_t)n_chunks * IMG_SLAB;
+        const bool leader = elect_one();
+        const int total_a = resident ? n_chunks : total_st;
+        for (int ia = 0; ia < total_a; ++ia) {
+            const int slot = ia % CF::NA, round = ia / CF::NA;
+            if (round > 0) mbar_wait(&sh.a_empty[slot], (uint32_t)(round - 1) & 1u);
+            if (leader) {
+                mbar_expect_tx(&sh.a_full[slot], CF::A_ST);
+                tma_bulk_g2s(smA + (size_t)slot * CF::A_ST, img + (size_t)(ia % n_chunks) * IMG_SLAB, CF::A_ST, &sh.a_full[slot]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == W_MMA) {
+        // =============================================================== MMA issue (warp-uniform, elected lane issues)
+        const bool leader = elect_one();
+        uint32_t it = 0;
+        for (int t = 0; t < g.nt; ++t) {
+            const int buf = t & 1;
+            if (t >= 2) mbar_wait(&sh.t_empty[buf], (uint32_t)((t >> 1) - 1) & 1u);       // the epilogue has drained this set
+            tc_fence_after();
+            const uint32_t d0 = tmem_base + (uint32_t)buf * TSET;
+            const uint32_t idesc = idesc_tf32(TCM, g.tile_wu(t) * 32);
+            for (int kc = 0; kc < n_chunks; ++kc, ++it) {
+                const uint32_t stage = it % CF::NB;
+                const uint32_t slot = resident ? (uint32_t)kc : it % CF::NA;
+                if (!resident || t == 0) mbar_wait(&sh.a_full[slot], resident ? 0u : (it / CF::NA) & 1u);
+                mbar_wait(&sh.b_full[stage], (it / CF::NB) & 1u);
+                tc_fence_after();
+                const uint32_t a_hi = s32(smA + (size_t)slot * CF::A_ST), a_lo = a_hi + CF::A_HALF;
+                const uint32_t b_hi = s32(smB + (size_t)stage * CF::B_ST), b_lo = b_hi + CF::B_HALF;
+                if (leader) {
+#pragma unroll
+                    for (int ks = 0; ks < KC / 8; ++ks) {
+                        const uint32_t ko = (uint32_t)ks * 32u;
+                        const uint32_t acc = (kc > 0 || ks > 0) ? 1u : 0u;
+                        if (X3) {
+                            umma_tf32(d0, kdesc(a_lo + ko), kdesc(b_hi + ko), idesc, acc);
+                            umma_tf32(d0, kdesc(a_hi + ko), kdesc(b_lo + ko), idesc, 1u);
+                            umma_tf32(d0, kdesc(a_hi + ko), kdesc(b_hi + ko), idesc, 1u);
+                        } else {
+                            umma_tf32(d0, kdesc(a_hi + ko), kdesc(b_hi + ko), idesc, acc);
+                        }
+                    }
+                    if (!resident) umma_commit(&sh.a_empty[slot]);
+                    umma_commit(&sh.b_empty[stage]);
+                }
+            }
+            if (leader) umma_commit(&sh.t_full[buf]);
+            __syncwarp();
+        }
+    } else {
+        // =============================================================== epilogue warps
+        const int lq = warp & 3;
+        const int erow = lq * 32 + lane;                         // accumulator row = TMEM lane
+        const int gr = row0 + erow;
+        const bool row_ok = gr < n_rows;
+        const uint32_t lane_addr = (uint32_t)(lq * 32) << 16;
+        float bias = 0.f;
+        int s_ = 0, kl_ = 0;
+        float* dst = nullptr;
+        bool accum = false;
+        if (row_ok) {
+            if (MODE == FWD) {
+                int seg, ml;
+                w_row(p, gr, ldw, &seg, &ml);
+                if (p.bias[seg]) bias = __ldg(p.bias[seg] + ml);
+            } else {
+                src_of(p, gr, &s_, &kl_);
+                dst = p.gsrc[s_];
+                accum = p.gsrc_accum[s_] != 0;
+            }
+        }
+        Wf run = {0.f, 0.f, 0.f};
+        for (int t = 0; t < g.nt; ++t) {
+            const int buf = t & 1;
+            mbar_wait(&sh.t_full[buf], (uint32_t)(t >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t tz = tmem_base + (uint32_t)buf * TSET + lane_addr;
+            const int col0 = g.tile_u0(t) * 32, wu = g.tile_wu(t);
+            for (int c8 = 0; c8 < wu; ++c8) {
+                float v[32];
+                {
+                    float a[16], b[16];
+                    tmem_ld16(tz + (uint32_t)(c8 * 32), a);
+                    tmem_ld16(tz + (uint32_t)(c8 * 32 + 16), b);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        v[i] = a[i];
+                        v[16 + i] = b[i];
+                    }
+                }
+                const int nb = col0 + c8 * 32;
+                int eb = nb / L, el = nb - eb * L;                // sample / position of the chunk's first column, then stepped by 4
+                if (MODE == FWD) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += bias;
+                    float sum = 0.f;
+                    int cnt = 0;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const int n = nb + j4 * 4;
+                        if (n < N) {                              // N % 4 == 0 and L % 4 == 0: a 4-group is whole and in one sample
+                            if (row_ok) {
+                                *reinterpret_cast<float4*>(p.Z + ((long long)eb * M + gr) * L + el) =
+                                    make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                            }
+                            el += 4;
+                            if (el >= L) { el -= L; ++eb; }
+                            sum += (v[j4 * 4] + v[j4 * 4 + 1]) + (v[j4 * 4 + 2] + v[j4 * 4 + 3]);
+                            cnt += 4;
+                        }
+                    }
+                    if (p.bn_mode == 1 && cnt > 0) {
+                        const float mean = sum / (float)cnt;
+                        float m2 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float d = v[j] - mean;
+                            if (nb + (j & ~3) < N) m2 = fmaf(d, d, m2);
+                        }
+                        const Wf w = {(float)cnt, mean, m2};
+                        run = wf_merge(run, w);
+                    }
+                } else if (dst) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const int n = nb + j4 * 4;
+                        if (n < N) {
+                            float* d = dst + ((long long)eb * p.src_C[s_] + kl_) * L + el;
+                            el += 4;
+                            if (el >= L) { el -= L; ++eb; }
+                            const float4 o = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                            // one add per element from this launch: the fire-and-forget reduction gives the same bits
+                            // as load + add + store, without the load latency in the epilogue
+                            if (accum) red_add_v4(d, o);
+                            else *reinterpret_cast<float4*>(d) = o;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&sh.t_empty[buf]);
+        }
+        if (MODE == FWD && p.bn_mode == 1) s_stat[erow] = make_float4(run.n, run.mean, run.m2, 0.f);
+    }
+
+    // ---- teardown (+ FWD: one statistics partial per CTA and row, finalize by the last CTA of the row tile)
+    tc_fence_before();
+    __syncthreads();
+    if (warp == W_TMA) tmem_dealloc(tmem_base, 512);
+    if (MODE == FWD) {
+        if (p.bn_mode == 2) {
+            if (blockIdx.x == 0 && tid < TCM) bn_eval_stats(p, row0 + tid, ldw);
+            return;
+        }
+        if (p.bn_mode != 1) return;
+        if (tid < TCM && row0 + tid < M) {
+            float* qd = p.stat_part + ((long long)blockIdx.x * M + row0 + tid) * 2;
+            qd[0] = s_stat[tid].y;
+            qd[1] = s_stat[tid].z;
+        }
+        if (!last_block(p.counter + blockIdx.y, gridDim.x)) return;
+        bn_finalize_rows(p, N, gx, [=](int x) { return min(N, span_lo(x + 1, U, gx) * 32) - span_lo(x, U, gx) * 32; }, row0, TCM, ldw,
+                         256);
+    }
+}
+
+template <int MODE, bool X3>
+static int launch_ws(const bmnas_conv_params* p, cudaStream_t stream) {
+    using CF = Cfg<X3>;
+    const int N = p->B * p->L;
+    const int row_tiles = ((MODE == DGRAD ? p->K : p->M) + TCM - 1) / TCM;
+    const int U = (N + 31) / 32;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_gemm_ws<MODE, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::DYN) != cudaSuccess)
+            return BMNAS_ELAUNCH;
+        configured = true;
+    }
+    int gx = kNumSMs / row_tiles;
+    if (g_ws_max_ctas > 0 && gx > g_ws_max_ctas) gx = g_ws_max_ctas;
+    if (gx < 1) gx = 1;
+    if (gx > U) gx = U;
+    dim3 grid(gx, row_tiles);
+    launch_k(k_gemm_ws<MODE, X3>, grid, THREADS, CF::DYN, stream, *p, N);
+    BMNAS_LAUNCH_CHECK();
+    return BMNAS_OK;
+}
+
+static bool al16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
+
+}  // namespace ws
+
+// bmnas_set_ws_gemm(0, 0) / BMNAS_WS_GEMM=0 keeps the panel kernel (A/B measurements)
+bool ws_enabled() {
+    if (g_ws_on < 0) {
+        const char* e = getenv("BMNAS_WS_GEMM");
+        g_ws_on = (e && e[0] == '1') ? 1 : 0;      // NOT YET VALIDATED ON HARDWARE: opt-in until tests/test_gpu_gemm.py::test_conv_ws_engine is green
+    }
+    return g_ws_on != 0;
+}
+
+bool ws_eligible(const bmnas_conv_params* p, int mode) {
+    if (!ws_enabled()) return false;
+    if (mode == ws::DGRAD && p->coef_a && !(ws::al16(p->coef_a) && ws::al16(p->coef_b) && ws::al16(p->coef_c))) return false;
+    if (mode == ws::DGRAD && (p->M & 3)) return false;
+    return true;
+}
+
+int ws_conv_fwd(const bmnas_conv_params* p, int x3, cudaStream_t stream) {
+    return x3 ? ws::launch_ws<ws::FWD, true>(p, stream) : ws::launch_ws<ws::FWD, false>(p, stream);
+}
+int ws_conv_dgrad(const bmnas_conv_params* p, int x3, cudaStream_t stream) {
+    return x3 ? ws::launch_ws<ws::DGRAD, true>(p, stream) : ws::launch_ws<ws::DGRAD, false>(p, stream);
+}
+
+}  // namespace bmnas
+
+extern "C" int bmnas_set_ws_gemm(int enable, int max_ctas) {
+    if (max_ctas < 0) return BMNAS_EINVAL;
+    bmnas::g_ws_on = enable ? 1 : 0;
+    bmnas::g_ws_max_ctas = max_ctas;
+    return BMNAS_OK;
+}

@@ -588,6 +588,13 @@ int bmnas_set_pdl(int on);
  * LinearGLU; x is y -- the searchable cell -- double-buffers its tiles, x != y -- the found cell -- stages them
  * per sample).  All variants draw identical dropout masks and agree to fp32 rounding. */
 int bmnas_set_node_variant(int v);
+
+/* Engine behind the tensor-core bmnas_conv_fwd / bmnas_conv_dgrad when bmnas_wprep images exist: enable = 1
+ * (default) the warp-specialised persistent kernel (csrc/gemm_ws.cu: producer warps, one MMA-issuing warp, a TMA warp
+ * for the weight ring, epilogue warps over two accumulator sets in tensor memory), 0 = the phase-serial panel kernel
+ * it replaced (kept for A/B measurements).  max_ctas > 0 caps the CTAs per accumulator row tile (test hook: more
+ * column tiles per CTA on small problems), 0 = one CTA per SM. */
+int bmnas_set_ws_gemm(int enable, int max_ctas);
 int bmnas_get_node_variant(void);
 
 /* rng_state = {seed, step}: advance the step counter on-device (one launch per search step) */

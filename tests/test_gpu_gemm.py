@@ -218,3 +218,102 @@ def test_linear_head(B, K, Nc, bias):
     assert _rel(lin.weight.grad, Wr.grad) < 1e-5
     if bias:
         assert _rel(lin.bias.grad, br.grad) < 1e-5
+
+
+WS_CASES = [
+    # B, L, src_C, seg_M, w_fold, max_ctas     (csrc/gemm_ws.cu: spans of several tiles, streamed / resident weight rings)
+    (5000, 8, [128, 128], [128], 1, 0),      # out_conv at large batch: 8 weight slabs streamed, 2 tiles per CTA
+    (5000, 8, [128], [256, 128], 2, 0),      # node conv: 3 row tiles forward, 12 slabs in the dgrad reduction
+    (96, 16, [256], [512, 256], 2, 0),       # Ego-large node conv: 6 row tiles x 24 CTAs, 64-column tiles
+    (96, 16, [256, 256, 256], [256], 1, 0),  # Ego-large out_conv: 24 slabs
+    (700, 8, [128], [256, 128], 2, 3),       # capped grid: 5600 columns on 3 CTAs -> 8 tiles per CTA (both accumulator sets reused)
+    (333, 4, [36, 60], [20, 44], 1, 2),      # ragged everything: 1332 columns (not a multiple of 32), K = 96, M = 64
+    (1200, 8, [64], [64], 1, 5),             # resident weight ring (2 slabs), 9600 columns on 5 CTAs
+]
+
+
+@pytest.mark.parametrize('mode', [1, 2])
+@pytest.mark.parametrize('case', range(len(WS_CASES)))
+def test_conv_ws_engine(mode, case):
+    """the warp-specialised tcgen05 GEMM (bmnas_set_ws_gemm) forward + dgrad against float64, and bit-for-bit
+    determinism of two launches; the panel kernel it replaces must agree to the same tolerance"""
+    N, lib = _lib()
+    dev = torch.device('cuda:0')
+    B, L, src_C, seg_M, w_fold, cap = WS_CASES[case]
+    srcs, Ws, bias = _conv_case(B, L, src_C, seg_M, w_fold, 90 + case, dev)
+    M, K = sum(seg_M), sum(src_C)
+    g = torch.Generator().manual_seed(170 + case)
+    GV = torch.randn(B, M, L, generator=g).to(dev)
+    ca, cb, cc = (torch.randn(M, generator=g).to(dev) for _ in range(3))
+    imgs = _images(N, lib, Ws, seg_M, K, w_fold, dev, fmt=0)
+    Zr, mr, rr, Weff, U = _ref_fwd(srcs, Ws, bias, w_fold)
+    tol = TOL[mode]
+    old = lib.bmnas_get_gemm_mode()
+    outs = {}
+    try:
+        lib.bmnas_set_gemm_mode(mode)
+        for engine in (1, 0, 1):
+            assert lib.bmnas_set_ws_gemm(engine, cap) == 0
+            st = _params(N, B, L, src_C, seg_M, w_fold, srcs, Ws)
+            Z = torch.full((B, M, L), float('nan'), device=dev)
+            mean, rstd = torch.zeros(M, device=dev), torch.zeros(M, device=dev)
+            rm = [torch.zeros(m, device=dev) for m in seg_M]
+            rv = [torch.ones(m, device=dev) for m in seg_M]
+            nbt = [torch.zeros((), dtype=torch.int64, device=dev) for _ in seg_M]
+            st.bn_mode = 1
+            for i in range(len(seg_M)):
+                st.bias[i] = bias[i].data_ptr()
+                st.running_mean[i], st.running_var[i], st.num_batches_tracked[i] = rm[i].data_ptr(), rv[i].data_ptr(), nbt[i].data_ptr()
+            part = torch.zeros(int(lib.bmnas_conv_stat_part_size(ctypes.byref(st))), device=dev)
+            cnt = torch.zeros(int(lib.bmnas_conv_num_counters(ctypes.byref(st))), dtype=torch.int32, device=dev)
+            st.Z, st.mean, st.rstd, st.stat_part, st.counter = Z.data_ptr(), mean.data_ptr(), rstd.data_ptr(), part.data_ptr(), cnt.data_ptr()
+            st.wimg_fwd, st.wimg_fmt = imgs[0].data_ptr(), 0
+            for _ in range(2):
+                N.launch('bmnas_conv_fwd', ctypes.byref(st), N.current_stream())
+            # dgrad with BatchNorm backward folded in, reading the Z just written
+            sd = _params(N, B, L, src_C, seg_M, w_fold, srcs, Ws)
+            sd.GV, sd.Z = GV.data_ptr(), Z.data_ptr()
+            sd.coef_a, sd.coef_b, sd.coef_c = ca.data_ptr(), cb.data_ptr(), cc.data_ptr()
+            sd.wimg_dgrad, sd.wimg_fmt = imgs[1].data_ptr(), 0
+            gs = [torch.full((B, c, L), 0.5, device=dev) for c in src_C]
+            for i in range(len(src_C)):
+                sd.gsrc[i] = gs[i].data_ptr()
+                sd.gsrc_accum[i] = 1 if i > 0 else 0
+            N.launch('bmnas_conv_dgrad', ctypes.byref(sd), N.current_stream())
+            # wgrad (split-K, atomically accumulated onto zeros): wgrad_ws.cu beyond 2560 columns / in mode 2
+            sw = _params(N, B, L, src_C, seg_M, w_fold, srcs, Ws)
+            sw.GV, sw.Z = GV.data_ptr(), Z.data_ptr()
+            sw.coef_a, sw.coef_b, sw.coef_c = ca.data_ptr(), cb.data_ptr(), cc.data_ptr()
+            gW = [torch.zeros(m, w_fold * K, device=dev) for m in seg_M]
+            gb = [torch.zeros(m, device=dev) for m in seg_M]
+            for i in range(len(seg_M)):
+                sw.gW[i], sw.gbias[i] = gW[i].data_ptr(), gb[i].data_ptr()
+            N.launch('bmnas_conv_wgrad', ctypes.byref(sw), N.current_stream())
+            torch.cuda.synchronize()
+            assert int(cnt.abs().sum()) == 0
+            assert all(int(n) == 2 for n in nbt)
+            assert _rel(Z, Zr) < tol, ('Z', engine, _rel(Z, Zr))
+            assert _rel(mean, mr) < max(tol, 2e-6) * 10 or (mean.double() - mr).abs().max() < tol
+            assert _rel(rstd, rr) < tol * 10, ('rstd', engine, _rel(rstd, rr))
+            dz = ca.double()[None, :, None] * GV.double() + cb.double()[None, :, None] * Z.double() + cc.double()[None, :, None]
+            dU = torch.einsum('mk,bml->bkl', Weff, dz)
+            off = 0
+            for i, c in enumerate(src_C):
+                ref = dU[:, off:off + c] + (0.5 if i > 0 else 0.0)
+                assert _rel(gs[i], ref) < tol, ('dgrad', engine, i, _rel(gs[i], ref))
+                off += c
+            dW = torch.einsum('bml,bkl->mk', dz, U)
+            dWc = torch.cat(gW, 0).double()
+            for f in range(w_fold):
+                assert _rel(dWc[:, f * K:(f + 1) * K], dW) < tol * 4, ('wgrad', engine, f, _rel(dWc[:, f * K:(f + 1) * K], dW))
+            assert _rel(torch.cat(gb), dz.sum(dim=(0, 2))) < tol * 4, ('bias', engine, _rel(torch.cat(gb), dz.sum(dim=(0, 2))))
+            if engine == 1:
+                key = (Z.clone(), mean.clone(), rstd.clone(), [t.clone() for t in gs])
+                if 'ws' in outs:       # second run of the warp-specialised engine: identical bits
+                    a = outs['ws']
+                    assert torch.equal(a[0], key[0]) and torch.equal(a[1], key[1]) and torch.equal(a[2], key[2])
+                    assert all(torch.equal(x, y) for x, y in zip(a[3], key[3]))
+                outs['ws'] = key
+    finally:
+        lib.bmnas_set_gemm_mode(old)
+        lib.bmnas_set_ws_gemm(1, 0)
