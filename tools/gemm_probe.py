@@ -10,14 +10,17 @@ lib = N.lib()
 dev = torch.device('cuda:0')
 Bs = [int(a) for a in sys.argv[1:]] or [96]
 for B in Bs:
-  for (L, src_C, seg_M, w_fold) in [(8, [128], [256, 128], 2), (8, [128, 128], [128], 1)]:
+  SHAPES = [(8, [128], [256, 128], 2), (8, [128, 128], [128], 1)]
+  if os.environ.get('PROBE_EGO') == '1':      # Ego-large: C = 256, L = 16, node_multiplier 3
+      SHAPES = [(16, [256], [512, 256], 2), (16, [256, 256, 256], [256], 1)]
+  for (L, src_C, seg_M, w_fold) in SHAPES:
     srcs, Ws, bias = T._conv_case(B, L, src_C, seg_M, w_fold, 1, dev)
     M, K = sum(seg_M), sum(src_C)
     Zr, mr, rr, Weff, U = T._ref_fwd(srcs, Ws, bias, w_fold)
     GV = torch.randn(B, M, L, device=dev)
     dU = torch.einsum('mk,bml->bkl', Weff, GV.double()); dW = torch.einsum('bml,bkl->mk', GV.double(), U)
     imgs = T._images(N, lib, Ws, seg_M, K, w_fold, dev) if os.environ.get('PROBE_IMG', '1') == '1' else None
-    for mode in (0, 1, 2):
+    for mode in [int(m) for m in os.environ.get('PROBE_MODES', '0,1,2').split(',')]:
         lib.bmnas_set_gemm_mode(mode)
         st = T._params(N, B, L, src_C, seg_M, w_fold, srcs, Ws)
         Z = torch.zeros(B, M, L, device=dev); mean = torch.zeros(M, device=dev); rstd = torch.zeros(M, device=dev)

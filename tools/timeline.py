@@ -36,7 +36,8 @@ def main():
         ex = ctypes.c_void_p(ss.graphs['step'].raw_cuda_graph_exec())
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         for i in range(NS):
-            ss.load_step(pp[i % 2])
+            if mode != 'nocopy':          # nocopy: graph launches back to back (is the ramp at the head of a step the stream -> graph hand-over?)
+                ss.load_step(pp[i % 2])
             if mode == 'upload':
                 rc = rt_.cudaGraphUpload(ex, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
                 assert rc == 0, rc
@@ -50,6 +51,8 @@ def main():
     # find step boundaries: the first memcpy after a kernel
     starts = [i for i, r in enumerate(rows) if ('emcpy' in r[2] or 'k_copy' in r[2]) and (i == 0 or not ('emcpy' in rows[i - 1][2] or 'k_copy' in rows[i - 1][2]))]
     # a step has two loads (dev + train) back to back -> boundaries every group; keep groups that start a step
+    if mode == 'nocopy':
+        starts = [i for i, r in enumerate(rows) if 'k_wprep' in r[2]][::2]
     print('# events', len(rows), 'memcpy groups', len(starts))
     per = len(starts) // NS if NS else 1
     b = starts[per * (NS - 2)] if len(starts) >= per * (NS - 1) else 0
