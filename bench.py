@@ -664,12 +664,37 @@ def run_ours(args):
         barrier()
         return time.perf_counter() - t0
     timed_pipelined(max(3, args.warmup))
-    e2e_wall = sorted(timed_pipelined(args.steps) for _ in range(min(reps, 5)))[min(reps, 5) // 2]
+    half_wall = sorted(timed_pipelined(args.steps) for _ in range(min(reps, 5)))[min(reps, 5) // 2]
+    ss.reset_pipeline()
+
+    def timed_step_pipeline(K):
+        """the same loop with the step-level pipeline: SearchStep.prefetch_step() sends the packed inputs of step i+1 to a
+        staging buffer on the copy stream while step i computes, step() moves them into the static buffers (one device copy)
+        and replays the one-graph step, read_loss_async() copies the step's two losses to pinned host memory behind the
+        step; the host consumes the loss of step i while step i+1 runs (every step's loss is read inside the region)."""
+        barrier()
+        t0 = time.perf_counter()
+        ss.prefetch_step(hppool[0])
+        pending = None
+        for i in range(K):
+            ss.step()
+            h = ss.read_loss_async()
+            if i + 1 < K:
+                ss.prefetch_step(hppool[(i + 1) % 4])
+            if pending is not None:
+                la_host, lw_host = pending.get()
+            pending = h
+        la_host, lw_host = pending.get()
+        barrier()
+        return time.perf_counter() - t0
+    timed_step_pipeline(max(3, args.warmup))
+    e2e_wall = sorted(timed_step_pipeline(args.steps) for _ in range(min(reps, 5)))[min(reps, 5) // 2]
+    ss.reset_pipeline()
     clk = clocks.stop() if rank == 0 else None
-    t = torch.tensor([dev_ms, e2e_wall * 1e3, serial_wall * 1e3, ff_ms], device=device, dtype=torch.float64)
+    t = torch.tensor([dev_ms, e2e_wall * 1e3, serial_wall * 1e3, ff_ms, half_wall * 1e3], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms_wall, serial_ms_wall, ff_ms = t.tolist()
+    dev_ms, e2e_ms_wall, serial_ms_wall, ff_ms, half_ms_wall = t.tolist()
     if world > 1:
         dp['replicas_after_timed_steps'] = replica_checksum(head, group, world, device)
     ms_per_step = dev_ms / args.steps
@@ -750,10 +775,15 @@ def run_ours(args):
             'full_fidelity_how': 'arch half + no-grad train-mode metrics forward on the dev batch (train_searchable/ntu.py:81-85) + '
                                  'weight half; device time',
             'e2e': {'value': round(e2e_value, 1), 'unit': 'samples/s',
-                    'h2d_bytes_per_step': 2 * (per_batch + lab_bytes), 'd2h_bytes_per_step': 4,
+                    'h2d_bytes_per_step': 2 * (per_batch + lab_bytes), 'd2h_bytes_per_step': 8,
                     'ms_per_step': round(e2e_ms_wall / args.steps, 4),
-                    'how': 'SearchStep.prefetch() from pinned host memory (copy stream; batch i+1 travels while step i '
-                           'computes) + SearchStep.step() + loss.item() every step, wall clock between barriers',
+                    'how': 'SearchStep.prefetch_step() from pinned host memory (copy stream -> staging buffer; the packed inputs of '
+                           'step i+1 travel while step i computes) + SearchStep.step() (device copy staging -> static buffers, one '
+                           'graph) + read_loss_async() every step (both losses to pinned host memory behind the step; the host '
+                           'reads the value of step i while step i+1 runs), wall clock between barriers',
+                    'sync_read_value': round(gB * args.steps / (half_ms_wall * 1e-3), 1),
+                    'sync_read_how': 'round-1 loop: per-half SearchStep.prefetch() + step() + a blocking loss.item() every step '
+                                     '(the GPU idles while the host reads and relaunches)',
                     'serial_value': round(gB * args.steps / (serial_ms_wall * 1e-3), 1),
                     'serial_how': 'SearchStep.load() + step() + loss.item(): copy, compute and read strictly in sequence'},
             'gpu_launches': (ss.launches_per_step or 0) * args.steps,

@@ -32,6 +32,17 @@ from .optim import FusedAdam
 LR_RING = 1024      # device ring of weight-step learning rates (bmnas_adam_params.lr_ring); refilled half a ring at a time
 
 
+class _LossHandle:
+    """result of SearchStep.read_loss_async(): get() -> (arch loss, weight loss) as Python floats"""
+
+    def __init__(self, host, ev):
+        self.host, self.ev = host, ev
+
+    def get(self):
+        self.ev.synchronize()
+        return float(self.host[0]), float(self.host[1])
+
+
 class SearchStep:
     def __init__(self, head, criterion, B, num_classes, loss_kind='ce', eta_max=1e-3, eta_min=1e-6, Ti=1, Tm=2,
                  nbpe=100.0, weight_decay=3e-4, arch_lr=3e-4, arch_wd=1e-3, use_graphs=True, group=None,
@@ -247,6 +258,65 @@ class SearchStep:
         ev.record(cs)
         self._ready[which] = ev
 
+    def prefetch_step(self, packed_host):
+        """load_step() for an input pipeline: the packed inputs of the NEXT step (pack_step(..., pinned=True)) travel
+        host -> device on a dedicated copy stream into one of two staging buffers while the current step computes; the
+        next step() then moves them into the static buffers with one device copy (bmnas_copy, ~4 us) and replays the
+        one-graph step.  The compute stream never waits for PCIe."""
+        if self.copy_stream is None:
+            self.copy_stream = torch.cuda.Stream(device=self.device)
+        if not hasattr(self, '_stage'):
+            self._stage = [torch.empty_like(self.packed) for _ in range(2)]
+            self._stage_free = [None, None]        # event: the device copy that last read staging buffer j has finished
+            self._stage_n = 0
+            self._staged = []                       # FIFO of (buffer index, 'copy landed' event)
+        j = self._stage_n % 2
+        self._stage_n += 1
+        cs = self.copy_stream
+        if self._stage_free[j] is not None:
+            cs.wait_event(self._stage_free[j])
+        with torch.cuda.stream(cs):
+            self._stage[j].copy_(packed_host, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(cs)
+        self._staged.append((j, ev))
+
+    def reset_pipeline(self):
+        """forget the input-pipeline state (after a synchronize): the next step() takes the one-graph path again"""
+        torch.cuda.synchronize(self.device)
+        self._ready = {'dev': None, 'train': None}
+        self._done = {'dev': None, 'train': None}
+        if hasattr(self, '_staged'):
+            self._staged = []
+            self._stage_free = [None, None]
+
+    def _consume_staged(self):
+        """the oldest prefetch_step() batch becomes the content of the static buffers (compute stream)"""
+        j, ev = self._staged.pop(0)
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        self.load_step(self._stage[j])
+        done = self._stage_free[j]
+        if done is None:
+            done = self._stage_free[j] = torch.cuda.Event()
+        done.record(cur)
+
+    def read_loss_async(self):
+        """device -> host read of the last step's (arch loss, weight loss) without stalling the launch of the next step:
+        the two scalars are copied into pinned host memory behind the step on the compute stream; .get() on the returned
+        handle waits for that copy only.  A training loop calls it every step and consumes the value one step later."""
+        if not hasattr(self, '_loss_ring'):
+            self._loss_ring = [torch.empty(2, dtype=torch.float32).pin_memory() for _ in range(4)]
+            self._loss_dev = torch.empty(2, dtype=torch.float32, device=self.device)
+            self._loss_n = 0
+        host = self._loss_ring[self._loss_n % 4]
+        self._loss_n += 1
+        torch.stack([self.loss['dev'].reshape(()), self.loss['train'].reshape(())], out=self._loss_dev)
+        host.copy_(self._loss_dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        return _LossHandle(host, ev)
+
     # ------------------------------------------------------------------ state snapshot (warm-up must not train)
     def _snapshot(self):
         import copy
@@ -340,8 +410,11 @@ class SearchStep:
     def step(self):
         """one search step on whatever currently sits in the static buffers; returns (arch loss, weight loss)
         as device scalars (no host sync)."""
+        if getattr(self, '_staged', None):
+            self._consume_staged()
         g = self.graphs.get('step')
-        if g is not None and self.copy_stream is None:          # (the prefetch pipeline hands over per half step)
+        half_pipeline = self._ready['dev'] is not None or self._ready['train'] is not None or self._done['dev'] is not None
+        if g is not None and not half_pipeline:                 # (the per-half prefetch() pipeline hands over per half step)
             if self.w_steps >= self._ring_until:
                 self._refill_lr()
             self.sched.step()

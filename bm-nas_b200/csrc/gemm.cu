@@ -473,11 +473,12 @@ extern "C" int bmnas_conv_image_fmt(int B, int L, int K, int M) {
     // by the GEMM's work, not by its column count alone: the small-N cp.async FFMA engine wins while the problem is
     // latency bound (NTU B=96: 768 x 384 x 128 = 38 M MACs), the tensor cores once there is arithmetic to amortise
     // their pipeline -- Ego-large (C=256, L=16, B=96: 1536 columns but 768 x 256 weights, 302 M MACs) belongs there.
-    // BMNAS_TC_MIN_MACS overrides the crossover (measured: profiles/r02_*_engine_crossover.txt).
+    // BMNAS_TC_MIN_MACS overrides the crossover.  Measured with the warp-specialised kernels (profiles/r02_engine_crossover.txt,
+    // NTU node conv): forward 20.3 (FFMA) vs 19.3 us (tcgen05) at B = 256 = 100 M MACs, 36.4 vs 21.0 at B = 512.
     static long long min_macs = -1;
     if (min_macs < 0) {
         const char* e = getenv("BMNAS_TC_MIN_MACS");
-        min_macs = e ? atoll(e) : 200000000LL;
+        min_macs = e ? atoll(e) : 100000000LL;
     }
     return (sg_ok && N * (long long)M * K <= min_macs) ? 1 : 0;
 }
@@ -585,9 +586,17 @@ extern "C" int bmnas_conv_wgrad(const bmnas_conv_params* p, void* stream) {
     // latency bound (B=96: 9 us vs 21 us); the UMMA ring wins from a few thousand reduction columns on (measured,
     // profiles/r01_v6_kernel_times_B1024.txt: 65 us vs 33 us at B*L = 8192).  FFMA mode (0) has no tensor-core
     // engine and the reduced-precision mode (2) keeps the single-pass TF32 kernel.
-    const long long Ncols = (long long)p->B * p->L;
+    // The crossover is on the GEMM's work, like bmnas_conv_image_fmt: NTU (M*K = 384 x 128) changes engine at 2560 columns as
+    // measured in round 1; Ego-large (768 x 256 weights, 1536 columns: 302 M MACs, 56 us on the FFMA kernel against
+    // ~15 us on wgrad_ws.cu) now lands on the tensor cores too.  BMNAS_TC_MIN_MACS_W overrides.
+    const long long macs = (long long)p->B * p->L * p->M * p->K;
+    static long long min_macs_w = -1;
+    if (min_macs_w < 0) {
+        const char* e_ = getenv("BMNAS_TC_MIN_MACS_W");
+        min_macs_w = e_ ? atoll(e_) : 60000000LL;
+    }
     const bool tc_ok = bmnas_gemm_mode_flag && tc_eligible(p, 2);
-    if (bmnas_gemm_mode_flag != 2 && sgw_eligible(p) && (Ncols <= 2560 || !tc_ok)) return sg_conv_wgrad(p, (cudaStream_t)stream);
+    if (bmnas_gemm_mode_flag != 2 && sgw_eligible(p) && (macs <= min_macs_w || !tc_ok)) return sg_conv_wgrad(p, (cudaStream_t)stream);
     if (bmnas_gemm_mode_flag && tc_eligible(p, 2)) return tc_conv_wgrad(p, gemm_x3(), (cudaStream_t)stream);
     const int N = p->B * p->L, L = p->L;
     const int tiles = ((p->K + TN - 1) / TN) * ((p->M + TM - 1) / TM);

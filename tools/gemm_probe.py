@@ -19,7 +19,8 @@ for B in Bs:
     Zr, mr, rr, Weff, U = T._ref_fwd(srcs, Ws, bias, w_fold)
     GV = torch.randn(B, M, L, device=dev)
     dU = torch.einsum('mk,bml->bkl', Weff, GV.double()); dW = torch.einsum('bml,bkl->mk', GV.double(), U)
-    imgs = T._images(N, lib, Ws, seg_M, K, w_fold, dev) if os.environ.get('PROBE_IMG', '1') == '1' else None
+    FMT = int(os.environ.get('PROBE_FMT', '0'))      # 0: tcgen05 slabs (ws / panel kernels), 1: plain fp32 (gemm_sg.cu FFMA kernels)
+    imgs = T._images(N, lib, Ws, seg_M, K, w_fold, dev, fmt=FMT) if os.environ.get('PROBE_IMG', '1') == '1' else None
     for mode in [int(m) for m in os.environ.get('PROBE_MODES', '0,1,2').split(',')]:
         lib.bmnas_set_gemm_mode(mode)
         st = T._params(N, B, L, src_C, seg_M, w_fold, srcs, Ws)
@@ -34,9 +35,9 @@ for B in Bs:
         part = torch.zeros(int(lib.bmnas_conv_stat_part_size(ctypes.byref(st))), device=dev)
         cnt = torch.zeros(int(lib.bmnas_conv_num_counters(ctypes.byref(st))), dtype=torch.int32, device=dev)
         st.Z, st.mean, st.rstd, st.stat_part, st.counter = Z.data_ptr(), mean.data_ptr(), rstd.data_ptr(), part.data_ptr(), cnt.data_ptr()
-        if imgs is not None: st.wimg_fwd = imgs[0].data_ptr()
+        if imgs is not None: st.wimg_fwd = imgs[0].data_ptr(); st.wimg_fmt = FMT
         sd = T._params(N, B, L, src_C, seg_M, w_fold, srcs, Ws); sd.GV = GV.data_ptr()
-        if imgs is not None: sd.wimg_dgrad = imgs[1].data_ptr()
+        if imgs is not None: sd.wimg_dgrad = imgs[1].data_ptr(); sd.wimg_fmt = FMT
         gs = [torch.zeros(B, c, L, device=dev) for c in src_C]
         for i in range(len(src_C)): sd.gsrc[i] = gs[i].data_ptr()
         sw = T._params(N, B, L, src_C, seg_M, w_fold, srcs, Ws); sw.GV = GV.data_ptr()

@@ -37,8 +37,8 @@ cap ln_bwd_B96 k_ln_bwd ""
 capL mixed_fwd_tf32_B8192 k_mixed_fwd mixed_fwd ""
 capL mixed_fwd_bf16_B8192 k_mixed_fwd mixed_fwd BMNAS_GEMM_MODE=3
 capL node_bwd_warp_B8192 k_node_bwd_warp node_bwd ""
-capL panel_dgrad_B8192 k_gemm_panelILi1E conv_dgrad ""
-capL panel_fwd_B8192 k_gemm_panelILi0E conv_fwd ""
-capL tc_wgrad_B8192 k_gemm_tc conv_wgrad ""
+capL ws_dgrad_B8192 k_gemm_wsILi1E conv_dgrad ""
+capL ws_fwd_B8192 k_gemm_wsILi0E conv_fwd ""
+capL ws_wgrad_B8192 k_wgrad_ws conv_wgrad ""
 capL ln_bwd_B8192 k_ln_bwd ln_bwd ""
 ls -la gpurun_out/*.ncu-rep | awk '{print $5, $9}'

@@ -36,7 +36,8 @@ for f in sorted(os.listdir('gpurun_out')):
             key = {'node_fwd': 'bmnas_node_fwd', 'node_bwd': 'bmnas_node_bwd', 'sg_fwd': 'bmnas_conv_fwd', 'sg_dgrad': 'bmnas_conv_dgrad',
                    'wgrad': 'bmnas_conv_wgrad', 'mix_bwd': 'bmnas_mix_bwd', 'ln_bwd': 'bmnas_ln_bwd', 'panel_fwd': 'bmnas_conv_fwd',
                    'node_fwd_warp': 'bmnas_node_fwd', 'node_bwd_warp': 'bmnas_node_bwd', 'mixed_fwd': 'bmnas_mixed_fwd', 'mixed_fwd_tf32': 'bmnas_mixed_fwd',
-                   'mixed_fwd_bf16': 'bmnas_mixed_fwd_bf16', 'panel_dgrad': 'bmnas_conv_dgrad', 'tc_wgrad': 'bmnas_conv_wgrad'}.get(m.group(1), m.group(1))
+                   'mixed_fwd_bf16': 'bmnas_mixed_fwd_bf16', 'panel_dgrad': 'bmnas_conv_dgrad', 'tc_wgrad': 'bmnas_conv_wgrad', 'ws_dgrad': 'bmnas_conv_dgrad', 'ws_fwd': 'bmnas_conv_fwd',
+                   'ws_wgrad': 'bmnas_conv_wgrad', 'mixed_small': 'bmnas_mixed_small_fwd', 'head': 'bmnas_head_fused'}.get(m.group(1), m.group(1))
             traffic[f'{key}@B{m.group(2)}'] = int(rd + wr)
     src = subprocess.run([sys.executable, 'tools/ncu_src.py', rep, '14'], capture_output=True, text=True).stdout
     lines.append('# hottest SASS lines (sampled stalls)')
