@@ -445,8 +445,8 @@ class Program:
         # weight images (refreshed by ONE bmnas_wprep launch at the start of every forward): the library picks the
         # format = GEMM engine for this problem size (plain fp32 for the small-N cp.async kernels, tcgen05 slabs beyond)
         img_f = img_d = None
-        fmt = int(N.lib().bmnas_conv_image_fmt(self.B, self.L, K, M))
-        fmt_f = fmt if fwd_fmt is None else fwd_fmt
+        fmt = int(N.lib().bmnas_conv_image_fmt_dgrad(self.B, self.L, K, M))        # engine of the dgrad GEMM
+        fmt_f = int(N.lib().bmnas_conv_image_fmt(self.B, self.L, K, M)) if fwd_fmt is None else fwd_fmt
         if fmt_f >= 0 and all(c % 4 == 0 for c in src_C) and all(sg['W'].data_ptr() % 16 == 0 for sg in segs):
             seg_list = [(sg['W'], sg['M']) for sg in segs]
             img_f = self.buf(int(N.lib().bmnas_wimg_floats_fmt(M, K, 0, fmt_f)))

@@ -483,6 +483,24 @@ extern "C" int bmnas_conv_image_fmt(int B, int L, int K, int M) {
     return (sg_ok && N * (long long)M * K <= min_macs) ? 1 : 0;
 }
 
+// ... and the same question for the dgrad GEMM of that conv (rows K, reduction M).  A SHORT reduction (M <= 128: at most 4
+// weight slabs, e.g. out_conv's dgrad) suits the warp-specialised tcgen05 kernel at every size measured -- NTU out_conv, us:
+// 5.3 vs 7.4 at B = 96, 6.2 vs 9.7 at B = 256, 8.3 vs 20.3 at B = 768 -- while the node conv's dgrad (M = 384) crosses over
+// near B = 192 (75 M MACs) (profiles/r02_engine_crossover.txt).  BMNAS_TC_MIN_MACS_D overrides the second threshold.
+extern "C" int bmnas_conv_image_fmt_dgrad(int B, int L, int K, int M) {
+    const int f = bmnas_conv_image_fmt(B, L, K, M);
+    if (f != 1) return f;                      // not eligible for the FFMA engine (or already on the tensor cores)
+    if (bmnas_gemm_mode_flag == 0) return f;
+    static long long min_macs_d = -1;
+    if (min_macs_d < 0) {
+        const char* e = getenv("BMNAS_TC_MIN_MACS_D");
+        min_macs_d = e ? atoll(e) : 75000000LL;
+    }
+    const long long macs = (long long)B * L * M * K;
+    if ((M <= 128 && K >= 128 && macs >= 20000000LL) || macs > min_macs_d) return 0;
+    return 1;
+}
+
 extern "C" long long bmnas_conv_stat_part_size(const bmnas_conv_params* p) {
     const long long N = (long long)p->B * p->L;
     return ((N + TN - 1) / TN) * p->M * 2;

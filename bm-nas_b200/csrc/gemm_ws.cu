@@ -8,16 +8,24 @@
 //
 // Work split: CTA (x, y) owns accumulator row tile y (128 rows) and a CONTIGUOUS span of 32-column units
 // [x U / gx, (x+1) U / gx): perfectly balanced over the 148 SMs whatever the batch; the span is cut into tiles of at
-// most 256 columns whose width becomes the N of the UMMA instruction (runtime instruction descriptor), so there is no
-// ragged last wave.  Two 256-column accumulator sets in tensor memory let the epilogue of tile i overlap the MMAs of
-// tile i + 1.
+// most 128 columns whose width becomes the N of the UMMA instruction (runtime instruction descriptor), so there is no
+// ragged last wave.
+//
+// Tensor memory: two accumulator SETS of 256 columns (the epilogue of tile i overlaps the MMAs of tile i + 1), each set =
+// [big | small] x 128 columns.  In 3xTF32 the hi*hi products accumulate in `big`, the two correction products (lo*hi,
+// hi*lo, 2^-11 of the former) in `small`, and the epilogue adds the two in fp32: the tensor core's accumulate truncates,
+// and with all three products in ONE accumulator that bias grew with the number of MMAs (measured 3-5x the error of the
+// FFMA engine on K = 128..384; split, the long chain only sees a third of the MMAs and the corrections keep their bits).
 //
 // Warp roles (448 threads, one CTA per SM), every hand-over an mbarrier:
-//   warps 0-7   producers: global fp32 -> registers (P register blocks of 4 reduction rows x 4 columns in flight per
-//               thread: 32-64 KB of loads in flight per SM) -> BatchNorm-backward fold (DGRAD) -> hi/lo tf32 split ->
-//               K-major SWIZZLE_128B activation stages (256 columns x 32 reduction elements)
-//   warps 8-11  epilogue: tcgen05.ld (thread = accumulator row), bias + Z store + Welford row statistics (FWD) or
-//               store / red.add into the source gradients (DGRAD)
+//   warps 0-7   producers.  Global loads are cp.async (LDGSTS) copies into a thread-private staging ring in shared memory,
+//               D units (= pipeline stages) deep, tracked by cp.async groups -- NOT register loads: with register
+//               prefetch the per-warp scoreboards serialised the units and the loop ran at one load latency per stage
+//               (measured: 2 us per 32 KB stage, tools/ws_timeline.py).  A unit = 4 reduction rows x 4 columns; the
+//               thread reads it back, applies the BatchNorm-backward fold (DGRAD), splits hi/lo tf32 and writes the
+//               K-major SWIZZLE_128B operand stage (128 columns x 32 reduction elements)
+//   warps 8-11  epilogue: tcgen05.ld (thread = accumulator row), big + small, bias + Z store + Welford row statistics
+//               (FWD) or store / red.add into the source gradients (DGRAD)
 //   warp 12     MMA issue (warp-uniform loop, one elected lane issues tcgen05.mma kind::tf32, 3 per k-step in 3xTF32)
 //   warp 13     weight slabs: TMA bulk copies of the bmnas_wprep image through a ring (resident when the whole
 //               reduction fits in it) + TMEM allocation
@@ -46,18 +54,21 @@ constexpr int FWD = 0, DGRAD = 1;
 constexpr int NPW = 8, NPROD = NPW * 32, NEPI = 128;
 constexpr int W_MMA = NPW + 4, W_TMA = W_MMA + 1;
 constexpr int THREADS = (W_TMA + 1) * 32;
-constexpr int BNMAX = 256;
-constexpr uint32_t TSET = 256;                   // TMEM columns per accumulator set
+constexpr int BNMAX = 128;                       // columns per tile
+constexpr uint32_t TSET = 256;                   // TMEM columns per accumulator set: [big 128 | small 128]
 
-template <bool X3>
+template <int MODE, bool X3>
 struct Cfg {
-    static constexpr uint32_t B_HALF = BNMAX * 128;                 // 32 KB: 256 columns x one 128-byte reduction row
+    static constexpr uint32_t B_HALF = BNMAX * 128;                 // 16 KB: 128 columns x one 128-byte reduction row
     static constexpr uint32_t B_ST = X3 ? 2 * B_HALF : B_HALF;     // [hi | lo]
     static constexpr uint32_t A_HALF = TCM * 128;                   // 16 KB
     static constexpr uint32_t A_ST = X3 ? 2 * A_HALF : A_HALF;
-    static constexpr int NB = X3 ? 2 : 4;
+    static constexpr int NB = 2;
     static constexpr int NA = X3 ? 3 : 4;
-    static constexpr uint32_t DYN = NB * B_ST + NA * A_ST + 1024;
+    static constexpr int NV = MODE == FWD ? 4 : 8;                  // 16-byte copies per unit and thread (DGRAD: GV and Z)
+    static constexpr int D = MODE == FWD ? 4 : 2;                   // units in flight per thread
+    static constexpr uint32_t STG = D * NV * NPROD * 16;           // staging ring: 64 KB
+    static constexpr uint32_t DYN = NB * B_ST + NA * A_ST + STG + 1024;
 };
 
 struct Bars {
@@ -68,21 +79,29 @@ struct Bars {
 // span / tile geometry shared by all roles
 struct Geo {
     int u_lo, su, nt;
-    // t * su < 2^31 for any span a 148-CTA grid sees below 2^31 columns (su <= U / gx, t < su / 8)
+    // t * su < 2^31 for any span a 148-CTA grid sees below 2^31 columns (su <= U / gx, t < su / 4)
     __device__ __forceinline__ int tile_u0(int t) const { return u_lo + (int)((unsigned)(t * su) / (unsigned)nt); }
     __device__ __forceinline__ int tile_wu(int t) const { return (int)((unsigned)((t + 1) * su) / (unsigned)nt) - (int)((unsigned)(t * su) / (unsigned)nt); }
 };
-// first 32-column unit of CTA x's span.  32-bit on purpose (x * U < 2^32 up to 9e8 columns): the BatchNorm finalize calls
-// this twice per partial, and a 64-bit division there cost ~0.18 us per CTA of the grid (measured: 22 us at 148 CTAs)
+// first 32-column unit of CTA x's span (32-bit on purpose: x * U < 2^32 up to 9e8 columns)
 __host__ __device__ __forceinline__ int span_lo(int x, int U, int gx) { return (int)((unsigned)x * (unsigned)U / (unsigned)gx); }
+
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, bool valid) {
+    // src-size 0 zero-fills the 16 bytes (padding columns / reduction rows past the end stay exactly zero)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s32(dst_smem)), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
 
 template <int MODE, bool X3>
 __global__ void __launch_bounds__(THREADS, 1) k_gemm_ws(const bmnas_conv_params p, const int N) {
-    using CF = Cfg<X3>;
+    using CF = Cfg<MODE, X3>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smB = smem;
     uint8_t* smA = smem + (size_t)CF::NB * CF::B_ST;
+    float4* stg = reinterpret_cast<float4*>(smA + (size_t)CF::NA * CF::A_ST);     // [D][NV][NPROD] 16-byte slots
     __shared__ Bars sh;
     float4* s_stat = reinterpret_cast<float4*>(smB);          // the activation ring is free once the last tile's MMAs are done
 
@@ -98,14 +117,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_ws(const bmnas_conv_params 
     Geo g;
     g.u_lo = span_lo((int)blockIdx.x, U, gx);
     g.su = span_lo((int)blockIdx.x + 1, U, gx) - g.u_lo;
-    g.nt = (g.su + 7) >> 3;
+    g.nt = (g.su + 3) >> 2;
     const int total_st = g.nt * n_chunks;                       // activation stages of this CTA
     const bool resident = n_chunks <= CF::NA;                   // the row tile's whole weight fits in the ring
 
     // ---- set-up that touches no global memory: overlaps the tail of the preceding kernel (PDL)
     if (tid == 0) {
         for (int i = 0; i < 4; ++i) {
-            mbar_init(&sh.b_full[i], NPROD);
+            mbar_init(&sh.b_full[i], NPW);                       // one arrival per producer warp
             mbar_init(&sh.b_empty[i], 1);
             mbar_init(&sh.a_full[i], 1);
             mbar_init(&sh.a_empty[i], 1);
@@ -127,125 +146,131 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_ws(const bmnas_conv_params 
 
     if (warp < NPW) {
         // =============================================================== producers
-        // block = 4 reduction rows (one 16-byte chunk kb of the 128-byte operand row) x 4 columns (column group cg);
+        // unit = stage: 4 reduction rows (the 16-byte chunk kb of the 128-byte operand row) x 4 columns (column group cg);
         // the 8 lanes of a quarter warp write the 8 chunks of ONE operand row: conflict-free 128-bit shared stores
-        const int kb = tid & 7, cg0 = tid >> 3;                 // column groups cg0 and cg0 + 32 of every stage
-        constexpr int P = MODE == FWD ? 4 : 2;                  // register blocks in flight per thread (even)
+        const int kb = tid & 7, cg = tid >> 3;
+        constexpr int D = CF::D, NV = CF::NV;
         const bool has_coef = MODE == DGRAD && p.coef_a != nullptr;
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 v[P][4], zz[MODE == DGRAD ? P : 1][4], ca[MODE == DGRAD ? P : 1], cb[MODE == DGRAD ? P : 1], cc[MODE == DGRAD ? P : 1];
-        const int total_st2 = total_st * 2;
+        float4 ca[MODE == DGRAD ? D : 1], cb[MODE == DGRAD ? D : 1], cc[MODE == DGRAD ? D : 1];
+        const float* any_src = MODE == FWD ? p.src[0] : p.GV;      // a valid address for zero-filled copies
 
-        // a cursor walks the units (tile t, reduction slab kc, half u) in order and keeps everything that only changes
-        // with the tile (column validity, sample / position of this thread's two column groups): no division per unit
+        // a cursor walks the stages (tile t, reduction slab kc) in order and keeps what only changes with the tile
         struct Cur {
-            int t, kc, w4;                   // tile, slab, tile width in 4-column groups
-            bool ok[2];                      // column group u lies inside the tile and the batch
-            long long b[2];                  // its sample ...
-            int l0[2];                       // ... and first position
+            int t, kc;
+            bool in;                         // this thread's column group lies inside the tile (it writes the operand stage)
+            bool ok;                         // ... and inside the batch (it has data to fetch)
+            long long b;                     // its sample ...
+            int l0;                          // ... and first position
         };
         auto set_tile = [&](Cur& c_) {
-            const int col0 = g.tile_u0(c_.t) * 32;
-            c_.w4 = g.tile_wu(c_.t) * 8;
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int cg = cg0 + u * 32, n = col0 + cg * 4;
-                c_.ok[u] = cg < c_.w4 && n < N;
-                const int b = n / L;
-                c_.b[u] = b;
-                c_.l0[u] = n - b * L;
-            }
+            const int n = g.tile_u0(c_.t) * 32 + cg * 4;
+            c_.in = cg < g.tile_wu(c_.t) * 8;
+            c_.ok = c_.in && n < N;
+            const int b = n / L;
+            c_.b = b;
+            c_.l0 = n - b * L;
         };
-        auto advance = [&](Cur& c_) {        // called after the u = 1 unit of a slab
+        auto advance = [&](Cur& c_) {
             if (++c_.kc == n_chunks) {
                 c_.kc = 0;
                 if (++c_.t < g.nt) set_tile(c_);
             }
         };
-        Cur lc = {0, 0, 0, {false, false}, {0, 0}, {0, 0}}, cc_ = lc;
+        Cur lc = {0, 0, false, false, 0, 0}, cc_ = lc;
         set_tile(lc);
         set_tile(cc_);
+        auto slot = [&](int d, int j) { return stg + ((d * NV + j) * NPROD + tid); };
+        const uint32_t stg_s = s32(stg) + (uint32_t)tid * 16u, smB_s = s32(smB);
+        auto slot_s = [&](int d, int j) { return stg_s + (uint32_t)((d * NV + j) * NPROD) * 16u; };
+        long long w_ld = 0, w_be = 0;                          // timeline: cycles thread 0 waited for its copies / for a free stage
 
-        auto load = [&](int q, const int u, float4 (&d)[4], float4 (&dz)[4], float4& a_, float4& b_, float4& c_) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) d[j] = z4;
-            if (MODE == DGRAD) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dz[j] = z4;
-                a_ = b_ = c_ = z4;
-            }
-            if (q >= total_st2) return;
-            const int r = lc.kc * KC + kb * 4;
-            if (lc.ok[u] && r < r_end) {
+        // issue the copies of stage q into staging slot d (always one cp.async group, empty past the end)
+        auto issue = [&](int q, const int d) {
+            if (q < total_st) {
+                const int r = lc.kc * KC + kb * 4;
+                const bool ok = lc.ok && r < r_end;
                 if (MODE == FWD) {
-                    int s, kl;
-                    src_of(p, r, &s, &kl);
-                    const float* u_ = p.src[s] + (lc.b[u] * p.src_C[s] + kl) * L + lc.l0[u];
+                    int s = 0, kl = 0;
+                    if (ok) src_of(p, r, &s, &kl);
+                    const float* u_ = ok ? p.src[s] + (lc.b * p.src_C[s] + kl) * L + lc.l0 : any_src;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) d[j] = __ldg(reinterpret_cast<const float4*>(u_ + (long long)j * L));
+                    for (int j = 0; j < 4; ++j) cp_async16(slot(d, j), u_ + (ok ? (long long)j * L : 0), ok);
                 } else {
-                    const long long idx = (lc.b[u] * M + r) * L + lc.l0[u];
+                    const long long idx = ok ? (lc.b * M + r) * L + lc.l0 : 0;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) d[j] = __ldg(reinterpret_cast<const float4*>(p.GV + idx + (long long)j * L));
+                    for (int j = 0; j < 4; ++j) cp_async16(slot(d, j), p.GV + idx + (ok ? (long long)j * L : 0), ok);
                     if (has_coef) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) dz[j] = __ldg(reinterpret_cast<const float4*>(p.Z + idx + (long long)j * L));
-                        a_ = __ldg(reinterpret_cast<const float4*>(p.coef_a + r));
-                        b_ = __ldg(reinterpret_cast<const float4*>(p.coef_b + r));
-                        c_ = __ldg(reinterpret_cast<const float4*>(p.coef_c + r));
+                        for (int j = 0; j < 4; ++j) cp_async16(slot(d, 4 + j), p.Z + idx + (ok ? (long long)j * L : 0), ok);
+                        ca[MODE == DGRAD ? d : 0] = ok ? __ldg(reinterpret_cast<const float4*>(p.coef_a + r)) : z4;
+                        cb[MODE == DGRAD ? d : 0] = ok ? __ldg(reinterpret_cast<const float4*>(p.coef_b + r)) : z4;
+                        cc[MODE == DGRAD ? d : 0] = ok ? __ldg(reinterpret_cast<const float4*>(p.coef_c + r)) : z4;
                     }
+                }
+                advance(lc);
+            }
+            cp_async_commit();
+        };
+        auto consume = [&](int q, const int d) {
+            long long c0_ = tl_on ? clock64() : 0;
+            cp_async_wait<D - 1>();                              // this thread's copies of stage q have landed
+            if (tl_on && tid == 0) w_ld += clock64() - c0_;
+            const int stage = q % CF::NB, round = q / CF::NB;
+            float4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = lds128(slot_s(d, j));
+            if (has_coef) {
+                // zero-filled (padding) units carry zero coefficients: they stay exactly zero
+                const float4 a_ = ca[MODE == DGRAD ? d : 0], b_ = cb[MODE == DGRAD ? d : 0], c_ = cc[MODE == DGRAD ? d : 0];
+                const float av[4] = {a_.x, a_.y, a_.z, a_.w}, bv[4] = {b_.x, b_.y, b_.z, b_.w}, cv[4] = {c_.x, c_.y, c_.z, c_.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 z = lds128(slot_s(d, 4 + j));
+                    v[j].x = fmaf(av[j], v[j].x, fmaf(bv[j], z.x, cv[j]));
+                    v[j].y = fmaf(av[j], v[j].y, fmaf(bv[j], z.y, cv[j]));
+                    v[j].z = fmaf(av[j], v[j].z, fmaf(bv[j], z.z, cv[j]));
+                    v[j].w = fmaf(av[j], v[j].w, fmaf(bv[j], z.w, cv[j]));
                 }
             }
-            if (u == 1) advance(lc);
-        };
-        auto consume = [&](int q, const int u, float4 (&d)[4], float4 (&dz)[4], const float4& a_, const float4& b_, const float4& c_) {
-            const int it = q >> 1;
-            const int stage = it % CF::NB, round = it / CF::NB;
-            if (u == 0 && round > 0) mbar_wait(&sh.b_empty[stage], (uint32_t)(round - 1) & 1u);
-            const int cg = cg0 + u * 32;
-            if (cg < cc_.w4) {
-                if (has_coef && cc_.ok[u] && cc_.kc * KC + kb * 4 < r_end) {   // padding columns / reduction rows stay exactly zero
-                    const float av[4] = {a_.x, a_.y, a_.z, a_.w}, bv[4] = {b_.x, b_.y, b_.z, b_.w}, cv[4] = {c_.x, c_.y, c_.z, c_.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        d[j].x = fmaf(av[j], d[j].x, fmaf(bv[j], dz[j].x, cv[j]));
-                        d[j].y = fmaf(av[j], d[j].y, fmaf(bv[j], dz[j].y, cv[j]));
-                        d[j].z = fmaf(av[j], d[j].z, fmaf(bv[j], dz[j].z, cv[j]));
-                        d[j].w = fmaf(av[j], d[j].w, fmaf(bv[j], dz[j].w, cv[j]));
-                    }
-                }
-                uint8_t* hi = smB + (size_t)stage * CF::B_ST;
-                uint8_t* lo = hi + CF::B_HALF;
+            c0_ = tl_on ? clock64() : 0;
+            if (round > 0) mbar_wait(&sh.b_empty[stage], (uint32_t)(round - 1) & 1u);
+            if (tl_on && tid == 0) w_be += clock64() - c0_;
+            if (cc_.in) {
+                const uint32_t hi = smB_s + (uint32_t)stage * CF::B_ST, lo = hi + CF::B_HALF;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {                   // column cg*4 + i of the block = (row0[i], row1[i], row2[i], row3[i])
                     float4 e;
-                    e.x = i == 0 ? d[0].x : i == 1 ? d[0].y : i == 2 ? d[0].z : d[0].w;
-                    e.y = i == 0 ? d[1].x : i == 1 ? d[1].y : i == 2 ? d[1].z : d[1].w;
-                    e.z = i == 0 ? d[2].x : i == 1 ? d[2].y : i == 2 ? d[2].z : d[2].w;
-                    e.w = i == 0 ? d[3].x : i == 1 ? d[3].y : i == 2 ? d[3].z : d[3].w;
-                    put_chunk<X3>(hi, lo, sw_off(cg * 4 + i, kb), e);
+                    e.x = i == 0 ? v[0].x : i == 1 ? v[0].y : i == 2 ? v[0].z : v[0].w;
+                    e.y = i == 0 ? v[1].x : i == 1 ? v[1].y : i == 2 ? v[1].z : v[1].w;
+                    e.z = i == 0 ? v[2].x : i == 1 ? v[2].y : i == 2 ? v[2].z : v[2].w;
+                    e.w = i == 0 ? v[3].x : i == 1 ? v[3].y : i == 2 ? v[3].z : v[3].w;
+                    put_chunk_fast<X3>(hi, lo, sw_off(cg * 4 + i, kb), e);
                 }
             }
-            if (u == 1) {
-                fence_proxy_async();                             // generic-proxy writes -> visible to the tensor core
-                mbar_arrive(&sh.b_full[stage]);
-                advance(cc_);
-                if (tid == 0 && it == 0) WS_TL(2);
-            }
+            fence_proxy_async();                                 // generic-proxy writes -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh.b_full[stage]);       // (256 arrivals per stage serialised on the barrier word)
+            advance(cc_);
+            if (tid == 0 && q == 0) WS_TL(2);
         };
 #pragma unroll
-        for (int s = 0; s < P; ++s)
-            load(s, s & 1, v[s], zz[MODE == DGRAD ? s : 0], ca[MODE == DGRAD ? s : 0], cb[MODE == DGRAD ? s : 0], cc[MODE == DGRAD ? s : 0]);
-        for (int q0 = 0; q0 < total_st2; q0 += P) {             // total_st2 is even and P is even: slot s always holds half u = s & 1
+        for (int d = 0; d < D; ++d) issue(d, d);
+        for (int q0 = 0; q0 < total_st; q0 += D) {
 #pragma unroll
-            for (int s = 0; s < P; ++s) {
-                if (q0 + s < total_st2) {
-                    consume(q0 + s, s & 1, v[s], zz[MODE == DGRAD ? s : 0], ca[MODE == DGRAD ? s : 0], cb[MODE == DGRAD ? s : 0], cc[MODE == DGRAD ? s : 0]);
-                    load(q0 + s + P, s & 1, v[s], zz[MODE == DGRAD ? s : 0], ca[MODE == DGRAD ? s : 0], cb[MODE == DGRAD ? s : 0], cc[MODE == DGRAD ? s : 0]);
+            for (int d = 0; d < D; ++d) {
+                if (q0 + d < total_st) {
+                    consume(q0 + d, d);
+                    issue(q0 + d + D, d);                        // refills the slot just read (the reads above feed the stores before it)
                 }
             }
         }
+        cp_async_wait<0>();
         if (tid == 0) WS_TL(3);
+        if (tl_on && tid == 0) {
+            g_ws_tl[16] = (unsigned long long)w_ld;
+            g_ws_tl[17] = (unsigned long long)w_be;
+        }
     } else if (warp == W_TMA) {
         // =============================================================== weight slabs (TMA bulk copies)
         constexpr uint32_t IMG_SLAB = 2u * TCM * KC * 4;       // image slab: [hi 16 KB | lo 16 KB]
@@ -266,17 +291,26 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_ws(const bmnas_conv_params 
         // =============================================================== MMA issue (warp-uniform, elected lane issues)
         const bool leader = elect_one();
         uint32_t it = 0;
+        long long w_af = 0, w_bf = 0, w_te = 0;                // timeline: cycles waited for weight slabs / activation stages / a free accumulator set
         for (int t = 0; t < g.nt; ++t) {
             const int buf = t & 1;
+            long long c2_ = tl_on ? clock64() : 0;
             if (t >= 2) mbar_wait(&sh.t_empty[buf], (uint32_t)((t >> 1) - 1) & 1u);       // the epilogue has drained this set
+            if (tl_on) w_te += clock64() - c2_;
             tc_fence_after();
-            const uint32_t d0 = tmem_base + (uint32_t)buf * TSET;
+            const uint32_t d_big = tmem_base + (uint32_t)buf * TSET, d_small = d_big + BNMAX;
             const uint32_t idesc = idesc_tf32(TCM, g.tile_wu(t) * 32);
             for (int kc = 0; kc < n_chunks; ++kc, ++it) {
                 const uint32_t stage = it % CF::NB;
                 const uint32_t slot = resident ? (uint32_t)kc : it % CF::NA;
+                long long c0_ = tl_on ? clock64() : 0;
                 if (!resident || t == 0) mbar_wait(&sh.a_full[slot], resident ? 0u : (it / CF::NA) & 1u);
+                long long c1_ = tl_on ? clock64() : 0;
                 mbar_wait(&sh.b_full[stage], (it / CF::NB) & 1u);
+                if (tl_on) {
+                    w_af += c1_ - c0_;
+                    w_bf += clock64() - c1_;
+                }
                 tc_fence_after();
                 const uint32_t a_hi = s32(smA + (size_t)slot * CF::A_ST), a_lo = a_hi + CF::A_HALF;
                 const uint32_t b_hi = s32(smB + (size_t)stage * CF::B_ST), b_lo = b_hi + CF::B_HALF;
@@ -286,12 +320,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_ws(const bmnas_conv_params 
                         const uint32_t ko = (uint32_t)ks * 32u;
                         const uint32_t acc = (kc > 0 || ks > 0) ? 1u : 0u;
                         if (X3) {
-                            umma_tf32(d0, kdesc(a_lo + ko), kdesc(b_hi + ko), idesc, acc);
-                            umma_tf32(d0, kdesc(a_hi + ko), kdesc(b_lo + ko), idesc, 1u);
-                            umma_tf32(d0, kdesc(a_hi + ko), kdesc(b_hi + ko), idesc, 1u);
-                        } else {
-                            umma_tf32(d0, kdesc(a_hi + ko), kdesc(b_hi + ko), idesc, acc);
+                            umma_tf32(d_small, kdesc(a_lo + ko), kdesc(b_hi + ko), idesc, acc);
+                            umma_tf32(d_small, kdesc(a_hi + ko), kdesc(b_lo + ko), idesc, 1u);
                         }
+                        umma_tf32(d_big, kdesc(a_hi + ko), kdesc(b_hi + ko), idesc, acc);
                     }
                     if (!resident) umma_commit(&sh.a_empty[slot]);
                     umma_commit(&sh.b_empty[stage]);
@@ -302,6 +334,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_ws(const bmnas_conv_params 
             if (t == 0) WS_TL(4);
         }
         WS_TL(5);
+        if (tl_on) {
+            g_ws_tl[18] = (unsigned long long)w_af;
+            g_ws_tl[19] = (unsigned long long)w_bf;
+            g_ws_tl[20] = (unsigned long long)w_te;
+            g_ws_tl[21] = (unsigned long long)it;
+        }
     } else {
         // =============================================================== epilogue warps
         const int lq = warp & 3;
@@ -324,7 +362,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_ws(const bmnas_conv_params 
                 accum = p.gsrc_accum[s_] != 0;
             }
         }
-        Wf run = {0.f, 0.f, 0.f};
+        // BatchNorm row statistics as pivoted sums: d = v - pivot, S = sum d, Q = sum d^2 in four independent chains (the
+        // Welford merge per 32 columns this replaces -- two divisions and a 32-deep dependent chain on ONE warp per
+        // scheduler -- made the epilogue the slowest role of the forward kernel).  The pivot is the mean of the row's first
+        // chunk, i.e. within sigma / sqrt(32) of the mean, so M2 = Q - S^2 / n loses no digits.
+        float pivot = 0.f, S0 = 0.f, S1 = 0.f, S2 = 0.f, S3 = 0.f, Q0 = 0.f, Q1 = 0.f, Q2 = 0.f, Q3 = 0.f;
+        int ncol = 0;
+        bool have_pivot = false;
         for (int t = 0; t < g.nt; ++t) {
             const int buf = t & 1;
             mbar_wait(&sh.t_full[buf], (uint32_t)(t >> 1) & 1u);
@@ -334,46 +378,51 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_ws(const bmnas_conv_params 
             for (int c8 = 0; c8 < wu; ++c8) {
                 float v[32];
                 {
-                    float a[16], b[16];
-                    tmem_ld16(tz + (uint32_t)(c8 * 32), a);
-                    tmem_ld16(tz + (uint32_t)(c8 * 32 + 16), b);
+                    // all tcgen05.ld of the chunk in flight, one wait
+                    uint32_t rb[32], rs_[32];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        v[i] = a[i];
-                        v[16 + i] = b[i];
+                    for (int h = 0; h < 2; ++h) {
+                        tmem_ld16_raw(tz + (uint32_t)(c8 * 32 + h * 16), &rb[h * 16]);
+                        if (X3) tmem_ld16_raw(tz + (uint32_t)(BNMAX + c8 * 32 + h * 16), &rs_[h * 16]);
                     }
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = X3 ? __uint_as_float(rb[i]) + __uint_as_float(rs_[i]) : __uint_as_float(rb[i]);
                 }
                 const int nb = col0 + c8 * 32;
                 int eb = nb / L, el = nb - eb * L;                // sample / position of the chunk's first column, then stepped by 4
                 if (MODE == FWD) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] += bias;
-                    float sum = 0.f;
-                    int cnt = 0;
+                    const int nval = min(32, N - nb);             // valid columns of the chunk (a multiple of 4, > 0)
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
-                        const int n = nb + j4 * 4;
-                        if (n < N) {                              // N % 4 == 0 and L % 4 == 0: a 4-group is whole and in one sample
+                        if (j4 * 4 < nval) {                      // N % 4 == 0 and L % 4 == 0: a 4-group is whole and in one sample
                             if (row_ok) {
                                 *reinterpret_cast<float4*>(p.Z + ((long long)eb * M + gr) * L + el) =
                                     make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
                             }
                             el += 4;
                             if (el >= L) { el -= L; ++eb; }
-                            sum += (v[j4 * 4] + v[j4 * 4 + 1]) + (v[j4 * 4 + 2] + v[j4 * 4 + 3]);
-                            cnt += 4;
                         }
                     }
-                    if (p.bn_mode == 1 && cnt > 0) {
-                        const float mean = sum / (float)cnt;
-                        float m2 = 0.f;
+                    if (p.bn_mode == 1) {
+                        if (!have_pivot) {
+                            float s = 0.f;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float d = v[j] - mean;
-                            if (nb + (j & ~3) < N) m2 = fmaf(d, d, m2);
+                            for (int j = 0; j < 32; ++j) s += j < nval ? v[j] : 0.f;
+                            pivot = s / (float)nval;
+                            have_pivot = true;
                         }
-                        const Wf w = {(float)cnt, mean, m2};
-                        run = wf_merge(run, w);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            if (j < nval) {
+                                const float d0 = v[j] - pivot, d1 = v[j + 1] - pivot, d2 = v[j + 2] - pivot, d3 = v[j + 3] - pivot;
+                                S0 += d0; S1 += d1; S2 += d2; S3 += d3;
+                                Q0 = fmaf(d0, d0, Q0); Q1 = fmaf(d1, d1, Q1); Q2 = fmaf(d2, d2, Q2); Q3 = fmaf(d3, d3, Q3);
+                            }
+                        }
+                        ncol += nval;
                     }
                 } else if (dst) {
 #pragma unroll
@@ -395,6 +444,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_ws(const bmnas_conv_params 
             tc_fence_before();
             mbar_arrive(&sh.t_empty[buf]);
             if (warp == NPW && t == 0) WS_TL(6);
+        }
+        Wf run = {0.f, 0.f, 0.f};
+        if (MODE == FWD && ncol > 0) {
+            const float S = (S0 + S1) + (S2 + S3), Q = (Q0 + Q1) + (Q2 + Q3), n = (float)ncol;
+            run.n = n;
+            run.mean = pivot + S / n;
+            run.m2 = fmaxf(Q - S * (S / n), 0.f);
         }
         if (warp == NPW) WS_TL(7);
         if (MODE == FWD && p.bn_mode == 1) s_stat[erow] = make_float4(run.n, run.mean, run.m2, 0.f);
@@ -424,8 +480,87 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_ws(const bmnas_conv_params 
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));
             g_ws_tl[10] = t__;
         }
-        bn_finalize_rows(p, N, gx, [=](int x) { return min(N, span_lo(x + 1, U, gx) * 32) - span_lo(x, U, gx) * 32; }, row0, TCM, ldw,
-                         256);
+        // ---- finalize of this row tile: Chan's merge of the gx per-CTA partials in two fixed-order passes with no division
+        //      per partial:  mean = sum_x n_x mean_x / N,   M2 = sum_x [M2_x + n_x (mean_x - mean)^2]
+        //      (the generic bn_finalize_rows chains one Welford merge -- a division -- per partial on two lanes per row:
+        //      17 us at 148 partials, measured; this form is ~2 us).  The column counts n_x go through shared memory.
+        // the partials of this row tile (gx x 128 rows x (mean, M2) = at most 148 KB) are fetched ONCE into the idle dynamic
+        // shared memory by all 448 threads, 128-bit and 8 loads in flight per thread: three L2 round trips instead of one per
+        // batch of partials on two lanes per row (13-17 us at 148 partials, measured)
+        float4* sp4 = reinterpret_cast<float4*>(smem);
+        const float2* sp = reinterpret_cast<const float2*>(smem);
+        int* cnt_s = reinterpret_cast<int*>(smem + (size_t)kNumSMs * TCM * 8);
+        {
+            const int total = gx * (TCM / 2);                    // float4 = two rows
+            for (int base = 0; base < total; base += THREADS * 8) {
+                float4 v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int idx = min(base + j * THREADS + tid, total - 1);
+                    const int x = idx >> 6, c2 = (idx & 63) * 2;
+                    const int rr = min(row0 + c2, M - 2);         // M % 4 == 0: a row pair is inside or outside together
+                    v[j] = __ldcg(reinterpret_cast<const float4*>(p.stat_part + ((long long)x * M + rr) * 2));
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int idx = base + j * THREADS + tid;
+                    if (idx < total) sp4[idx] = v[j];
+                }
+            }
+        }
+        for (int x = tid; x < gx; x += THREADS) cnt_s[x] = min(N, span_lo(x + 1, U, gx) * 32) - span_lo(x, U, gx) * 32;
+        __syncthreads();
+        if (tid == 0 && g_ws_tl_on) {
+            unsigned long long t__;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));
+            g_ws_tl[12] = t__;
+        }
+        // three threads per row (384 threads), each a contiguous third of the partials in four independent chains; the thirds meet
+        // in shared memory and are added in a fixed order (deterministic)
+        float* red3 = reinterpret_cast<float*>(cnt_s + kNumSMs);                 // [3][TCM]
+        const int r = tid & (TCM - 1), gsel = tid >> 7, m = row0 + r;
+        const int per = (gx + 2) / 3, x_lo = min(gsel * per, gx), x_hi = min(x_lo + per, gx);
+        auto third_sum = [&](auto term) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            int x = x_lo;
+            for (; x + 4 <= x_hi; x += 4) {
+                a0 += term(x);
+                a1 += term(x + 1);
+                a2 += term(x + 2);
+                a3 += term(x + 3);
+            }
+            for (; x < x_hi; ++x) a0 += term(x);
+            return (a0 + a1) + (a2 + a3);
+        };
+        if (tid < 3 * TCM) red3[gsel * TCM + r] = third_sum([&](int x) { return (float)cnt_s[x] * sp[x * TCM + r].x; });
+        __syncthreads();
+        const float mean = ((red3[r] + red3[TCM + r]) + red3[2 * TCM + r]) / (float)N;
+        __syncthreads();
+        if (tid == 0 && g_ws_tl_on) {
+            unsigned long long t__;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));
+            g_ws_tl[13] = t__;
+        }
+        if (tid < 3 * TCM)
+            red3[gsel * TCM + r] = third_sum([&](int x) {
+                const float2 pv = sp[x * TCM + r];
+                const float d = pv.x - mean;
+                return fmaf((float)cnt_s[x] * d, d, pv.y);
+            });
+        __syncthreads();
+        if (tid < TCM && m < M) {
+            const float m2 = (red3[r] + red3[TCM + r]) + red3[2 * TCM + r];
+            int sg, ml;
+            w_row(p, m, ldw, &sg, &ml);
+            p.mean[m] = mean;
+            p.rstd[m] = 1.f / sqrtf(m2 / (float)N + p.eps);
+            if (p.running_mean[sg] != nullptr) {
+                const float unb = m2 / (float)max(N - 1, 1);
+                p.running_mean[sg][ml] = (1.f - p.momentum) * p.running_mean[sg][ml] + p.momentum * mean;
+                p.running_var[sg][ml] = (1.f - p.momentum) * p.running_var[sg][ml] + p.momentum * unb;
+                if (ml == 0 && p.num_batches_tracked[sg]) *p.num_batches_tracked[sg] += 1;
+            }
+        }
         if (tid == 0 && g_ws_tl_on) {
             unsigned long long t__;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));
@@ -436,7 +571,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_ws(const bmnas_conv_params 
 
 template <int MODE, bool X3>
 static int launch_ws(const bmnas_conv_params* p, cudaStream_t stream) {
-    using CF = Cfg<X3>;
+    using CF = Cfg<MODE, X3>;
     const int N = p->B * p->L;
     const int row_tiles = ((MODE == DGRAD ? p->K : p->M) + TCM - 1) / TCM;
     const int U = (N + 31) / 32;

@@ -96,6 +96,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// tcgen05.ld of 16 columns without the wait (issue several, then ONE tcgen05.wait::ld)
+__device__ __forceinline__ void tmem_ld16_raw(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
 // sum of the same 16 columns of the first `used` of NA accumulators (accumulator a starts BNC columns after a-1)
 template <int NA, int BNC>
 __device__ __forceinline__ void tmem_ld16_sum(uint32_t taddr, float (&v)[16], int used) {
@@ -144,6 +152,28 @@ __device__ __forceinline__ float tf32_hi(float v) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
     return __uint_as_float(r);
+}
+
+// round-to-nearest tf32 of a FINITE fp32 value as two integer ops (ties away from zero, like cvt.rna): the compiler's
+// cvt.rna.tf32.f32 expands to four (it also routes Inf / NaN around the add).  Used where the operand staging is bound by
+// instruction issue (gemm_ws.cu, wgrad_ws.cu); the inputs there are activations / gradients of a finite forward pass.
+__device__ __forceinline__ float tf32_rn_fast(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
+// explicit shared-space accesses (32-bit shared addresses): through a generic pointer carved out of the dynamic shared
+// array the compiler emitted LD.E / ST.E (generic, long-scoreboard) in the operand staging loops
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// hi_s / lo_s: shared addresses of the hi / lo operand images
+template <bool X3>
+__device__ __forceinline__ void put_chunk_fast(uint32_t hi_s, uint32_t lo_s, uint32_t off, float4 v) {
+    const float4 h = make_float4(tf32_rn_fast(v.x), tf32_rn_fast(v.y), tf32_rn_fast(v.z), tf32_rn_fast(v.w));
+    sts128(hi_s + off, h);
+    if (X3) sts128(lo_s + off, make_float4(tf32_rn_fast(v.x - h.x), tf32_rn_fast(v.y - h.y), tf32_rn_fast(v.z - h.z), tf32_rn_fast(v.w - h.w)));
 }
 
 // write one 16-byte K-chunk (4 reduction elements of one operand row) as hi (and lo) tf32 values

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_ws(const bmnas_conv_params
         fence_barrier_init();
     }
     if (tid < TCM) rowsum[tid] = 0.f;
-    if (warp == W_MMA) tmem_alloc(&tmem_base_s, BNK);
+    if (warp == W_MMA) tmem_alloc(&tmem_base_s, 2 * BNK);        // [big | small] accumulators (see gemm_ws.cu)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -127,10 +127,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_ws(const bmnas_conv_params
             const int st = q >> 1;
             const int stage = st % CF::NS, round = st / CF::NS;
             if (u == 0 && round > 0) mbar_wait(&s_empty[stage], (uint32_t)(round - 1) & 1u);
-            uint8_t* a_hi = smem + (size_t)stage * CF::STAGE;
-            uint8_t* a_lo = a_hi + CF::HALF;
-            uint8_t* b_hi = a_hi + CF::OPND;
-            uint8_t* b_lo = b_hi + CF::HALF;
+            const uint32_t a_hi = s32(smem) + (uint32_t)stage * CF::STAGE, a_lo = a_hi + CF::HALF;
+            const uint32_t b_hi = a_hi + CF::OPND, b_lo = b_hi + CF::HALF;
             const bool in = r_beg + st * KC + c * 4 < r_end;      // reduction columns past the range stay exactly zero
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -146,8 +144,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_ws(const bmnas_conv_params
                     }
                     rs[it] += (v.x + v.y) + (v.z + v.w);
                 }
-                put_chunk<X3>(a_hi, a_lo, sw_off(row, c), v);
-                put_chunk<X3>(b_hi, b_lo, sw_off(row, c), x_[j]);
+                put_chunk_fast<X3>(a_hi, a_lo, sw_off(row, c), v);
+                put_chunk_fast<X3>(b_hi, b_lo, sw_off(row, c), x_[j]);
             }
             if (u == 1) {
                 fence_proxy_async();                             // generic-proxy writes -> visible to the tensor core
@@ -191,13 +189,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_ws(const bmnas_conv_params
                 for (int ks = 0; ks < KC / 8; ++ks) {
                     const uint32_t ko = (uint32_t)ks * 32u;
                     const uint32_t acc = (st > 0 || ks > 0) ? 1u : 0u;
-                    if (X3) {
-                        umma_tf32(tmem_d, kdesc(a_lo + ko), kdesc(b_hi + ko), IDESC, acc);
-                        umma_tf32(tmem_d, kdesc(a_hi + ko), kdesc(b_lo + ko), IDESC, 1u);
-                        umma_tf32(tmem_d, kdesc(a_hi + ko), kdesc(b_hi + ko), IDESC, 1u);
-                    } else {
-                        umma_tf32(tmem_d, kdesc(a_hi + ko), kdesc(b_hi + ko), IDESC, acc);
+                    if (X3) {      // the two correction products accumulate apart from hi*hi (truncating tensor-core accumulate)
+                        umma_tf32(tmem_d + BNK, kdesc(a_lo + ko), kdesc(b_hi + ko), IDESC, acc);
+                        umma_tf32(tmem_d + BNK, kdesc(a_hi + ko), kdesc(b_lo + ko), IDESC, 1u);
                     }
+                    umma_tf32(tmem_d, kdesc(a_hi + ko), kdesc(b_hi + ko), IDESC, acc);
                 }
                 umma_commit(&s_empty[stage]);
                 if (st + 1 == n_st) umma_commit(&s_done);
@@ -220,7 +216,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_ws(const bmnas_conv_params
 #pragma unroll 1
         for (int g16 = 0; g16 < BNK / 16; ++g16) {
             float v[16];
-            tmem_ld16(t_row + (uint32_t)(g16 * 16), v);
+            if (X3) tmem_ld16_sum<2, BNK>(t_row + (uint32_t)(g16 * 16), v, 2);
+            else tmem_ld16(t_row + (uint32_t)(g16 * 16), v);
             if (grow) {
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
@@ -237,7 +234,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_ws(const bmnas_conv_params
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == W_MMA) tmem_dealloc(tmem_d, BNK);
+    if (warp == W_MMA) tmem_dealloc(tmem_d, 2 * BNK);
 }
 
 template <bool X3>

@@ -192,6 +192,9 @@ long long bmnas_wprep_items(int M, int K, int fmt);                 /* work item
 /* image format for a conv over B*L columns: -1 = none (shape not eligible), 0 = tcgen05 slabs, 1 = plain fp32
  * (small column counts: the fp32 cp.async GEMMs beat 3xTF32 UMMA there; see gemm_sg.cu) */
 int bmnas_conv_image_fmt(int B, int L, int K, int M);
+/* the same choice for the dgrad GEMM of that conv (its weight image may use another format than the forward one:
+ * bmnas_wprep writes either image in either format) */
+int bmnas_conv_image_fmt_dgrad(int B, int L, int K, int M);
 
 /* ------------------------------------------------------------------------
  * Adaptive max pooling of a raw backbone feature map onto the (C_in, L) grid: the first stage of the reshape

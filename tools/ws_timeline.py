@@ -10,7 +10,7 @@ lib = N.lib()
 dev = torch.device('cuda:0')
 NAMES = ['entry', 'setup + pdl_wait done', 'producers: first stage full', 'producers: done', 'MMA: first tile issued',
          'MMA: all issued', 'epilogue: first tile done', 'epilogue: done', 'teardown barrier passed', 'last_block passed',
-         'finalize start (last CTA)', 'finalize done (last CTA)']
+         'finalize start (last CTA)', 'finalize done (last CTA)', 'finalize: partials in smem', 'finalize: pass 1 done']
 tl = (ctypes.c_ulonglong * 32)()
 for B in [int(a) for a in sys.argv[1:]] or [8192]:
     for (L, src_C, seg_M, w_fold) in [(8, [128], [256, 128], 2), (8, [128, 128], [128], 1)]:
@@ -53,3 +53,7 @@ for B in [int(a) for a in sys.argv[1:]] or [8192]:
             for i, nm in enumerate(NAMES):
                 if tl[i] >= t0 and (name == 'bmnas_conv_fwd' or i < 9):
                     print(f'  {nm:<34s} {(tl[i] - t0) / 1e3:8.2f} us')
+            mhz = 1965.0
+            print(f'  stages {tl[21]}: producer thread 0 waited {tl[16] / mhz:.1f} us for its copies, {tl[17] / mhz:.1f} us for a free stage; '
+                  f'MMA warp waited {tl[18] / mhz:.1f} us for weight slabs, {tl[19] / mhz:.1f} us for activation stages, '
+                  f'{tl[20] / mhz:.1f} us for a free accumulator set')
