@@ -127,6 +127,10 @@ class Program:
         self.n_bwd_launches = 0
         self.want_backward = True    # False: a no-grad forward (metrics pass, inference): nothing is kept for a backward
         self._cur_tag = None
+        # one-graph search step (bmnas.search): the weight half's bmnas_wprep runs on the side branch of the ARCH half (the
+        # Architect does not touch the weights), so it leaves the critical path of the step
+        self.side_extra = None       # callable(stream_ptr): extra work forked next to the gradient-span clear
+        self._prep_hoisted = None    # event: this plan's weight images (and Philox step) were already advanced elsewhere
 
     def fused_mixed_ok(self, ops, alias=True):
         """shape-level test for the fused NodeMixedOp forward kernel (the library re-checks pointers / alignment)"""
@@ -276,15 +280,23 @@ class Program:
         for t in self._zero_ranges:
             N.launch('bmnas_zero', ctypes.c_void_p(t.data_ptr()), ctypes.c_longlong(t.numel() * t.element_size()), stream_ptr)
 
+    def run_prep(self, s):
+        """the per-forward preamble: Philox step counter + weight images (bmnas_wprep) on stream pointer s"""
+        if self.rng_state is not None and not self._rng_in_prep:
+            N.launch('bmnas_rng_advance', ctypes.c_void_p(self.rng_state.data_ptr()), s)
+        for c in self._prep_calls:
+            c(s)
+
     def run_forward(self):
         s = N.current_stream()
         self._zero_ev = None
         early = EARLY_ZERO[0] and self._zero_ranges and self.want_backward and SIDE_WGRAD and not N.VALIDATE_ONLY
         fork_at = min(EARLY_ZERO_AT, len(self.fwd) - 1) if early else -1
-        if self.rng_state is not None and not self._rng_in_prep:
-            N.launch('bmnas_rng_advance', ctypes.c_void_p(self.rng_state.data_ptr()), s)
-        for c in self._prep_calls:
-            c(s)
+        if self._prep_hoisted is not None:
+            torch.cuda.current_stream().wait_event(self._prep_hoisted)
+            self._prep_hoisted = None
+        else:
+            self.run_prep(s)
         for i, c in enumerate(self.fwd):
             c(s)
             if i == fork_at:
@@ -298,6 +310,8 @@ class Program:
                 self._zero(ctypes.c_void_p(side.cuda_stream))
                 self._zero_ev = torch.cuda.Event()
                 self._zero_ev.record(side)
+                if self.side_extra is not None:
+                    self.side_extra(ctypes.c_void_p(side.cuda_stream), side)
         self.generation += 1
 
     def run_backward(self):

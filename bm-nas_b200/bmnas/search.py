@@ -328,6 +328,21 @@ class SearchStep:
                 'rng': [(p.rng_state.clone() if p.rng_state is not None else None) for p in self._programs()]}
         return snap
 
+    def _hoist_pair(self):
+        """(arch-half plan, weight-half plan) of the fusion network when the weight half's preamble may run during the arch
+        half: pruned plans (two distinct programs), the gradient-span clear forked during the forward (the side branch the
+        preamble rides on), a single device"""
+        import os
+        from . import program as _prog
+        if not self.prune_grads or os.environ.get('BMNAS_HOIST_PREP', '1') == '0' or not _prog.SIDE_WGRAD:
+            return None
+        cache = self.head.fusion_net.__dict__.get('_bm_cache', {})
+        pa = [r.prog for k, r in cache.items() if 'arch' in k and r.prog.training and r.prog.want_backward and r.prog.B == self.B]
+        pw = [r.prog for k, r in cache.items() if 'weights' in k and r.prog.training and r.prog.want_backward and r.prog.B == self.B]
+        if len(pa) != 1 or len(pw) != 1 or not pa[0]._zero_ranges or not pw[0]._prep_calls:
+            return None
+        return pa[0], pw[0]
+
     def _programs(self):
         return [r.prog for r in self.head.fusion_net.__dict__.get('_bm_cache', {}).values()]
 
@@ -387,10 +402,27 @@ class SearchStep:
         # boundary is an ordinary graph edge
         g = torch.cuda.CUDAGraph()
         self._step_out = {}
+        hoist = self._hoist_pair()
         with torch.cuda.graph(g, stream=s):
-            for which in ('dev', 'train'):
-                loss = self._half(which)
-                self._step_out[which] = (loss, self.logits[which])
+            if hoist is not None:
+                # the weight half's preamble (bmnas_wprep + Philox step) on the side branch of the arch half: the Architect
+                # only moves alpha/beta/gamma, so the weights the images are made of are already final
+                pa, pw = hoist
+
+                def extra(sp, side, pw=pw):
+                    pw.run_prep(sp)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    pw._prep_hoisted = ev
+                pa.side_extra = extra
+            try:
+                for which in ('dev', 'train'):
+                    loss = self._half(which)
+                    self._step_out[which] = (loss, self.logits[which])
+            finally:
+                if hoist is not None:
+                    hoist[0].side_extra = None
+                    hoist[1]._prep_hoisted = None
         self.graphs['step'] = g
         if restore:
             self._restore(snap)

@@ -483,10 +483,13 @@ extern "C" int bmnas_conv_image_fmt(int B, int L, int K, int M) {
     return (sg_ok && N * (long long)M * K <= min_macs) ? 1 : 0;
 }
 
-// ... and the same question for the dgrad GEMM of that conv (rows K, reduction M).  A SHORT reduction (M <= 128: at most 4
-// weight slabs, e.g. out_conv's dgrad) suits the warp-specialised tcgen05 kernel at every size measured -- NTU out_conv, us:
-// 5.3 vs 7.4 at B = 96, 6.2 vs 9.7 at B = 256, 8.3 vs 20.3 at B = 768 -- while the node conv's dgrad (M = 384) crosses over
-// near B = 192 (75 M MACs) (profiles/r02_engine_crossover.txt).  BMNAS_TC_MIN_MACS_D overrides the second threshold.
+// ... and the same question for the dgrad GEMM of that conv (rows K, reduction M): its crossover is lower than the forward's
+// -- no BatchNorm finalize at the end, and the BatchNorm-backward fold rides in the staging pass.  Measured, NTU node conv
+// (M = 384), us FFMA vs tcgen05: 12.4 vs 12.7 at B = 192 (75 M MACs), 18.6 vs 12.9 at B = 384
+// (profiles/r02_engine_crossover.txt).  A short reduction (out_conv's dgrad, M = 128) is faster on the tensor-core kernel even
+// at B = 96 stand-alone (5.3 vs 7.4 us), but inside the captured step the FFMA kernel's weight prefetch ahead of
+// griddepcontrol.wait and its small footprint (it shares SMs with its predecessor) win the difference back: the step time did
+// not move (0.554 vs 0.558 ms), so small problems stay on the FFMA engine.  BMNAS_TC_MIN_MACS_D overrides the threshold.
 extern "C" int bmnas_conv_image_fmt_dgrad(int B, int L, int K, int M) {
     const int f = bmnas_conv_image_fmt(B, L, K, M);
     if (f != 1) return f;                      // not eligible for the FFMA engine (or already on the tensor cores)
@@ -496,9 +499,7 @@ extern "C" int bmnas_conv_image_fmt_dgrad(int B, int L, int K, int M) {
         const char* e = getenv("BMNAS_TC_MIN_MACS_D");
         min_macs_d = e ? atoll(e) : 75000000LL;
     }
-    const long long macs = (long long)B * L * M * K;
-    if ((M <= 128 && K >= 128 && macs >= 20000000LL) || macs > min_macs_d) return 0;
-    return 1;
+    return (long long)B * L * M * K > min_macs_d ? 0 : 1;
 }
 
 extern "C" long long bmnas_conv_stat_part_size(const bmnas_conv_params* p) {
