@@ -15,11 +15,18 @@ def main():
     c = dict(bench.CONFIGS[cfgname])
     if '--batch' in sys.argv:
         c['B'] = int(sys.argv[sys.argv.index('--batch') + 1])
-    dev = torch.device('cuda', 0)
-    torch.cuda.set_device(0)
+    # under torchrun (WORLD_SIZE > 1): the data-parallel step, rank 0 prints its timeline (TL_NCCL=1: NCCL path)
+    world, rank, local = int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('RANK', 0)), int(os.environ.get('LOCAL_RANK', 0))
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(local)
+    group = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+        group = dist.group.WORLD
     torch.manual_seed(2)
-    head, ss = bench.build_search(c, dev, group=None, use_graphs=True, peer_step=None)
-    pool = bench.make_pool(c, 4, 100, dev)
+    head, ss = bench.build_search(c, dev, group=group, use_graphs=True, peer_step=(False if os.environ.get('TL_NCCL') == '1' else None))
+    pool = bench.make_pool(c, 4, 100 + rank, dev)
     ss.load('dev', *pool[0]); ss.load('train', *pool[1])
     ss.prepare(warmup=3, restore=False)
     pp = [ss.pack_step(pool[2 * j][0], pool[2 * j][1], pool[2 * j + 1][0], pool[2 * j + 1][1], device=dev) for j in range(2)]
@@ -43,6 +50,11 @@ def main():
                 assert rc == 0, rc
             ss.step()
         torch.cuda.synchronize()
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank != 0:
+            os._exit(0)
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     evs.sort(key=lambda e: e.time_range.start)
     # one step = from one 'Memcpy DtoD' group to the next: split at the first copy of each step
@@ -78,3 +90,6 @@ def main():
 
 if __name__ == '__main__':
     main()
+    if int(os.environ.get('WORLD_SIZE', 1)) > 1:
+        sys.stdout.flush()
+        os._exit(0)
