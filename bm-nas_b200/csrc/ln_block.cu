@@ -13,7 +13,10 @@ namespace bmnas {
 
 constexpr int LTH = 256;
 constexpr int kLnMaxBlocksFwd = kNumSMs * 8;
-constexpr int kLnMaxBlocksBwd = kNumSMs * 2;
+// backward: 60 registers x 256 threads -> four CTAs fit an SM.  Two per SM (round 1) left the kernel at 25 % warp occupancy
+// with every phase of a sample waiting on a global round trip (ncu: long_sb 30 %, DRAM 13 %); the price of more CTAs is the
+// LayerNorm-affine gradient flush (2 E atomics per CTA), ~1 M more L2 atomics per launch at B = 8 192
+constexpr int kLnMaxBlocksBwd = kNumSMs * 4;
 
 __host__ __device__ inline size_t lrnd4(size_t n) { return (n + 3) & ~(size_t)3; }
 __host__ __device__ inline size_t ln_smem_floats(int Ctot, int L, bool bwd) {
