@@ -11,7 +11,16 @@
 
 namespace bmnas {
 
-constexpr int LTH = 256;
+// threads per CTA (one sample): 256 up to 256 four-element groups per sample, 512 / 1024 for larger samples (Ego-large's
+// cell tail is 16 384 elements) -- see node_apply.cu.  Device code reads the size from blockDim.
+constexpr int LTH0 = 256, LTH_MAX = 1024;
+#define LTH ((int)blockDim.x)
+static inline int ln_threads(int Ctot, int L) {
+    const int groups = (Ctot * L + 3) / 4;
+    int n = LTH0;
+    while (n < groups && n < LTH_MAX) n *= 2;
+    return n;
+}
 constexpr int kLnMaxBlocksFwd = kNumSMs * 8;
 // backward: 60 registers x 256 threads -> four CTAs fit an SM.  Two per SM (round 1) left the kernel at 25 % warp occupancy
 // with every phase of a sample waiting on a global round trip (ncu: long_sb 30 %, DRAM 13 %); the price of more CTAs is the
@@ -158,7 +167,7 @@ __device__ __forceinline__ void ln_stats(const float* vs, int E, float* red, flo
 }
 
 template <int G>
-__global__ void __launch_bounds__(LTH) k_ln_fwd(const bmnas_ln_params p) {
+__global__ void __launch_bounds__(LTH_MAX) k_ln_fwd(const bmnas_ln_params p) {
     pdl_prologue();
     extern __shared__ __align__(16) float smem[];
     const int E = p.Ctot * p.L;
@@ -203,7 +212,7 @@ __device__ __forceinline__ void ln_chan_add(float* acc, int m, float v, int lane
 }
 
 template <int G, bool SEG>
-__global__ void __launch_bounds__(LTH) k_ln_bwd(const bmnas_ln_params p) {
+__global__ void __launch_bounds__(LTH_MAX) k_ln_bwd(const bmnas_ln_params p) {
     pdl_prologue();
     extern __shared__ __align__(16) float smem[];
     const int L = p.L, Ctot = p.Ctot, E = Ctot * L, NG = E / G;
@@ -430,10 +439,10 @@ extern "C" int bmnas_ln_fwd(const bmnas_ln_params* p, void* stream) {
     const int blocks = p->B < kLnMaxBlocksFwd ? p->B : kLnMaxBlocksFwd;
     if (vec) {
         if ((e = ln_smem_attr(k_ln_fwd<4>, smem, &configured[1]))) return e;
-        launch_k(k_ln_fwd<4>, blocks, LTH, smem, (cudaStream_t)stream, *p);
+        launch_k(k_ln_fwd<4>, blocks, ln_threads(p->Ctot, p->L), smem, (cudaStream_t)stream, *p);
     } else {
         if ((e = ln_smem_attr(k_ln_fwd<1>, smem, &configured[0]))) return e;
-        launch_k(k_ln_fwd<1>, blocks, LTH, smem, (cudaStream_t)stream, *p);
+        launch_k(k_ln_fwd<1>, blocks, ln_threads(p->Ctot, p->L), smem, (cudaStream_t)stream, *p);
     }
     BMNAS_LAUNCH_CHECK();
     return BMNAS_OK;
@@ -452,13 +461,13 @@ extern "C" int bmnas_ln_bwd(const bmnas_ln_params* p, void* stream) {
     const int blocks = p->B < kLnMaxBlocksBwd ? p->B : kLnMaxBlocksBwd;
     if (vec && seg) {
         if ((e = ln_smem_attr(k_ln_bwd<4, true>, smem, &configured[0]))) return e;
-        launch_k(k_ln_bwd<4, true>, blocks, LTH, smem, (cudaStream_t)stream, *p);
+        launch_k(k_ln_bwd<4, true>, blocks, ln_threads(p->Ctot, p->L), smem, (cudaStream_t)stream, *p);
     } else if (vec) {
         if ((e = ln_smem_attr(k_ln_bwd<4, false>, smem, &configured[1]))) return e;
-        launch_k(k_ln_bwd<4, false>, blocks, LTH, smem, (cudaStream_t)stream, *p);
+        launch_k(k_ln_bwd<4, false>, blocks, ln_threads(p->Ctot, p->L), smem, (cudaStream_t)stream, *p);
     } else {
         if ((e = ln_smem_attr(k_ln_bwd<1, false>, smem, &configured[2]))) return e;
-        launch_k(k_ln_bwd<1, false>, blocks, LTH, smem, (cudaStream_t)stream, *p);
+        launch_k(k_ln_bwd<1, false>, blocks, ln_threads(p->Ctot, p->L), smem, (cudaStream_t)stream, *p);
     }
     BMNAS_LAUNCH_CHECK();
     return BMNAS_OK;

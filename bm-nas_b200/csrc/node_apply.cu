@@ -14,7 +14,18 @@
 
 namespace bmnas {
 
-constexpr int NTH = 256;
+// threads of the CTA-per-sample kernels: 256 while a sample is at most 256 four-element groups (NTU: C*L = 1024), more for
+// larger samples -- a CTA owns a whole sample and every phase ends in a block barrier, so at Ego-large (C*L = 4096, 96
+// samples on 148 SMs) 256 threads left each SM with 8 warps working through 16 elements per thread and phase: 36 us forward /
+// 60 us backward, latency bound (ncu: 12 % warps active, long_sb + short_sb 47 %).  Device code reads the size from blockDim.
+constexpr int NTH0 = 256, NTH_FWD_MAX = 1024, NTH_BWD_MAX = 512;    // backward: 80 registers per thread
+#define NTH ((int)blockDim.x)
+static inline int node_threads(int C, int L, bool bwd) {
+    const int groups = (C * L + 3) / 4;
+    int n = NTH0;
+    while (n < groups && n < (bwd ? NTH_BWD_MAX : NTH_FWD_MAX)) n *= 2;
+    return n;
+}
 constexpr int kNodeMaxBlocksFwd = kNumSMs * 8;
 constexpr int kNodeMaxBlocksBwd = kNumSMs * 2;
 
@@ -25,14 +36,14 @@ struct NodeSmem {
 
 __host__ __device__ inline size_t rnd4(size_t n) { return (n + 3) & ~(size_t)3; }
 
-__host__ __device__ inline size_t node_smem_floats(int C, int L, int M, bool bwd) {
+__host__ __device__ inline size_t node_smem_floats(int C, int L, int M, bool bwd, int nth) {
     const size_t CL = rnd4((size_t)C * L), LL = rnd4((size_t)L * L), Mr = rnd4((size_t)M);
     size_t n = 0;
     n += 3 * CL;                            // xs, ys, as
-    n += 2 * LL + (LL > NTH ? LL : NTH);    // S, S2, Sp
+    n += 2 * LL + (LL > (size_t)nth ? LL : (size_t)nth);    // S, S2, Sp
     n += 8 * 32 + 8;                        // red, gw
     n += 4 * Mr;                            // rs, mr, bw, bb
-    if (bwd) n += 5 * CL + 2 * Mr + (2 * Mr + 8) + BMNAS_MAX_OPS * NTH;  // gs, dxs, dys, lnG, lnH, S1s, S2s, tot, dgs
+    if (bwd) n += 5 * CL + 2 * Mr + (2 * Mr + 8) + BMNAS_MAX_OPS * (size_t)nth;  // gs, dxs, dys, lnG, lnH, S1s, S2s, tot, dgs
     return n + 16;
 }
 
@@ -45,7 +56,7 @@ __device__ __forceinline__ NodeSmem node_carve(float* base, int C, int L, int M,
     s.as = q; q += CL;
     s.S = q; q += LL;
     s.S2 = q; q += LL;
-    s.Sp = q; q += (LL > NTH ? LL : NTH);
+    s.Sp = q; q += (LL > (size_t)NTH ? LL : (size_t)NTH);
     s.red = q; q += 8 * 32;
     s.gw = q; q += 8;
     s.rs = q; q += Mr;
@@ -278,7 +289,7 @@ __device__ __forceinline__ void attn_forward(const bmnas_node_params& p, const N
 }
 
 template <int G>
-__global__ void __launch_bounds__(NTH) k_node_fwd(const bmnas_node_params p) {
+__global__ void __launch_bounds__(NTH_FWD_MAX) k_node_fwd(const bmnas_node_params p) {
     // early section (p.early_ok: x / y were produced at least two kernels ago, i.e. the conv GEMM sits between
     // their producer and this kernel): tile loads and the whole attention primitive of the CTA's first sample run
     // BEFORE pdl_wait(), overlapping the conv kernel; Z / mean / rstd are only touched after it
@@ -1398,7 +1409,7 @@ __device__ __forceinline__ void chan_add(float* acc, int m, float v, int lanes, 
 }
 
 template <int G, bool SEG>
-__global__ void __launch_bounds__(NTH) k_node_bwd(const bmnas_node_params p) {
+__global__ void __launch_bounds__(NTH_BWD_MAX) k_node_bwd(const bmnas_node_params p) {
     // early section (p.early_ok): x, y, Z, mean, rstd are forward tensors, complete long before any backward kernel;
     // the tile loads, the BatchNorm constants and the recomputation of the attention primitive for the CTA's first
     // sample run BEFORE pdl_wait() and overlap the kernel that produces gout
@@ -1914,7 +1925,8 @@ extern "C" int bmnas_get_node_variant(void) { return node_variant_flag; }
 extern "C" int bmnas_node_fwd(const bmnas_node_params* p, void* stream) {
     int e = node_check(p, false);
     if (e) return e;
-    const size_t smem = node_smem_floats(p->C, p->L, p->M, false) * sizeof(float);
+    const int nth = node_threads(p->C, p->L, false);
+    const size_t smem = node_smem_floats(p->C, p->L, p->M, false, nth) * sizeof(float);
     if (smem > 227 * 1024) return BMNAS_EINVAL;
     BMNAS_DRY_RETURN();
     if (node_use_warp(p, false)) return node_fwd_warp_dispatch(p, (cudaStream_t)stream);
@@ -1924,9 +1936,9 @@ extern "C" int bmnas_node_fwd(const bmnas_node_params* p, void* stream) {
     if (e) return e;
     const int blocks = p->B < kNodeMaxBlocksFwd ? p->B : kNodeMaxBlocksFwd;
     if (vec)
-        launch_k(k_node_fwd<4>, blocks, NTH, smem, (cudaStream_t)stream, *p);
+        launch_k(k_node_fwd<4>, blocks, nth, smem, (cudaStream_t)stream, *p);
     else
-        launch_k(k_node_fwd<1>, blocks, NTH, smem, (cudaStream_t)stream, *p);
+        launch_k(k_node_fwd<1>, blocks, nth, smem, (cudaStream_t)stream, *p);
     BMNAS_LAUNCH_CHECK();
     return BMNAS_OK;
 }
@@ -1934,7 +1946,8 @@ extern "C" int bmnas_node_fwd(const bmnas_node_params* p, void* stream) {
 extern "C" int bmnas_node_bwd(const bmnas_node_params* p, void* stream) {
     int e = node_check(p, true);
     if (e) return e;
-    const size_t smem = node_smem_floats(p->C, p->L, p->M, true) * sizeof(float);
+    const int nth = node_threads(p->C, p->L, true);
+    const size_t smem = node_smem_floats(p->C, p->L, p->M, true, nth) * sizeof(float);
     if (smem > 227 * 1024) return BMNAS_EINVAL;
     BMNAS_DRY_RETURN();
     if (node_variant_flag != 1 && node_bwd_warp_ok(p) && (node_variant_flag == 2 || p->B >= kWarpBwdMinB))
@@ -1946,13 +1959,13 @@ extern "C" int bmnas_node_bwd(const bmnas_node_params* p, void* stream) {
     const int blocks = p->B < kNodeMaxBlocksBwd ? p->B : kNodeMaxBlocksBwd;
     if (vec && seg) {
         if ((e = node_smem_attr(k_node_bwd<4, true>, smem, &configured[0]))) return e;
-        launch_k(k_node_bwd<4, true>, blocks, NTH, smem, (cudaStream_t)stream, *p);
+        launch_k(k_node_bwd<4, true>, blocks, nth, smem, (cudaStream_t)stream, *p);
     } else if (vec) {
         if ((e = node_smem_attr(k_node_bwd<4, false>, smem, &configured[1]))) return e;
-        launch_k(k_node_bwd<4, false>, blocks, NTH, smem, (cudaStream_t)stream, *p);
+        launch_k(k_node_bwd<4, false>, blocks, nth, smem, (cudaStream_t)stream, *p);
     } else {
         if ((e = node_smem_attr(k_node_bwd<1, false>, smem, &configured[2]))) return e;
-        launch_k(k_node_bwd<1, false>, blocks, NTH, smem, (cudaStream_t)stream, *p);
+        launch_k(k_node_bwd<1, false>, blocks, nth, smem, (cudaStream_t)stream, *p);
     }
     BMNAS_LAUNCH_CHECK();
     return BMNAS_OK;
