@@ -255,6 +255,44 @@ def test_full_size_vs_oracle(name):
             assert_close(sd[k], Pc[k], 1e-5, k)
 
 
+SWEEP = [(C, L, B) for C in (64, 128, 192, 256) for L in (4, 8, 16) for B in (24,)] + [(256, 16, 96), (192, 16, 7)]
+
+
+@pytest.mark.parametrize('C,L,B', SWEEP, ids=[f'C{c}-L{l}-B{b}' for c, l, b in SWEEP])
+def test_shape_sweep_vs_oracle(C, L, B):
+    """SURVEY 7.2b property sweep: the whole searchable head (forward, loss, every weight and architecture gradient,
+    BatchNorm buffers) against the oracle over C x L, i.e. over every dispatch the shapes select -- fused small-batch
+    MixedOp vs conv + node kernels (one co-resident wave or not), 256 / 512 / 1024-thread CTAs of the node and
+    LayerNorm-tail kernels (C*L from 256 to 4096), FFMA vs tensor-core GEMM engines, ragged batch."""
+    cfg = O.Cfg(C, L, 4, 2, 2, 2, 2, 0.1)
+    ncls, kind = 7, 'ce'
+    P = O.init_params(cfg, ncls, seed=11, prefix='cell')
+    arch = O.init_arch(cfg, seed=11, scale=0.5)
+    feats, labels = O.synthetic_batch(cfg, B, ncls, seed=12, loss=kind)
+    head = U.build_head(cfg, ncls, P, arch)
+    head.train()
+    masks = U.random_masks(head, B, cfg.C, cfg.L, 13, cfg.drpt)
+    U.inject_masks(head, masks)
+    lv, logits, gw, ga, Pc = _oracle_fb(cfg, P, arch, feats, labels, masks, kind)
+    dbl = lambda t: t.double() if t.is_floating_point() else t
+    lv64, logits64, gw64, ga64, _ = _oracle_fb(cfg, {k: dbl(v) for k, v in P.items()}, [a.double() for a in arch],
+                                               [f.double() for f in feats], dbl(labels), masks, kind)
+    out = head([f.to(U.DEV) for f in feats])
+    loss = _loss_mod(kind)(out, labels.to(U.DEV))
+    loss.backward()
+    torch.cuda.synchronize()
+    _close_vs_referee(out, logits, logits64, TOL, 'logits')
+    _close_vs_referee(loss, lv, lv64, TOL, 'loss')
+    for k, p in head.named_parameters():
+        _close_vs_referee(p.grad, gw[k], gw64[k], GTOL, 'grad ' + k, atol=_bias_atol(k))
+    for i, a in enumerate(head.arch_parameters()):
+        _close_vs_referee(a.grad, ga[i], ga64[i], GTOL, f'garch{i}')
+    sd = head.state_dict()
+    for k in Pc:
+        if 'running' in k or 'num_batches' in k:
+            assert_close(sd[k], Pc[k], 1e-5, k)
+
+
 # ------------------------------------------------------------------ full search loop (Architect + FusedAdam + schedule)
 def _static_masks(head, d, prefix):
     """injected masks as static device tensors (refilled per step, so the same pointers work under graphs)"""
