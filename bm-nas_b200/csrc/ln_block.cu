@@ -14,10 +14,11 @@ namespace bmnas {
 // threads per CTA (one sample): 256 up to 256 four-element groups per sample, 512 / 1024 for larger samples (Ego-large's
 // cell tail is 16 384 elements) -- see node_apply.cu.  Device code reads the size from blockDim.
 constexpr int LTH0 = 256, LTH_MAX = 1024;
-#define LTH ((int)blockDim.x)
-static inline int ln_threads(int Ctot, int L) {
+static inline int ln_threads(int Ctot, int L, int B) {
     const int groups = (Ctot * L + 3) / 4;
     int n = LTH0;
+    if (B > 2 * kNumSMs) return n;     // enough samples to fill the machine with 256-thread CTAs (wider ones cost occupancy:
+                                       // B = 8192, E = 2048: forward 41 -> 67 us, backward 105 -> 140 us with 512 threads)
     while (n < groups && n < LTH_MAX) n *= 2;
     return n;
 }
@@ -127,6 +128,7 @@ __device__ __forceinline__ void ln_pre(const bmnas_ln_params& p, const float* cs
     }
 }
 
+template <int LTH>
 __device__ __forceinline__ void ln_consts(const bmnas_ln_params& p, float* cst) {
     if (p.mode == 1) {
         const int Cr = (int)lrnd4((size_t)p.Ctot);
@@ -141,7 +143,7 @@ __device__ __forceinline__ void ln_consts(const bmnas_ln_params& p, float* cst) 
     __syncthreads();
 }
 
-template <int G>
+template <int G, int LTH>
 __device__ __forceinline__ void ln_stats(const float* vs, int E, float* red, float* mean, float* rstd) {
     float s0[1] = {0.f}, s1[1] = {0.f};
     for (int g = threadIdx.x; g < E / G; g += LTH) {
@@ -166,15 +168,15 @@ __device__ __forceinline__ void ln_stats(const float* vs, int E, float* red, flo
     *rstd = 1.f / sqrtf(s1[0] / (float)E + kLnEps);
 }
 
-template <int G>
-__global__ void __launch_bounds__(LTH_MAX) k_ln_fwd(const bmnas_ln_params p) {
+template <int G, int LTH>
+__global__ void __launch_bounds__(LTH) k_ln_fwd(const bmnas_ln_params p) {
     pdl_prologue();
     extern __shared__ __align__(16) float smem[];
     const int E = p.Ctot * p.L;
     float* vs = smem;
     float* red = smem + lrnd4((size_t)E);
     float* cst = red + 4 * 32;
-    ln_consts(p, cst);
+    ln_consts<LTH>(p, cst);
     for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
         __syncthreads();
         for (int g = threadIdx.x; g < E / G; g += LTH) {
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(LTH_MAX) k_ln_fwd(const bmnas_ln_params p) {
         }
         __syncthreads();
         float mean, rstd;
-        ln_stats<G>(vs, E, red, &mean, &rstd);
+        ln_stats<G, LTH>(vs, E, red, &mean, &rstd);
         for (int g = threadIdx.x; g < E / G; g += LTH) {
             const int e0 = g * G;
             float v[G], w[G], bb[G], o[G];
@@ -211,8 +213,8 @@ __device__ __forceinline__ void ln_chan_add(float* acc, int m, float v, int lane
     }
 }
 
-template <int G, bool SEG>
-__global__ void __launch_bounds__(LTH_MAX) k_ln_bwd(const bmnas_ln_params p) {
+template <int G, bool SEG, int LTH>
+__global__ void __launch_bounds__(LTH) k_ln_bwd(const bmnas_ln_params p) {
     pdl_prologue();
     extern __shared__ __align__(16) float smem[];
     const int L = p.L, Ctot = p.Ctot, E = Ctot * L, NG = E / G;
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(LTH_MAX) k_ln_bwd(const bmnas_ln_params p) {
         S1s[c] = 0.f;
         S2s[c] = 0.f;
     }
-    ln_consts(p, cst);
+    ln_consts<LTH>(p, cst);
     for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
         __syncthreads();
         for (int g = threadIdx.x; g < NG; g += LTH) {
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(LTH_MAX) k_ln_bwd(const bmnas_ln_params p) {
         }
         __syncthreads();
         float mean, rstd;
-        ln_stats<G>(vs, E, red, &mean, &rstd);
+        ln_stats<G, LTH>(vs, E, red, &mean, &rstd);
         const float* gb = p.gout + (long long)b * E;
         float qs[2] = {0.f, 0.f};
         for (int g = threadIdx.x; g < NG; g += LTH) {
@@ -428,6 +430,29 @@ using namespace bmnas;
 
 extern "C" long long bmnas_ln_partials_size(const bmnas_ln_params* p) { return 2LL * p->Ctot; }
 
+template <class Kern>
+static int ln_launch(Kern kern, size_t* configured, int blocks, int threads, size_t smem, const bmnas_ln_params* p, cudaStream_t stream) {
+    if (int e = ln_smem_attr(kern, smem, configured)) return e;
+    launch_k(kern, blocks, threads, smem, stream, *p);
+    BMNAS_LAUNCH_CHECK();
+    return BMNAS_OK;
+}
+
+template <int LTH>
+static int ln_fwd_t(const bmnas_ln_params* p, bool vec, int blocks, size_t smem, cudaStream_t stream) {
+    static size_t configured[2] = {0, 0};
+    return vec ? ln_launch(k_ln_fwd<4, LTH>, &configured[1], blocks, LTH, smem, p, stream)
+               : ln_launch(k_ln_fwd<1, LTH>, &configured[0], blocks, LTH, smem, p, stream);
+}
+
+template <int LTH>
+static int ln_bwd_t(const bmnas_ln_params* p, bool vec, bool seg, int blocks, size_t smem, cudaStream_t stream) {
+    static size_t configured[3] = {0, 0, 0};
+    if (vec && seg) return ln_launch(k_ln_bwd<4, true, LTH>, &configured[0], blocks, LTH, smem, p, stream);
+    if (vec) return ln_launch(k_ln_bwd<4, false, LTH>, &configured[1], blocks, LTH, smem, p, stream);
+    return ln_launch(k_ln_bwd<1, false, LTH>, &configured[2], blocks, LTH, smem, p, stream);
+}
+
 extern "C" int bmnas_ln_fwd(const bmnas_ln_params* p, void* stream) {
     int e = ln_check(p, false);
     if (e) return e;
@@ -435,17 +460,11 @@ extern "C" int bmnas_ln_fwd(const bmnas_ln_params* p, void* stream) {
     if (smem > 227 * 1024) return BMNAS_EINVAL;
     BMNAS_DRY_RETURN();
     const bool vec = ln_vec_ok(p);
-    static size_t configured[2] = {0, 0};
     const int blocks = p->B < kLnMaxBlocksFwd ? p->B : kLnMaxBlocksFwd;
-    if (vec) {
-        if ((e = ln_smem_attr(k_ln_fwd<4>, smem, &configured[1]))) return e;
-        launch_k(k_ln_fwd<4>, blocks, ln_threads(p->Ctot, p->L), smem, (cudaStream_t)stream, *p);
-    } else {
-        if ((e = ln_smem_attr(k_ln_fwd<1>, smem, &configured[0]))) return e;
-        launch_k(k_ln_fwd<1>, blocks, ln_threads(p->Ctot, p->L), smem, (cudaStream_t)stream, *p);
-    }
-    BMNAS_LAUNCH_CHECK();
-    return BMNAS_OK;
+    const int th = ln_threads(p->Ctot, p->L, p->B);
+    if (th >= 1024) return ln_fwd_t<1024>(p, vec, blocks, smem, (cudaStream_t)stream);
+    if (th >= 512) return ln_fwd_t<512>(p, vec, blocks, smem, (cudaStream_t)stream);
+    return ln_fwd_t<256>(p, vec, blocks, smem, (cudaStream_t)stream);
 }
 
 extern "C" int bmnas_ln_bwd(const bmnas_ln_params* p, void* stream) {
@@ -457,18 +476,9 @@ extern "C" int bmnas_ln_bwd(const bmnas_ln_params* p, void* stream) {
     const bool vec = ln_vec_ok(p);
     const int lanes = p->L / 4;
     const bool seg = vec && lanes >= 1 && lanes <= 32 && (lanes & (lanes - 1)) == 0;
-    static size_t configured[3] = {0, 0, 0};
     const int blocks = p->B < kLnMaxBlocksBwd ? p->B : kLnMaxBlocksBwd;
-    if (vec && seg) {
-        if ((e = ln_smem_attr(k_ln_bwd<4, true>, smem, &configured[0]))) return e;
-        launch_k(k_ln_bwd<4, true>, blocks, ln_threads(p->Ctot, p->L), smem, (cudaStream_t)stream, *p);
-    } else if (vec) {
-        if ((e = ln_smem_attr(k_ln_bwd<4, false>, smem, &configured[1]))) return e;
-        launch_k(k_ln_bwd<4, false>, blocks, ln_threads(p->Ctot, p->L), smem, (cudaStream_t)stream, *p);
-    } else {
-        if ((e = ln_smem_attr(k_ln_bwd<1, false>, smem, &configured[2]))) return e;
-        launch_k(k_ln_bwd<1, false>, blocks, ln_threads(p->Ctot, p->L), smem, (cudaStream_t)stream, *p);
-    }
-    BMNAS_LAUNCH_CHECK();
-    return BMNAS_OK;
+    const int th = ln_threads(p->Ctot, p->L, p->B);
+    if (th >= 1024) return ln_bwd_t<1024>(p, vec, seg, blocks, smem, (cudaStream_t)stream);
+    if (th >= 512) return ln_bwd_t<512>(p, vec, seg, blocks, smem, (cudaStream_t)stream);
+    return ln_bwd_t<256>(p, vec, seg, blocks, smem, (cudaStream_t)stream);
 }

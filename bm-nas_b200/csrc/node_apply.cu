@@ -20,9 +20,10 @@ namespace bmnas {
 // 60 us backward, latency bound (ncu: 12 % warps active, long_sb + short_sb 47 %).  Device code reads the size from blockDim.
 constexpr int NTH0 = 256, NTH_FWD_MAX = 1024, NTH_BWD_MAX = 512;    // backward: 80 registers per thread
 #define NTH ((int)blockDim.x)
-static inline int node_threads(int C, int L, bool bwd) {
+static inline int node_threads(int C, int L, bool bwd, int B) {
     const int groups = (C * L + 3) / 4;
     int n = NTH0;
+    if (B > 2 * kNumSMs) return n;     // the machine is full of 256-thread CTAs anyway: wider ones would only cost occupancy
     while (n < groups && n < (bwd ? NTH_BWD_MAX : NTH_FWD_MAX)) n *= 2;
     return n;
 }
@@ -1925,7 +1926,7 @@ extern "C" int bmnas_get_node_variant(void) { return node_variant_flag; }
 extern "C" int bmnas_node_fwd(const bmnas_node_params* p, void* stream) {
     int e = node_check(p, false);
     if (e) return e;
-    const int nth = node_threads(p->C, p->L, false);
+    const int nth = node_threads(p->C, p->L, false, p->B);
     const size_t smem = node_smem_floats(p->C, p->L, p->M, false, nth) * sizeof(float);
     if (smem > 227 * 1024) return BMNAS_EINVAL;
     BMNAS_DRY_RETURN();
@@ -1946,7 +1947,7 @@ extern "C" int bmnas_node_fwd(const bmnas_node_params* p, void* stream) {
 extern "C" int bmnas_node_bwd(const bmnas_node_params* p, void* stream) {
     int e = node_check(p, true);
     if (e) return e;
-    const int nth = node_threads(p->C, p->L, true);
+    const int nth = node_threads(p->C, p->L, true, p->B);
     const size_t smem = node_smem_floats(p->C, p->L, p->M, true, nth) * sizeof(float);
     if (smem > 227 * 1024) return BMNAS_EINVAL;
     BMNAS_DRY_RETURN();
