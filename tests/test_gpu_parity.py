@@ -523,4 +523,7 @@ def test_reshape_layer_full_size_vs_oracle(shape, C_in):
     torch.cuda.synchronize()
     assert_close(out, o, TOL, 'out')
     for k, p in mod.named_parameters():
-        assert_close(p.grad, leaves['op.' + k].grad, GTOL, k, atol=(2e-4 if k.endswith('conv.bias') else 1e-7))
+        # conv.bias feeds a train-mode BatchNorm: its gradient is analytically ZERO, what both sides compute is the rounding
+        # noise of sum_n (a GV + b Z + c) over up to 6144 O(1) terms (~N * 2^-24 * |term|), whose value depends on the
+        # summation order of the engine (FFMA split-K, tcgen05 split-K, MKL): the bound is a noise bound
+        assert_close(p.grad, leaves['op.' + k].grad, GTOL, k, atol=(5e-4 if k.endswith('conv.bias') else 1e-7))
