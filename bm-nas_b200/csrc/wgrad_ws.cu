@@ -12,7 +12,8 @@
 // exactly one 16-byte K-chunk of the K-major SWIZZLE_128B operand row, so staging is load -> (fold) -> hi/lo split ->
 // store with no transposition.  The kernel it replaces (k_gemm_tc<WGRAD>) staged, synchronised the CTA, issued and
 // waited in turn; here
-//   warps 0-7   producers: 4 register units (6 x 128-bit loads each) in flight per thread = 96 KB per SM; the 8 lanes of
+//   warps 0-7   producers: 4 units (6 x 16-byte cp.async copies each) in flight per thread = 96 KB per SM, staged through a
+//               thread-private shared-memory ring; the 8 lanes of
 //               a quarter warp own the 8 chunks of ONE operand row (conflict-free shared stores; 4 rows x 4 samples =
 //               16 fully used sectors per load instruction); row sums of dz (the bias gradient) accumulate in registers
 //   warp 8      MMA issue: waits on the stage's mbarrier, issues the 4 k-steps (x3 in 3xTF32), commits the stage back
@@ -35,9 +36,19 @@ struct Cfg {
     static constexpr uint32_t HALF = TCM * 128;                    // 16 KB: 128 operand rows x one 128-byte reduction row
     static constexpr uint32_t OPND = X3 ? 2 * HALF : HALF;        // one operand of a stage: [hi | lo]
     static constexpr uint32_t STAGE = 2 * OPND;                    // [A (dz rows) | B (U rows)]
-    static constexpr int NS = X3 ? 3 : 6;
-    static constexpr uint32_t DYN = NS * STAGE + 1024;
+    static constexpr int NS = 2;
+    static constexpr int D = 4;                                    // half-stage units in flight per thread (even)
+    static constexpr uint32_t STG = D * 6 * NPROD * 16;           // staging ring: [D][GV0 GV1 Z0 Z1 X0 X1][thread] 16-byte slots = 96 KB
+    static constexpr uint32_t DYN = NS * STAGE + STG + 1024;
 };
+
+__device__ __forceinline__ void cp_async16(uint32_t dst_s, const void* src, bool valid) {
+    // src-size 0 zero-fills the 16 bytes (rows / reduction columns past the end stay exactly zero)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_s), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
 
 template <bool X3>
 __global__ void __launch_bounds__(THREADS, 1) k_wgrad_ws(const bmnas_conv_params p, const int N, const int chunkN) {
@@ -56,7 +67,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_ws(const bmnas_conv_params
 
     if (tid == 0) {
         for (int i = 0; i < CF::NS; ++i) {
-            mbar_init(&s_full[i], NPROD);
+            mbar_init(&s_full[i], NPW);                          // one arrival per producer warp
             mbar_init(&s_empty[i], 1);
         }
         mbar_init(&s_done, 1);
@@ -102,67 +113,83 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_ws(const bmnas_conv_params
                 b_C[it] = p.src_C[s];
             }
         }
-        constexpr int P = 4;                                  // even: a register slot always holds the same half-stage u
-        float4 g[P][2], zz[P][2], x[P][2];
+        // Global loads are cp.async copies into a thread-private staging ring (D half-stage units deep, tracked by cp.async
+        // groups), not register loads: with register prefetch the four prefetch slots all waited on the warp's scoreboards
+        // (ncu: 43 % of the samples on the first use of a loaded value) -- see gemm_ws.cu.
+        constexpr int D = CF::D;
+        const uint32_t stg_s = s32(smem + (size_t)CF::NS * CF::STAGE) + (uint32_t)tid * 16u;
+        auto slot_s = [&](int d, int j) { return stg_s + (uint32_t)((d * 6 + j) * NPROD) * 16u; };
         const int total_q = n_st * 2;
-        auto load = [&](int q, const int u, float4 (&g_)[2], float4 (&z_)[2], float4 (&x_)[2]) {
-            g_[0] = g_[1] = z_[0] = z_[1] = x_[0] = x_[1] = z4;
-            if (q >= total_q) return;
+        auto issue = [&](int q, const int d) {
+            const int u = d & 1;
+            if (q < total_q) {
+                const int st = q >> 1;
+                const int n = r_beg + st * KC + c * 4;
+                const bool in = n < r_end;
+                const int b = in ? n / L : 0, l0 = in ? n - b * L : 0;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int it = 2 * u + j;
+                    const bool va = in && ((a_ok >> it) & 1);
+                    const long long idx = va ? ((long long)b * M + row0 + it * 32 + rl) * L + l0 : 0;
+                    cp_async16(slot_s(d, j), p.GV + idx, va);
+                    if (has_coef) cp_async16(slot_s(d, 2 + j), p.Z + idx, va);
+                    const bool vb = in && ((b_ok >> it) & 1);
+                    cp_async16(slot_s(d, 4 + j), vb ? asrc[it] + (long long)b * b_C[it] * L + l0 : p.GV, vb);
+                }
+            }
+            cp_async_commit();
+        };
+        auto consume = [&](int q, const int d) {
+            const int u = d & 1;
+            cp_async_wait<D - 1>();                              // this thread's copies of unit q have landed
             const int st = q >> 1;
-            const int n = r_beg + st * KC + c * 4;
-            if (n >= r_end) return;
-            const int b = n / L, l0 = n - b * L;
+            const int stage = st % CF::NS, round = st / CF::NS;
+            float4 v[2], xv[2];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int it = 2 * u + j;
-                if ((a_ok >> it) & 1) {
-                    const long long idx = ((long long)b * M + row0 + it * 32 + rl) * L + l0;
-                    g_[j] = __ldg(reinterpret_cast<const float4*>(p.GV + idx));
-                    if (has_coef) z_[j] = __ldg(reinterpret_cast<const float4*>(p.Z + idx));
+                v[j] = lds128(slot_s(d, j));
+                xv[j] = lds128(slot_s(d, 4 + j));
+                const bool in = r_beg + st * KC + c * 4 < r_end;  // reduction columns past the range stay exactly zero
+                if (in && ((a_ok >> it) & 1)) {
+                    if (has_coef) {
+                        const float4 z = lds128(slot_s(d, 2 + j));
+                        v[j].x = fmaf(ka[it], v[j].x, fmaf(kb[it], z.x, kc_[it]));
+                        v[j].y = fmaf(ka[it], v[j].y, fmaf(kb[it], z.y, kc_[it]));
+                        v[j].z = fmaf(ka[it], v[j].z, fmaf(kb[it], z.z, kc_[it]));
+                        v[j].w = fmaf(ka[it], v[j].w, fmaf(kb[it], z.w, kc_[it]));
+                    }
+                    rs[it] += (v[j].x + v[j].y) + (v[j].z + v[j].w);
                 }
-                if ((b_ok >> it) & 1) x_[j] = __ldg(reinterpret_cast<const float4*>(asrc[it] + (long long)b * b_C[it] * L + l0));
             }
-        };
-        auto consume = [&](int q, const int u, float4 (&g_)[2], float4 (&z_)[2], float4 (&x_)[2]) {
-            const int st = q >> 1;
-            const int stage = st % CF::NS, round = st / CF::NS;
             if (u == 0 && round > 0) mbar_wait(&s_empty[stage], (uint32_t)(round - 1) & 1u);
             const uint32_t a_hi = s32(smem) + (uint32_t)stage * CF::STAGE, a_lo = a_hi + CF::HALF;
             const uint32_t b_hi = a_hi + CF::OPND, b_lo = b_hi + CF::HALF;
-            const bool in = r_beg + st * KC + c * 4 < r_end;      // reduction columns past the range stay exactly zero
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const int it = 2 * u + j;
-                const int row = it * 32 + rl;
-                float4 v = g_[j];
-                if (in && ((a_ok >> it) & 1)) {
-                    if (has_coef) {
-                        v.x = fmaf(ka[it], v.x, fmaf(kb[it], z_[j].x, kc_[it]));
-                        v.y = fmaf(ka[it], v.y, fmaf(kb[it], z_[j].y, kc_[it]));
-                        v.z = fmaf(ka[it], v.z, fmaf(kb[it], z_[j].z, kc_[it]));
-                        v.w = fmaf(ka[it], v.w, fmaf(kb[it], z_[j].w, kc_[it]));
-                    }
-                    rs[it] += (v.x + v.y) + (v.z + v.w);
-                }
-                put_chunk_fast<X3>(a_hi, a_lo, sw_off(row, c), v);
-                put_chunk_fast<X3>(b_hi, b_lo, sw_off(row, c), x_[j]);
+                const int row = (2 * u + j) * 32 + rl;
+                put_chunk_fast<X3>(a_hi, a_lo, sw_off(row, c), v[j]);
+                put_chunk_fast<X3>(b_hi, b_lo, sw_off(row, c), xv[j]);
             }
             if (u == 1) {
                 fence_proxy_async();                             // generic-proxy writes -> visible to the tensor core
-                mbar_arrive(&s_full[stage]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_full[stage]);
             }
         };
 #pragma unroll
-        for (int s = 0; s < P; ++s) load(s, s & 1, g[s], zz[s], x[s]);
-        for (int q0 = 0; q0 < total_q; q0 += P) {
+        for (int d = 0; d < D; ++d) issue(d, d);
+        for (int q0 = 0; q0 < total_q; q0 += D) {               // total_q and D are even: slot d always holds half u = d & 1
 #pragma unroll
-            for (int s = 0; s < P; ++s) {
-                if (q0 + s < total_q) {
-                    consume(q0 + s, s & 1, g[s], zz[s], x[s]);
-                    load(q0 + s + P, s & 1, g[s], zz[s], x[s]);
+            for (int d = 0; d < D; ++d) {
+                if (q0 + d < total_q) {
+                    consume(q0 + d, d);
+                    issue(q0 + d + D, d);                        // refills the slot just read
                 }
             }
         }
+        cp_async_wait<0>();
         // bias gradient: the 8 lanes that share a row (consecutive lanes) fold their partial row sums
         if (want_bias) {
 #pragma unroll
