@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_ws(const bmnas_conv_params 
     uint8_t* smA = smem + (size_t)CF::NB * CF::B_ST;
     float4* stg = reinterpret_cast<float4*>(smA + (size_t)CF::NA * CF::A_ST);     // [D][NV][NPROD] 16-byte slots
     __shared__ Bars sh;
-    float4* s_stat = reinterpret_cast<float4*>(smB);          // the activation ring is free once the last tile's MMAs are done
+    __shared__ float2 s_stat[TCM];                            // per-row (mean, M2) of this CTA: epilogue warps -> stat_part writers
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool tl_on = g_ws_tl_on != 0 && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && lane == 0;
@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_ws(const bmnas_conv_params 
             run.m2 = fmaxf(Q - S * (S / n), 0.f);
         }
         if (warp == NPW) WS_TL(7);
-        if (MODE == FWD && p.bn_mode == 1) s_stat[erow] = make_float4(run.n, run.mean, run.m2, 0.f);
+        if (MODE == FWD && p.bn_mode == 1) s_stat[erow] = make_float2(run.mean, run.m2);
     }
 
     // ---- teardown (+ FWD: one statistics partial per CTA and row, finalize by the last CTA of the row tile)
@@ -469,8 +469,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_ws(const bmnas_conv_params 
         if (p.bn_mode != 1) return;
         if (tid < TCM && row0 + tid < M) {
             float* qd = p.stat_part + ((long long)blockIdx.x * M + row0 + tid) * 2;
-            qd[0] = s_stat[tid].y;
-            qd[1] = s_stat[tid].z;
+            qd[0] = s_stat[tid].x;
+            qd[1] = s_stat[tid].y;
         }
         const bool lastb = last_block(p.counter + blockIdx.y, gridDim.x);
         if (tid == 0) WS_TL(9);
